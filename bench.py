@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py — the headline metric of BASELINE.json on B200:
+
+    unrolled solver-steps x cells / sec   (karman-2d 128x64, msteps=32, batch 3 sims per GPU)
+
+One "step" = one full training iteration of the hot path (msteps unrolled solver steps + CNN
+correction forward, the hand-written adjoint sweep, the gradient all-reduce and the TF1-Adam
+update) on one batch of synthetic simulations.  `value` times it with the batch resident in HBM;
+`e2e` times the same iteration through the public host-facing call (pinned host batch -> H2D ->
+step -> D2H loss).  `--impl reference` times the CPU restatement of the reference semantics
+(oracle/sol_oracle.py, fp32, reference-style CG, torch-CPU conv + autograd) on the box's host
+cores — PhiFlow/TensorFlow themselves are not installable here.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "unrolled solver-steps x cells / sec (karman-2d 128x64 msteps=32)"
+UNIT = "step-cells/s"
+REYNOLDS = [10000.0 * 2 ** (i + 4) for i in range(6)]      # karman-2d/Makefile:22
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--Y", type=int, default=128)
+    ap.add_argument("--X", type=int, default=64)
+    ap.add_argument("--msteps", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=3, help="simulations per GPU (SOL-32: -b 3)")
+    ap.add_argument("--spin", type=int, default=200, help="spin-up solver steps for the synthetic wake")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cluster", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-msteps", type=int, default=4, help="unroll length of the bounded CPU sample")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler (pynvml; the recipe's nvidia-smi line as a fallback)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle timed on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference(Y, X, B, msteps, steps, warmup, spin=20):
+    """One training iteration of the CPU restatement (fp32, reference-style CG with the reference's
+    stop rule, torch-CPU conv2d, torch autograd adjoint, TF1 Adam), timed on all host cores."""
+    import torch
+    from oracle import sol_oracle as so
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
+    geom, rho, vy, vx, re, gty, gtx, sig = so.make_case(Y=Y, X=X, B=B, msteps=msteps, spin=spin, dtype=torch.float32)
+    params = [p.requires_grad_() for p in so.init_params(seed=0, dtype=torch.float32)]
+    m_ = [torch.zeros_like(p) for p in params]
+    v_ = [torch.zeros_like(p) for p in params]
+    times = []
+    stats = {}
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for p in params:
+            p.grad = None
+        loss, _ = so.unrolled_loss(params, rho, vy, vx, re, gty, gtx, geom, sig, msteps, solver="cg", tol=1e-5, max_it=2000,
+                                   stats=stats)
+        loss.backward()
+        with torch.no_grad():
+            for k, p in enumerate(params):
+                new, m_[k], v_[k] = so.adam_tf1_step(p, p.grad, m_[k], v_[k], it + 1, 1e-4)
+                p.copy_(new)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    t = sum(times) / len(times)
+    kf = float(torch.cat([x.float() for x in stats.get("fwd_iters", [torch.zeros(1)])]).mean())
+    kb = float(torch.cat([x.float() for x in stats.get("bwd_iters", [torch.zeros(1)])]).mean())
+    return dict(value=msteps * B * Y * X / t, sec_per_iter=t, cores=ncores, k_fwd=kf, k_bwd=kb,
+                sample="%d iterations of karman-2d %dx%d batch %d msteps=%d (bounded sample of the msteps=32 workload; "
+                       "throughput per step-cell is unroll-length invariant)" % (steps, Y, X, B, msteps))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    warm = 1 if args.warmup > 0 else 0
+    r = cpu_reference(args.Y, args.X, args.batch, args.cpu_msteps, steps, warm)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": r["sec_per_iter"] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "karman-2d %dx%d SOL-32 (batch %d sims, msteps %d)" % (args.Y, args.X, args.batch, args.msteps),
+                   "sample": r["sample"], "cg": "reference SparseCG recurrences, max|r|<1e-5, <=2000 it",
+                   "mean_cg_iters": [r["k_fwd"], r["k_bwd"]]},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of the reference semantics (PhiFlow 1.5.1 / TF 1.15 not installable offline)",
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def synth_batch(plan, engine, torch, B, msteps, rank, spin, seed=0):
+    """Synthetic wake, produced by the GPU engine itself: reference warm start
+    (karman.py:107-110) advanced `spin` solver steps, ground truth = the next msteps uncorrected
+    states + N(0, 0.01^2)."""
+    dev = plan.device
+    Y, X = plan.Y, plan.X
+    re = torch.tensor([REYNOLDS[(rank * B + b) % len(REYNOLDS)] for b in range(B)], device=dev, dtype=torch.float32)
+    vy = torch.ones(B, Y + 1, X, device=dev)
+    vx = torch.zeros(B, Y, X + 1, device=dev)
+    P, Q = (Y + 1) // 2, (X + 1) // 2
+    vx[:, P + 10:P + 20, Q - 2:Q + 2] = 1.0
+    for _ in range(spin):
+        o = plan.step_fwd(re, vy, vx)
+        vy, vx = o["vy"], o["vx"]
+    g = torch.Generator(device="cpu").manual_seed(seed + 17 * rank)
+    gy, gx = [], []
+    cy, cx = vy, vx
+    for _ in range(msteps):
+        o = plan.step_fwd(re, cy, cx)
+        cy, cx = o["vy"], o["vx"]
+        gy.append(cy + 0.01 * torch.randn(cy.shape, generator=g).to(dev))
+        gx.append(cx + 0.01 * torch.randn(cx.shape, generator=g).to(dev))
+    sig = (float(vy.abs().std()), float(vx.abs().std()) + 1e-3, float(torch.tensor(REYNOLDS).abs().std(unbiased=False)))
+    return re, vy.contiguous(), vx.contiguous(), torch.stack(gy).contiguous(), torch.stack(gx).contiguous(), sig
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    from solver_in_the_loop_b200 import engine
+    from solver_in_the_loop_b200.trainer import SolTrainer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus or world == 1, "launch with torch.distributed.run --nproc-per-node N for --gpus N"
+    dev = torch.device("cuda", local)
+    Y, X, B, m = args.Y, args.X, args.batch, args.msteps
+    lib_launch0 = None
+
+    plan = engine.Plan.karman(Y, X, B)
+    plan.set_cg(tol_abs=1e-7, tol_rel=1e-6, max_it=4000, cluster=args.cluster)     # accurate solves for the spin-up
+    re, vy0, vx0, gt_vy, gt_vx, sig = synth_batch(plan, engine, torch, B, m, rank, args.spin)
+    if world > 1:   # identical normalisation on every rank (dataStats are global in the reference)
+        s = torch.tensor(sig[:2], device=dev)
+        dist.all_reduce(s); s /= world
+        sig = (float(s[0]), float(s[1]), sig[2])
+    plan.set_cg(tol_abs=1e-5, tol_rel=0.0, max_it=2000, cluster=args.cluster)      # the reference's stop rule (SparseCG)
+    trainer = SolTrainer(plan, m, B, sig, lr=1e-4, seed=0, use_graph=not args.no_graph)
+    # small initial correction keeps the 32-step unroll in the physical regime (as a trained net does)
+    trainer.weights.mul_(0.1)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ device-resident timing (`value`)
+    for _ in range(max(args.warmup, 3)):
+        trainer.train_step(re, vy0, vx0, gt_vy, gt_vx)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = plan.lib.sol_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = trainer.train_step(re, vy0, vx0, gt_vy, gt_vx)
+    e1.record()
+    barrier()
+    launches = plan.lib.sol_launch_count() - l0
+    t_dev = e0.elapsed_time(e1) / 1e3
+    clocks = sampler.stop()
+    iters = trainer.unroll.cg_iters().float()
+    k_fwd, k_bwd = float(iters[0].mean()), float(iters[1].mean())
+
+    # ------------------------------------------------------------------ end-to-end timing (`e2e`)
+    host = [t.cpu().pin_memory() for t in (re, vy0, vx0, gt_vy, gt_vx)]
+    for _ in range(3):
+        trainer.train_step_host(*host)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
+    e2.record()
+    for _ in range(args.steps):
+        loss_host = trainer.train_step_host(*host)
+    e3.record()
+    barrier()
+    t_e2e = max(e2.elapsed_time(e3) / 1e3, 0.0)
+    t_e2e_wall = time.perf_counter() - tw0
+
+    # ------------------------------------------------------------------ pressure-solve kernel roofline (live, CUDA events)
+    plan.set_cg(tol_abs=1e-5, tol_rel=0.0, max_it=2000, cluster=args.cluster)
+    o = plan.step_fwd(re, vy0, vx0)
+    adv_y, adv_x = plan.advect(o["vy1"], o["vx1"])
+    for _ in range(3):
+        plan.project(adv_y, adv_x)
+    nrep = 20
+    torch.cuda.synchronize()
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e4.record()
+    for _ in range(nrep):
+        py, px, it_k = plan.project(adv_y, adv_x)
+    e5.record()
+    torch.cuda.synchronize()
+    t_solve = e4.elapsed_time(e5) / 1e3 / nrep
+    K = float(it_k.float().mean())
+    alg_bytes = (40.0 * K + 8.0) * Y * X * B        # per cell per solve
+    peak, peak_src = load_peaks()
+    achieved = alg_bytes / t_solve / 1e9
+
+    # max over ranks
+    tt = torch.tensor([t_dev, t_e2e, t_solve], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e, t_solve_max = [float(x) for x in tt]
+
+    step_cells = m * B * Y * X * world
+    value = step_cells * args.steps / t_dev
+    e2e_val = step_cells * args.steps / t_e2e
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference(Y, X, B, args.cpu_msteps, 2, 1)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+               "mean_cg_iters": [r["k_fwd"], r["k_bwd"]]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "karman-2d %dx%d SOL-32: msteps=%d, %d sims/GPU, Re in reference Makefile set" % (Y, X, m, B),
+                       "global_batch": B * world, "parallelism": "dp%d over simulations, 1 all-reduce/step" % world,
+                       "cg": "max|r|<1e-5 per sim, <=2000 it (reference stop rule)", "mean_cg_iters": [k_fwd, k_bwd],
+                       "l2": "working set (activation stash %.2f GB/iter) exceeds the 126 MB L2; no explicit flush"
+                             % (trainer.unroll.workspace.numel() / 1e9),
+                       "cuda_graph": not args.no_graph, "loss": float(loss_host)},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": trainer.h2d_bytes_per_step(), "d2h_bytes_per_step": 4,
+                    "ms_per_step": t_e2e / args.steps * 1e3, "wall_ms_per_step": t_e2e_wall / args.steps * 1e3},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "k_cg (fused projection: divergence + CG + gradient subtract)", "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "cg_iters": K, "us_per_launch": t_solve * 1e6,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "note": "CG state is register/SMEM-resident: DRAM traffic is ~20 B/cell regardless of K; "
+                                 "achieved = (40K+8) B/cell algorithmic bytes / CUDA-event launch time"},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,346 @@
+// Persistent conjugate-gradient pressure projection for sm_100a.
+//
+// Replaces PhiFlow's divergence_free()/SparseCG (reference call sites karman_train.py:167-168,185;
+// SURVEY.md §8a rows a8-a11): hard-BC face masking, staggered divergence, CG on the 5-point
+// Laplace with Dirichlet p=0 outside (OPEN) and Neumann at obstacle faces, gradient subtract —
+// ONE kernel launch per projection.
+//
+// B200 mapping: one CTA (or one thread-block cluster of CL CTAs, split along y) per simulation.
+// Each thread owns a column strip of R cells; x, r, p of all CG vectors live in REGISTERS for the
+// whole solve, the search direction p is exchanged through a shared-memory tile with a 1-cell
+// halo (cluster: boundary rows are pushed into the neighbour CTA's halo through DSMEM), the two
+// dot products per iteration are warp-shuffle + shared-memory reductions (cluster: DSMEM slots).
+// HBM traffic is therefore the compulsory minimum: read v (8 B/cell), write v (8 B/cell) and
+// optionally p (4 B/cell), independent of the iteration count K; the ALGORITHMIC traffic a
+// streaming CG would need is (40 K + 8) B/cell, which is what bench.py reports
+// against the HBM roofline.
+//
+// The recurrences are standard CG (x=0; r=p=d; a=rr/(p.Ap); x+=a p; r-=a Ap; b=rr'/rr; p=r+b p),
+// algebraically identical to the reference's (a=(p.r)/(p.q), b=(r.q)/(p.q)) with the same
+// max|r| < tol stop rule, applied per simulation.
+#include <cooperative_groups.h>
+
+#include "sol_cells.cuh"
+#include "sol_internal.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace sol {
+
+struct CgArgs {
+    int Y, X, B;
+    const float* diag;            // [Y*X]
+    const unsigned char* active;  // [Y*X]
+    const float* my;              // [(Y+1)*X]
+    const float* mx;              // [Y*(X+1)]
+    const float* rhs;             // mode 0: [B,Y,X]
+    float* p_out;                 // [B,Y,X] or null
+    const float* vy_in;           // mode 1
+    const float* vx_in;
+    float* vy_out;
+    float* vx_out;
+    float tol_abs, tol_rel;
+    int max_it;
+    int* iters;                   // [B] or null
+};
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float wmax(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block/cluster-wide reduction of (sum s, max m).  Every thread of every CTA of the cluster returns
+// bit-identical results (xor butterflies are symmetric; partials are combined in a fixed order).
+// wpart: [2][2][32], clpart: [2][2][8] shared floats, par = reduction parity (double buffering).
+template <int CL>
+__device__ __forceinline__ void reduce_sm(float& s, float& m, float* wpart, float* clpart, int par, int warp, int lane,
+                                          int nwarps, int rank) {
+    s = wsum(s);
+    m = wmax(m);
+    float* ws = wpart + (par * 2 + 0) * 32;
+    float* wm = wpart + (par * 2 + 1) * 32;
+    if (lane == 0) { ws[warp] = s; wm[warp] = m; }
+    __syncthreads();
+    s = (lane < nwarps) ? ws[lane] : 0.0f;
+    m = (lane < nwarps) ? wm[lane] : 0.0f;
+    s = wsum(s);
+    m = wmax(m);
+    if (CL > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        float* cs = clpart + (par * 2 + 0) * 8;
+        float* cm = clpart + (par * 2 + 1) * 8;
+        if (warp == 0 && lane < CL) {
+            float* rs = cluster.map_shared_rank(cs, lane);
+            float* rm = cluster.map_shared_rank(cm, lane);
+            rs[rank] = s;
+            rm[rank] = m;
+        }
+        cluster.sync();
+        float S = 0.0f, M = 0.0f;
+#pragma unroll
+        for (int c = 0; c < CL; ++c) { S += cs[c]; M = fmaxf(M, cm[c]); }
+        s = S; m = M;
+    }
+}
+
+// MODE 0: solve A p = rhs.  MODE 1: fused projection of a velocity field.
+template <int R, int CL, int MODE>
+__global__ void __launch_bounds__(1024, 1) k_cg(const CgArgs a) {
+    extern __shared__ float smem[];
+    const int X = a.X, Y = a.Y;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int TY = blockDim.y;
+    const int tid = ty * X + tx;
+    const int nthreads = X * TY;
+    const int nwarps = nthreads >> 5;
+    const int lane = tid & 31, warp = tid >> 5;
+    int rank = 0;
+    if (CL > 1) rank = (int)cg::this_cluster().block_rank();
+    const int b = blockIdx.y;
+    const int rows_cta = TY * R;
+    const int PITCH = X + 2;
+    float* ps = smem;                              // (rows_cta+2) * PITCH, halo ring of zeros
+    float* wpart = ps + (rows_cta + 2) * PITCH;    // 2*2*32
+    float* clpart = wpart + 128;                   // 2*2*8
+
+    for (int k = tid; k < (rows_cta + 2) * PITCH; k += nthreads) ps[k] = 0.0f;
+
+    const int lr0 = ty * R;                // first local row of this thread's strip
+    const int j0 = rank * rows_cta + lr0;  // first global row
+    const size_t NC = (size_t)Y * X, NY = (size_t)(Y + 1) * X, NX = (size_t)Y * (X + 1);
+
+    // Almost every cell is "regular" (fluid, 4 accessible neighbours: OPEN borders count as
+    // accessible).  Threads whose whole strip is regular use q = nb - 4 p with no per-cell data in
+    // registers; the few threads next to the obstacle re-read diag/active (L1-resident) instead.
+    float x[R], r[R], p[R];
+    unsigned act = 0u;
+    bool regular = true;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        const int c = (j0 + k) * X + tx;
+        const bool ak = a.active[c] != 0;
+        if (ak) act |= 1u << k;
+        regular = regular && ak && (a.diag[c] == 4.0f);
+        x[k] = 0.0f;
+    }
+    if (MODE == 1) {
+        const float* vy = a.vy_in + (size_t)b * NY;
+        const float* vx = a.vx_in + (size_t)b * NX;
+        float vlo = a.my[j0 * X + tx] * vy[j0 * X + tx];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int j = j0 + k;
+            const float vhi = a.my[(j + 1) * X + tx] * vy[(j + 1) * X + tx];
+            const float xl = a.mx[j * (X + 1) + tx] * vx[j * (X + 1) + tx];
+            const float xr = a.mx[j * (X + 1) + tx + 1] * vx[j * (X + 1) + tx + 1];
+            r[k] = (vhi - vlo) + (xr - xl);
+            vlo = vhi;
+        }
+    } else {
+        const float* rhs = a.rhs + (size_t)b * NC;
+#pragma unroll
+        for (int k = 0; k < R; ++k) r[k] = ((act >> k) & 1u) ? rhs[(j0 + k) * X + tx] : 0.0f;
+    }
+
+    float rr = 0.0f, rmax = 0.0f;
+#pragma unroll
+    for (int k = 0; k < R; ++k) { p[k] = r[k]; rr = fmaf(r[k], r[k], rr); rmax = fmaxf(rmax, fabsf(r[k])); }
+    int par = 0;
+    __syncthreads();   // ps zero-fill complete before anyone writes p into it
+    if (CL > 1) cg::this_cluster().sync();   // ... including remote halo pushes
+    reduce_sm<CL>(rr, rmax, wpart, clpart, par, warp, lane, nwarps, rank); par ^= 1;
+    const float tol = fmaxf(a.tol_abs, a.tol_rel * rmax);
+
+    int it = 0;
+    while (it < a.max_it && rmax > 0.0f && rmax >= tol) {
+        // ---- publish p (own tile + halo rows of the neighbouring CTAs) ----
+#pragma unroll
+        for (int k = 0; k < R; ++k) ps[(lr0 + k + 1) * PITCH + tx + 1] = p[k];
+        if (CL > 1) {
+            cg::cluster_group cluster = cg::this_cluster();
+            if (ty == 0 && rank > 0) {
+                float* rp = cluster.map_shared_rank(ps, rank - 1);
+                rp[(rows_cta + 1) * PITCH + tx + 1] = p[0];
+            }
+            if (ty == TY - 1 && rank < CL - 1) {
+                float* rp = cluster.map_shared_rank(ps, rank + 1);
+                rp[0 * PITCH + tx + 1] = p[R - 1];
+            }
+            cluster.sync();
+        } else {
+            __syncthreads();
+        }
+        // ---- q = A p, pq = p.q ----
+        float q[R];
+        float pq = 0.0f, dummy = 0.0f;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int row = (lr0 + k + 1) * PITCH + tx + 1;
+            const float up = (k + 1 < R) ? p[k + 1] : ps[row + PITCH];
+            const float dn = (k > 0) ? p[k - 1] : ps[row - PITCH];
+            const float nb = (up + dn) + (ps[row - 1] + ps[row + 1]);
+            if (regular) q[k] = fmaf(-4.0f, p[k], nb);
+            else q[k] = ((act >> k) & 1u) ? fmaf(-__ldg(a.diag + (j0 + k) * X + tx), p[k], nb) : 0.0f;
+            pq = fmaf(p[k], q[k], pq);
+        }
+        reduce_sm<CL>(pq, dummy, wpart, clpart, par, warp, lane, nwarps, rank); par ^= 1;
+        const float alpha = (pq != 0.0f) ? rr / pq : 0.0f;
+        float rr_new = 0.0f;
+        rmax = 0.0f;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            x[k] = fmaf(alpha, p[k], x[k]);
+            r[k] = fmaf(-alpha, q[k], r[k]);
+            rr_new = fmaf(r[k], r[k], rr_new);
+            rmax = fmaxf(rmax, fabsf(r[k]));
+        }
+        reduce_sm<CL>(rr_new, rmax, wpart, clpart, par, warp, lane, nwarps, rank); par ^= 1;
+        const float beta = (rr != 0.0f) ? rr_new / rr : 0.0f;
+        rr = rr_new;
+#pragma unroll
+        for (int k = 0; k < R; ++k) p[k] = fmaf(beta, p[k], r[k]);
+        ++it;
+    }
+
+    if (a.iters && tid == 0 && rank == 0) a.iters[b] = it;
+
+    if (MODE == 0) {
+        const float* rhs = a.rhs + (size_t)b * NC;
+        float* po = a.p_out + (size_t)b * NC;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int c = (j0 + k) * X + tx;
+            // solid rows of the reference matrix decouple: -diag * p = rhs
+            po[c] = ((act >> k) & 1u) ? x[k] : -rhs[c] / a.diag[c];
+        }
+        if (CL > 1) cg::this_cluster().sync();   // keep smem alive until all remote traffic is done
+        return;
+    }
+
+    // ---- MODE 1: publish the pressure and subtract its masked gradient ----
+#pragma unroll
+    for (int k = 0; k < R; ++k) ps[(lr0 + k + 1) * PITCH + tx + 1] = x[k];
+    if (CL > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        if (ty == TY - 1 && rank < CL - 1) {
+            float* rp = cluster.map_shared_rank(ps, rank + 1);
+            rp[0 * PITCH + tx + 1] = x[R - 1];
+        }
+        cluster.sync();
+    } else {
+        __syncthreads();
+    }
+    {
+        const float* vy = a.vy_in + (size_t)b * NY;
+        const float* vx = a.vx_in + (size_t)b * NX;
+        float* vyo = a.vy_out + (size_t)b * NY;
+        float* vxo = a.vx_out + (size_t)b * NX;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int j = j0 + k;
+            const int row = (lr0 + k + 1) * PITCH + tx + 1;
+            const float pdn = (k > 0) ? x[k - 1] : ps[row - PITCH];   // p[j-1,i]; zero halo at j = 0
+            const float plf = ps[row - 1];                            // p[j,i-1]; zero halo at i = 0
+            vyo[j * X + tx] = a.my[j * X + tx] * (vy[j * X + tx] - (x[k] - pdn));
+            vxo[j * (X + 1) + tx] = a.mx[j * (X + 1) + tx] * (vx[j * (X + 1) + tx] - (x[k] - plf));
+            if (tx == X - 1) vxo[j * (X + 1) + X] = a.mx[j * (X + 1) + X] * (vx[j * (X + 1) + X] + x[k]);
+        }
+        if (j0 + R == Y) vyo[Y * X + tx] = a.my[Y * X + tx] * (vy[Y * X + tx] + x[R - 1]);
+        if (a.p_out) {
+            float* po = a.p_out + (size_t)b * NC;
+#pragma unroll
+            for (int k = 0; k < R; ++k) po[(j0 + k) * X + tx] = x[k];
+        }
+    }
+    if (CL > 1) cg::this_cluster().sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int R, int CL, int MODE>
+static int launch_cg_t(const CgArgs& a, cudaStream_t st, int TY) {
+    const int rows_cta = TY * R;
+    const size_t smem = ((size_t)(rows_cta + 2) * (a.X + 2) + 128 + 32) * sizeof(float);
+    auto kern = k_cg<R, CL, MODE>;
+    static size_t attr_smem = 48 * 1024;
+    if (smem > attr_smem) {
+        SOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(CL, a.B, 1);
+    cfg.blockDim = dim3(a.X, TY, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (CL > 1) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    SOL_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
+template <int MODE>
+static int dispatch_cg(const CgArgs& a, cudaStream_t st, int CL, int R, int TY) {
+#define SOL_CG_CASE(RR, CC) \
+    if (R == RR && CL == CC) return launch_cg_t<RR, CC, MODE>(a, st, TY);
+    SOL_CG_CASE(1, 1) SOL_CG_CASE(2, 1) SOL_CG_CASE(4, 1) SOL_CG_CASE(8, 1) SOL_CG_CASE(16, 1)
+    SOL_CG_CASE(1, 2) SOL_CG_CASE(2, 2) SOL_CG_CASE(4, 2) SOL_CG_CASE(8, 2) SOL_CG_CASE(16, 2)
+    SOL_CG_CASE(1, 4) SOL_CG_CASE(2, 4) SOL_CG_CASE(4, 4) SOL_CG_CASE(8, 4) SOL_CG_CASE(16, 4)
+    SOL_CG_CASE(1, 8) SOL_CG_CASE(2, 8) SOL_CG_CASE(4, 8) SOL_CG_CASE(8, 8) SOL_CG_CASE(16, 8)
+#undef SOL_CG_CASE
+    return fail(SOL_ERR_UNSUPPORTED, "cg: no kernel for this (rows/thread, cluster) combination");
+}
+
+// choose (CL, R, TY) with Y = CL*TY*R, X*TY <= 1024, R in {1,2,4,8,16}
+static bool cg_geometry(int Y, int X, int want_cl, int& CL, int& R, int& TY) {
+    if (X % 32 != 0 || X > 1024 || X < 32) return false;
+    const int max_ty = 1024 / X;
+    const int cls[4] = {1, 2, 4, 8};
+    // pass 0: strips of <= 8 rows (x, r, p, q, diag fit the 64-register budget of a 1024-thread
+    // CTA); pass 1: allow 16-row strips as a fallback for very tall grids
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int ci = 0; ci < 4; ++ci) {
+            const int cl = cls[ci];
+            if (want_cl > 0 && cl != want_cl) continue;
+            if (Y % cl) continue;
+            const int rows = Y / cl;
+            const int rs[5] = {1, 2, 4, 8, 16};
+            for (int ri = 0; ri < (pass == 0 ? 4 : 5); ++ri) {   // smallest R (most threads) that fits
+                const int rr = rs[ri];
+                if (rows % rr) continue;
+                const int ty = rows / rr;
+                if (ty <= max_ty && ty >= 1) { CL = cl; R = rr; TY = ty; return true; }
+            }
+        }
+    }
+    return false;
+}
+
+int launch_cg(const sol_plan* p, cudaStream_t st, int B, int mode, const float* rhs, float* p_out, const float* vy,
+              const float* vx, float* vy_out, float* vx_out, int* iters) {
+    if (p->boundary != SOL_BOUNDARY_OPEN) return fail(SOL_ERR_UNSUPPORTED, "pressure solve requires an OPEN-boundary plan");
+    CgArgs a;
+    a.Y = p->Y; a.X = p->X; a.B = B;
+    a.diag = p->diag; a.active = p->active; a.my = p->face_my; a.mx = p->face_mx;
+    a.rhs = rhs; a.p_out = p_out; a.vy_in = vy; a.vx_in = vx; a.vy_out = vy_out; a.vx_out = vx_out;
+    a.tol_abs = p->tol_abs; a.tol_rel = p->tol_rel; a.max_it = p->max_it; a.iters = iters;
+    int CL, R, TY;
+    if (!cg_geometry(p->Y, p->X, p->cluster, CL, R, TY))
+        return fail(SOL_ERR_UNSUPPORTED, "cg: grid must have X a multiple of 32 (<=1024) and Y = cluster*TY*R with R in {1,2,4,8,16}");
+    if (mode == 0) return dispatch_cg<0>(a, st, CL, R, TY);
+    return dispatch_cg<1>(a, st, CL, R, TY);
+}
+
+}  // namespace sol

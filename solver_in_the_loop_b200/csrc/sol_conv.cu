@@ -1,0 +1,451 @@
+// 5x5 'same' convolutions of the correction CNN (keras Conv2D, reference
+// karman-2d/karman_train.py:101-138), NHWC activations, Keras kernel layout [5,5,Cin,Cout].
+//
+// This file holds the fp32 SIMT kernels: the exact-fp32 baseline every other conv path in the
+// repo is validated against.
+//   k_conv5x5_c32   32->32 layers (10 of the 12 layers; also the data gradient via flipped weights)
+//                   register tile 8 pixels x 4 couts per thread, input tile + halo in shared
+//                   memory (float4 over cin), weights streamed through L1 (100 KB, L1-resident),
+//                   5-tap sliding window along x so each shared load feeds 20+ FMAs.
+//   k_conv5x5_thin  first / last layers (Cin or Cout <= 4)
+//   k_wgrad_c32     weight gradient of the 32->32 layers: every thread owns 80 (tap,cin,cout)
+//                   accumulators in registers for the whole pixel range of its CTA; per-CTA partial
+//                   sums go to a private slot (no atomics, deterministic), reduced by
+//                   k_wgrad_finalize once per optimiser step.
+//   k_wgrad_thin    weight gradient of the thin layers (atomics; tiny)
+#include "sol_internal.cuh"
+
+namespace sol {
+
+struct ConvArgs {
+    const float* in;
+    const float* w;
+    const float* bias;
+    const float* addend;
+    const float* ref;
+    float* out;
+    int B, Y, X;
+    int act;
+    float slope;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope, float ref) {
+    if (act == SOL_ACT_LRELU) return v > 0.0f ? v : slope * v;
+    if (act == SOL_ACT_DLRELU) return ref > 0.0f ? v : slope * v;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 32 -> 32
+// ------------------------------------------------------------------------------------------------
+template <int TH>
+__global__ void __launch_bounds__(TH * 32, (TH <= 4 ? 3 : 2)) k_conv5x5_c32(const ConvArgs a) {
+    constexpr int TW = 32, PW = TW + 4, PH = TH + 4, C = 32;
+    extern __shared__ float4 tile4[];   // [PH][PW][8]
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
+    const float* inb = a.in + (size_t)b * a.Y * a.X * C;
+    for (int idx = tid; idx < PH * PW * 8; idx += TH * 32) {
+        const int c4 = idx & 7, pix = idx >> 3;
+        const int tyy = pix / PW, txx = pix - tyy * PW;
+        const int gy = y0 + tyy - 2, gx = x0 + txx - 2;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gy >= 0 && gy < a.Y && gx >= 0 && gx < a.X)
+            v = __ldg(reinterpret_cast<const float4*>(inb + ((size_t)gy * a.X + gx) * C) + c4);
+        tile4[idx] = v;
+    }
+    __syncthreads();
+
+    const int cog = tid & 7, pg = tid >> 3, row = pg >> 2, xseg = pg & 3;
+    float acc[8][4];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) { acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = 0.0f; }
+    const float4* w4 = reinterpret_cast<const float4*>(a.w);   // [(tap*32 + ci)*8 + cog]
+
+#pragma unroll 1
+    for (int dy = 0; dy < 5; ++dy) {
+        const float4* trow = tile4 + ((row + dy) * PW + xseg * 8) * 8;
+#pragma unroll 1
+        for (int c4 = 0; c4 < 8; ++c4) {
+            float4 iv[12];
+#pragma unroll
+            for (int t = 0; t < 12; ++t) iv[t] = trow[t * 8 + c4];
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx) {
+                const float4* wp = w4 + ((dy * 5 + dx) * 32 + c4 * 4) * 8 + cog;
+                const float4 w0 = __ldg(wp), w1 = __ldg(wp + 8), w2 = __ldg(wp + 16), w3 = __ldg(wp + 24);
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    const float4 v = iv[p + dx];
+                    acc[p][0] = fmaf(v.x, w0.x, fmaf(v.y, w1.x, fmaf(v.z, w2.x, fmaf(v.w, w3.x, acc[p][0]))));
+                    acc[p][1] = fmaf(v.x, w0.y, fmaf(v.y, w1.y, fmaf(v.z, w2.y, fmaf(v.w, w3.y, acc[p][1]))));
+                    acc[p][2] = fmaf(v.x, w0.z, fmaf(v.y, w1.z, fmaf(v.z, w2.z, fmaf(v.w, w3.z, acc[p][2]))));
+                    acc[p][3] = fmaf(v.x, w0.w, fmaf(v.y, w1.w, fmaf(v.z, w2.w, fmaf(v.w, w3.w, acc[p][3]))));
+                }
+            }
+        }
+    }
+
+    const int gy = y0 + row;
+    if (gy >= a.Y) return;
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.bias) bv = __ldg(reinterpret_cast<const float4*>(a.bias) + cog);
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        const int gx = x0 + xseg * 8 + p;
+        if (gx >= a.X) continue;
+        const size_t o4 = (((size_t)b * a.Y + gy) * a.X + gx) * 8 + cog;
+        float4 v = make_float4(acc[p][0] + bv.x, acc[p][1] + bv.y, acc[p][2] + bv.z, acc[p][3] + bv.w);
+        if (a.addend) {
+            const float4 ad = __ldg(reinterpret_cast<const float4*>(a.addend) + o4);
+            v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
+        }
+        float4 rf = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.act == SOL_ACT_DLRELU) rf = __ldg(reinterpret_cast<const float4*>(a.ref) + o4);
+        v.x = apply_act(v.x, a.act, a.slope, rf.x);
+        v.y = apply_act(v.y, a.act, a.slope, rf.y);
+        v.z = apply_act(v.z, a.act, a.slope, rf.z);
+        v.w = apply_act(v.w, a.act, a.slope, rf.w);
+        reinterpret_cast<float4*>(a.out)[o4] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// thin layers: one output pixel per thread, 16x16 tiles
+// ------------------------------------------------------------------------------------------------
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256) k_conv5x5_thin(const ConvArgs a) {
+    constexpr int T = 16, P = T + 4;
+    constexpr int CINP = (CIN % 2 == 0) ? CIN + 1 : CIN;   // odd pixel stride: conflict-free scalar reads
+    extern __shared__ float sm[];
+    float* tin = sm;                       // [P*P][CINP]
+    float* ws = sm + P * P * CINP;         // [25*CIN*COUT]
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * T, y0 = blockIdx.y * T, b = blockIdx.z;
+    const float* inb = a.in + (size_t)b * a.Y * a.X * CIN;
+    for (int idx = tid; idx < P * P * CIN; idx += 256) {
+        const int c = idx % CIN, pix = idx / CIN;
+        const int tyy = pix / P, txx = pix - tyy * P;
+        const int gy = y0 + tyy - 2, gx = x0 + txx - 2;
+        float v = 0.0f;
+        if (gy >= 0 && gy < a.Y && gx >= 0 && gx < a.X) v = __ldg(inb + ((size_t)gy * a.X + gx) * CIN + c);
+        tin[pix * CINP + c] = v;
+    }
+    for (int idx = tid; idx < 25 * CIN * COUT; idx += 256) ws[idx] = __ldg(a.w + idx);
+    __syncthreads();
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = 0.0f;
+#pragma unroll 1
+    for (int tap = 0; tap < 25; ++tap) {
+        const int dy = tap / 5, dx = tap - dy * 5;
+        const float* tp = tin + ((ty + dy) * P + tx + dx) * CINP;
+        const float* wp = ws + tap * CIN * COUT;
+#pragma unroll 4
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float v = tp[ci];
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) acc[c] = fmaf(v, wp[ci * COUT + c], acc[c]);
+        }
+    }
+    const int gy = y0 + ty, gx = x0 + tx;
+    if (gy >= a.Y || gx >= a.X) return;
+    const size_t o = (((size_t)b * a.Y + gy) * a.X + gx) * COUT;
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) {
+        float v = acc[c];
+        if (a.bias) v += __ldg(a.bias + c);
+        if (a.addend) v += __ldg(a.addend + o + c);
+        const float rf = (a.act == SOL_ACT_DLRELU) ? __ldg(a.ref + o + c) : 0.0f;
+        a.out[o + c] = apply_act(v, a.act, a.slope, rf);
+    }
+}
+
+template <int CIN, int COUT>
+static int launch_thin(const ConvArgs& a, cudaStream_t st) {
+    constexpr int CINP = (CIN % 2 == 0) ? CIN + 1 : CIN;
+    const size_t smem = (size_t)(20 * 20 * CINP + 25 * CIN * COUT) * sizeof(float);
+    auto kern = k_conv5x5_thin<CIN, COUT>;
+    static bool attr_done = false;   // one process per GPU: set once, outside any later graph capture
+    if (smem > 48 * 1024 && !attr_done) {
+        SOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    dim3 grid(cdiv(a.X, 16), cdiv(a.Y, 16), a.B);
+    kern<<<grid, 256, smem, st>>>(a);
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
+int launch_conv5x5(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const float* in, const float* w, const float* bias,
+                   const float* addend, const float* ref, int act, float slope, float* out) {
+    ConvArgs a;
+    a.in = in; a.w = w; a.bias = bias; a.addend = addend; a.ref = ref; a.out = out;
+    a.B = B; a.Y = Y; a.X = X; a.act = act; a.slope = slope;
+    if (act == SOL_ACT_DLRELU && !ref) return fail(SOL_ERR_INVALID, "conv5x5: SOL_ACT_DLRELU needs ref");
+    if (Cin == 32 && Cout == 32) {
+        // pick the tile height that gives at least ~one CTA per SM
+        const long ctas8 = (long)cdiv(X, 32) * cdiv(Y, 8) * B;
+        if (ctas8 >= 148) {
+            const size_t smem = (size_t)12 * 36 * 8 * sizeof(float4);
+            static bool attr_done = false;
+            if (!attr_done) {
+                SOL_CUDA(cudaFuncSetAttribute(k_conv5x5_c32<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_done = true;
+            }
+            k_conv5x5_c32<8><<<dim3(cdiv(X, 32), cdiv(Y, 8), B), 256, smem, st>>>(a);
+        } else {
+            const size_t smem = (size_t)8 * 36 * 8 * sizeof(float4);
+            k_conv5x5_c32<4><<<dim3(cdiv(X, 32), cdiv(Y, 4), B), 128, smem, st>>>(a);
+        }
+        SOL_LAUNCHED();
+        return SOL_OK;
+    }
+#define SOL_THIN(CI, CO) \
+    if (Cin == CI && Cout == CO) return launch_thin<CI, CO>(a, st);
+    SOL_THIN(3, 32) SOL_THIN(4, 32) SOL_THIN(2, 32) SOL_THIN(32, 2) SOL_THIN(32, 3) SOL_THIN(32, 4)
+#undef SOL_THIN
+    return fail(SOL_ERR_UNSUPPORTED, "conv5x5: unsupported (Cin, Cout) pair");
+}
+
+// ------------------------------------------------------------------------------------------------
+// wT[tap][co][ci] = w[24 - tap][ci][co]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_flip_weights(int Cin, int Cout, const float* __restrict__ w, float* __restrict__ wT) {
+    const int n = 25 * Cin * Cout;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const int ci = idx % Cin;
+        const int co = (idx / Cin) % Cout;
+        const int tap = idx / (Cin * Cout);
+        wT[idx] = w[((24 - tap) * Cin + ci) * Cout + co];
+    }
+}
+
+int launch_flip_weights(cudaStream_t st, int Cin, int Cout, const float* w, float* wT) {
+    const int n = 25 * Cin * Cout;
+    k_flip_weights<<<cdiv(n, 256), 256, 0, st>>>(Cin, Cout, w, wT);
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient, 32 -> 32
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_E = 25 * 32 * 32 + 32;   // entries per partial slot (weights + bias)
+constexpr int WG_MAX_CTAS = 148;
+
+struct WgradArgs {
+    const float* in;
+    const float* g;
+    float* part;
+    int B, Y, X;
+    int accumulate;
+};
+
+__global__ void __launch_bounds__(320, 1) k_wgrad_c32(const WgradArgs a) {
+    extern __shared__ float4 wsm[];
+    const int X = a.X, Y = a.Y;
+    const int PWX = X + 4;
+    float4* tin = wsm;                 // [5][PWX][8]
+    float4* tg = wsm + 5 * PWX * 8;    // [X][8]
+    const int tid = threadIdx.x;
+    const int co4 = tid & 7, ci4 = (tid >> 3) & 7, dy = tid >> 6;
+    float acc[5][4][4];
+    float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int d = 0; d < 5; ++d)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { acc[d][q][0] = acc[d][q][1] = acc[d][q][2] = acc[d][q][3] = 0.0f; }
+    const int rows_total = a.B * Y;
+    const int r_begin = (int)((long)blockIdx.x * rows_total / gridDim.x);
+    const int r_end = (int)((long)(blockIdx.x + 1) * rows_total / gridDim.x);
+    const bool do_bias = (ci4 == 0 && dy == 0);
+#pragma unroll 1
+    for (int r = r_begin; r < r_end; ++r) {
+        const int b = r / Y, y = r - b * Y;
+        __syncthreads();
+        for (int idx = tid; idx < 5 * PWX * 8; idx += 320) {
+            const int c4 = idx & 7, pix = idx >> 3;
+            const int rr = pix / PWX, xx = pix - rr * PWX;
+            const int gy = y + rr - 2, gx = xx - 2;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gy >= 0 && gy < Y && gx >= 0 && gx < X)
+                v = __ldg(reinterpret_cast<const float4*>(a.in + (((size_t)b * Y + gy) * X + gx) * 32) + c4);
+            tin[idx] = v;
+        }
+        for (int idx = tid; idx < X * 8; idx += 320)
+            tg[idx] = __ldg(reinterpret_cast<const float4*>(a.g + ((size_t)b * Y + y) * X * 32) + idx);
+        __syncthreads();
+        const float4* inrow = tin + dy * PWX * 8;
+#pragma unroll 1
+        for (int x0 = 0; x0 < X; x0 += 4) {
+            float4 wv[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) wv[t] = inrow[(x0 + t) * 8 + ci4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 g4 = tg[(x0 + u) * 8 + co4];
+                if (do_bias) { bacc[0] += g4.x; bacc[1] += g4.y; bacc[2] += g4.z; bacc[3] += g4.w; }
+#pragma unroll
+                for (int d = 0; d < 5; ++d) {
+                    const float4 v = wv[u + d];
+                    acc[d][0][0] = fmaf(v.x, g4.x, acc[d][0][0]); acc[d][0][1] = fmaf(v.x, g4.y, acc[d][0][1]);
+                    acc[d][0][2] = fmaf(v.x, g4.z, acc[d][0][2]); acc[d][0][3] = fmaf(v.x, g4.w, acc[d][0][3]);
+                    acc[d][1][0] = fmaf(v.y, g4.x, acc[d][1][0]); acc[d][1][1] = fmaf(v.y, g4.y, acc[d][1][1]);
+                    acc[d][1][2] = fmaf(v.y, g4.z, acc[d][1][2]); acc[d][1][3] = fmaf(v.y, g4.w, acc[d][1][3]);
+                    acc[d][2][0] = fmaf(v.z, g4.x, acc[d][2][0]); acc[d][2][1] = fmaf(v.z, g4.y, acc[d][2][1]);
+                    acc[d][2][2] = fmaf(v.z, g4.z, acc[d][2][2]); acc[d][2][3] = fmaf(v.z, g4.w, acc[d][2][3]);
+                    acc[d][3][0] = fmaf(v.w, g4.x, acc[d][3][0]); acc[d][3][1] = fmaf(v.w, g4.y, acc[d][3][1]);
+                    acc[d][3][2] = fmaf(v.w, g4.z, acc[d][3][2]); acc[d][3][3] = fmaf(v.w, g4.w, acc[d][3][3]);
+                }
+            }
+        }
+    }
+    float4* part4 = reinterpret_cast<float4*>(a.part + (size_t)blockIdx.x * WG_E);
+#pragma unroll
+    for (int d = 0; d < 5; ++d)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int o4 = (((dy * 5 + d) * 32 + ci4 * 4 + q) * 32 + co4 * 4) >> 2;
+            float4 v = make_float4(acc[d][q][0], acc[d][q][1], acc[d][q][2], acc[d][q][3]);
+            if (a.accumulate) { const float4 o = part4[o4]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            part4[o4] = v;
+        }
+    if (do_bias) {
+        const int o4 = (25 * 32 * 32 + co4 * 4) >> 2;
+        float4 v = make_float4(bacc[0], bacc[1], bacc[2], bacc[3]);
+        if (a.accumulate) { const float4 o = part4[o4]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+        part4[o4] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_wgrad_finalize(int nctas, const float* __restrict__ part, float* __restrict__ dW,
+                                                        float* __restrict__ db, int accumulate) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= WG_E) return;
+    float s = 0.0f;
+    for (int c = 0; c < nctas; ++c) s += part[(size_t)c * WG_E + e];
+    float* dst = (e < 25 * 32 * 32) ? (dW + e) : (db + (e - 25 * 32 * 32));
+    *dst = accumulate ? (*dst + s) : s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient, thin layers (atomics into dW / db)
+// ------------------------------------------------------------------------------------------------
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256) k_wgrad_thin(const float* __restrict__ in, const float* __restrict__ g, float* dW, float* db,
+                                                    int B, int Y, int X) {
+    constexpr int TR = 8, TWT = 32, PR = TR + 4, PWT = TWT + 4;
+    constexpr int CINP = (CIN % 2 == 0) ? CIN + 1 : CIN;
+    constexpr int COUTP = (COUT % 2 == 0) ? COUT + 1 : COUT;
+    extern __shared__ float sm[];
+    float* tin = sm;                          // [PR*PWT][CINP]
+    float* tg = sm + PR * PWT * CINP;         // [TR*TWT][COUTP]
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TWT, y0 = blockIdx.y * TR, b = blockIdx.z;
+    for (int idx = tid; idx < PR * PWT * CIN; idx += 256) {
+        const int c = idx % CIN, pix = idx / CIN;
+        const int tyy = pix / PWT, txx = pix - tyy * PWT;
+        const int gy = y0 + tyy - 2, gx = x0 + txx - 2;
+        float v = 0.0f;
+        if (gy >= 0 && gy < Y && gx >= 0 && gx < X) v = __ldg(in + (((size_t)b * Y + gy) * X + gx) * CIN + c);
+        tin[pix * CINP + c] = v;
+    }
+    for (int idx = tid; idx < TR * TWT * COUT; idx += 256) {
+        const int c = idx % COUT, pix = idx / COUT;
+        const int tyy = pix / TWT, txx = pix - tyy * TWT;
+        const int gy = y0 + tyy, gx = x0 + txx;
+        float v = 0.0f;
+        if (gy < Y && gx < X) v = __ldg(g + (((size_t)b * Y + gy) * X + gx) * COUT + c);
+        tg[pix * COUTP + c] = v;
+    }
+    __syncthreads();
+    constexpr int E = 25 * CIN * COUT;
+    for (int e = tid; e < E + COUT; e += 256) {
+        float acc = 0.0f;
+        if (e < E) {
+            const int co = e % COUT, ci = (e / COUT) % CIN, tap = e / (COUT * CIN);
+            const int dy = tap / 5, dx = tap - dy * 5;
+#pragma unroll 1
+            for (int yy = 0; yy < TR; ++yy) {
+                const float* ip = tin + ((yy + dy) * PWT + dx) * CINP + ci;
+                const float* gp = tg + (yy * TWT) * COUTP + co;
+#pragma unroll 8
+                for (int xx = 0; xx < TWT; ++xx) acc = fmaf(ip[xx * CINP], gp[xx * COUTP], acc);
+            }
+            atomicAdd(dW + e, acc);
+        } else {
+            const int co = e - E;
+            for (int pix = 0; pix < TR * TWT; ++pix) acc += tg[pix * COUTP + co];
+            atomicAdd(db + co, acc);
+        }
+    }
+}
+
+template <int CIN, int COUT>
+static int launch_wgrad_thin(cudaStream_t st, int B, int Y, int X, const float* in, const float* g, float* dW, float* db) {
+    constexpr int CINP = (CIN % 2 == 0) ? CIN + 1 : CIN;
+    constexpr int COUTP = (COUT % 2 == 0) ? COUT + 1 : COUT;
+    const size_t smem = (size_t)(12 * 36 * CINP + 8 * 32 * COUTP) * sizeof(float);
+    auto kern = k_wgrad_thin<CIN, COUT>;
+    static bool attr_done = false;
+    if (smem > 48 * 1024 && !attr_done) {
+        SOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    kern<<<dim3(cdiv(X, 32), cdiv(Y, 8), B), 256, smem, st>>>(in, g, dW, db, B, Y, X);
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
+size_t wgrad_workspace_floats(int Cin, int Cout) {
+    if (Cin == 32 && Cout == 32) return (size_t)WG_MAX_CTAS * WG_E;
+    return 0;
+}
+
+static int wgrad_ctas(int B, int Y) {
+    const int rows = B * Y;
+    return rows < WG_MAX_CTAS ? rows : WG_MAX_CTAS;
+}
+
+int launch_wgrad(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const float* in, const float* g_out, float* dW, float* db,
+                 int accumulate, float* partials, bool finalize) {
+    if (Cin == 32 && Cout == 32) {
+        if (!partials) return fail(SOL_ERR_WORKSPACE, "wgrad 32->32 needs the partials workspace");
+        if (X % 4) return fail(SOL_ERR_UNSUPPORTED, "wgrad 32->32 needs X % 4 == 0");
+        const int nctas = wgrad_ctas(B, Y);
+        if (in) {
+            WgradArgs a;
+            a.in = in; a.g = g_out; a.part = partials; a.B = B; a.Y = Y; a.X = X;
+            // stand-alone call (finalize=true): partials are scratch; engine call: partials carry the
+            // running sum over the unrolled steps and `accumulate` applies to them
+            a.accumulate = finalize ? 0 : accumulate;
+            const size_t smem = ((size_t)5 * (X + 4) * 8 + (size_t)X * 8) * sizeof(float4);
+            static size_t attr_smem = 0;
+            if (smem > attr_smem) {
+                SOL_CUDA(cudaFuncSetAttribute(k_wgrad_c32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_smem = smem;
+            }
+            k_wgrad_c32<<<nctas, 320, smem, st>>>(a);
+            SOL_LAUNCHED();
+        }
+        if (finalize) {
+            k_wgrad_finalize<<<cdiv(WG_E, 256), 256, 0, st>>>(nctas, partials, dW, db, accumulate);
+            SOL_LAUNCHED();
+        }
+        return SOL_OK;
+    }
+    if (!in) return SOL_OK;   // finalize-only call on a thin layer: nothing to do
+    if (!accumulate) {
+        SOL_CUDA(cudaMemsetAsync(dW, 0, (size_t)25 * Cin * Cout * sizeof(float), st));
+        SOL_CUDA(cudaMemsetAsync(db, 0, (size_t)Cout * sizeof(float), st));
+    }
+#define SOL_WTHIN(CI, CO) \
+    if (Cin == CI && Cout == CO) return launch_wgrad_thin<CI, CO>(st, B, Y, X, in, g_out, dW, db);
+    SOL_WTHIN(3, 32) SOL_WTHIN(4, 32) SOL_WTHIN(2, 32) SOL_WTHIN(32, 2)
+#undef SOL_WTHIN
+    return fail(SOL_ERR_UNSUPPORTED, "wgrad: unsupported (Cin, Cout) pair");
+}
+
+}  // namespace sol

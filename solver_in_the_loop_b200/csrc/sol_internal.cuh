@@ -1,0 +1,121 @@
+// Internal declarations shared by the translation units of libsol_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <vector>
+
+#include "../../include/sol_b200.h"
+
+namespace sol {
+
+extern thread_local char g_err[512];
+extern std::atomic<unsigned long long> g_launches;
+
+inline int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+
+#define SOL_CUDA(call)                                                                           \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            snprintf(sol::g_err, sizeof(sol::g_err), "%s:%d: %s -> %s", __FILE__, __LINE__, #call, \
+                     cudaGetErrorString(e__));                                                   \
+            return SOL_ERR_CUDA;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+#define SOL_CHECK(cond, msg)                                                             \
+    do {                                                                                 \
+        if (!(cond)) {                                                                   \
+            snprintf(sol::g_err, sizeof(sol::g_err), "%s:%d: %s", __FILE__, __LINE__, msg); \
+            return SOL_ERR_INVALID;                                                      \
+        }                                                                                \
+    } while (0)
+
+#define SOL_TRY(call)            \
+    do {                         \
+        int rc__ = (call);       \
+        if (rc__ != SOL_OK) return rc__; \
+    } while (0)
+
+// count + check a kernel launch
+#define SOL_LAUNCHED()                                   \
+    do {                                                 \
+        sol::g_launches.fetch_add(1, std::memory_order_relaxed); \
+        SOL_CUDA(cudaGetLastError());                    \
+    } while (0)
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace sol
+
+struct sol_plan {
+    int Y = 0, X = 0, B_max = 0;
+    float dx = 1.f;
+    int boundary = SOL_BOUNDARY_OPEN;
+    int sm_count = 148;
+    // device-resident constants (shared by the whole batch)
+    unsigned char* active = nullptr;   // [Y*X] 1 = fluid cell
+    float* diag = nullptr;             // [Y*X] #accessible neighbours, >= 1
+    float* face_my = nullptr;          // [(Y+1)*X] hard-BC face mask
+    float* face_mx = nullptr;          // [Y*(X+1)]
+    float* inflow = nullptr;           // [Y*X] or null
+    float* bc_mask_y = nullptr;        // [(Y+1)*X] or null
+    float* bc_val_y = nullptr;
+    // CG controls
+    float tol_abs = 1e-5f, tol_rel = 0.f;
+    int max_it = 2000;
+    int cluster = 0;
+    size_t NY() const { return (size_t)(Y + 1) * X; }
+    size_t NX() const { return (size_t)Y * (X + 1); }
+    size_t NC() const { return (size_t)Y * X; }
+};
+
+namespace sol {
+
+// ---- stencil stage launchers (sol_stencil.cu) ----
+int launch_diffuse_bc(const sol_plan* p, cudaStream_t st, int B, const float* re, float dt, float res,
+                      const float* vy, const float* vx, float* vy_out, float* vx_out);
+int launch_diffuse_bc_bwd(const sol_plan* p, cudaStream_t st, int B, const float* re, float dt, float res,
+                          const float* gy, const float* gx, float* gy_in, float* gx_in, const float* add_y, const float* add_x);
+int launch_advect(const sol_plan* p, cudaStream_t st, int B, float dt, const float* vy, const float* vx, const float* rho,
+                  float* vy_out, float* vx_out, float* rho_out);
+int launch_advect_bwd(const sol_plan* p, cudaStream_t st, int B, float dt, const float* vy, const float* vx,
+                      const float* gy_out, const float* gx_out, float* gy, float* gx);
+int launch_divergence(const sol_plan* p, cudaStream_t st, int B, const float* vy, const float* vx, float* div);
+int launch_to_feature(const sol_plan* p, cudaStream_t st, int B, const float* vy, const float* vx, const float* re,
+                      float sy, float sx, float sr, float* feat);
+// v_out = v + sigma*corr (zero on the far row/col); optional loss + loss gradient
+int launch_correct_loss(const sol_plan* p, cudaStream_t st, int B, const float* vy, const float* vx, const float* corr,
+                        float sy, float sx, const float* gt_vy, const float* gt_vx, float inv_m,
+                        float* vy_out, float* vx_out, float* gl_vy, float* gl_vx, float* loss);
+// g_corr[B,Y,X,2] = sigma * G[:Y,:X]
+int launch_corr_bwd(const sol_plan* p, cudaStream_t st, int B, const float* Gy, const float* Gx, float sy, float sx, float* g_corr);
+// G3 = G + g_feat[...,0:2]/sigma (padded)
+int launch_feat_bwd(const sol_plan* p, cudaStream_t st, int B, const float* Gy, const float* Gx, const float* g_feat, int cfeat,
+                    float sy, float sx, float* Gy_out, float* Gx_out);
+int launch_burgers_diffuse(const sol_plan* p, cudaStream_t st, int B, float amount, const float* ky, const float* kx,
+                           const float* vy, const float* vx, const float* fy, const float* fx, float dtf,
+                           float* vy_out, float* vx_out);
+int launch_adam(cudaStream_t st, size_t n, float* theta, const float* g, float* m, float* v, float lr_t, float b1, float b2,
+                float eps, float gscale);
+
+// ---- pressure projection (sol_cg.cu) ----
+int launch_cg(const sol_plan* p, cudaStream_t st, int B, int mode, const float* rhs, float* p_out, const float* vy,
+              const float* vx, float* vy_out, float* vx_out, int* iters);
+
+// ---- convolutions (sol_conv.cu) ----
+int launch_conv5x5(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const float* in, const float* w, const float* bias,
+                   const float* addend, const float* ref, int act, float slope, float* out);
+int launch_flip_weights(cudaStream_t st, int Cin, int Cout, const float* w, float* wT);
+size_t wgrad_workspace_floats(int Cin, int Cout);
+int launch_wgrad(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const float* in, const float* g_out, float* dW, float* db,
+                 int accumulate, float* partials, bool finalize);
+
+}  // namespace sol

