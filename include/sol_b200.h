@@ -67,6 +67,13 @@ int sol_plan_destroy(sol_plan* plan);
  * iterations (reference SparseCG: tol_abs=1e-5, tol_rel=0, max_it=2000).  cluster = CTAs per
  * simulation (1,2,4,8; 0 = auto). */
 int sol_plan_set_cg(sol_plan* plan, float tol_abs, float tol_rel, int max_it, int cluster);
+/* Tuning knobs that never change results beyond fp32 round-off:
+ *   "cg_rows"   rows of the grid each CG thread keeps in registers (0 = auto, 2/4/8/16) */
+int sol_plan_set_option(sol_plan* plan, const char* name, int value);
+/* Process-wide knobs:
+ *   "conv_path" 0 = auto, 1 = fp32 SIMT kernels, 2 = tcgen05 tensor-core kernels (3xTF32, fp32-accurate)
+ *   "tc_base_offset_mode" (debug) how the UMMA shared-memory descriptors encode unaligned starts */
+int sol_set_option(const char* name, int value);
 
 /* ---- stage entry points (one reference op each) --------------------------------------------- */
 

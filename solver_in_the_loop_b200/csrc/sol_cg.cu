@@ -49,51 +49,53 @@ __device__ __forceinline__ float wsum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__device__ __forceinline__ float wmax(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
+// max of NON-NEGATIVE floats in one REDUX instruction: for x >= 0 the IEEE bit patterns are ordered
+__device__ __forceinline__ float wmax_nonneg(float v) {
+    return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v)));
 }
 
-// Block/cluster-wide reduction of (sum s, max m).  Every thread of every CTA of the cluster returns
-// bit-identical results (xor butterflies are symmetric; partials are combined in a fixed order).
-// wpart: [2][2][32], clpart: [2][2][8] shared floats, par = reduction parity (double buffering).
-template <int CL>
+// Block/cluster-wide reduction of a sum s (and, if WITH_MAX, of a non-negative max m).  Every thread
+// of every CTA of the cluster returns bit-identical results (xor butterflies are symmetric; partials
+// are combined in a fixed order).  wpart: [2][2][32], clpart: [2][2][8] shared floats,
+// par = reduction parity (double buffering: a buffer is rewritten only two reductions later, and a
+// barrier separates every pair of reductions).
+template <int CL, bool WITH_MAX>
 __device__ __forceinline__ void reduce_sm(float& s, float& m, float* wpart, float* clpart, int par, int warp, int lane,
                                           int nwarps, int rank) {
     s = wsum(s);
-    m = wmax(m);
+    if (WITH_MAX) m = wmax_nonneg(m);
     float* ws = wpart + (par * 2 + 0) * 32;
     float* wm = wpart + (par * 2 + 1) * 32;
-    if (lane == 0) { ws[warp] = s; wm[warp] = m; }
+    if (lane == 0) { ws[warp] = s; if (WITH_MAX) wm[warp] = m; }
     __syncthreads();
     s = (lane < nwarps) ? ws[lane] : 0.0f;
-    m = (lane < nwarps) ? wm[lane] : 0.0f;
     s = wsum(s);
-    m = wmax(m);
+    if (WITH_MAX) { m = (lane < nwarps) ? wm[lane] : 0.0f; m = wmax_nonneg(m); }
     if (CL > 1) {
         cg::cluster_group cluster = cg::this_cluster();
         float* cs = clpart + (par * 2 + 0) * 8;
         float* cm = clpart + (par * 2 + 1) * 8;
         if (warp == 0 && lane < CL) {
             float* rs = cluster.map_shared_rank(cs, lane);
-            float* rm = cluster.map_shared_rank(cm, lane);
             rs[rank] = s;
-            rm[rank] = m;
+            if (WITH_MAX) { float* rm = cluster.map_shared_rank(cm, lane); rm[rank] = m; }
         }
         cluster.sync();
         float S = 0.0f, M = 0.0f;
 #pragma unroll
-        for (int c = 0; c < CL; ++c) { S += cs[c]; M = fmaxf(M, cm[c]); }
+        for (int c = 0; c < CL; ++c) { S += cs[c]; if (WITH_MAX) M = fmaxf(M, cm[c]); }
         s = S; m = M;
     }
 }
 
 // MODE 0: solve A p = rhs.  MODE 1: fused projection of a velocity field.
-template <int R, int CL, int MODE>
-__global__ void __launch_bounds__(1024, 1) k_cg(const CgArgs a) {
+// X (cells per row, = threads per row), R (rows per thread) and NT (max threads per CTA) are
+// compile-time so that every shared-memory address in the iteration loop is base + immediate.
+template <int X, int R, int CL, int MODE, int NT>
+__global__ void __launch_bounds__(NT, 1) k_cg(const CgArgs a) {
     extern __shared__ float smem[];
-    const int X = a.X, Y = a.Y;
+    constexpr int PITCH = X + 2;
+    const int Y = a.Y;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int TY = blockDim.y;
     const int tid = ty * X + tx;
@@ -104,7 +106,6 @@ __global__ void __launch_bounds__(1024, 1) k_cg(const CgArgs a) {
     if (CL > 1) rank = (int)cg::this_cluster().block_rank();
     const int b = blockIdx.y;
     const int rows_cta = TY * R;
-    const int PITCH = X + 2;
     float* ps = smem;                              // (rows_cta+2) * PITCH, halo ring of zeros
     float* wpart = ps + (rows_cta + 2) * PITCH;    // 2*2*32
     float* clpart = wpart + 128;                   // 2*2*8
@@ -114,10 +115,11 @@ __global__ void __launch_bounds__(1024, 1) k_cg(const CgArgs a) {
     const int lr0 = ty * R;                // first local row of this thread's strip
     const int j0 = rank * rows_cta + lr0;  // first global row
     const size_t NC = (size_t)Y * X, NY = (size_t)(Y + 1) * X, NX = (size_t)Y * (X + 1);
+    float* const pc = ps + (lr0 + 1) * PITCH + tx + 1;   // this thread's first cell in the tile
 
     // Almost every cell is "regular" (fluid, 4 accessible neighbours: OPEN borders count as
-    // accessible).  Threads whose whole strip is regular use q = nb - 4 p with no per-cell data in
-    // registers; the few threads next to the obstacle re-read diag/active (L1-resident) instead.
+    // accessible).  Warps whose cells are all regular run q = nb - 4 p with no per-cell data in
+    // registers; the few warps next to the obstacle re-read diag/active (L1-resident) instead.
     float x[R], r[R], p[R];
     unsigned act = 0u;
     bool regular = true;
@@ -129,6 +131,7 @@ __global__ void __launch_bounds__(1024, 1) k_cg(const CgArgs a) {
         regular = regular && ak && (a.diag[c] == 4.0f);
         x[k] = 0.0f;
     }
+    regular = __all_sync(0xffffffffu, regular);     // warp-uniform fast path
     if (MODE == 1) {
         const float* vy = a.vy_in + (size_t)b * NY;
         const float* vx = a.vx_in + (size_t)b * NX;
@@ -154,14 +157,14 @@ __global__ void __launch_bounds__(1024, 1) k_cg(const CgArgs a) {
     int par = 0;
     __syncthreads();   // ps zero-fill complete before anyone writes p into it
     if (CL > 1) cg::this_cluster().sync();   // ... including remote halo pushes
-    reduce_sm<CL>(rr, rmax, wpart, clpart, par, warp, lane, nwarps, rank); par ^= 1;
+    reduce_sm<CL, true>(rr, rmax, wpart, clpart, par, warp, lane, nwarps, rank); par ^= 1;
     const float tol = fmaxf(a.tol_abs, a.tol_rel * rmax);
 
     int it = 0;
     while (it < a.max_it && rmax > 0.0f && rmax >= tol) {
         // ---- publish p (own tile + halo rows of the neighbouring CTAs) ----
 #pragma unroll
-        for (int k = 0; k < R; ++k) ps[(lr0 + k + 1) * PITCH + tx + 1] = p[k];
+        for (int k = 0; k < R; ++k) pc[k * PITCH] = p[k];
         if (CL > 1) {
             cg::cluster_group cluster = cg::this_cluster();
             if (ty == 0 && rank > 0) {
@@ -179,18 +182,27 @@ __global__ void __launch_bounds__(1024, 1) k_cg(const CgArgs a) {
         // ---- q = A p, pq = p.q ----
         float q[R];
         float pq = 0.0f, dummy = 0.0f;
+        if (regular) {
 #pragma unroll
-        for (int k = 0; k < R; ++k) {
-            const int row = (lr0 + k + 1) * PITCH + tx + 1;
-            const float up = (k + 1 < R) ? p[k + 1] : ps[row + PITCH];
-            const float dn = (k > 0) ? p[k - 1] : ps[row - PITCH];
-            const float nb = (up + dn) + (ps[row - 1] + ps[row + 1]);
-            if (regular) q[k] = fmaf(-4.0f, p[k], nb);
-            else q[k] = ((act >> k) & 1u) ? fmaf(-__ldg(a.diag + (j0 + k) * X + tx), p[k], nb) : 0.0f;
-            pq = fmaf(p[k], q[k], pq);
+            for (int k = 0; k < R; ++k) {
+                const float up = (k + 1 < R) ? p[k + 1] : pc[(k + 1) * PITCH];
+                const float dn = (k > 0) ? p[k - 1] : pc[(k - 1) * PITCH];
+                const float nb = (up + dn) + (pc[k * PITCH - 1] + pc[k * PITCH + 1]);
+                q[k] = fmaf(-4.0f, p[k], nb);
+                pq = fmaf(p[k], q[k], pq);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const float up = (k + 1 < R) ? p[k + 1] : pc[(k + 1) * PITCH];
+                const float dn = (k > 0) ? p[k - 1] : pc[(k - 1) * PITCH];
+                const float nb = (up + dn) + (pc[k * PITCH - 1] + pc[k * PITCH + 1]);
+                q[k] = ((act >> k) & 1u) ? fmaf(-__ldg(a.diag + (j0 + k) * X + tx), p[k], nb) : 0.0f;
+                pq = fmaf(p[k], q[k], pq);
+            }
         }
-        reduce_sm<CL>(pq, dummy, wpart, clpart, par, warp, lane, nwarps, rank); par ^= 1;
-        const float alpha = (pq != 0.0f) ? rr / pq : 0.0f;
+        reduce_sm<CL, false>(pq, dummy, wpart, clpart, par, warp, lane, nwarps, rank); par ^= 1;
+        const float alpha = (pq != 0.0f) ? __fdividef(rr, pq) : 0.0f;
         float rr_new = 0.0f;
         rmax = 0.0f;
 #pragma unroll
@@ -200,8 +212,8 @@ __global__ void __launch_bounds__(1024, 1) k_cg(const CgArgs a) {
             rr_new = fmaf(r[k], r[k], rr_new);
             rmax = fmaxf(rmax, fabsf(r[k]));
         }
-        reduce_sm<CL>(rr_new, rmax, wpart, clpart, par, warp, lane, nwarps, rank); par ^= 1;
-        const float beta = (rr != 0.0f) ? rr_new / rr : 0.0f;
+        reduce_sm<CL, true>(rr_new, rmax, wpart, clpart, par, warp, lane, nwarps, rank); par ^= 1;
+        const float beta = (rr != 0.0f) ? __fdividef(rr_new, rr) : 0.0f;
         rr = rr_new;
 #pragma unroll
         for (int k = 0; k < R; ++k) p[k] = fmaf(beta, p[k], r[k]);
@@ -225,7 +237,7 @@ __global__ void __launch_bounds__(1024, 1) k_cg(const CgArgs a) {
 
     // ---- MODE 1: publish the pressure and subtract its masked gradient ----
 #pragma unroll
-    for (int k = 0; k < R; ++k) ps[(lr0 + k + 1) * PITCH + tx + 1] = x[k];
+    for (int k = 0; k < R; ++k) pc[k * PITCH] = x[k];
     if (CL > 1) {
         cg::cluster_group cluster = cg::this_cluster();
         if (ty == TY - 1 && rank < CL - 1) {
@@ -244,9 +256,8 @@ __global__ void __launch_bounds__(1024, 1) k_cg(const CgArgs a) {
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             const int j = j0 + k;
-            const int row = (lr0 + k + 1) * PITCH + tx + 1;
-            const float pdn = (k > 0) ? x[k - 1] : ps[row - PITCH];   // p[j-1,i]; zero halo at j = 0
-            const float plf = ps[row - 1];                            // p[j,i-1]; zero halo at i = 0
+            const float pdn = (k > 0) ? x[k - 1] : pc[(k - 1) * PITCH];   // p[j-1,i]; zero halo at j = 0
+            const float plf = pc[k * PITCH - 1];                          // p[j,i-1]; zero halo at i = 0
             vyo[j * X + tx] = a.my[j * X + tx] * (vy[j * X + tx] - (x[k] - pdn));
             vxo[j * (X + 1) + tx] = a.mx[j * (X + 1) + tx] * (vx[j * (X + 1) + tx] - (x[k] - plf));
             if (tx == X - 1) vxo[j * (X + 1) + X] = a.mx[j * (X + 1) + X] * (vx[j * (X + 1) + X] + x[k]);
@@ -262,11 +273,11 @@ __global__ void __launch_bounds__(1024, 1) k_cg(const CgArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int R, int CL, int MODE>
+template <int X, int R, int CL, int MODE, int NT>
 static int launch_cg_t(const CgArgs& a, cudaStream_t st, int TY) {
     const int rows_cta = TY * R;
-    const size_t smem = ((size_t)(rows_cta + 2) * (a.X + 2) + 128 + 32) * sizeof(float);
-    auto kern = k_cg<R, CL, MODE>;
+    const size_t smem = ((size_t)(rows_cta + 2) * (X + 2) + 128 + 32) * sizeof(float);
+    auto kern = k_cg<X, R, CL, MODE, NT>;
     static size_t attr_smem = 48 * 1024;
     if (smem > attr_smem) {
         SOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -274,7 +285,7 @@ static int launch_cg_t(const CgArgs& a, cudaStream_t st, int TY) {
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(CL, a.B, 1);
-    cfg.blockDim = dim3(a.X, TY, 1);
+    cfg.blockDim = dim3(X, TY, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -291,38 +302,36 @@ static int launch_cg_t(const CgArgs& a, cudaStream_t st, int TY) {
     return SOL_OK;
 }
 
-template <int MODE>
+template <int X, int MODE>
 static int dispatch_cg(const CgArgs& a, cudaStream_t st, int CL, int R, int TY) {
-#define SOL_CG_CASE(RR, CC) \
-    if (R == RR && CL == CC) return launch_cg_t<RR, CC, MODE>(a, st, TY);
-    SOL_CG_CASE(1, 1) SOL_CG_CASE(2, 1) SOL_CG_CASE(4, 1) SOL_CG_CASE(8, 1) SOL_CG_CASE(16, 1)
-    SOL_CG_CASE(1, 2) SOL_CG_CASE(2, 2) SOL_CG_CASE(4, 2) SOL_CG_CASE(8, 2) SOL_CG_CASE(16, 2)
-    SOL_CG_CASE(1, 4) SOL_CG_CASE(2, 4) SOL_CG_CASE(4, 4) SOL_CG_CASE(8, 4) SOL_CG_CASE(16, 4)
-    SOL_CG_CASE(1, 8) SOL_CG_CASE(2, 8) SOL_CG_CASE(4, 8) SOL_CG_CASE(8, 8) SOL_CG_CASE(16, 8)
+    // R <= 8: up to 1024 threads (64 registers each); R == 16: up to 512 threads (128 registers)
+#define SOL_CG_CASE(RR, CC, NTT) \
+    if (R == RR && CL == CC) return launch_cg_t<X, RR, CC, MODE, NTT>(a, st, TY);
+    SOL_CG_CASE(2, 1, 1024) SOL_CG_CASE(4, 1, 1024) SOL_CG_CASE(8, 1, 1024) SOL_CG_CASE(16, 1, 512)
+    SOL_CG_CASE(2, 2, 1024) SOL_CG_CASE(4, 2, 1024) SOL_CG_CASE(8, 2, 1024) SOL_CG_CASE(16, 2, 512)
+    SOL_CG_CASE(2, 4, 1024) SOL_CG_CASE(4, 4, 1024) SOL_CG_CASE(8, 4, 1024) SOL_CG_CASE(16, 4, 512)
+    SOL_CG_CASE(2, 8, 1024) SOL_CG_CASE(4, 8, 1024) SOL_CG_CASE(8, 8, 1024) SOL_CG_CASE(16, 8, 512)
 #undef SOL_CG_CASE
     return fail(SOL_ERR_UNSUPPORTED, "cg: no kernel for this (rows/thread, cluster) combination");
 }
 
-// choose (CL, R, TY) with Y = CL*TY*R, X*TY <= 1024, R in {1,2,4,8,16}
-static bool cg_geometry(int Y, int X, int want_cl, int& CL, int& R, int& TY) {
-    if (X % 32 != 0 || X > 1024 || X < 32) return false;
-    const int max_ty = 1024 / X;
+// choose (CL, R, TY) with Y = CL*TY*R; threads = X*TY <= 1024 (R <= 8) or <= 512 (R == 16)
+static bool cg_geometry(int Y, int X, int want_cl, int want_r, int& CL, int& R, int& TY) {
+    if (!(X == 32 || X == 64 || X == 128)) return false;
     const int cls[4] = {1, 2, 4, 8};
-    // pass 0: strips of <= 8 rows (x, r, p, q, diag fit the 64-register budget of a 1024-thread
-    // CTA); pass 1: allow 16-row strips as a fallback for very tall grids
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int ci = 0; ci < 4; ++ci) {
-            const int cl = cls[ci];
-            if (want_cl > 0 && cl != want_cl) continue;
-            if (Y % cl) continue;
-            const int rows = Y / cl;
-            const int rs[5] = {1, 2, 4, 8, 16};
-            for (int ri = 0; ri < (pass == 0 ? 4 : 5); ++ri) {   // smallest R (most threads) that fits
-                const int rr = rs[ri];
-                if (rows % rr) continue;
-                const int ty = rows / rr;
-                if (ty <= max_ty && ty >= 1) { CL = cl; R = rr; TY = ty; return true; }
-            }
+    const int rs[4] = {8, 4, 16, 2};      // preference order
+    for (int ci = 0; ci < 4; ++ci) {
+        const int cl = cls[ci];
+        if (want_cl > 0 && cl != want_cl) continue;
+        if (Y % cl) continue;
+        const int rows = Y / cl;
+        for (int ri = 0; ri < 4; ++ri) {
+            const int rr = rs[ri];
+            if (want_r > 0 && rr != want_r) continue;
+            if (rows % rr) continue;
+            const int ty = rows / rr;
+            const int max_threads = (rr == 16) ? 512 : 1024;
+            if (ty >= 1 && X * ty <= max_threads) { CL = cl; R = rr; TY = ty; return true; }
         }
     }
     return false;
@@ -337,10 +346,16 @@ int launch_cg(const sol_plan* p, cudaStream_t st, int B, int mode, const float* 
     a.rhs = rhs; a.p_out = p_out; a.vy_in = vy; a.vx_in = vx; a.vy_out = vy_out; a.vx_out = vx_out;
     a.tol_abs = p->tol_abs; a.tol_rel = p->tol_rel; a.max_it = p->max_it; a.iters = iters;
     int CL, R, TY;
-    if (!cg_geometry(p->Y, p->X, p->cluster, CL, R, TY))
-        return fail(SOL_ERR_UNSUPPORTED, "cg: grid must have X a multiple of 32 (<=1024) and Y = cluster*TY*R with R in {1,2,4,8,16}");
-    if (mode == 0) return dispatch_cg<0>(a, st, CL, R, TY);
-    return dispatch_cg<1>(a, st, CL, R, TY);
+    if (!cg_geometry(p->Y, p->X, p->cluster, p->cg_rows, CL, R, TY))
+        return fail(SOL_ERR_UNSUPPORTED, "cg: needs X in {32,64,128} and Y = cluster*TY*R with R in {2,4,8,16} and X*TY <= 1024");
+#define SOL_CG_X(XX)                                          \
+    if (p->X == XX) {                                         \
+        if (mode == 0) return dispatch_cg<XX, 0>(a, st, CL, R, TY); \
+        return dispatch_cg<XX, 1>(a, st, CL, R, TY);          \
+    }
+    SOL_CG_X(32) SOL_CG_X(64) SOL_CG_X(128)
+#undef SOL_CG_X
+    return fail(SOL_ERR_UNSUPPORTED, "cg: unsupported X");
 }
 
 }  // namespace sol

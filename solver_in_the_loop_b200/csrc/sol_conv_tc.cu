@@ -1,0 +1,365 @@
+// 5x5 32->32 convolution on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), fp32-accurate
+// through 3xTF32 operand splitting.  Drop-in for k_conv5x5_c32 (same NHWC fp32 inputs/outputs and
+// epilogue), used for the forward layers and — with flipped weights — the data gradient.
+//
+// Implicit GEMM per CTA:  D[128 pixels, 32 cout] += sum over 25 taps, 32 cin
+//   * CTA tile = 8 (x) x 16 (y) output pixels -> UMMA M = 128, N = 32, K = 8 per instruction (tf32)
+//   * ONE TMA box load brings the input halo tile [20 rows][12 px][32 ch] fp32 (30 KB, 128B-swizzled,
+//     out-of-image pixels zero-filled by TMA = Keras 'same' padding).  A pixel is one 128-byte
+//     swizzle row, the 8 pixels of a tile row are one 8-row core group, so the A operand of tap
+//     (dy,dx) is the SAME shared-memory tile addressed with start = base + (dy*12+dx)*128 B and
+//     stride-byte-offset = one halo row (1536 B): no im2col copy, 25x reuse of the staged tile.
+//   * 3xTF32: the epilogue warps split the staged fp32 tile once into hi = rn_tf32(x) and
+//     lo = rn_tf32(x - hi) (in place + a second 30 KB tile); weights are pre-split on the device
+//     once per optimiser step.  D += Ahi*Bhi + Ahi*Blo + Alo*Bhi with fp32 accumulation in TMEM.
+//   * weights stream per tap (8 KB, K-major, 128B-swizzled) through a 6-stage TMA/mbarrier ring.
+//   * warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2..5 =
+//     operand splitter, then epilogue (tcgen05.ld 32 lanes x 32 columns -> bias / residual /
+//     LeakyReLU(-derivative) -> 128-byte row stores).
+#include <cuda.h>
+
+#include "sol_internal.cuh"
+
+namespace sol {
+
+namespace {
+
+constexpr int TC_TX = 8;        // tile width  (pixels)
+constexpr int TC_TY = 16;       // tile height (pixels)
+constexpr int TC_HW = 12;       // halo box width  (8 + 4); the swizzle phase is address-based, so any row pitch works
+constexpr int TC_HH = 20;       // halo box height (16 + 4)
+constexpr int TC_A_BYTES = TC_HH * TC_HW * 128;   // 30720
+constexpr int TC_B_BYTES = 32 * 128;              // one tap, one half (hi or lo): 4096; a stage = hi + lo = 8192
+constexpr int TC_STAGES = 6;      // 6 taps of weights in flight; 2 x 109 KB CTAs per SM
+constexpr int TC_THREADS = 192;
+// dynamic shared memory layout (offsets from a 1024-aligned base)
+constexpr int TC_OFF_AHI = 0;
+constexpr int TC_OFF_ALO = TC_A_BYTES;
+constexpr int TC_OFF_B = 2 * TC_A_BYTES;                            // [stage][hi|lo][4096]
+constexpr int TC_OFF_BAR = TC_OFF_B + TC_STAGES * 2 * TC_B_BYTES;   // mbarriers
+constexpr int TC_SMEM = TC_OFF_BAR + 256 + 1024;                    // + alignment slack
+
+struct TcArgs {
+    int base_offset_mode;   // 1: descriptor base_offset = (start >> 7) & 7 (PTX rule); 0: leave it zero
+    const float* bias;
+    const float* addend;
+    const float* ref;
+    float* out;
+    int B, Y, X;
+    int act;
+    float slope;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+// round-to-nearest fp32 -> tf32 (low 13 mantissa bits zero): both halves of the 3xTF32 split are
+// exactly representable, so the tensor core's operand truncation is a no-op and the split error is
+// the symmetric 2^-22 rounding of the low part
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, SM100):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 (distance between 8-row core groups) | [46,48) version = 1
+//   [49,52) base offset = (start >> 7) & 7 when the start is not 1024-aligned | [61,64) layout 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, int base_offset_mode) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    if (base_offset_mode) d |= (uint64_t)((saddr >> 7) & 7) << 49;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2,
+// K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+
+}  // namespace
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w, const TcArgs a) {
+    extern __shared__ uint8_t tc_smem_raw[];
+    // 1024-byte alignment for the 128B swizzle atoms
+    const uint32_t raw = smem_u32(tc_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gbase = tc_smem_raw + (base - raw);
+    const uint32_t s_ahi = base + TC_OFF_AHI, s_alo = base + TC_OFF_ALO, s_b = base + TC_OFF_B;
+    const uint32_t s_bar = base + TC_OFF_BAR;
+    const uint32_t bar_afull = s_bar + 0, bar_asplit = s_bar + 8, bar_acc = s_bar + 16;
+    const uint32_t bar_bfull = s_bar + 32, bar_bempty = s_bar + 32 + 8 * TC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + TC_OFF_BAR + 32 + 16 * TC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x0 = blockIdx.x * TC_TX, y0 = blockIdx.y * TC_TY, b = blockIdx.z;
+
+    if (warp == 0 && lane == 0) {
+        mbar_init(bar_afull, 1);
+        mbar_init(bar_asplit, 128);
+        mbar_init(bar_acc, 1);
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM: 32 fp32 accumulator columns x 128 lanes
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar_afull, TC_A_BYTES);
+            tma_load_4d(s_ahi, &map_in, bar_afull, 0, x0 - 2, y0 - 2, b);
+            for (int tap = 0; tap < 25; ++tap) {
+                const int s = tap % TC_STAGES;
+                const uint32_t ph = (uint32_t)(tap / TC_STAGES) & 1u;
+                mbar_wait(bar_bempty + 8 * s, ph ^ 1u);     // first pass: fresh barrier, parity 1 passes
+                mbar_arrive_expect_tx(bar_bfull + 8 * s, 2 * TC_B_BYTES);
+                tma_load_2d(s_b + 2 * s * TC_B_BYTES, &map_w, bar_bfull + 8 * s, 0, tap * 64);   // 32 hi rows + 32 lo rows
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            mbar_wait(bar_asplit, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int tap = 0; tap < 25; ++tap) {
+                const int s = tap % TC_STAGES;
+                const uint32_t ph = (uint32_t)(tap / TC_STAGES) & 1u;
+                mbar_wait(bar_bfull + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int dy = tap / 5, dx = tap - dy * 5;
+                const uint32_t a_off = (uint32_t)(dy * TC_HW + dx) * 128u;
+                const uint32_t bhi = s_b + (2 * s + 0) * TC_B_BYTES, blo = s_b + (2 * s + 1) * TC_B_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t d_ahi = make_desc(s_ahi + a_off + ks * 32, TC_HW * 128, a.base_offset_mode);
+                    const uint64_t d_alo = make_desc(s_alo + a_off + ks * 32, TC_HW * 128, a.base_offset_mode);
+                    const uint64_t d_bhi = make_desc(bhi + ks * 32, 1024, 0);
+                    const uint64_t d_blo = make_desc(blo + ks * 32, 1024, 0);
+                    umma_tf32(tmem_acc, d_ahi, d_bhi, TC_IDESC, (tap | ks) != 0 ? 1u : 0u);
+                    umma_tf32(tmem_acc, d_ahi, d_blo, TC_IDESC, 1u);
+                    umma_tf32(tmem_acc, d_alo, d_bhi, TC_IDESC, 1u);
+                }
+                umma_commit(bar_bempty + 8 * s);     // frees the weight slot when these MMAs retire
+            }
+            umma_commit(bar_acc);                    // accumulator complete
+        }
+    } else {
+        // ================= splitter, then epilogue (warps 2..5 = 128 threads) =================
+        const int t = threadIdx.x - 64;
+        mbar_wait(bar_afull, 0);
+        float4* hi4 = reinterpret_cast<float4*>(gbase + TC_OFF_AHI);
+        float4* lo4 = reinterpret_cast<float4*>(gbase + TC_OFF_ALO);
+#pragma unroll 4
+        for (int i = t; i < TC_A_BYTES / 16; i += 128) {
+            const float4 v = hi4[i];
+            float4 h, l;
+            h.x = tf32_rn(v.x); l.x = tf32_rn(v.x - h.x);
+            h.y = tf32_rn(v.y); l.y = tf32_rn(v.y - h.y);
+            h.z = tf32_rn(v.z); l.z = tf32_rn(v.z - h.z);
+            h.w = tf32_rn(v.w); l.w = tf32_rn(v.w - h.w);
+            hi4[i] = h;
+            lo4[i] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
+        mbar_arrive(bar_asplit);
+
+        // ---- epilogue: TMEM lane = pixel row of the tile, 32 columns = cout ----
+        mbar_wait(bar_acc, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;                 // this warp may touch TMEM lanes [32q, 32q+32)
+        const int r = q * 32 + lane;            // accumulator row = pixel
+        uint32_t v[32];
+        const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int gy = y0 + (r >> 3), gx = x0 + (r & 7);
+        if (gy < a.Y && gx < a.X) {
+            const size_t o = (((size_t)b * a.Y + gy) * a.X + gx) * 32;
+            float4* out4 = reinterpret_cast<float4*>(a.out + o);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 f = make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
+                                       __uint_as_float(v[4 * c + 3]));
+                if (a.bias) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias) + c);
+                    f.x += bv.x; f.y += bv.y; f.z += bv.z; f.w += bv.w;
+                }
+                if (a.addend) {
+                    const float4 ad = __ldg(reinterpret_cast<const float4*>(a.addend + o) + c);
+                    f.x += ad.x; f.y += ad.y; f.z += ad.z; f.w += ad.w;
+                }
+                if (a.act == SOL_ACT_LRELU) {
+                    f.x = f.x > 0.f ? f.x : a.slope * f.x; f.y = f.y > 0.f ? f.y : a.slope * f.y;
+                    f.z = f.z > 0.f ? f.z : a.slope * f.z; f.w = f.w > 0.f ? f.w : a.slope * f.w;
+                } else if (a.act == SOL_ACT_DLRELU) {
+                    const float4 rf = __ldg(reinterpret_cast<const float4*>(a.ref + o) + c);
+                    f.x = rf.x > 0.f ? f.x : a.slope * f.x; f.y = rf.y > 0.f ? f.y : a.slope * f.y;
+                    f.z = rf.z > 0.f ? f.z : a.slope * f.z; f.w = rf.w > 0.f ? f.w : a.slope * f.w;
+                }
+                out4[c] = f;
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(32u) : "memory");
+    }
+}
+
+// wprep[tap][hi|lo][n][k]: hi / lo halves of  Bt[tap][n][k] = w[tap][k][n]   (w: Keras [5,5,K=Cin,N=Cout])
+__global__ void __launch_bounds__(256) k_prep_tc_weights(const float* __restrict__ w, float* __restrict__ wprep) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 25 * 32 * 32) return;
+    const int k = idx & 31, n = (idx >> 5) & 31, tap = idx >> 10;
+    const float v = w[(tap * 32 + k) * 32 + n];
+    const float h = tf32_rn(v);
+    wprep[((tap * 2 + 0) * 32 + n) * 32 + k] = h;
+    wprep[((tap * 2 + 1) * 32 + n) * 32 + k] = tf32_rn(v - h);
+}
+
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+int g_tc_base_offset_mode = 0;   // measured on B200: the swizzle phase comes from the absolute address bits; base_offset stays 0
+int g_conv_path = 0;
+
+size_t tc_weights_floats() { return (size_t)2 * 25 * 32 * 32; }
+
+int launch_prep_tc_weights(cudaStream_t st, const float* w, float* wprep) {
+    k_prep_tc_weights<<<cdiv(25 * 32 * 32, 256), 256, 0, st>>>(w, wprep);
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
+int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, const float* wprep, const float* bias,
+                      const float* addend, const float* ref, int act, float slope, float* out) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    if (((uintptr_t)in & 15) || ((uintptr_t)wprep & 15)) return fail(SOL_ERR_INVALID, "conv tc: operands must be 16-byte aligned");
+    alignas(64) CUtensorMap map_in, map_w;
+    {
+        cuuint64_t dims[4] = {32, (cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)B};
+        cuuint64_t strides[3] = {128, (cuuint64_t)X * 128, (cuuint64_t)Y * X * 128};
+        cuuint32_t box[4] = {32, TC_HW, TC_HH, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&map_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled(activations) failed");
+    }
+    {
+        cuuint64_t dims[2] = {32, 1600};
+        cuuint64_t strides[1] = {128};
+        cuuint32_t box[2] = {32, 64};
+        cuuint32_t es[2] = {1, 1};
+        CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)wprep, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed");
+    }
+    TcArgs a;
+    a.base_offset_mode = g_tc_base_offset_mode;
+    a.bias = bias; a.addend = addend; a.ref = ref; a.out = out; a.B = B; a.Y = Y; a.X = X; a.act = act; a.slope = slope;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SOL_CUDA(cudaFuncSetAttribute(k_conv5x5_c32_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+        attr_done = true;
+    }
+    dim3 grid(cdiv(X, TC_TX), cdiv(Y, TC_TY), B);
+    k_conv5x5_c32_tc<<<grid, TC_THREADS, TC_SMEM, st>>>(map_in, map_w, a);
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
+int launch_conv5x5_c32_auto(cudaStream_t st, int B, int Y, int X, const float* in, const float* w, const float* wprep,
+                            const float* bias, const float* addend, const float* ref, int act, float slope, float* out) {
+    if (g_conv_path != 2) return launch_conv5x5(st, B, Y, X, 32, 32, in, w, bias, addend, ref, act, slope, out);
+    if (act == SOL_ACT_DLRELU && !ref) return fail(SOL_ERR_INVALID, "conv5x5: SOL_ACT_DLRELU needs ref");
+    if (!wprep) {
+        // stand-alone call: split the weights into a process-wide scratch buffer (stream-ordered reuse)
+        static float* scratch = nullptr;
+        if (!scratch) SOL_CUDA(cudaMalloc((void**)&scratch, tc_weights_floats() * sizeof(float)));
+        SOL_TRY(launch_prep_tc_weights(st, w, scratch));
+        wprep = scratch;
+    }
+    return launch_conv5x5_tc(st, B, Y, X, in, wprep, bias, addend, ref, act, slope, out);
+}
+
+}  // namespace sol

@@ -134,6 +134,30 @@ extern "C" int sol_plan_set_cg(sol_plan* p, float tol_abs, float tol_rel, int ma
     return SOL_OK;
 }
 
+extern "C" int sol_plan_set_option(sol_plan* p, const char* name, int value) {
+    SOL_CHECK(p != nullptr && name != nullptr, "sol_plan_set_option: NULL pointer");
+    if (strcmp(name, "cg_rows") == 0) {
+        SOL_CHECK(value == 0 || value == 2 || value == 4 || value == 8 || value == 16, "cg_rows must be 0,2,4,8,16");
+        p->cg_rows = value;
+        return SOL_OK;
+    }
+    return fail(SOL_ERR_INVALID, "sol_plan_set_option: unknown option");
+}
+
+extern "C" int sol_set_option(const char* name, int value) {
+    SOL_CHECK(name != nullptr, "sol_set_option: NULL name");
+    if (strcmp(name, "conv_path") == 0) {
+        SOL_CHECK(value >= 0 && value <= 2, "conv_path must be 0,1,2");
+        sol::g_conv_path = value;
+        return SOL_OK;
+    }
+    if (strcmp(name, "tc_base_offset_mode") == 0) {
+        sol::g_tc_base_offset_mode = value ? 1 : 0;
+        return SOL_OK;
+    }
+    return fail(SOL_ERR_INVALID, "sol_set_option: unknown option");
+}
+
 #define SOL_PLAN_B(p, B)                                               \
     SOL_CHECK((p) != nullptr, "plan is NULL");                         \
     SOL_CHECK((B) >= 1 && (B) <= (p)->B_max, "batch size out of range for this plan")
@@ -244,6 +268,8 @@ extern "C" int sol_burgers_step_bwd(sol_plan* p, void* stream, int B, float dt, 
 extern "C" int sol_conv5x5(void* stream, int B, int Y, int X, int Cin, int Cout, const float* in, const float* w, const float* bias,
                            const float* addend, const float* ref, int act, float slope, float* out) {
     SOL_CHECK(in && w && out && B >= 1 && Y >= 1 && X >= 1, "sol_conv5x5: bad arguments");
+    if (Cin == 32 && Cout == 32)
+        return launch_conv5x5_c32_auto((cudaStream_t)stream, B, Y, X, in, w, nullptr, bias, addend, ref, act, slope, out);
     return launch_conv5x5((cudaStream_t)stream, B, Y, X, Cin, Cout, in, w, bias, addend, ref, act, slope, out);
 }
 
@@ -298,9 +324,11 @@ struct sol_unroll {
     float *G_vy[2], *G_vx[2], *H_vy, *H_vx, *K_vy, *K_vx;
     float *g_corr, *g_feat, *gbuf[3];
     float* wT;
+    float *wprep_fwd, *wprep_bwd;   // [10 layers][2*25*32*32] pre-split tensor-core weights
     float* partials;   // [n_c32][WG_MAX_CTAS][25632]
     size_t partial_stride = 0;
     int* iters;
+    float* re_buf;     // private copy of Re[B]: the adjoint sweep must not depend on the caller keeping `re` alive
     bool forward_done = false, have_loss = false;
     const float* last_re = nullptr;
     unsigned long long graph_kernels = 0;
@@ -354,9 +382,12 @@ int carve(sol_unroll* u, void* ws, size_t* total) {
     u->g_feat = cv.take<float>(NC * c.cin0);
     for (int k = 0; k < 3; ++k) u->gbuf[k] = cv.take<float>(nA);
     u->wT = cv.take<float>(u->nparams);
+    u->wprep_fwd = cv.take<float>(tc_weights_floats() * 10);
+    u->wprep_bwd = cv.take<float>(tc_weights_floats() * 10);
     u->partial_stride = wgrad_workspace_floats(32, 32);
     u->partials = cv.take<float>(u->partial_stride * 10);
     u->iters = cv.take<int>((size_t)2 * c.msteps * c.B);
+    u->re_buf = cv.take<float>(c.B);
     *total = align_up(cv.off, 256);
     return SOL_OK;
 }
@@ -377,6 +408,7 @@ int cnn_forward(sol_unroll* u, cudaStream_t st, const float* w, const StepStash&
     const int B = u->cfg.B, Y = p->Y, X = p->X;
     const float a = 0.3f;   // keras LeakyReLU default
     const std::vector<LayerDesc>& L = u->L;
+    const bool tc = sol::g_conv_path == 2;
     SOL_TRY(launch_conv5x5(st, B, Y, X, L[0].cin, 32, s.feat, w + L[0].w_off, w + L[0].b_off, nullptr, nullptr, SOL_ACT_LRELU, a, s.acts[0]));
     for (int k = 1; k <= 5; ++k) {
         const LayerDesc& l1 = L[2 * k - 1];
@@ -384,8 +416,10 @@ int cnn_forward(sol_unroll* u, cudaStream_t st, const float* w, const StepStash&
         float* a_prev = s.acts[2 * k - 2];
         float* t_k = s.acts[2 * k - 1];
         float* a_k = s.acts[2 * k];
-        SOL_TRY(launch_conv5x5(st, B, Y, X, 32, 32, a_prev, w + l1.w_off, w + l1.b_off, nullptr, nullptr, SOL_ACT_LRELU, a, t_k));
-        SOL_TRY(launch_conv5x5(st, B, Y, X, 32, 32, t_k, w + l2.w_off, w + l2.b_off, a_prev, nullptr, SOL_ACT_LRELU, a, a_k));
+        const float* p1 = tc ? u->wprep_fwd + tc_weights_floats() * (2 * k - 2) : nullptr;
+        const float* p2 = tc ? u->wprep_fwd + tc_weights_floats() * (2 * k - 1) : nullptr;
+        SOL_TRY(launch_conv5x5_c32_auto(st, B, Y, X, a_prev, w + l1.w_off, p1, w + l1.b_off, nullptr, nullptr, SOL_ACT_LRELU, a, t_k));
+        SOL_TRY(launch_conv5x5_c32_auto(st, B, Y, X, t_k, w + l2.w_off, p2, w + l2.b_off, a_prev, nullptr, SOL_ACT_LRELU, a, a_k));
     }
     return launch_conv5x5(st, B, Y, X, 32, 2, s.acts[10], w + L[11].w_off, w + L[11].b_off, nullptr, nullptr, SOL_ACT_NONE, a, corr);
 }
@@ -397,6 +431,7 @@ int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, cons
     const float a = 0.3f;
     const std::vector<LayerDesc>& L = u->L;
     const float* wT = u->wT;
+    const bool tc = sol::g_conv_path == 2;
     float* gS = u->gbuf[0];
     float* gT = u->gbuf[1];
     float* gN = u->gbuf[2];
@@ -410,9 +445,11 @@ int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, cons
         const float* t_k = s.acts[2 * k - 1];
         // gS = d/d(a_{k-1} + conv_{2k}(t_k) + b)
         SOL_TRY(launch_wgrad(st, B, Y, X, 32, 32, t_k, gS, nullptr, nullptr, !first, u->partials + u->partial_stride * (2 * k - 1), false));
-        SOL_TRY(launch_conv5x5(st, B, Y, X, 32, 32, gS, wT + l2.w_off, nullptr, nullptr, t_k, SOL_ACT_DLRELU, a, gT));
+        const float* p2 = tc ? u->wprep_bwd + tc_weights_floats() * (2 * k - 1) : nullptr;
+        const float* p1 = tc ? u->wprep_bwd + tc_weights_floats() * (2 * k - 2) : nullptr;
+        SOL_TRY(launch_conv5x5_c32_auto(st, B, Y, X, gS, wT + l2.w_off, p2, nullptr, nullptr, t_k, SOL_ACT_DLRELU, a, gT));
         SOL_TRY(launch_wgrad(st, B, Y, X, 32, 32, a_prev, gT, nullptr, nullptr, !first, u->partials + u->partial_stride * (2 * k - 2), false));
-        SOL_TRY(launch_conv5x5(st, B, Y, X, 32, 32, gT, wT + l1.w_off, nullptr, gS, a_prev, SOL_ACT_DLRELU, a, gN));
+        SOL_TRY(launch_conv5x5_c32_auto(st, B, Y, X, gT, wT + l1.w_off, p1, nullptr, gS, a_prev, SOL_ACT_DLRELU, a, gN));
         float* tmp = gS; gS = gN; gN = tmp;
     }
     // input layer (cin0 -> 32): gS is the gradient w.r.t. its pre-activation
@@ -427,7 +464,12 @@ int do_forward(sol_unroll* u, cudaStream_t st, const float* weights, const float
     const int B = c.B, m = c.msteps;
     const size_t NY = p->NY() * B, NX = p->NX() * B, NC = p->NC() * B;
     const bool dens = c.with_density && rho0 != nullptr;
+    SOL_CUDA(cudaMemcpyAsync(u->re_buf, re, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
+    re = u->re_buf;
     if (gt_vy) SOL_CUDA(cudaMemsetAsync(loss_steps, 0, sizeof(float) * m, st));
+    if (sol::g_conv_path == 2)
+        for (int l = 1; l <= 10; ++l)
+            SOL_TRY(launch_prep_tc_weights(st, weights + u->L[l].w_off, u->wprep_fwd + tc_weights_floats() * (l - 1)));
     const float* cvy = vy0; const float* cvx = vx0; const float* crho = dens ? rho0 : nullptr;
     for (int i = 0; i < m; ++i) {
         StepStash& s = u->stash[i];
@@ -445,7 +487,7 @@ int do_forward(sol_unroll* u, cudaStream_t st, const float* weights, const float
         cvy = nvy; cvx = nvx; crho = nrho;
     }
     u->forward_done = true;
-    u->last_re = re;
+    u->last_re = u->re_buf;
     u->have_loss = gt_vy != nullptr;
     return SOL_OK;
 }
@@ -457,6 +499,9 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
     SOL_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * u->nparams, st));
     for (size_t l = 0; l < u->L.size(); ++l)
         SOL_TRY(launch_flip_weights(st, u->L[l].cin, u->L[l].cout, weights + u->L[l].w_off, u->wT + u->L[l].w_off));
+    if (sol::g_conv_path == 2)
+        for (int l = 1; l <= 10; ++l)
+            SOL_TRY(launch_prep_tc_weights(st, u->wT + u->L[l].w_off, u->wprep_bwd + tc_weights_floats() * (l - 1)));
     const float* Gy = u->stash[m - 1].gl_vy;
     const float* Gx = u->stash[m - 1].gl_vx;
     for (int i = m - 1; i >= 0; --i) {
@@ -544,7 +589,7 @@ extern "C" int sol_unroll_train_iter(sol_unroll* u, void* stream, const float* w
     const void* key[9] = {weights, re, rho0, vy0, vx0, gt_vy, gt_vx, loss_steps, grad_weights};
     if (!u->cfg.use_graph) {
         SOL_TRY(do_forward(u, caller, weights, re, rho0, vy0, vx0, gt_vy, gt_vx, loss_steps, nullptr, nullptr, nullptr));
-        return do_backward(u, caller, weights, re, grad_weights, nullptr, nullptr);
+        return do_backward(u, caller, weights, u->re_buf, grad_weights, nullptr, nullptr);
     }
     if (!u->gstream) {
         SOL_CUDA(cudaStreamCreateWithFlags(&u->gstream, cudaStreamNonBlocking));
@@ -554,7 +599,7 @@ extern "C" int sol_unroll_train_iter(sol_unroll* u, void* stream, const float* w
     cudaStream_t st = u->gstream;
     auto run = [&]() -> int {
         SOL_TRY(do_forward(u, st, weights, re, rho0, vy0, vx0, gt_vy, gt_vx, loss_steps, nullptr, nullptr, nullptr));
-        return do_backward(u, st, weights, re, grad_weights, nullptr, nullptr);
+        return do_backward(u, st, weights, u->re_buf, grad_weights, nullptr, nullptr);
     };
     auto join = [&]() -> int {
         SOL_CUDA(cudaEventRecord(u->ev_join, st));

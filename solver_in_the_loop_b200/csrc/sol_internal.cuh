@@ -72,6 +72,7 @@ struct sol_plan {
     float tol_abs = 1e-5f, tol_rel = 0.f;
     int max_it = 2000;
     int cluster = 0;
+    int cg_rows = 0;   // rows per thread in the CG kernel (0 = auto)
     size_t NY() const { return (size_t)(Y + 1) * X; }
     size_t NX() const { return (size_t)Y * (X + 1); }
     size_t NC() const { return (size_t)Y * X; }
@@ -117,5 +118,16 @@ int launch_flip_weights(cudaStream_t st, int Cin, int Cout, const float* w, floa
 size_t wgrad_workspace_floats(int Cin, int Cout);
 int launch_wgrad(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const float* in, const float* g_out, float* dW, float* db,
                  int accumulate, float* partials, bool finalize);
+
+// ---- tensor-core convolution (sol_conv_tc.cu) ----
+extern int g_conv_path;             // 0 auto (= SIMT for now), 1 SIMT fp32, 2 tcgen05 3xTF32
+extern int g_tc_base_offset_mode;
+size_t tc_weights_floats();
+int launch_prep_tc_weights(cudaStream_t st, const float* w, float* wprep);
+int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, const float* wprep, const float* bias,
+                      const float* addend, const float* ref, int act, float slope, float* out);
+// 32->32 layers: tensor-core path when enabled (wprep = pre-split weights or NULL for internal scratch), else SIMT
+int launch_conv5x5_c32_auto(cudaStream_t st, int B, int Y, int X, const float* in, const float* w, const float* wprep,
+                            const float* bias, const float* addend, const float* ref, int act, float slope, float* out);
 
 }  // namespace sol

@@ -41,6 +41,11 @@ def _host(a, dtype):
     return arr, arr.ctypes.data_as(C.c_void_p)
 
 
+def set_option(name: str, value: int):
+    """Process-wide knob, e.g. set_option("conv_path", 2) selects the tcgen05 convolution kernels."""
+    check(_lib.load().sol_set_option(name.encode(), int(value)))
+
+
 class Plan:
     """Scene geometry (reference: KarmanFlow.__init__, Domain/Fluid set-up, velBCy/velBCyMask)."""
 
@@ -81,6 +86,9 @@ class Plan:
 
     def set_cg(self, tol_abs: float = 1e-5, tol_rel: float = 0.0, max_it: int = 2000, cluster: int = 0):
         check(self.lib.sol_plan_set_cg(self.handle, tol_abs, tol_rel, max_it, cluster))
+
+    def set_option(self, name: str, value: int):
+        check(self.lib.sol_plan_set_option(self.handle, name.encode(), int(value)))
 
     def close(self):
         if getattr(self, "handle", None):
