@@ -68,7 +68,9 @@ int sol_plan_destroy(sol_plan* plan);
  * simulation (1,2,4,8; 0 = auto). */
 int sol_plan_set_cg(sol_plan* plan, float tol_abs, float tol_rel, int max_it, int cluster);
 /* Tuning knobs that never change results beyond fp32 round-off:
- *   "cg_rows"   rows of the grid each CG thread keeps in registers (0 = auto, 2/4/8/16) */
+ *   "cg_rows"    rows of the grid each CG thread keeps in registers (0 = auto, 2/4/8/16)
+ *   "cg_precond" 1 (default) = multigrid-preconditioned CG where the grid supports it (same stop
+ *                rule, ~15x fewer iterations), 0 = the reference's unpreconditioned recurrences */
 int sol_plan_set_option(sol_plan* plan, const char* name, int value);
 /* Process-wide knobs:
  *   "conv_path" 0 = auto, 1 = fp32 SIMT kernels, 2 = tcgen05 tensor-core kernels (3xTF32, fp32-accurate)

@@ -17,11 +17,12 @@ for (Y, X) in [(128, 64), (256, 128)]:
         re, vy0, vx0, gy, gx, sig = bench.synth_batch(plan, engine, torch, B, 1, 0, 30)
         o = plan.step_fwd(re, vy0, vx0)
         ay, ax = plan.advect(o["vy1"], o["vx1"])
-        for cl in (1, 2, 4, 8):
-            for rows in (4, 8, 16):
+        for cl, rows, pre in [(1, 8, 0), (1, 16, 0), (1, 8, 1), (1, 16, 1), (4, 8, 0), (8, 4, 0)]:
+            if True:
                 try:
                     plan.set_cg(1e-5, 0.0, 2000, cl)
                     plan.set_option("cg_rows", rows)
+                    plan.set_option("cg_precond", pre)
                     for _ in range(3):
                         py, px, it = plan.project(ay, ax)
                     torch.cuda.synchronize()
@@ -34,8 +35,8 @@ for (Y, X) in [(128, 64), (256, 128)]:
                     us = e0.elapsed_time(e1) * 1e3 / 20
                     K = float(it.float().mean())
                     alg = (40 * K + 8) * Y * X * B
-                    print("grid %dx%d B=%3d cluster=%d rows=%2d: %8.1f us  K=%.0f  %.3f us/iter  alg %.0f GB/s" %
-                          (Y, X, B, cl, rows, us, K, us / max(K, 1), alg / us / 1e3), flush=True)
+                    print("grid %dx%d B=%3d cluster=%d rows=%2d precond=%d: %8.1f us  K=%.0f  %.3f us/iter  alg(40K+8) %.0f GB/s" %
+                          (Y, X, B, cl, rows, pre, us, K, us / max(K, 1), alg / us / 1e3), flush=True)
                 except Exception as e:   # unsupported combination
-                    print("grid %dx%d B=%3d cluster=%d rows=%2d: unsupported (%s)" % (Y, X, B, cl, rows, str(e)[:60]), flush=True)
+                    print("grid %dx%d B=%3d cluster=%d rows=%2d precond=%d: unsupported (%s)" % (Y, X, B, cl, rows, pre, str(e)[:60]), flush=True)
         plan.close()

@@ -340,6 +340,8 @@ static bool cg_geometry(int Y, int X, int want_cl, int want_r, int& CL, int& R, 
 int launch_cg(const sol_plan* p, cudaStream_t st, int B, int mode, const float* rhs, float* p_out, const float* vy,
               const float* vx, float* vy_out, float* vx_out, int* iters) {
     if (p->boundary != SOL_BOUNDARY_OPEN) return fail(SOL_ERR_UNSUPPORTED, "pressure solve requires an OPEN-boundary plan");
+    if (p->cg_precond && p->cluster <= 1 && mg_supported(p))
+        return launch_cg_mg(p, st, B, mode, rhs, p_out, vy, vx, vy_out, vx_out, iters);
     CgArgs a;
     a.Y = p->Y; a.X = p->X; a.B = B;
     a.diag = p->diag; a.active = p->active; a.my = p->face_my; a.mx = p->face_mx;

@@ -32,6 +32,7 @@ constexpr int TC_A_BYTES = TC_HH * TC_HW * 128;   // 30720
 constexpr int TC_B_BYTES = 32 * 128;              // one tap, one half (hi or lo): 4096; a stage = hi + lo = 8192
 constexpr int TC_STAGES = 6;      // 6 taps of weights in flight; 2 x 109 KB CTAs per SM
 constexpr int TC_THREADS = 192;
+constexpr int TC_NACC = 8;        // independent TMEM accumulators, used round-robin (see kernel comment)
 // dynamic shared memory layout (offsets from a 1024-aligned base)
 constexpr int TC_OFF_AHI = 0;
 constexpr int TC_OFF_ALO = TC_A_BYTES;
@@ -138,6 +139,10 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int x0 = blockIdx.x * TC_TX, y0 = blockIdx.y * TC_TY, b = blockIdx.z;
+    // Every CTA streams the same 25 weight tiles; if all CTAs walked them in the same order the 200
+    // co-resident CTAs would hammer the same few L2 lines at the same time (measured: ~1500 cycles per
+    // tap).  Each CTA therefore starts at a different tap and wraps around.
+    const int tap0 = (int)((blockIdx.x + blockIdx.y * gridDim.x + blockIdx.z * gridDim.x * gridDim.y) * 7u % 25u);
 
     if (warp == 0 && lane == 0) {
         mbar_init(bar_afull, 1);
@@ -146,9 +151,9 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {   // TMEM: 32 fp32 accumulator columns x 128 lanes
+    if (warp == 1) {   // TMEM: TC_NACC accumulators of 32 fp32 columns x 128 lanes
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32u * TC_NACC) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -161,9 +166,10 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
         if (lane == 0) {
             mbar_arrive_expect_tx(bar_afull, TC_A_BYTES);
             tma_load_4d(s_ahi, &map_in, bar_afull, 0, x0 - 2, y0 - 2, b);
-            for (int tap = 0; tap < 25; ++tap) {
-                const int s = tap % TC_STAGES;
-                const uint32_t ph = (uint32_t)(tap / TC_STAGES) & 1u;
+            for (int n = 0; n < 25; ++n) {
+                const int s = n % TC_STAGES;
+                const uint32_t ph = (uint32_t)(n / TC_STAGES) & 1u;
+                int tap = tap0 + n; if (tap >= 25) tap -= 25;
                 mbar_wait(bar_bempty + 8 * s, ph ^ 1u);     // first pass: fresh barrier, parity 1 passes
                 mbar_arrive_expect_tx(bar_bfull + 8 * s, 2 * TC_B_BYTES);
                 tma_load_2d(s_b + 2 * s * TC_B_BYTES, &map_w, bar_bfull + 8 * s, 0, tap * 64);   // 32 hi rows + 32 lo rows
@@ -174,23 +180,30 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
         if (lane == 0) {
             mbar_wait(bar_asplit, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int tap = 0; tap < 25; ++tap) {
-                const int s = tap % TC_STAGES;
-                const uint32_t ph = (uint32_t)(tap / TC_STAGES) & 1u;
+            for (int n = 0; n < 25; ++n) {
+                const int s = n % TC_STAGES;
+                const uint32_t ph = (uint32_t)(n / TC_STAGES) & 1u;
+                int tap = tap0 + n; if (tap >= 25) tap -= 25;
                 mbar_wait(bar_bfull + 8 * s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const int dy = tap / 5, dx = tap - dy * 5;
                 const uint32_t a_off = (uint32_t)(dy * TC_HW + dx) * 128u;
                 const uint32_t bhi = s_b + (2 * s + 0) * TC_B_BYTES, blo = s_b + (2 * s + 1) * TC_B_BYTES;
+                // An N=32 tf32 UMMA is ~16 cycles of tensor-pipe work but ~130 cycles of latency, and
+                // accumulations into the SAME TMEM tile serialise on that latency (measured: 300
+                // chained MMAs = 38K cycles).  The 300 MMAs of a tile are therefore dealt round-robin
+                // onto TC_NACC independent accumulators (summed with RN fp32 adds in the epilogue),
+                // which also divides the tensor core's truncating-accumulate bias by TC_NACC.
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     const uint64_t d_ahi = make_desc(s_ahi + a_off + ks * 32, TC_HW * 128, a.base_offset_mode);
                     const uint64_t d_alo = make_desc(s_alo + a_off + ks * 32, TC_HW * 128, a.base_offset_mode);
                     const uint64_t d_bhi = make_desc(bhi + ks * 32, 1024, 0);
                     const uint64_t d_blo = make_desc(blo + ks * 32, 1024, 0);
-                    umma_tf32(tmem_acc, d_ahi, d_bhi, TC_IDESC, (tap | ks) != 0 ? 1u : 0u);
-                    umma_tf32(tmem_acc, d_ahi, d_blo, TC_IDESC, 1u);
-                    umma_tf32(tmem_acc, d_alo, d_bhi, TC_IDESC, 1u);
+                    const int n0 = n * 12 + ks * 3;
+                    umma_tf32(tmem_acc + 32u * (uint32_t)((n0 + 0) % TC_NACC), d_ahi, d_bhi, TC_IDESC, (n0 + 0) >= TC_NACC ? 1u : 0u);
+                    umma_tf32(tmem_acc + 32u * (uint32_t)((n0 + 1) % TC_NACC), d_ahi, d_blo, TC_IDESC, (n0 + 1) >= TC_NACC ? 1u : 0u);
+                    umma_tf32(tmem_acc + 32u * (uint32_t)((n0 + 2) % TC_NACC), d_alo, d_bhi, TC_IDESC, (n0 + 2) >= TC_NACC ? 1u : 0u);
                 }
                 umma_commit(bar_bempty + 8 * s);     // frees the weight slot when these MMAs retire
             }
@@ -221,26 +234,33 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;                 // this warp may touch TMEM lanes [32q, 32q+32)
         const int r = q * 32 + lane;            // accumulator row = pixel
-        uint32_t v[32];
-        const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float acc[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
+#pragma unroll 1
+        for (int j = 0; j < TC_NACC; ++j) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + 32u * (uint32_t)j;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[c] += __uint_as_float(v[c]);
+        }
         const int gy = y0 + (r >> 3), gx = x0 + (r & 7);
         if (gy < a.Y && gx < a.X) {
             const size_t o = (((size_t)b * a.Y + gy) * a.X + gx) * 32;
             float4* out4 = reinterpret_cast<float4*>(a.out + o);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                float4 f = make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
-                                       __uint_as_float(v[4 * c + 3]));
+                float4 f = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
                 if (a.bias) {
                     const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias) + c);
                     f.x += bv.x; f.y += bv.y; f.z += bv.z; f.w += bv.w;
@@ -267,7 +287,7 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
     if (warp == 1) {
         __syncwarp();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(32u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(32u * TC_NACC) : "memory");
     }
 }
 

@@ -6,6 +6,7 @@
 // cost per training iteration is one cudaGraphLaunch instead of TensorFlow's graph executor.
 #include <math.h>
 
+#include <algorithm>
 #include <new>
 
 #include "sol_internal.cuh"
@@ -50,6 +51,86 @@ template <typename T>
 int upload(T** dst, const T* src, size_t n) {
     SOL_CUDA(cudaMalloc((void**)dst, n * sizeof(T)));
     SOL_CUDA(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return SOL_OK;
+}
+
+// Build the multigrid hierarchy of the pressure operator on the host (see sol_cg_mg.cu).
+int build_mg(sol_plan* p, const std::vector<unsigned char>& act0) {
+    sol_mg& h = p->mg;
+    h.valid = false;
+    std::vector<std::vector<unsigned char>> act;
+    std::vector<int> LY, LX;
+    act.push_back(act0); LY.push_back(p->Y); LX.push_back(p->X);
+    while (LX.back() > 4 && LX.back() % 2 == 0 && LY.back() % 2 == 0 && (int)act.size() < MG_MAX_LEVELS) {
+        const int Yf = LY.back(), Xf = LX.back(), Yc = Yf / 2, Xc = Xf / 2;
+        const std::vector<unsigned char>& af = act.back();
+        std::vector<unsigned char> ac((size_t)Yc * Xc);
+        for (int j = 0; j < Yc; ++j)
+            for (int i = 0; i < Xc; ++i) {
+                const int s = af[(2 * j) * Xf + 2 * i] + af[(2 * j) * Xf + 2 * i + 1] + af[(2 * j + 1) * Xf + 2 * i] + af[(2 * j + 1) * Xf + 2 * i + 1];
+                ac[(size_t)j * Xc + i] = s >= 2 ? 1 : 0;
+            }
+        act.push_back(ac); LY.push_back(Yc); LX.push_back(Xc);
+    }
+    const int nlev = (int)act.size();
+    if (nlev < 2 || LY.back() * LX.back() > 64) return SOL_OK;   // not supported: plain CG is used
+    auto diag_of = [&](int l, int j, int i) -> float {
+        auto acc = [&](int jj, int ii) -> float {
+            if (jj < 0 || jj >= LY[l] || ii < 0 || ii >= LX[l]) return 1.0f;
+            return act[l][(size_t)jj * LX[l] + ii] ? 1.0f : 0.0f;
+        };
+        const float d = acc(j - 1, i) + acc(j + 1, i) + acc(j, i - 1) + acc(j, i + 1);
+        return d < 1.0f ? 1.0f : d;
+    };
+    std::vector<float> dinv, diag;
+    for (int l = 1; l < nlev - 1; ++l) {
+        h.coff[l] = (int)dinv.size();
+        for (int j = 0; j < LY[l]; ++j)
+            for (int i = 0; i < LX[l]; ++i) {
+                const float d = diag_of(l, j, i);
+                diag.push_back(d);
+                dinv.push_back(act[l][(size_t)j * LX[l] + i] ? -h.omega / d : 0.0f);
+            }
+    }
+    // dense inverse on the coarsest level (active cells only), Gauss-Jordan with partial pivoting in double
+    const int lc = nlev - 1, Yc = LY[lc], Xc = LX[lc], Nc = Yc * Xc;
+    std::vector<double> A((size_t)Nc * Nc, 0.0), Inv((size_t)Nc * Nc, 0.0);
+    for (int j = 0; j < Yc; ++j)
+        for (int i = 0; i < Xc; ++i) {
+            const int c = j * Xc + i;
+            Inv[(size_t)c * Nc + c] = 1.0;
+            if (!act[lc][c]) { A[(size_t)c * Nc + c] = 1.0; continue; }
+            A[(size_t)c * Nc + c] = -(double)diag_of(lc, j, i);
+            const int nb[4][2] = {{j - 1, i}, {j + 1, i}, {j, i - 1}, {j, i + 1}};
+            for (auto& q : nb)
+                if (q[0] >= 0 && q[0] < Yc && q[1] >= 0 && q[1] < Xc && act[lc][q[0] * Xc + q[1]]) A[(size_t)c * Nc + q[0] * Xc + q[1]] = 1.0;
+        }
+    for (int col = 0; col < Nc; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < Nc; ++r)
+            if (fabs(A[(size_t)r * Nc + col]) > fabs(A[(size_t)piv * Nc + col])) piv = r;
+        if (fabs(A[(size_t)piv * Nc + col]) < 1e-12) return SOL_OK;   // singular: leave MG disabled
+        if (piv != col)
+            for (int k = 0; k < Nc; ++k) { std::swap(A[(size_t)piv * Nc + k], A[(size_t)col * Nc + k]); std::swap(Inv[(size_t)piv * Nc + k], Inv[(size_t)col * Nc + k]); }
+        const double d = A[(size_t)col * Nc + col];
+        for (int k = 0; k < Nc; ++k) { A[(size_t)col * Nc + k] /= d; Inv[(size_t)col * Nc + k] /= d; }
+        for (int r = 0; r < Nc; ++r) {
+            if (r == col) continue;
+            const double f = A[(size_t)r * Nc + col];
+            if (f == 0.0) continue;
+            for (int k = 0; k < Nc; ++k) { A[(size_t)r * Nc + k] -= f * A[(size_t)col * Nc + k]; Inv[(size_t)r * Nc + k] -= f * Inv[(size_t)col * Nc + k]; }
+        }
+    }
+    std::vector<float> cinv((size_t)Nc * Nc);
+    for (int r = 0; r < Nc; ++r)
+        for (int k = 0; k < Nc; ++k) cinv[(size_t)r * Nc + k] = (act[lc][r] && act[lc][k]) ? (float)Inv[(size_t)r * Nc + k] : 0.0f;
+    if (dinv.empty()) { dinv.push_back(0.f); diag.push_back(1.f); }
+    SOL_TRY(upload(&h.dinv, dinv.data(), dinv.size()));
+    SOL_TRY(upload(&h.diag, diag.data(), diag.size()));
+    SOL_TRY(upload(&h.cinv, cinv.data(), cinv.size()));
+    h.nlev = nlev;
+    for (int l = 0; l < nlev; ++l) { h.LY[l] = LY[l]; h.LX[l] = LX[l]; }
+    h.valid = true;
     return SOL_OK;
 }
 
@@ -112,6 +193,7 @@ extern "C" int sol_plan_create(int Y, int X, int B_max, float dx, int boundary, 
         if (rc == SOL_OK && inflow) rc = upload(&p->inflow, inflow, NC);
         if (rc == SOL_OK && bc_mask_y) rc = upload(&p->bc_mask_y, bc_mask_y, NY);
         if (rc == SOL_OK && bc_val_y) rc = upload(&p->bc_val_y, bc_val_y, NY);
+        if (rc == SOL_OK) rc = build_mg(p, act);
         if (rc != SOL_OK) { sol_plan_destroy(p); return rc; }
     }
     *out = p;
@@ -122,6 +204,7 @@ extern "C" int sol_plan_destroy(sol_plan* p) {
     if (!p) return SOL_OK;
     cudaFree(p->active); cudaFree(p->diag); cudaFree(p->face_my); cudaFree(p->face_mx);
     cudaFree(p->inflow); cudaFree(p->bc_mask_y); cudaFree(p->bc_val_y);
+    cudaFree(p->mg.dinv); cudaFree(p->mg.diag); cudaFree(p->mg.cinv);
     delete p;
     return SOL_OK;
 }
@@ -139,6 +222,11 @@ extern "C" int sol_plan_set_option(sol_plan* p, const char* name, int value) {
     if (strcmp(name, "cg_rows") == 0) {
         SOL_CHECK(value == 0 || value == 2 || value == 4 || value == 8 || value == 16, "cg_rows must be 0,2,4,8,16");
         p->cg_rows = value;
+        return SOL_OK;
+    }
+    if (strcmp(name, "cg_precond") == 0) {
+        SOL_CHECK(value == 0 || value == 1, "cg_precond must be 0 or 1");
+        p->cg_precond = value;
         return SOL_OK;
     }
     return fail(SOL_ERR_INVALID, "sol_plan_set_option: unknown option");

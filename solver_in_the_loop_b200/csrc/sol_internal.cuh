@@ -55,6 +55,20 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace sol
 
+constexpr int MG_MAX_LEVELS = 8;
+
+// geometric multigrid hierarchy of the pressure operator (built once per plan, see sol_cg_mg.cu)
+struct sol_mg {
+    bool valid = false;
+    int nlev = 0;                         // levels including the fine grid (0) and the coarsest
+    int LY[MG_MAX_LEVELS] = {0}, LX[MG_MAX_LEVELS] = {0};
+    int coff[MG_MAX_LEVELS] = {0};        // offsets of levels 1..nlev-2 in dinv / diag
+    float* dinv = nullptr;                // device: -omega/diag on fluid cells, 0 on solid
+    float* diag = nullptr;                // device
+    float* cinv = nullptr;                // device: dense inverse on the coarsest level
+    float omega = 0.8f;
+};
+
 struct sol_plan {
     int Y = 0, X = 0, B_max = 0;
     float dx = 1.f;
@@ -73,6 +87,8 @@ struct sol_plan {
     int max_it = 2000;
     int cluster = 0;
     int cg_rows = 0;   // rows per thread in the CG kernel (0 = auto)
+    int cg_precond = 1; // 1 = multigrid-preconditioned CG when the grid supports it, 0 = plain CG (reference recurrences)
+    sol_mg mg;
     size_t NY() const { return (size_t)(Y + 1) * X; }
     size_t NX() const { return (size_t)Y * (X + 1); }
     size_t NC() const { return (size_t)Y * X; }
@@ -110,6 +126,11 @@ int launch_adam(cudaStream_t st, size_t n, float* theta, const float* g, float* 
 // ---- pressure projection (sol_cg.cu) ----
 int launch_cg(const sol_plan* p, cudaStream_t st, int B, int mode, const float* rhs, float* p_out, const float* vy,
               const float* vx, float* vy_out, float* vx_out, int* iters);
+
+// ---- multigrid-preconditioned CG (sol_cg_mg.cu) ----
+bool mg_supported(const sol_plan* p);
+int launch_cg_mg(const sol_plan* p, cudaStream_t st, int B, int mode, const float* rhs, float* p_out, const float* vy,
+                 const float* vx, float* vy_out, float* vx_out, int* iters);
 
 // ---- convolutions (sol_conv.cu) ----
 int launch_conv5x5(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const float* in, const float* w, const float* bias,
