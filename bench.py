@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--conv-path", type=int, default=0, help="0 auto, 1 fp32 SIMT, 2 tcgen05 3xTF32")
+    ap.add_argument("--wgrad-path", type=int, default=0, help="0 auto, 1 per-step SIMT, 2 deferred tcgen05")
     ap.add_argument("--cg-rows", type=int, default=0)
     ap.add_argument("--cg-precond", type=int, default=1, help="1 = multigrid-preconditioned CG, 0 = the reference's plain CG")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -230,6 +231,7 @@ def main():
     lib_launch0 = None
 
     engine.set_option("conv_path", args.conv_path)
+    engine.set_option("wgrad_path", args.wgrad_path)
     plan = engine.Plan.karman(Y, X, B)
     plan.set_option("cg_rows", args.cg_rows)
     plan.set_option("cg_precond", args.cg_precond)
@@ -330,7 +332,7 @@ def main():
                        "cg": "max|r|<1e-5 per sim, <=2000 it (reference stop rule)", "mean_cg_iters": [k_fwd, k_bwd],
                        "l2": "working set (activation stash %.2f GB/iter) exceeds the 126 MB L2; no explicit flush"
                              % (trainer.unroll.workspace.numel() / 1e9),
-                       "cuda_graph": not args.no_graph, "conv_path": args.conv_path, "loss": float(loss_host)},
+                       "cuda_graph": not args.no_graph, "conv_path": args.conv_path, "wgrad_path": args.wgrad_path, "cg_precond": args.cg_precond, "loss": float(loss_host)},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": trainer.h2d_bytes_per_step(), "d2h_bytes_per_step": 4,
                     "ms_per_step": t_e2e / args.steps * 1e3, "wall_ms_per_step": t_e2e_wall / args.steps * 1e3},
             "gpu_launches": int(launches),

@@ -74,6 +74,7 @@ int sol_plan_set_cg(sol_plan* plan, float tol_abs, float tol_rel, int max_it, in
 int sol_plan_set_option(sol_plan* plan, const char* name, int value);
 /* Process-wide knobs:
  *   "conv_path" 0 = auto, 1 = fp32 SIMT kernels, 2 = tcgen05 tensor-core kernels (3xTF32, fp32-accurate)
+ *   "wgrad_path" 0 = auto, 1 = per-step fp32 SIMT weight gradients, 2 = deferred tcgen05 weight-gradient GEMM
  *   "tc_base_offset_mode" (debug) how the UMMA shared-memory descriptors encode unaligned starts */
 int sol_set_option(const char* name, int value);
 

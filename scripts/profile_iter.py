@@ -22,11 +22,13 @@ ap.add_argument("--graph", action="store_true")
 ap.add_argument("--cluster", type=int, default=0)
 ap.add_argument("--iters", type=int, default=1)
 ap.add_argument("--conv-path", type=int, default=0)
+ap.add_argument("--wgrad-path", type=int, default=0)
 ap.add_argument("--cg-rows", type=int, default=0)
 ap.add_argument("--cg-precond", type=int, default=1)
 a = ap.parse_args()
 torch.cuda.set_device(0)
 engine.set_option("conv_path", a.conv_path)
+engine.set_option("wgrad_path", a.wgrad_path)
 plan = engine.Plan.karman(a.Y, a.X, a.batch)
 plan.set_option("cg_rows", a.cg_rows)
 plan.set_option("cg_precond", a.cg_precond)

@@ -89,11 +89,12 @@ __device__ __forceinline__ float block_max(float v, float* red, int& par, int wa
 
 // one damped-Jacobi sweep on a shared-memory level: dst = src + dinv * (b - A src)   (first: dst = dinv * b)
 __device__ __forceinline__ void mg_sweep(const float* __restrict__ src, float* __restrict__ dst, const float* __restrict__ bb,
-                                         const float* __restrict__ dinv, const float* __restrict__ diag, int Yl, int Xl, bool first,
+                                         const float* __restrict__ dinv, const float* __restrict__ diag, int Yl, int lgX, bool first,
                                          int tid, int nthreads) {
+    const int Xl = 1 << lgX;
     const int P = Xl + 2;
-    for (int c = tid; c < Yl * Xl; c += nthreads) {
-        const int j = c / Xl, i = c - j * Xl;
+    for (int c = tid; c < (Yl << lgX); c += nthreads) {
+        const int j = c >> lgX, i = c & (Xl - 1);
         const int o = (j + 1) * P + i + 1;
         float zn;
         if (first) {
@@ -110,10 +111,80 @@ __device__ __forceinline__ void mg_sweep(const float* __restrict__ src, float* _
 
 }  // namespace
 
+// Fine-level per-thread compute pieces, specialised on REG = "every cell of this warp is a regular
+// fluid cell (diag 4)": the regular version touches no per-cell data at all; the general version (the
+// few warps next to the obstacle) re-reads diag/active through L1.  `t` points at the thread's first
+// cell in the tile that holds the published vector (halo ring = 0).
+template <int X, int R, bool REG>
+struct FineOps {
+    static constexpr int PITCH = X + 2;
+    // az_k = (A v)_k ; returns also dinv_k = -omega/diag_k (0 on solid cells)
+    __device__ static __forceinline__ void az_dinv(const float* __restrict__ t, const float (&v)[R], int k, float vdn, unsigned act,
+                                                   const float* __restrict__ dg, float dinv_reg, float omega, float& az, float& dinv) {
+        const float up = (k + 1 < R) ? v[k + 1] : t[(k + 1) * PITCH];
+        const float nb = (up + vdn) + (t[k * PITCH - 1] + t[k * PITCH + 1]);
+        if (REG) {
+            az = fmaf(-4.0f, v[k], nb);
+            dinv = dinv_reg;
+        } else {
+            const bool ak = (act >> k) & 1u;
+            const float d = __ldg(dg + k * X);
+            az = ak ? fmaf(-d, v[k], nb) : 0.0f;
+            dinv = ak ? __fdividef(-omega, d) : 0.0f;
+        }
+    }
+    // z <- z + dinv (r - A z), Jacobi (all neighbours are old values)
+    __device__ static __forceinline__ void smooth(const float* __restrict__ t, float (&z)[R], const float (&r)[R], unsigned act,
+                                                  const float* __restrict__ dg, float dinv_reg, float omega) {
+        float old_prev = t[-PITCH];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const float zc = z[k];
+            float az, dinv;
+            az_dinv(t, z, k, old_prev, act, dg, dinv_reg, omega, az, dinv);
+            z[k] = fmaf(dinv, r[k] - az, zc);
+            old_prev = zc;
+        }
+    }
+    // first sweep from z = 0
+    __device__ static __forceinline__ void smooth0(float (&z)[R], const float (&r)[R], unsigned act, const float* __restrict__ dg,
+                                                   float dinv_reg, float omega) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            if (REG) z[k] = dinv_reg * r[k];
+            else z[k] = ((act >> k) & 1u) ? __fdividef(-omega, __ldg(dg + k * X)) * r[k] : 0.0f;
+        }
+    }
+    // res_k = r_k - (A z)_k on fluid cells (0 on solid)
+    __device__ static __forceinline__ float residual(const float* __restrict__ t, const float (&z)[R], const float (&r)[R], int k,
+                                                     unsigned act, const float* __restrict__ dg) {
+        const float vdn = (k > 0) ? z[k - 1] : t[-PITCH];
+        float az, dinv;
+        az_dinv(t, z, k, vdn, act, dg, 0.0f, 1.0f, az, dinv);
+        if (REG) return r[k] - az;
+        return ((act >> k) & 1u) ? r[k] - az : 0.0f;
+    }
+    // q = A p (into q), returns sum p.q
+    __device__ static __forceinline__ float apply(const float* __restrict__ t, const float (&p)[R], float (&q)[R], unsigned act,
+                                                  const float* __restrict__ dg) {
+        float pq = 0.0f;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const float vdn = (k > 0) ? p[k - 1] : t[-PITCH];
+            float az, dinv;
+            az_dinv(t, p, k, vdn, act, dg, 0.0f, 1.0f, az, dinv);
+            q[k] = az;
+            pq = fmaf(p[k], az, pq);
+        }
+        return pq;
+    }
+};
+
 template <int X, int R, int MODE>
 __global__ void __launch_bounds__(512, 1) k_cg_mg(const MgArgs a) {
     extern __shared__ float smem[];
     constexpr int PITCH = X + 2;
+    constexpr int LGX = (X == 32) ? 5 : 6;
     const int Y = a.Y;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int TY = blockDim.y;
@@ -127,18 +198,18 @@ __global__ void __launch_bounds__(512, 1) k_cg_mg(const MgArgs a) {
 
     for (int k = tid; k < a.s_tiles_end; k += nthreads) smem[k] = 0.0f;
     for (int l = 1; l < nlev - 1; ++l) {
-        const int n = a.LY[l] * a.LX[l];
+        const int n = a.LY[l] << (LGX - l);
         for (int c = tid; c < n; c += nthreads) {
             smem[a.s_dinv[l] + c] = __ldg(a.dinv_g + a.coff[l] + c);
             smem[a.s_diag[l] + c] = __ldg(a.diag_g + a.coff[l] + c);
         }
     }
 
-    const int lr0 = ty * R;
-    const int j0 = lr0;
+    const int j0 = ty * R;
     const size_t NC = (size_t)Y * X, NY = (size_t)(Y + 1) * X, NX = (size_t)Y * (X + 1);
-    float* const T0 = smem + a.s_t0 + (lr0 + 1) * PITCH + tx + 1;   // own first cell in tile 0 / 1
-    float* const T1 = smem + a.s_t1 + (lr0 + 1) * PITCH + tx + 1;
+    float* const T0 = smem + a.s_t0 + (j0 + 1) * PITCH + tx + 1;   // own first cell in tile 0 / 1
+    float* const T1 = smem + a.s_t1 + (j0 + 1) * PITCH + tx + 1;
+    const float* const dg = a.diag + j0 * X + tx;                   // own first cell in the diag array
     int pp = 0;
 
     float x[R], r[R], p[R], z[R];
@@ -152,7 +223,7 @@ __global__ void __launch_bounds__(512, 1) k_cg_mg(const MgArgs a) {
         regular = regular && ak && (a.diag[c] == 4.0f);
         x[k] = 0.0f;
     }
-    regular = __all_sync(0xffffffffu, regular);
+    regular = __all_sync(0xffffffffu, regular);      // warp-uniform
     if (MODE == 1) {
         const float* vy = a.vy_in + (size_t)b * NY;
         const float* vx = a.vx_in + (size_t)b * NX;
@@ -173,11 +244,11 @@ __global__ void __launch_bounds__(512, 1) k_cg_mg(const MgArgs a) {
     }
     __syncthreads();   // tiles zero-filled, coarse constants staged
 
-    // ---- fine-level helpers --------------------------------------------------------------------
     const float omega = a.omega;
     const float dinv_reg = -0.25f * omega;
-    auto fine_diag = [&](int k) -> float { return regular ? 4.0f : __ldg(a.diag + (j0 + k) * X + tx); };
-    // publish a register vector into the next ping-pong tile; returns the thread's base pointer in it
+    using FR = FineOps<X, R, true>;
+    using FG = FineOps<X, R, false>;
+    // publish a register vector into the next ping-pong tile (one barrier); returns the thread's base pointer
     auto publish = [&](const float (&v)[R]) -> const float* {
         float* t = pp ? T1 : T0;
 #pragma unroll
@@ -186,53 +257,28 @@ __global__ void __launch_bounds__(512, 1) k_cg_mg(const MgArgs a) {
         pp ^= 1;
         return t;
     };
-    // z <- z + dinv * (r - A z)  (Jacobi: all neighbours are the OLD values)
     auto fine_smooth = [&]() {
         const float* t = publish(z);
-        float old_prev = 0.0f;
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-            const float zc = z[k];
-            const float up = (k + 1 < R) ? z[k + 1] : t[(k + 1) * PITCH];
-            const float dn = (k > 0) ? old_prev : t[(k - 1) * PITCH];
-            const float nb = (up + dn) + (t[k * PITCH - 1] + t[k * PITCH + 1]);
-            const bool ak = (act >> k) & 1u;
-            const float dg = fine_diag(k);
-            const float az = nb - dg * zc;
-            const float dinv = regular ? dinv_reg : (ak ? -omega / dg : 0.0f);
-            z[k] = fmaf(dinv, r[k] - az, zc);
-            old_prev = zc;
-        }
+        if (regular) FR::smooth(t, z, r, act, dg, dinv_reg, omega);
+        else FG::smooth(t, z, r, act, dg, dinv_reg, omega);
     };
 
     // ---- the V(2,2)-cycle: z = M^{-1} r ---------------------------------------------------------
     auto vcycle = [&]() {
-        // pre-smooth 1 (z = 0): z = dinv * r
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-            const bool ak = (act >> k) & 1u;
-            z[k] = regular ? dinv_reg * r[k] : (ak ? (-omega / fine_diag(k)) * r[k] : 0.0f);
-        }
+        if (regular) FR::smooth0(z, r, act, dg, dinv_reg, omega);
+        else FG::smooth0(z, r, act, dg, dinv_reg, omega);
         fine_smooth();   // pre-smooth 2
-        {   // residual + restriction to level 1
+        {   // residual + restriction to level 1 (sum of the 4 children: 2 rows in-thread, 2 columns by shuffle)
             const float* t = publish(z);
-            const int l1 = 1;
             const bool l1_coarsest = (nlev == 2);
-            float* b1 = smem + a.s_b[l1];
-            const float* dinv1 = smem + a.s_dinv[l1];
-            const int X1 = X / 2;
+            float* b1 = smem + a.s_b[1];
+            const float* dinv1 = smem + a.s_dinv[1];
+            constexpr int X1 = X / 2;
 #pragma unroll
             for (int k = 0; k < R; k += 2) {
-                float s = 0.0f;
-#pragma unroll
-                for (int kk = k; kk < k + 2; ++kk) {
-                    const float up = (kk + 1 < R) ? z[kk + 1] : t[(kk + 1) * PITCH];
-                    const float dn = (kk > 0) ? z[kk - 1] : t[(kk - 1) * PITCH];
-                    const float nb = (up + dn) + (t[kk * PITCH - 1] + t[kk * PITCH + 1]);
-                    const bool ak = (act >> kk) & 1u;
-                    const float az = nb - fine_diag(kk) * z[kk];
-                    s += (regular || ak) ? (r[kk] - az) : 0.0f;
-                }
+                float s;
+                if (regular) s = FR::residual(t, z, r, k, act, dg) + FR::residual(t, z, r, k + 1, act, dg);
+                else s = FG::residual(t, z, r, k, act, dg) + FG::residual(t, z, r, k + 1, act, dg);
                 s += __shfl_xor_sync(0xffffffffu, s, 1);
                 if ((tx & 1) == 0) {
                     const int cc = ((j0 + k) >> 1) * X1 + (tx >> 1);
@@ -243,28 +289,29 @@ __global__ void __launch_bounds__(512, 1) k_cg_mg(const MgArgs a) {
         }
         // ---- coarse levels, down ----
         for (int l = 1; l < nlev - 1; ++l) {
-            const int Yl = a.LY[l], Xl = a.LX[l], P = Xl + 2;
+            const int Yl = a.LY[l], lgX = LGX - l, Xl = 1 << lgX, P = Xl + 2;
             float* u0 = smem + a.s_u0[l];
             float* u1 = smem + a.s_u1[l];
             const float* bl = smem + a.s_b[l];
             const float* dinv = smem + a.s_dinv[l];
             const float* diag = smem + a.s_diag[l];
-            mg_sweep(u1, u0, bl, dinv, diag, Yl, Xl, true, tid, nthreads);    // pre 1 -> u0 (src unused)
-            mg_sweep(u0, u1, bl, dinv, diag, Yl, Xl, false, tid, nthreads);   // pre 2 -> u1
+            mg_sweep(u1, u0, bl, dinv, diag, Yl, lgX, true, tid, nthreads);    // pre 1 -> u0 (src unused)
+            mg_sweep(u0, u1, bl, dinv, diag, Yl, lgX, false, tid, nthreads);   // pre 2 -> u1
             // residual of u1, restricted to level l+1
-            const int Yn = a.LY[l + 1], Xn = a.LX[l + 1];
+            const int lgXn = lgX - 1, Xn = 1 << lgXn;
+            const int Nn = a.LY[l + 1] << lgXn;
             float* bn = smem + a.s_b[l + 1];
             const bool next_coarsest = (l + 1 == nlev - 1);
             const float* dinvn = smem + a.s_dinv[l + 1];
-            for (int cc = tid; cc < Yn * Xn; cc += nthreads) {
-                const int jc = cc / Xn, ic = cc - jc * Xn;
+            for (int cc = tid; cc < Nn; cc += nthreads) {
+                const int jc = cc >> lgXn, ic = cc & (Xn - 1);
                 float s = 0.0f;
 #pragma unroll
                 for (int dj = 0; dj < 2; ++dj)
 #pragma unroll
                     for (int di = 0; di < 2; ++di) {
                         const int j = 2 * jc + dj, i = 2 * ic + di;
-                        const int c = j * Xl + i, o = (j + 1) * P + i + 1;
+                        const int c = (j << lgX) + i, o = (j + 1) * P + i + 1;
                         const float zc = u1[o];
                         const float nb = (u1[o - P] + u1[o + P]) + (u1[o - 1] + u1[o + 1]);
                         s += (dinv[c] != 0.0f) ? bl[c] - (nb - diag[c] * zc) : 0.0f;
@@ -276,50 +323,53 @@ __global__ void __launch_bounds__(512, 1) k_cg_mg(const MgArgs a) {
         // ---- coarsest level: exact solve with the host-inverted matrix ----
         {
             const int lc = nlev - 1;
-            const int Nc = a.LY[lc] * a.LX[lc];
+            const int Nc = a.LY[lc] << (LGX - lc);
             const float* bc = smem + a.s_b[lc];
             float* zc = smem + a.s_zc;
             if (tid < Nc) {
-                float s = 0.0f;
+                float s0 = 0.0f, s1 = 0.0f;
                 const float* row = a.cinv + tid * Nc;
-                for (int j = 0; j < Nc; ++j) s = fmaf(__ldg(row + j), bc[j], s);
-                zc[tid] = s;
+                for (int j = 0; j < Nc; j += 2) {
+                    s0 = fmaf(__ldg(row + j), bc[j], s0);
+                    s1 = fmaf(__ldg(row + j + 1), bc[j + 1], s1);
+                }
+                zc[tid] = s0 + s1;
             }
             __syncthreads();
         }
         // ---- coarse levels, up ----
         for (int l = nlev - 2; l >= 1; --l) {
-            const int Yl = a.LY[l], Xl = a.LX[l], P = Xl + 2;
+            const int Yl = a.LY[l], lgX = LGX - l, Xl = 1 << lgX, P = Xl + 2;
             float* u0 = smem + a.s_u0[l];
             float* u1 = smem + a.s_u1[l];
             const float* bl = smem + a.s_b[l];
             const float* dinv = smem + a.s_dinv[l];
             const float* diag = smem + a.s_diag[l];
-            const int Xn = a.LX[l + 1], Pn = Xn + 2;
+            const int Xn = Xl >> 1, Pn = Xn + 2;
             const bool next_coarsest = (l + 1 == nlev - 1);
             const float* un = next_coarsest ? (smem + a.s_zc) : (smem + a.s_u0[l + 1]);
-            for (int c = tid; c < Yl * Xl; c += nthreads) {     // prolong: u0 = u1 + P z_{l+1}
-                const int j = c / Xl, i = c - j * Xl;
+            for (int c = tid; c < (Yl << lgX); c += nthreads) {     // prolong: u0 = u1 + P z_{l+1}
+                const int j = c >> lgX, i = c & (Xl - 1);
                 const int o = (j + 1) * P + i + 1;
                 const int jc = j >> 1, ic = i >> 1;
                 const float zn = next_coarsest ? un[jc * Xn + ic] : un[(jc + 1) * Pn + ic + 1];
                 u0[o] = u1[o] + ((dinv[c] != 0.0f) ? zn : 0.0f);
             }
             __syncthreads();
-            mg_sweep(u0, u1, bl, dinv, diag, Yl, Xl, false, tid, nthreads);   // post 1 -> u1
-            mg_sweep(u1, u0, bl, dinv, diag, Yl, Xl, false, tid, nthreads);   // post 2 -> u0
+            mg_sweep(u0, u1, bl, dinv, diag, Yl, lgX, false, tid, nthreads);   // post 1 -> u1
+            mg_sweep(u1, u0, bl, dinv, diag, Yl, lgX, false, tid, nthreads);   // post 2 -> u0
         }
         // ---- prolong into the fine level, post-smooth twice ----
         {
             const bool l1_coarsest = (nlev == 2);
-            const int X1 = X / 2, P1 = X1 + 2;
+            constexpr int X1 = X / 2, P1 = X1 + 2;
             const float* u = l1_coarsest ? (smem + a.s_zc) : (smem + a.s_u0[1]);
 #pragma unroll
-            for (int k = 0; k < R; ++k) {
+            for (int k = 0; k < R; k += 2) {
                 const int jc = (j0 + k) >> 1, ic = tx >> 1;
                 const float zn = l1_coarsest ? u[jc * X1 + ic] : u[(jc + 1) * P1 + ic + 1];
-                const bool ak = (act >> k) & 1u;
-                z[k] += (regular || ak) ? zn : 0.0f;
+                z[k] += (regular || ((act >> k) & 1u)) ? zn : 0.0f;
+                z[k + 1] += (regular || ((act >> (k + 1)) & 1u)) ? zn : 0.0f;
             }
         }
         fine_smooth();
@@ -342,16 +392,9 @@ __global__ void __launch_bounds__(512, 1) k_cg_mg(const MgArgs a) {
         rz = block_sum(rz, red, par, warp, lane, nwarps);
         while (true) {
             const float* t = publish(p);
-            float pq = 0.0f;
-#pragma unroll
-            for (int k = 0; k < R; ++k) {    // q = A p, kept in z (dead until the next V-cycle)
-                const float up = (k + 1 < R) ? p[k + 1] : t[(k + 1) * PITCH];
-                const float dn = (k > 0) ? p[k - 1] : t[(k - 1) * PITCH];
-                const float nb = (up + dn) + (t[k * PITCH - 1] + t[k * PITCH + 1]);
-                const bool ak = (act >> k) & 1u;
-                z[k] = (regular || ak) ? nb - fine_diag(k) * p[k] : 0.0f;
-                pq = fmaf(p[k], z[k], pq);
-            }
+            float pq;      // q = A p is kept in z (dead until the next V-cycle)
+            if (regular) pq = FR::apply(t, p, z, act, dg);
+            else pq = FG::apply(t, p, z, act, dg);
             pq = block_sum(pq, red, par, warp, lane, nwarps);
             const float alpha = (pq != 0.0f) ? __fdividef(rz, pq) : 0.0f;
             rmax = 0.0f;

@@ -404,6 +404,12 @@ size_t wgrad_workspace_floats(int Cin, int Cout) {
     return 0;
 }
 
+int launch_wgrad_finalize_n(cudaStream_t st, int nctas, const float* partials, float* dW, float* db, int accumulate) {
+    k_wgrad_finalize<<<cdiv(WG_E, 256), 256, 0, st>>>(nctas, partials, dW, db, accumulate);
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
 static int wgrad_ctas(int B, int Y) {
     const int rows = B * Y;
     return rows < WG_MAX_CTAS ? rows : WG_MAX_CTAS;

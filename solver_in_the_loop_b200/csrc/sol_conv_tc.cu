@@ -16,9 +16,8 @@
 //   * warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2..5 =
 //     operand splitter, then epilogue (tcgen05.ld 32 lanes x 32 columns -> bias / residual /
 //     LeakyReLU(-derivative) -> 128-byte row stores).
-#include <cuda.h>
-
 #include "sol_internal.cuh"
+#include "sol_tc_common.cuh"
 
 namespace sol {
 
@@ -32,7 +31,8 @@ constexpr int TC_A_BYTES = TC_HH * TC_HW * 128;   // 30720
 constexpr int TC_B_BYTES = 32 * 128;              // one tap, one half (hi or lo): 4096; a stage = hi + lo = 8192
 constexpr int TC_STAGES = 6;      // 6 taps of weights in flight; 2 x 109 KB CTAs per SM
 constexpr int TC_THREADS = 192;
-constexpr int TC_NACC = 8;        // independent TMEM accumulators, used round-robin (see kernel comment)
+constexpr int TC_NSET = 2;        // independent accumulator sets {[hh|hl] 64 cols, lh 32 cols}, used alternately
+constexpr int TC_TMEM_COLS = 256; // 2 x 96 columns, power of two
 // dynamic shared memory layout (offsets from a 1024-aligned base)
 constexpr int TC_OFF_AHI = 0;
 constexpr int TC_OFF_ALO = TC_A_BYTES;
@@ -51,76 +51,12 @@ struct TcArgs {
     float slope;
 };
 
-// ---- PTX wrappers -------------------------------------------------------------------------------
-// round-to-nearest fp32 -> tf32 (low 13 mantissa bits zero): both halves of the 3xTF32 split are
-// exactly representable, so the tensor core's operand truncation is a no-op and the split error is
-// the symmetric 2^-22 rounding of the low part
-__device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// K-major, 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, SM100):
-//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major)
-//   [32,46) stride byte offset >> 4 (distance between 8-row core groups) | [46,48) version = 1
-//   [49,52) base offset = (start >> 7) & 7 when the start is not 1024-aligned | [61,64) layout 2 = SWIZZLE_128B
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, int base_offset_mode) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    if (base_offset_mode) d |= (uint64_t)((saddr >> 7) & 7) << 49;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
+using namespace tc;
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2,
 // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t TC_IDESC32 = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t TC_IDESC64 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
 }  // namespace
 
@@ -153,7 +89,7 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
     }
     if (warp == 1) {   // TMEM: TC_NACC accumulators of 32 fp32 columns x 128 lanes
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32u * TC_NACC) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TC_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -162,53 +98,63 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
     const uint32_t tmem_acc = *tmem_slot;
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
+        // ================= TMA producer (warp-uniform control flow, one elected lane issues) =================
+        const bool leader = elect_one();
+        if (leader) {
             mbar_arrive_expect_tx(bar_afull, TC_A_BYTES);
             tma_load_4d(s_ahi, &map_in, bar_afull, 0, x0 - 2, y0 - 2, b);
-            for (int n = 0; n < 25; ++n) {
-                const int s = n % TC_STAGES;
-                const uint32_t ph = (uint32_t)(n / TC_STAGES) & 1u;
-                int tap = tap0 + n; if (tap >= 25) tap -= 25;
-                mbar_wait(bar_bempty + 8 * s, ph ^ 1u);     // first pass: fresh barrier, parity 1 passes
+        }
+#pragma unroll 1
+        for (int n = 0; n < 25; ++n) {
+            const int s = n % TC_STAGES;
+            const uint32_t ph = (uint32_t)(n / TC_STAGES) & 1u;
+            int tap = tap0 + n; if (tap >= 25) tap -= 25;
+            mbar_wait(bar_bempty + 8 * s, ph ^ 1u);     // first pass: fresh barrier, parity 1 passes
+            if (leader) {
                 mbar_arrive_expect_tx(bar_bfull + 8 * s, 2 * TC_B_BYTES);
                 tma_load_2d(s_b + 2 * s * TC_B_BYTES, &map_w, bar_bfull + 8 * s, 0, tap * 64);   // 32 hi rows + 32 lo rows
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer (one thread) =================
-        if (lane == 0) {
-            mbar_wait(bar_asplit, 0);
+        // ================= MMA issuer =================
+        // An N<=64 tf32 UMMA is only 16-32 cycles of tensor-pipe work, so the issue path matters: the
+        // whole warp runs the (uniform) control flow and one elected lane issues; descriptors are a
+        // per-tile constant plus a 16-byte-unit offset; [Bhi;Blo] are adjacent in the weight stage so
+        // Ahi*Bhi and Ahi*Blo are ONE N=64 instruction ([hh|hl] accumulator) next to the N=32 Alo*Bhi.
+        // Accumulations into the same TMEM tile serialise on the MMA latency and the tensor core
+        // accumulates with truncation, so two independent accumulator sets are used alternately and
+        // summed with RN fp32 adds in the epilogue.
+        const bool leader = elect_one();
+        const uint64_t dA_hi = make_desc(s_ahi, TC_HW * 128, 0);
+        const uint64_t dA_lo = make_desc(s_alo, TC_HW * 128, 0);
+        const uint64_t dB = make_desc(s_b, 1024, 0);
+        mbar_wait(bar_asplit, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int n = 0; n < 25; ++n) {
+            const int s = n % TC_STAGES;
+            const uint32_t ph = (uint32_t)(n / TC_STAGES) & 1u;
+            int tap = tap0 + n; if (tap >= 25) tap -= 25;
+            mbar_wait(bar_bfull + 8 * s, ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int n = 0; n < 25; ++n) {
-                const int s = n % TC_STAGES;
-                const uint32_t ph = (uint32_t)(n / TC_STAGES) & 1u;
-                int tap = tap0 + n; if (tap >= 25) tap -= 25;
-                mbar_wait(bar_bfull + 8 * s, ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (leader) {
                 const int dy = tap / 5, dx = tap - dy * 5;
-                const uint32_t a_off = (uint32_t)(dy * TC_HW + dx) * 128u;
-                const uint32_t bhi = s_b + (2 * s + 0) * TC_B_BYTES, blo = s_b + (2 * s + 1) * TC_B_BYTES;
-                // An N=32 tf32 UMMA is ~16 cycles of tensor-pipe work but ~130 cycles of latency, and
-                // accumulations into the SAME TMEM tile serialise on that latency (measured: 300
-                // chained MMAs = 38K cycles).  The 300 MMAs of a tile are therefore dealt round-robin
-                // onto TC_NACC independent accumulators (summed with RN fp32 adds in the epilogue),
-                // which also divides the tensor core's truncating-accumulate bias by TC_NACC.
+                const uint64_t a_off = (uint64_t)((dy * TC_HW + dx) * 8);            // 128 B rows in 16 B units
+                const uint64_t b_off = (uint64_t)(s * (2 * TC_B_BYTES / 16));
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t d_ahi = make_desc(s_ahi + a_off + ks * 32, TC_HW * 128, a.base_offset_mode);
-                    const uint64_t d_alo = make_desc(s_alo + a_off + ks * 32, TC_HW * 128, a.base_offset_mode);
-                    const uint64_t d_bhi = make_desc(bhi + ks * 32, 1024, 0);
-                    const uint64_t d_blo = make_desc(blo + ks * 32, 1024, 0);
-                    const int n0 = n * 12 + ks * 3;
-                    umma_tf32(tmem_acc + 32u * (uint32_t)((n0 + 0) % TC_NACC), d_ahi, d_bhi, TC_IDESC, (n0 + 0) >= TC_NACC ? 1u : 0u);
-                    umma_tf32(tmem_acc + 32u * (uint32_t)((n0 + 1) % TC_NACC), d_ahi, d_blo, TC_IDESC, (n0 + 1) >= TC_NACC ? 1u : 0u);
-                    umma_tf32(tmem_acc + 32u * (uint32_t)((n0 + 2) % TC_NACC), d_alo, d_bhi, TC_IDESC, (n0 + 2) >= TC_NACC ? 1u : 0u);
+                    const uint32_t set = (uint32_t)(ks & 1);
+                    const uint32_t acc1 = tmem_acc + set * 96u, acc2 = acc1 + 64u;
+                    const uint32_t first = (n == 0 && ks < 2) ? 0u : 1u;
+                    umma_tf32(acc1, dA_hi + a_off + 2 * ks, dB + b_off + 2 * ks, TC_IDESC64, first);   // [hh | hl]
+                    umma_tf32(acc2, dA_lo + a_off + 2 * ks, dB + b_off + 2 * ks, TC_IDESC32, first);   // lh
                 }
                 umma_commit(bar_bempty + 8 * s);     // frees the weight slot when these MMAs retire
             }
-            umma_commit(bar_acc);                    // accumulator complete
+            __syncwarp();
         }
+        if (leader) umma_commit(bar_acc);            // accumulators complete
+        __syncwarp();
     } else {
         // ================= splitter, then epilogue (warps 2..5 = 128 threads) =================
         const int t = threadIdx.x - 64;
@@ -238,7 +184,7 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
 #pragma unroll
         for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
 #pragma unroll 1
-        for (int j = 0; j < TC_NACC; ++j) {
+        for (int j = 0; j < 3 * TC_NSET; ++j) {       // per set: hh, hl, lh column blocks
             uint32_t v[32];
             const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + 32u * (uint32_t)j;
             asm volatile(
@@ -287,7 +233,7 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
     if (warp == 1) {
         __syncwarp();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(32u * TC_NACC) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)TC_TMEM_COLS) : "memory");
     }
 }
 
@@ -303,11 +249,8 @@ __global__ void __launch_bounds__(256) k_prep_tc_weights(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
+namespace tc {
+EncodeTiledFn get_encode_tiled() {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -318,9 +261,11 @@ static EncodeTiledFn get_encode() {
     }
     return fn;
 }
+}  // namespace tc
 
 int g_tc_base_offset_mode = 0;   // measured on B200: the swizzle phase comes from the absolute address bits; base_offset stays 0
 int g_conv_path = 0;
+int g_wgrad_path = 0;
 
 size_t tc_weights_floats() { return (size_t)2 * 25 * 32 * 32; }
 
@@ -332,7 +277,7 @@ int launch_prep_tc_weights(cudaStream_t st, const float* w, float* wprep) {
 
 int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, const float* wprep, const float* bias,
                       const float* addend, const float* ref, int act, float slope, float* out) {
-    EncodeTiledFn enc = get_encode();
+    tc::EncodeTiledFn enc = tc::get_encode_tiled();
     if (!enc) return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     if (((uintptr_t)in & 15) || ((uintptr_t)wprep & 15)) return fail(SOL_ERR_INVALID, "conv tc: operands must be 16-byte aligned");
     alignas(64) CUtensorMap map_in, map_w;

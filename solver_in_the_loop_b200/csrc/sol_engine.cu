@@ -239,6 +239,11 @@ extern "C" int sol_set_option(const char* name, int value) {
         sol::g_conv_path = value;
         return SOL_OK;
     }
+    if (strcmp(name, "wgrad_path") == 0) {
+        SOL_CHECK(value >= 0 && value <= 2, "wgrad_path must be 0,1,2");
+        sol::g_wgrad_path = value;
+        return SOL_OK;
+    }
     if (strcmp(name, "tc_base_offset_mode") == 0) {
         sol::g_tc_base_offset_mode = value ? 1 : 0;
         return SOL_OK;
@@ -413,6 +418,8 @@ struct sol_unroll {
     float *g_corr, *g_feat, *gbuf[3];
     float* wT;
     float *wprep_fwd, *wprep_bwd;   // [10 layers][2*25*32*32] pre-split tensor-core weights
+    float* gst;        // deferred weight gradient: [10 layers][msteps][B,Y,X,32] output-gradient stash
+    size_t nA = 0;
     float* partials;   // [n_c32][WG_MAX_CTAS][25632]
     size_t partial_stride = 0;
     int* iters;
@@ -472,6 +479,8 @@ int carve(sol_unroll* u, void* ws, size_t* total) {
     u->wT = cv.take<float>(u->nparams);
     u->wprep_fwd = cv.take<float>(tc_weights_floats() * 10);
     u->wprep_bwd = cv.take<float>(tc_weights_floats() * 10);
+    u->nA = nA;
+    u->gst = cv.take<float>(nA * 10 * c.msteps);
     u->partial_stride = wgrad_workspace_floats(32, 32);
     u->partials = cv.take<float>(u->partial_stride * 10);
     u->iters = cv.take<int>((size_t)2 * c.msteps * c.B);
@@ -513,16 +522,20 @@ int cnn_forward(sol_unroll* u, cudaStream_t st, const float* w, const StepStash&
 }
 
 int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, const StepStash& s, const float* g_corr, float* g_feat,
-                 int first) {
+                 int first, int step) {
     const sol_plan* p = u->plan;
     const int B = u->cfg.B, Y = p->Y, X = p->X;
     const float a = 0.3f;
     const std::vector<LayerDesc>& L = u->L;
     const float* wT = u->wT;
     const bool tc = sol::g_conv_path == 2;
-    float* gS = u->gbuf[0];
-    float* gT = u->gbuf[1];
-    float* gN = u->gbuf[2];
+    const bool deferred = sol::g_wgrad_path == 2;   // weight gradients of the 32->32 layers in one GEMM per layer after the sweep
+    // output-gradient tensor of layer l (1..10) for this step
+    auto gout = [&](int l, float* fallback) -> float* {
+        return deferred ? u->gst + ((size_t)(l - 1) * u->cfg.msteps + step) * u->nA : fallback;
+    };
+    float* gS = gout(10, u->gbuf[0]);
+    float* spare[3] = {u->gbuf[0], u->gbuf[1], u->gbuf[2]};
     // output layer (32 -> 2)
     SOL_TRY(launch_wgrad(st, B, Y, X, 32, 2, s.acts[10], g_corr, gw + L[11].w_off, gw + L[11].b_off, 1, nullptr, false));
     SOL_TRY(launch_conv5x5(st, B, Y, X, 2, 32, g_corr, wT + L[11].w_off, nullptr, nullptr, s.acts[10], SOL_ACT_DLRELU, a, gS));
@@ -531,14 +544,21 @@ int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, cons
         const LayerDesc& l2 = L[2 * k];
         const float* a_prev = s.acts[2 * k - 2];
         const float* t_k = s.acts[2 * k - 1];
+        // pick scratch buffers that do not alias gS (non-deferred mode rotates three buffers)
+        float* fT = spare[0] == gS ? spare[1] : spare[0];
+        float* gT = gout(2 * k - 1, fT);
+        float* fN = (spare[0] != gS && spare[0] != gT) ? spare[0] : ((spare[1] != gS && spare[1] != gT) ? spare[1] : spare[2]);
+        float* gN = (k >= 2) ? gout(2 * k - 2, fN) : fN;
         // gS = d/d(a_{k-1} + conv_{2k}(t_k) + b)
-        SOL_TRY(launch_wgrad(st, B, Y, X, 32, 32, t_k, gS, nullptr, nullptr, !first, u->partials + u->partial_stride * (2 * k - 1), false));
+        if (!deferred)
+            SOL_TRY(launch_wgrad(st, B, Y, X, 32, 32, t_k, gS, nullptr, nullptr, !first, u->partials + u->partial_stride * (2 * k - 1), false));
         const float* p2 = tc ? u->wprep_bwd + tc_weights_floats() * (2 * k - 1) : nullptr;
         const float* p1 = tc ? u->wprep_bwd + tc_weights_floats() * (2 * k - 2) : nullptr;
         SOL_TRY(launch_conv5x5_c32_auto(st, B, Y, X, gS, wT + l2.w_off, p2, nullptr, nullptr, t_k, SOL_ACT_DLRELU, a, gT));
-        SOL_TRY(launch_wgrad(st, B, Y, X, 32, 32, a_prev, gT, nullptr, nullptr, !first, u->partials + u->partial_stride * (2 * k - 2), false));
+        if (!deferred)
+            SOL_TRY(launch_wgrad(st, B, Y, X, 32, 32, a_prev, gT, nullptr, nullptr, !first, u->partials + u->partial_stride * (2 * k - 2), false));
         SOL_TRY(launch_conv5x5_c32_auto(st, B, Y, X, gT, wT + l1.w_off, p1, nullptr, gS, a_prev, SOL_ACT_DLRELU, a, gN));
-        float* tmp = gS; gS = gN; gN = tmp;
+        gS = gN;
     }
     // input layer (cin0 -> 32): gS is the gradient w.r.t. its pre-activation
     SOL_TRY(launch_wgrad(st, B, Y, X, L[0].cin, 32, s.feat, gS, gw + L[0].w_off, gw + L[0].b_off, 1, nullptr, false));
@@ -595,7 +615,7 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
     for (int i = m - 1; i >= 0; --i) {
         StepStash& s = u->stash[i];
         SOL_TRY(launch_corr_bwd(p, st, B, Gy, Gx, c.sig_vy, c.sig_vx, u->g_corr));
-        SOL_TRY(cnn_backward(u, st, weights, gw, s, u->g_corr, u->g_feat, i == m - 1));
+        SOL_TRY(cnn_backward(u, st, weights, gw, s, u->g_corr, u->g_feat, i == m - 1, i));
         SOL_TRY(launch_feat_bwd(p, st, B, Gy, Gx, u->g_feat, c.cin0, c.sig_vy, c.sig_vx, u->H_vy, u->H_vx));
         SOL_TRY(launch_cg(p, st, B, 1, nullptr, nullptr, u->H_vy, u->H_vx, u->K_vy, u->K_vx, u->iters + (size_t)(m + i) * B));
         SOL_TRY(launch_advect_bwd(p, st, B, c.dt, s.vy1, s.vx1, u->K_vy, u->K_vx, u->H_vy, u->H_vx));
@@ -606,6 +626,19 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
         } else if (g_vy0 && g_vx0) {
             SOL_TRY(launch_diffuse_bc_bwd(p, st, B, re, c.dt, c.res, u->H_vy, u->H_vx, g_vy0, g_vx0, nullptr, nullptr));
         }
+    }
+    if (sol::g_wgrad_path == 2) {
+        // deferred weight gradients: one tensor-core GEMM per layer over all msteps x B x Y x X pixels
+        const size_t in_stride = (m > 1) ? (size_t)(u->stash[1].acts[0] - u->stash[0].acts[0]) : u->nA;
+        for (int l = 1; l <= 10; ++l) {
+            int nctas = 0;
+            float* part = u->partials + u->partial_stride * (l - 1);
+            const float* gl = u->gst + (size_t)(l - 1) * m * u->nA;
+            SOL_TRY(launch_wgrad_c32_tc(st, p->sm_count, m, B, p->Y, p->X, u->stash[0].acts[l - 1], in_stride, gl, u->nA, part, &nctas));
+            SOL_TRY(launch_wgrad_finalize_n(st, nctas, part, gw + u->L[l].w_off, gw + u->L[l].b_off, 0));
+            SOL_TRY(launch_colsum32(st, gl, (size_t)m * B * p->NC(), gw + u->L[l].b_off));
+        }
+        return SOL_OK;
     }
     for (int l = 1; l <= 10; ++l)
         SOL_TRY(launch_wgrad(st, B, p->Y, p->X, 32, 32, nullptr, nullptr, gw + u->L[l].w_off, gw + u->L[l].b_off, 0,

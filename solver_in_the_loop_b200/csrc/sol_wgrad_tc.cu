@@ -1,0 +1,281 @@
+// Weight gradient of the 32->32 5x5 layers on the tensor cores (tcgen05, 3xTF32), DEFERRED over the
+// whole unrolled sweep: dW[tap][ci][co] = sum over ALL msteps x B x Y x X pixels of
+// in[pix+tap][ci] * g[pix][co], one launch per layer instead of one per (layer, step).
+//
+// The 180 GB of HBM make this the natural B200 formulation: the adjoint sweep leaves every layer's
+// output gradient in a stash (1 GB for SOL-32), and the reduction over ~800k pixels becomes ONE
+// GEMM with K = pixels per layer — the per-step SIMT kernel with its 148 x 100 KB partial-sum
+// round trips per (layer, step) disappears.
+//
+// GEMM mapping (per CTA, persistent over pixel tiles of 8 x 16):
+//   K = pixels.  Both operands are "MN-major": a pixel row of the staged tiles is 128 B = 32 channels,
+//   8 consecutive pixels (one tile row) form one 8-row swizzle atom = one K=8 UMMA step.
+//   A = activations:  M = 128 = 4 taps x 32 cin.  The 4 M-blocks of a descriptor are 4 horizontally
+//       adjacent taps of the SAME staged halo tile: leading-byte-offset = 128 B (one pixel), start =
+//       halo + ((y+dy)*12 + x + dx0)*128.  (The swizzle phase is a function of the absolute
+//       shared-memory address, so overlapping, non-1024-aligned atoms are consistent with what TMA wrote.)
+//   B = output gradient: N = 32 cout, one atom per tile row.
+//   D[(tap,cin)][cout] lives in TMEM: 5 kernel rows x {dx 0..3, dx 4..7} = 10 accumulators of
+//   128 lanes x 32 columns; consecutive MMAs go to different accumulators (MMA-latency chains).
+//   3xTF32: A and G tiles are split once into hi/lo by the 4 helper warps; D += Ahi*Ghi + Ahi*Glo + Alo*Ghi.
+//   The TMEM accumulators persist across all tiles of the CTA; at the end they are written to a
+//   per-CTA partial slot, reduced by k_wgrad_finalize (sol_conv.cu).
+#include "sol_internal.cuh"
+#include "sol_tc_common.cuh"
+
+namespace sol {
+
+namespace {
+
+using namespace tc;
+
+constexpr int WG_TX = 8, WG_TY = 16, WG_HW = 12, WG_HH = 20;
+constexpr int WG_A_BYTES = WG_HH * WG_HW * 128;     // 30720
+constexpr int WG_G_BYTES = WG_TY * WG_TX * 128;     // 16384
+constexpr int WG_STAGE_BYTES = 2 * WG_A_BYTES + 2 * WG_G_BYTES;   // Ahi, Alo, Ghi, Glo = 94208
+constexpr int WG_NSTAGE = 2;
+constexpr int WG_OFF_BAR = WG_NSTAGE * WG_STAGE_BYTES;            // 188416
+constexpr int WG_SMEM = WG_OFF_BAR + 256 + 1024;
+constexpr int WG_THREADS = 192;
+constexpr int WG_TMEM_COLS = 512;                                 // 10 x 32 columns used
+// M=128, N=32, tf32, A and B MN-major (bits 15, 16)
+constexpr uint32_t WG_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+
+struct WgTcArgs {
+    float* part;        // [gridDim.x][25*32*32 + 32]
+    int tiles_x, tiles_y, images;   // tiles per image row / column, number of images (msteps*B)
+    int B;              // images per step (the 5th tensor dimension is the step)
+    int accumulate;
+};
+
+}  // namespace
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+k_wgrad_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_g, const WgTcArgs a) {
+    extern __shared__ uint8_t wg_smem_raw[];
+    const uint32_t raw = smem_u32(wg_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gbase = wg_smem_raw + (base - raw);
+    const uint32_t s_bar = base + WG_OFF_BAR;
+    // barriers: full[s] (TMA landed), split[s] (hi/lo ready), empty[s] (MMAs retired), acc (all done)
+    const uint32_t bar_full = s_bar, bar_split = s_bar + 8 * WG_NSTAGE, bar_empty = s_bar + 16 * WG_NSTAGE, bar_acc = s_bar + 24 * WG_NSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + WG_OFF_BAR + 24 * WG_NSTAGE + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_image = a.tiles_x * a.tiles_y;
+    const int ntiles = tiles_per_image * a.images;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < WG_NSTAGE; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_split + 8 * s, 128);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)WG_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        const bool leader = elect_one();
+        int n = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++n) {
+            const int s = n % WG_NSTAGE;
+            const uint32_t ph = (uint32_t)(n / WG_NSTAGE) & 1u;
+            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+            if (leader) {
+                const int img = t / tiles_per_image, rem = t - img * tiles_per_image;
+                const int tyi = rem / a.tiles_x, txi = rem - tyi * a.tiles_x;
+                const int step = img / a.B, bb = img - step * a.B;
+                const uint32_t st = base + s * WG_STAGE_BYTES;
+                mbar_arrive_expect_tx(bar_full + 8 * s, WG_A_BYTES + WG_G_BYTES);
+                tma_load_5d(st, &map_in, bar_full + 8 * s, 0, txi * WG_TX - 2, tyi * WG_TY - 2, bb, step);
+                tma_load_5d(st + 2 * WG_A_BYTES, &map_g, bar_full + 8 * s, 0, txi * WG_TX, tyi * WG_TY, bb, step);
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        const bool leader = elect_one();
+        int n = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++n) {
+            const int s = n % WG_NSTAGE;
+            const uint32_t ph = (uint32_t)(n / WG_NSTAGE) & 1u;
+            mbar_wait(bar_split + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (leader) {
+                const uint32_t st = base + s * WG_STAGE_BYTES;
+                const uint64_t dA_hi = make_desc_mn(st, 128, 1024);
+                const uint64_t dA_lo = make_desc_mn(st + WG_A_BYTES, 128, 1024);
+                const uint64_t dG_hi = make_desc_mn(st + 2 * WG_A_BYTES, 128, 1024);
+                const uint64_t dG_lo = make_desc_mn(st + 2 * WG_A_BYTES + WG_G_BYTES, 128, 1024);
+#pragma unroll 1
+                for (int y = 0; y < WG_TY; ++y) {
+                    const uint64_t g_off = (uint64_t)(y * 64);                    // one tile row = 1024 B
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {                                 // hi*hi, hi*lo, lo*hi
+                        const uint64_t dA = (j == 2) ? dA_lo : dA_hi;
+                        const uint64_t dG = ((j == 1) ? dG_lo : dG_hi) + g_off;
+                        const uint32_t accum = (n == 0 && y == 0 && j == 0) ? 0u : 1u;
+#pragma unroll
+                        for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+                            for (int g = 0; g < 2; ++g) {
+                                const uint64_t a_off = (uint64_t)(((y + dy) * WG_HW + g * 4) * 8);
+                                umma_tf32(tmem_acc + 32u * (uint32_t)(dy * 2 + g), dA + a_off, dG, WG_IDESC, accum);
+                            }
+                    }
+                }
+                umma_commit(bar_empty + 8 * s);
+            }
+            __syncwarp();
+        }
+        if (leader) umma_commit(bar_acc);
+        __syncwarp();
+    } else {
+        // ================= splitter (warps 2..5), then accumulator dump =================
+        const int tt = threadIdx.x - 64;
+        int n = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++n) {
+            const int s = n % WG_NSTAGE;
+            const uint32_t ph = (uint32_t)(n / WG_NSTAGE) & 1u;
+            mbar_wait(bar_full + 8 * s, ph);
+            float4* ahi = reinterpret_cast<float4*>(gbase + s * WG_STAGE_BYTES);
+            float4* alo = reinterpret_cast<float4*>(gbase + s * WG_STAGE_BYTES + WG_A_BYTES);
+            float4* ghi = reinterpret_cast<float4*>(gbase + s * WG_STAGE_BYTES + 2 * WG_A_BYTES);
+            float4* glo = reinterpret_cast<float4*>(gbase + s * WG_STAGE_BYTES + 2 * WG_A_BYTES + WG_G_BYTES);
+#pragma unroll 4
+            for (int i = tt; i < WG_A_BYTES / 16; i += 128) {
+                const float4 v = ahi[i];
+                float4 h, l;
+                h.x = tf32_rn(v.x); l.x = tf32_rn(v.x - h.x);
+                h.y = tf32_rn(v.y); l.y = tf32_rn(v.y - h.y);
+                h.z = tf32_rn(v.z); l.z = tf32_rn(v.z - h.z);
+                h.w = tf32_rn(v.w); l.w = tf32_rn(v.w - h.w);
+                ahi[i] = h; alo[i] = l;
+            }
+#pragma unroll 4
+            for (int i = tt; i < WG_G_BYTES / 16; i += 128) {
+                const float4 v = ghi[i];
+                float4 h, l;
+                h.x = tf32_rn(v.x); l.x = tf32_rn(v.x - h.x);
+                h.y = tf32_rn(v.y); l.y = tf32_rn(v.y - h.y);
+                h.z = tf32_rn(v.z); l.z = tf32_rn(v.z - h.z);
+                h.w = tf32_rn(v.w); l.w = tf32_rn(v.w - h.w);
+                ghi[i] = h; glo[i] = l;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(bar_split + 8 * s);
+        }
+        // ---- dump: accumulator (dy, g), lane m -> tap dx = 4g + m/32, cin = m%32, 32 columns = cout
+        mbar_wait(bar_acc, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;
+        float* part = a.part + (size_t)blockIdx.x * (25 * 32 * 32 + 32);
+        if (tt < 32) part[25 * 32 * 32 + tt] = 0.0f;     // bias slot: the bias gradient comes from k_colsum32
+#pragma unroll 1
+        for (int acc = 0; acc < 10; ++acc) {
+            const int dy = acc >> 1, g = acc & 1;
+            const int dx = 4 * g + q;
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + 32u * (uint32_t)acc, v);
+            if (dx < 5) {
+                float4* dst = reinterpret_cast<float4*>(part + (((dy * 5 + dx) * 32 + lane) * 32));
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 f = make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
+                                           __uint_as_float(v[4 * c + 3]));
+                    if (a.accumulate) { const float4 o = dst[c]; f.x += o.x; f.y += o.y; f.z += o.z; f.w += o.w; }
+                    dst[c] = f;
+                }
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)WG_TMEM_COLS) : "memory");
+    }
+}
+
+// db[co] (+)= sum over pixels of g[pix][co]
+__global__ void __launch_bounds__(256) k_colsum32(const float* __restrict__ g, size_t npix, float* db) {
+    const int c4 = threadIdx.x & 7;          // 4 channels per thread
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t p = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3); p < npix; p += (size_t)gridDim.x * 32) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(g + p * 32) + c4);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    __shared__ float4 sm[256];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = threadIdx.x; k < 256; k += 8) { t.x += sm[k].x; t.y += sm[k].y; t.z += sm[k].z; t.w += sm[k].w; }
+        atomicAdd(db + 4 * threadIdx.x + 0, t.x);
+        atomicAdd(db + 4 * threadIdx.x + 1, t.y);
+        atomicAdd(db + 4 * threadIdx.x + 2, t.z);
+        atomicAdd(db + 4 * threadIdx.x + 3, t.w);
+    }
+}
+
+int launch_colsum32(cudaStream_t st, const float* g, size_t npix, float* db) {
+    k_colsum32<<<148, 256, 0, st>>>(g, npix, db);
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
+// in: activations of `steps` unrolled steps, image (step, b) at in + step*in_step_stride + b*Y*X*32 floats;
+// g:  output gradients, image (step, b) at g + step*g_step_stride + b*Y*X*32.
+// part: sm_count x (25*32*32+32) floats; dW = sum over CTAs (k_wgrad_finalize).
+int launch_wgrad_c32_tc(cudaStream_t st, int sm_count, int steps, int B, int Y, int X, const float* in, size_t in_step_stride,
+                        const float* g, size_t g_step_stride, float* part, int* nctas_out) {
+    tc::EncodeTiledFn enc = tc::get_encode_tiled();
+    if (!enc) return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    if (X % WG_TX || Y % WG_TY) return fail(SOL_ERR_UNSUPPORTED, "wgrad tc: needs X % 8 == 0 and Y % 16 == 0");
+    if ((in_step_stride * 4) % 16 || (g_step_stride * 4) % 16) return fail(SOL_ERR_INVALID, "wgrad tc: step strides must be 16-byte multiples");
+    alignas(64) CUtensorMap map_in, map_g;
+    const cuuint64_t dims[5] = {32, (cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)B, (cuuint64_t)steps};
+    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    {
+        const cuuint64_t strides[4] = {128, (cuuint64_t)X * 128, (cuuint64_t)Y * X * 128, (cuuint64_t)in_step_stride * 4};
+        const cuuint32_t box[5] = {32, WG_HW, WG_HH, 1, 1};
+        if (enc(&map_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)in, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled(wgrad activations) failed");
+    }
+    {
+        const cuuint64_t strides[4] = {128, (cuuint64_t)X * 128, (cuuint64_t)Y * X * 128, (cuuint64_t)g_step_stride * 4};
+        const cuuint32_t box[5] = {32, WG_TX, WG_TY, 1, 1};
+        if (enc(&map_g, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)g, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled(wgrad gradients) failed");
+    }
+    WgTcArgs a;
+    a.part = part; a.tiles_x = X / WG_TX; a.tiles_y = Y / WG_TY; a.images = steps * B; a.B = B; a.accumulate = 0;
+    const int ntiles = a.tiles_x * a.tiles_y * a.images;
+    int nctas = sm_count < 148 ? sm_count : 148;
+    if (nctas > ntiles) nctas = ntiles;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SOL_CUDA(cudaFuncSetAttribute(k_wgrad_c32_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+        attr_done = true;
+    }
+    k_wgrad_c32_tc<<<nctas, WG_THREADS, WG_SMEM, st>>>(map_in, map_g, a);
+    SOL_LAUNCHED();
+    if (nctas_out) *nctas_out = nctas;
+    return SOL_OK;
+}
+
+}  // namespace sol
