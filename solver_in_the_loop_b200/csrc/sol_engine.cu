@@ -376,6 +376,19 @@ extern "C" size_t sol_conv5x5_wgrad_workspace(int Cin, int Cout) { return wgrad_
 extern "C" int sol_conv5x5_wgrad(void* stream, int B, int Y, int X, int Cin, int Cout, const float* in, const float* g_out, float* dW,
                                  float* db, int accumulate, float* partials) {
     SOL_CHECK(in && g_out && dW && db, "sol_conv5x5_wgrad: NULL pointer");
+    if (Cin == 32 && Cout == 32 && sol::g_wgrad_path == 2) {
+        // tensor-core GEMM over the pixels of this one batch (the engine defers it over all unrolled steps)
+        SOL_CHECK(partials != nullptr, "sol_conv5x5_wgrad: partials workspace required");
+        cudaStream_t st = (cudaStream_t)stream;
+        int dev = 0, sms = 148, nctas = 0;
+        SOL_CUDA(cudaGetDevice(&dev));
+        SOL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const size_t stride = (size_t)B * Y * X * 32;
+        SOL_TRY(launch_wgrad_c32_tc(st, sms, 1, B, Y, X, in, stride, g_out, stride, partials, &nctas));
+        if (!accumulate) SOL_CUDA(cudaMemsetAsync(db, 0, 32 * sizeof(float), st));
+        SOL_TRY(launch_wgrad_finalize_n(st, nctas, partials, dW, db, accumulate));
+        return launch_colsum32(st, g_out, (size_t)B * Y * X, db);
+    }
     return launch_wgrad((cudaStream_t)stream, B, Y, X, Cin, Cout, in, g_out, dW, db, accumulate, partials, true);
 }
 

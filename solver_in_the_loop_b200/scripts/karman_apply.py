@@ -1,0 +1,78 @@
+"""Inference rollout — the drop-in for karman-2d/karman_apply.py (same flags): simulator.step +
+model.predict + add correction for `--simsteps` frames, writing denTf/velTf/corTf npz frames."""
+import argparse
+import logging
+import os
+import pickle
+
+import numpy as np
+import torch
+
+from .. import formats
+from ..phi_compat import OPEN, CorrectionModel, Domain, Fluid, KarmanFlow, StaggeredGrid, box, to_feature, to_staggered, unstack_staggered_tensor
+
+log = logging.getLogger("karman_apply")
+
+
+def parse(argv=None):
+    ap = argparse.ArgumentParser(description="Parameter Parser", formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    ap.add_argument("--gpu", default="0"); ap.add_argument("--cuda", action="store_true")
+    ap.add_argument("-o", "--output", default=None); ap.add_argument("-r", "--res", default=32, type=int)
+    ap.add_argument("-l", "--len", default=100, type=int); ap.add_argument("--re", default=1e6, type=float)
+    ap.add_argument("--initdH", default=None); ap.add_argument("--initvH", default=None)
+    ap.add_argument("-t", "--simsteps", default=500, type=int); ap.add_argument("-s", "--scale", default=4, type=int)
+    ap.add_argument("--stats", default=None, help="dataStats.pickle of the training run")
+    ap.add_argument("--model", default=None, help="model.npz (Keras-ordered weights)")
+    return ap.parse_args(argv)
+
+
+def main(argv=None):
+    p = vars(parse(argv))
+    logging.basicConfig(level=logging.INFO)
+    torch.cuda.set_device(int(p["gpu"].split(",")[0]))
+    res, L = p["res"], p["len"]
+    st = Fluid(Domain(resolution=[res * 2, res], box=box[0:L * 2, 0:L], boundaries=OPEN), buoyancy_factor=0)
+    if p["initvH"]:
+        vn = torch.from_numpy(formats.downsample(formats.read_zipped_array(p["initvH"]), p["scale"], True).astype(np.float32)).cuda()
+    else:
+        vn = st.velocity.staggered_tensor()
+        vn[..., 0] = 1.0
+        vn[..., vn.shape[1] // 2 + 10:vn.shape[1] // 2 + 20, vn.shape[2] // 2 - 2:vn.shape[2] // 2 + 2, 1] = 1.0
+    v0 = StaggeredGrid(unstack_staggered_tensor(vn), st.velocity.box)
+    d0 = None
+    if p["initdH"]:
+        d0 = torch.from_numpy(formats.downsample(formats.read_zipped_array(p["initdH"]), p["scale"], False).astype(np.float32)).cuda()
+    st = st.copied_with(density=d0, velocity=v0)
+    bc = np.zeros(tuple(st.velocity.data[0].data.shape))
+    bc[..., 0:2, 0:bc.shape[2] - 1, 0] = 1.0
+    bc[..., 0:bc.shape[1], 0:1, 0] = 1.0
+    bc[..., 0:bc.shape[1], -1:, 0] = 1.0
+    velBCy, velBCyMask = bc, np.copy(bc)
+    with open(p["stats"], "rb") as f:
+        data_stats = pickle.load(f)
+    model = CorrectionModel.load(p["model"])
+    std_in = torch.tensor([*data_stats["std"][1], data_stats["ext.std"][0]], dtype=torch.float32, device="cuda")
+    std_out = torch.tensor(data_stats["std"][1], dtype=torch.float32, device="cuda")
+    sim_path = formats.sim_dir(p["output"], 0) if p["output"] else None
+    cv = st.staggered_grid(name="corr", value=0)
+
+    def write(i):
+        if sim_path is None:
+            return
+        for name, arr in (("denTf", st.density.data), ("velTf", st.velocity.staggered_tensor()), ("corTf", cv.staggered_tensor())):
+            formats.write_zipped_array(os.path.join(sim_path, "%s_%06d.npz" % (name, i)), arr.cpu().numpy())
+
+    write(0)
+    simulator = KarmanFlow()
+    for i in range(1, p["simsteps"]):
+        st = simulator.step(st, re=p["re"], res=res, velBCy=velBCy, velBCyMask=velBCyMask)
+        inputf = to_feature([st], p["re"]) / std_in
+        cv_pred = model.predict(inputf) * std_out
+        cv = to_staggered(cv_pred, st.velocity.box)
+        st = st.copied_with(velocity=st.velocity + cv)
+        write(i)
+    return st
+
+
+if __name__ == "__main__":
+    main()
