@@ -180,8 +180,8 @@ struct FineOps {
     }
 };
 
-template <int X, int R, int MODE>
-__global__ void __launch_bounds__(512, 1) k_cg_mg(const MgArgs a) {
+template <int X, int R, int MODE, int NT>
+__global__ void __launch_bounds__(NT, 1) k_cg_mg(const MgArgs a) {
     extern __shared__ float smem[];
     constexpr int PITCH = X + 2;
     constexpr int LGX = (X == 32) ? 5 : 6;
@@ -455,9 +455,9 @@ __global__ void __launch_bounds__(512, 1) k_cg_mg(const MgArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int X, int R, int MODE>
+template <int X, int R, int MODE, int NT>
 static int launch_mg_t(const MgArgs& a, cudaStream_t st, int TY, size_t smem_bytes) {
-    auto kern = k_cg_mg<X, R, MODE>;
+    auto kern = k_cg_mg<X, R, MODE, NT>;
     static size_t attr_smem = 48 * 1024;
     if (smem_bytes > attr_smem) {
         SOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
@@ -471,9 +471,9 @@ static int launch_mg_t(const MgArgs& a, cudaStream_t st, int TY, size_t smem_byt
 bool mg_supported(const sol_plan* p) {
     if (!p->mg.valid) return false;
     if (!(p->X == 32 || p->X == 64)) return false;
-    // rows per thread R in {8, 16} with X * (Y / R) <= 512
-    for (int R : {16, 8})
-        if (p->Y % R == 0 && p->X * (p->Y / R) <= 512 && p->Y / R >= 1) return true;
+    // rows per thread R = 16 (<= 512 threads, 128 registers) or 8 (<= 1024 threads, 64 registers)
+    if (p->Y % 16 == 0 && p->X * (p->Y / 16) <= 512) return true;
+    if (p->Y % 8 == 0 && p->X * (p->Y / 8) <= 1024) return true;
     return false;
 }
 
@@ -488,9 +488,8 @@ int launch_cg_mg(const sol_plan* p, cudaStream_t st, int B, int mode, const floa
     a.tol_abs = p->tol_abs; a.tol_rel = p->tol_rel; a.max_it = p->max_it; a.iters = iters;
     a.nlev = h.nlev; a.dinv_g = h.dinv; a.diag_g = h.diag; a.cinv = h.cinv; a.omega = h.omega;
     int R = 0;
-    for (int cand : {16, 8})
-        if (p->Y % cand == 0 && p->X * (p->Y / cand) <= 512) { R = cand; break; }
-    if (p->cg_rows == 8 && p->Y % 8 == 0 && p->X * (p->Y / 8) <= 512) R = 8;
+    if (p->Y % 16 == 0 && p->X * (p->Y / 16) <= 512) R = 16;
+    if ((R == 0 || p->cg_rows == 8) && p->Y % 8 == 0 && p->X * (p->Y / 8) <= 1024) R = 8;
     if (!R) return fail(SOL_ERR_UNSUPPORTED, "cg_mg: no thread geometry for this grid");
     const int TY = p->Y / R;
     // shared-memory carve-up (floats)
@@ -513,12 +512,12 @@ int launch_cg_mg(const sol_plan* p, cudaStream_t st, int B, int mode, const floa
     a.s_red = off; off += 64;
     const size_t smem_bytes = (size_t)off * sizeof(float);
     if (smem_bytes > 227 * 1024) return fail(SOL_ERR_UNSUPPORTED, "cg_mg: grid too large for one CTA");
-#define SOL_MG_CASE(XX, RR)                                                      \
-    if (p->X == XX && R == RR) {                                                 \
-        if (mode == 0) return launch_mg_t<XX, RR, 0>(a, st, TY, smem_bytes);     \
-        return launch_mg_t<XX, RR, 1>(a, st, TY, smem_bytes);                    \
+#define SOL_MG_CASE(XX, RR, NTT)                                                      \
+    if (p->X == XX && R == RR) {                                                      \
+        if (mode == 0) return launch_mg_t<XX, RR, 0, NTT>(a, st, TY, smem_bytes);     \
+        return launch_mg_t<XX, RR, 1, NTT>(a, st, TY, smem_bytes);                    \
     }
-    SOL_MG_CASE(32, 8) SOL_MG_CASE(32, 16) SOL_MG_CASE(64, 8) SOL_MG_CASE(64, 16)
+    SOL_MG_CASE(32, 8, 1024) SOL_MG_CASE(32, 16, 512) SOL_MG_CASE(64, 8, 1024) SOL_MG_CASE(64, 16, 512)
 #undef SOL_MG_CASE
     return fail(SOL_ERR_UNSUPPORTED, "cg_mg: unsupported (X, rows/thread)");
 }

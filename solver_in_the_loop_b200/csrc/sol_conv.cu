@@ -123,15 +123,56 @@ __global__ void __launch_bounds__(256) k_conv5x5_thin(const ConvArgs a) {
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * T, y0 = blockIdx.y * T, b = blockIdx.z;
     const float* inb = a.in + (size_t)b * a.Y * a.X * CIN;
-    for (int idx = tid; idx < P * P * CIN; idx += 256) {
-        const int c = idx % CIN, pix = idx / CIN;
-        const int tyy = pix / P, txx = pix - tyy * P;
-        const int gy = y0 + tyy - 2, gx = x0 + txx - 2;
-        float v = 0.0f;
-        if (gy >= 0 && gy < a.Y && gx >= 0 && gx < a.X) v = __ldg(inb + ((size_t)gy * a.X + gx) * CIN + c);
-        tin[pix * CINP + c] = v;
+    // staging loops are fully unrolled (compile-time trip counts) so that every thread has all of its
+    // global loads in flight at once — a rolled loop exposes one L2 latency per iteration
+    if constexpr (CIN % 4 == 0) {
+        constexpr int NV = CIN / 4, TOTAL = P * P * NV, ITER = (TOTAL + 255) / 256;
+        float4 v[ITER];
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int idx = tid + it * 256;
+            const int c4 = idx % NV, pix = idx / NV;
+            const int tyy = pix / P, txx = pix - tyy * P;
+            const int gy = y0 + tyy - 2, gx = x0 + txx - 2;
+            v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < TOTAL && gy >= 0 && gy < a.Y && gx >= 0 && gx < a.X)
+                v[it] = __ldg(reinterpret_cast<const float4*>(inb + ((size_t)gy * a.X + gx) * CIN) + c4);
+        }
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int idx = tid + it * 256;
+            if (idx < TOTAL) {
+                const int c4 = idx % NV, pix = idx / NV;
+                float* d = tin + pix * CINP + c4 * 4;
+                d[0] = v[it].x; d[1] = v[it].y; d[2] = v[it].z; d[3] = v[it].w;
+            }
+        }
+    } else {
+        constexpr int TOTAL = P * P * CIN, ITER = (TOTAL + 255) / 256;
+        float v[ITER];
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int idx = tid + it * 256;
+            const int c = idx % CIN, pix = idx / CIN;
+            const int tyy = pix / P, txx = pix - tyy * P;
+            const int gy = y0 + tyy - 2, gx = x0 + txx - 2;
+            v[it] = 0.0f;
+            if (idx < TOTAL && gy >= 0 && gy < a.Y && gx >= 0 && gx < a.X) v[it] = __ldg(inb + ((size_t)gy * a.X + gx) * CIN + c);
+        }
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int idx = tid + it * 256;
+            if (idx < TOTAL) tin[(idx / CIN) * CINP + idx % CIN] = v[it];
+        }
     }
-    for (int idx = tid; idx < 25 * CIN * COUT; idx += 256) ws[idx] = __ldg(a.w + idx);
+    {
+        constexpr int TOTALW = 25 * CIN * COUT, ITERW = (TOTALW + 255) / 256;
+        float wv[ITERW];
+#pragma unroll
+        for (int it = 0; it < ITERW; ++it) { const int idx = tid + it * 256; wv[it] = (idx < TOTALW) ? __ldg(a.w + idx) : 0.0f; }
+#pragma unroll
+        for (int it = 0; it < ITERW; ++it) { const int idx = tid + it * 256; if (idx < TOTALW) ws[idx] = wv[it]; }
+    }
     __syncthreads();
     const int tx = tid & 15, ty = tid >> 4;
     float acc[COUT];
@@ -344,21 +385,47 @@ __global__ void __launch_bounds__(256) k_wgrad_thin(const float* __restrict__ in
     float* tg = sm + PR * PWT * CINP;         // [TR*TWT][COUTP]
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * TWT, y0 = blockIdx.y * TR, b = blockIdx.z;
-    for (int idx = tid; idx < PR * PWT * CIN; idx += 256) {
-        const int c = idx % CIN, pix = idx / CIN;
-        const int tyy = pix / PWT, txx = pix - tyy * PWT;
-        const int gy = y0 + tyy - 2, gx = x0 + txx - 2;
-        float v = 0.0f;
-        if (gy >= 0 && gy < Y && gx >= 0 && gx < X) v = __ldg(in + (((size_t)b * Y + gy) * X + gx) * CIN + c);
-        tin[pix * CINP + c] = v;
+    {
+        constexpr int TOTAL = PR * PWT * CIN, ITER = (TOTAL + 255) / 256, CH = 8;
+#pragma unroll 1
+        for (int it0 = 0; it0 < ITER; it0 += CH) {      // chunks of 8 loads in flight
+            float v[CH];
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                const int idx = tid + (it0 + k) * 256;
+                const int c = idx % CIN, pix = idx / CIN;
+                const int tyy = pix / PWT, txx = pix - tyy * PWT;
+                const int gy = y0 + tyy - 2, gx = x0 + txx - 2;
+                v[k] = 0.0f;
+                if (idx < TOTAL && gy >= 0 && gy < Y && gx >= 0 && gx < X) v[k] = __ldg(in + (((size_t)b * Y + gy) * X + gx) * CIN + c);
+            }
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                const int idx = tid + (it0 + k) * 256;
+                if (idx < TOTAL) tin[(idx / CIN) * CINP + idx % CIN] = v[k];
+            }
+        }
     }
-    for (int idx = tid; idx < TR * TWT * COUT; idx += 256) {
-        const int c = idx % COUT, pix = idx / COUT;
-        const int tyy = pix / TWT, txx = pix - tyy * TWT;
-        const int gy = y0 + tyy, gx = x0 + txx;
-        float v = 0.0f;
-        if (gy < Y && gx < X) v = __ldg(g + (((size_t)b * Y + gy) * X + gx) * COUT + c);
-        tg[pix * COUTP + c] = v;
+    {
+        constexpr int TOTAL = TR * TWT * COUT, ITER = (TOTAL + 255) / 256, CH = 8;
+#pragma unroll 1
+        for (int it0 = 0; it0 < ITER; it0 += CH) {
+            float v[CH];
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                const int idx = tid + (it0 + k) * 256;
+                const int c = idx % COUT, pix = idx / COUT;
+                const int tyy = pix / TWT, txx = pix - tyy * TWT;
+                const int gy = y0 + tyy, gx = x0 + txx;
+                v[k] = 0.0f;
+                if (idx < TOTAL && gy < Y && gx < X) v[k] = __ldg(g + (((size_t)b * Y + gy) * X + gx) * COUT + c);
+            }
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                const int idx = tid + (it0 + k) * 256;
+                if (idx < TOTAL) tg[(idx / COUT) * COUTP + idx % COUT] = v[k];
+            }
+        }
     }
     __syncthreads();
     constexpr int E = 25 * CIN * COUT;

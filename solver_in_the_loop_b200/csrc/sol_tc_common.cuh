@@ -87,16 +87,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes
 }
 
 
-// MN-major (the M/N index is the contiguous one), 128B-swizzled descriptor: an "atom" is 8 K-rows of
-// 128 B (32 fp32 along M/N); lbo = byte distance between consecutive 32-element M/N blocks,
-// sbo = byte distance between consecutive 8-row K groups.
+// MN-major tf32 operands (the M/N index is the contiguous one).  For 32-bit MN-major operands the only
+// legal swizzled layout is SWIZZLE_128B_BASE32B (cute: Layout_MN_SW128_32B_Atom; TMA:
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 32-byte chunks of a 128-byte row are XOR-swizzled with the
+// row index mod 4; an atom is 4 K-rows x 128 B (32 fp32 along M/N).
+//   lbo = byte distance between consecutive 32-element M/N blocks,
+//   sbo = byte distance between consecutive 4-row K groups (512 when the K rows are contiguous).
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)1 << 61;       // LayoutType::SWIZZLE_128B_BASE32B
     return d;
 }
 

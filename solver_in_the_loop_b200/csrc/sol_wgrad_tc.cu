@@ -8,16 +8,18 @@
 // round trips per (layer, step) disappears.
 //
 // GEMM mapping (per CTA, persistent over pixel tiles of 8 x 16):
-//   K = pixels.  Both operands are "MN-major": a pixel row of the staged tiles is 128 B = 32 channels,
-//   8 consecutive pixels (one tile row) form one 8-row swizzle atom = one K=8 UMMA step.
+//   K = pixels.  Both operands are "MN-major" tf32 (layout SWIZZLE_128B_BASE32B, the only legal one for
+//   32-bit MN-major operands): a pixel row of the staged tiles is 128 B = 32 channels, 8 consecutive
+//   pixels (one tile row) are two 4-row swizzle atoms = one K=8 UMMA step.
 //   A = activations:  M = 128 = 4 taps x 32 cin.  The 4 M-blocks of a descriptor are 4 horizontally
 //       adjacent taps of the SAME staged halo tile: leading-byte-offset = 128 B (one pixel), start =
 //       halo + ((y+dy)*12 + x + dx0)*128.  (The swizzle phase is a function of the absolute
 //       shared-memory address, so overlapping, non-1024-aligned atoms are consistent with what TMA wrote.)
 //   B = output gradient: N = 32 cout, one atom per tile row.
-//   D[(tap,cin)][cout] lives in TMEM: 5 kernel rows x {dx 0..3, dx 4..7} = 10 accumulators of
-//   128 lanes x 32 columns; consecutive MMAs go to different accumulators (MMA-latency chains).
-//   3xTF32: A and G tiles are split once into hi/lo by the 4 helper warps; D += Ahi*Ghi + Ahi*Glo + Alo*Ghi.
+//   D[(tap,cin)][cout] lives in TMEM: 7 tap groups (5 horizontal dx 0..3, one vertical dx=4/dy 0..3, one
+//   for tap (4,4)) x 64 columns; consecutive MMAs go to different accumulators (MMA-latency chains).
+//   3xTF32: A and G tiles are split once into hi/lo by the 4 helper warps; [G_hi|G_lo] are two N-blocks of
+//   one descriptor, so D[:,0:64] += Ahi*[Ghi|Glo] is ONE N=64 MMA, then D[:,0:32] += Alo*Ghi.
 //   The TMEM accumulators persist across all tiles of the CTA; at the end they are written to a
 //   per-CTA partial slot, reduced by k_wgrad_finalize (sol_conv.cu).
 #include "sol_internal.cuh"
@@ -37,9 +39,11 @@ constexpr int WG_NSTAGE = 2;
 constexpr int WG_OFF_BAR = WG_NSTAGE * WG_STAGE_BYTES;            // 188416
 constexpr int WG_SMEM = WG_OFF_BAR + 256 + 1024;
 constexpr int WG_THREADS = 192;
-constexpr int WG_TMEM_COLS = 512;                                 // 10 x 32 columns used
-// M=128, N=32, tf32, A and B MN-major (bits 15, 16)
-constexpr uint32_t WG_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr int WG_TMEM_COLS = 512;                                 // 7 tap groups x 64 columns used
+constexpr int WG_NGROUP = 7;
+// M=128, tf32, A and B MN-major (bits 15, 16), N = 32 or 64
+constexpr uint32_t WG_IDESC32 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t WG_IDESC64 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
 struct WgTcArgs {
     float* part;        // [gridDim.x][25*32*32 + 32]
@@ -113,25 +117,32 @@ k_wgrad_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (leader) {
                 const uint32_t st = base + s * WG_STAGE_BYTES;
-                const uint64_t dA_hi = make_desc_mn(st, 128, 1024);
-                const uint64_t dA_lo = make_desc_mn(st + WG_A_BYTES, 128, 1024);
-                const uint64_t dG_hi = make_desc_mn(st + 2 * WG_A_BYTES, 128, 1024);
-                const uint64_t dG_lo = make_desc_mn(st + 2 * WG_A_BYTES + WG_G_BYTES, 128, 1024);
+                // A: 4 M-blocks = 4 taps; block stride (LBO) = 128 B for horizontally adjacent taps, one
+                // halo row (12*128 B) for vertically adjacent ones.  G: [G_hi | G_lo] as two N-blocks
+                // (LBO = distance between the two tiles) -> Ahi*Ghi and Ahi*Glo in ONE N=64 MMA.
+                const uint64_t dAh_hi = make_desc_mn(st, 128, 512), dAh_lo = make_desc_mn(st + WG_A_BYTES, 128, 512);
+                const uint64_t dAv_hi = make_desc_mn(st, WG_HW * 128, 512), dAv_lo = make_desc_mn(st + WG_A_BYTES, WG_HW * 128, 512);
+                const uint64_t dG64 = make_desc_mn(st + 2 * WG_A_BYTES, WG_G_BYTES, 512);      // [hi | lo]
+                const uint64_t dG32 = make_desc_mn(st + 2 * WG_A_BYTES, 128, 512);             // hi only
 #pragma unroll 1
                 for (int y = 0; y < WG_TY; ++y) {
                     const uint64_t g_off = (uint64_t)(y * 64);                    // one tile row = 1024 B
+                    const uint32_t accum = (n == 0 && y == 0) ? 0u : 1u;
+                    // pass 0: D[:, 0:64] (+)= A_hi x [G_hi | G_lo]   pass 1: D[:, 0:32] += A_lo x G_hi
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) {                                 // hi*hi, hi*lo, lo*hi
-                        const uint64_t dA = (j == 2) ? dA_lo : dA_hi;
-                        const uint64_t dG = ((j == 1) ? dG_lo : dG_hi) + g_off;
-                        const uint32_t accum = (n == 0 && y == 0 && j == 0) ? 0u : 1u;
+                    for (int j = 0; j < 2; ++j) {
+                        const uint64_t dG = (j == 0 ? dG64 : dG32) + g_off;
+                        const uint32_t idesc = (j == 0) ? WG_IDESC64 : WG_IDESC32;
+                        const uint32_t acc_flag = (j == 0) ? accum : 1u;
 #pragma unroll
-                        for (int dy = 0; dy < 5; ++dy)
-#pragma unroll
-                            for (int g = 0; g < 2; ++g) {
-                                const uint64_t a_off = (uint64_t)(((y + dy) * WG_HW + g * 4) * 8);
-                                umma_tf32(tmem_acc + 32u * (uint32_t)(dy * 2 + g), dA + a_off, dG, WG_IDESC, accum);
-                            }
+                        for (int grp = 0; grp < WG_NGROUP; ++grp) {
+                            // groups 0..4: taps (dy=grp, dx=0..3); group 5: taps (dy=0..3, dx=4); group 6: tap (4,4) (+3 unused)
+                            const int dy0 = (grp < 5) ? grp : (grp == 5 ? 0 : 4);
+                            const int dx0 = (grp < 5) ? 0 : 4;
+                            const uint64_t a_off = (uint64_t)(((y + dy0) * WG_HW + dx0) * 8);
+                            const uint64_t dA = (grp == 5) ? ((j == 0) ? dAv_hi : dAv_lo) : ((j == 0) ? dAh_hi : dAh_lo);
+                            umma_tf32(tmem_acc + 64u * (uint32_t)grp, dA + a_off, dG, idesc, acc_flag);
+                        }
                     }
                 }
                 umma_commit(bar_empty + 8 * s);
@@ -182,17 +193,24 @@ k_wgrad_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         float* part = a.part + (size_t)blockIdx.x * (25 * 32 * 32 + 32);
         if (tt < 32) part[25 * 32 * 32 + tt] = 0.0f;     // bias slot: the bias gradient comes from k_colsum32
 #pragma unroll 1
-        for (int acc = 0; acc < 10; ++acc) {
-            const int dy = acc >> 1, g = acc & 1;
-            const int dx = 4 * g + q;
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + 32u * (uint32_t)acc, v);
+        for (int grp = 0; grp < WG_NGROUP; ++grp) {
+            // M-block q of group grp -> tap
+            int dy, dx;
+            if (grp < 5) { dy = grp; dx = q; }
+            else if (grp == 5) { dy = q; dx = 4; }
+            else { dy = 4; dx = 4 + q; }
+            uint32_t v0[32], v1[32];
+            const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + 64u * (uint32_t)grp;
+            tmem_ld_32x32(taddr, v0);            // hh + lh
+            tmem_ld_32x32(taddr + 32u, v1);      // hl
             if (dx < 5) {
                 float4* dst = reinterpret_cast<float4*>(part + (((dy * 5 + dx) * 32 + lane) * 32));
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    float4 f = make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
-                                           __uint_as_float(v[4 * c + 3]));
+                    float4 f = make_float4(__uint_as_float(v0[4 * c]) + __uint_as_float(v1[4 * c]),
+                                           __uint_as_float(v0[4 * c + 1]) + __uint_as_float(v1[4 * c + 1]),
+                                           __uint_as_float(v0[4 * c + 2]) + __uint_as_float(v1[4 * c + 2]),
+                                           __uint_as_float(v0[4 * c + 3]) + __uint_as_float(v1[4 * c + 3]));
                     if (a.accumulate) { const float4 o = dst[c]; f.x += o.x; f.y += o.y; f.z += o.z; f.w += o.w; }
                     dst[c] = f;
                 }
@@ -252,14 +270,14 @@ int launch_wgrad_c32_tc(cudaStream_t st, int sm_count, int steps, int B, int Y, 
         const cuuint64_t strides[4] = {128, (cuuint64_t)X * 128, (cuuint64_t)Y * X * 128, (cuuint64_t)in_step_stride * 4};
         const cuuint32_t box[5] = {32, WG_HW, WG_HH, 1, 1};
         if (enc(&map_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)in, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled(wgrad activations) failed");
     }
     {
         const cuuint64_t strides[4] = {128, (cuuint64_t)X * 128, (cuuint64_t)Y * X * 128, (cuuint64_t)g_step_stride * 4};
         const cuuint32_t box[5] = {32, WG_TX, WG_TY, 1, 1};
         if (enc(&map_g, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)g, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled(wgrad gradients) failed");
     }
     WgTcArgs a;
