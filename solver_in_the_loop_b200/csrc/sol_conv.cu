@@ -374,84 +374,112 @@ __global__ void __launch_bounds__(256) k_wgrad_finalize(int nctas, const float* 
 // ------------------------------------------------------------------------------------------------
 // weight gradient, thin layers (atomics into dW / db)
 // ------------------------------------------------------------------------------------------------
+// Persistent over tiles of (possibly many) images: every thread keeps its (tap,cin,cout) entries in
+// registers across all tiles of its CTA and issues one atomic per entry at the end.  Image z = step*B + b
+// lives at in + step*in_step_stride + b*Y*X*CIN (and likewise for g), so the same kernel serves the
+// per-step call (steps = 1) and the deferred call over the whole unrolled sweep.
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(256) k_wgrad_thin(const float* __restrict__ in, const float* __restrict__ g, float* dW, float* db,
-                                                    int B, int Y, int X) {
+                                                    int steps, int B, int Y, int X, size_t in_step_stride, size_t g_step_stride) {
     constexpr int TR = 8, TWT = 32, PR = TR + 4, PWT = TWT + 4;
     constexpr int CINP = (CIN % 2 == 0) ? CIN + 1 : CIN;
     constexpr int COUTP = (COUT % 2 == 0) ? COUT + 1 : COUT;
+    constexpr int E = 25 * CIN * COUT;
+    constexpr int NE = (E + COUT + 255) / 256;
     extern __shared__ float sm[];
     float* tin = sm;                          // [PR*PWT][CINP]
     float* tg = sm + PR * PWT * CINP;         // [TR*TWT][COUTP]
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TWT, y0 = blockIdx.y * TR, b = blockIdx.z;
-    {
-        constexpr int TOTAL = PR * PWT * CIN, ITER = (TOTAL + 255) / 256, CH = 8;
+    const int tiles_x = (X + TWT - 1) / TWT, tiles_y = (Y + TR - 1) / TR;
+    const int tiles_img = tiles_x * tiles_y;
+    const int ntiles = tiles_img * steps * B;
+    float acc[NE];
+#pragma unroll
+    for (int k = 0; k < NE; ++k) acc[k] = 0.0f;
 #pragma unroll 1
-        for (int it0 = 0; it0 < ITER; it0 += CH) {      // chunks of 8 loads in flight
-            float v[CH];
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int img = tile / tiles_img, rem = tile - img * tiles_img;
+        const int tyi = rem / tiles_x, txi = rem - tyi * tiles_x;
+        const int step = img / B, b = img - step * B;
+        const int x0 = txi * TWT, y0 = tyi * TR;
+        const float* inb = in + (size_t)step * in_step_stride + (size_t)b * Y * X * CIN;
+        const float* gb = g + (size_t)step * g_step_stride + (size_t)b * Y * X * COUT;
+        __syncthreads();     // previous tile fully consumed
+        {
+            constexpr int TOTAL = PR * PWT * CIN, ITER = (TOTAL + 255) / 256, CH = 8;
+#pragma unroll 1
+            for (int it0 = 0; it0 < ITER; it0 += CH) {      // chunks of 8 loads in flight
+                float v[CH];
 #pragma unroll
-            for (int k = 0; k < CH; ++k) {
-                const int idx = tid + (it0 + k) * 256;
-                const int c = idx % CIN, pix = idx / CIN;
-                const int tyy = pix / PWT, txx = pix - tyy * PWT;
-                const int gy = y0 + tyy - 2, gx = x0 + txx - 2;
-                v[k] = 0.0f;
-                if (idx < TOTAL && gy >= 0 && gy < Y && gx >= 0 && gx < X) v[k] = __ldg(in + (((size_t)b * Y + gy) * X + gx) * CIN + c);
-            }
+                for (int k = 0; k < CH; ++k) {
+                    const int idx = tid + (it0 + k) * 256;
+                    const int c = idx % CIN, pix = idx / CIN;
+                    const int tyy = pix / PWT, txx = pix - tyy * PWT;
+                    const int gy = y0 + tyy - 2, gx = x0 + txx - 2;
+                    v[k] = 0.0f;
+                    if (idx < TOTAL && gy >= 0 && gy < Y && gx >= 0 && gx < X) v[k] = __ldg(inb + ((size_t)gy * X + gx) * CIN + c);
+                }
 #pragma unroll
-            for (int k = 0; k < CH; ++k) {
-                const int idx = tid + (it0 + k) * 256;
-                if (idx < TOTAL) tin[(idx / CIN) * CINP + idx % CIN] = v[k];
+                for (int k = 0; k < CH; ++k) {
+                    const int idx = tid + (it0 + k) * 256;
+                    if (idx < TOTAL) tin[(idx / CIN) * CINP + idx % CIN] = v[k];
+                }
             }
         }
-    }
-    {
-        constexpr int TOTAL = TR * TWT * COUT, ITER = (TOTAL + 255) / 256, CH = 8;
+        {
+            constexpr int TOTAL = TR * TWT * COUT, ITER = (TOTAL + 255) / 256, CH = 8;
 #pragma unroll 1
-        for (int it0 = 0; it0 < ITER; it0 += CH) {
-            float v[CH];
+            for (int it0 = 0; it0 < ITER; it0 += CH) {
+                float v[CH];
 #pragma unroll
-            for (int k = 0; k < CH; ++k) {
-                const int idx = tid + (it0 + k) * 256;
-                const int c = idx % COUT, pix = idx / COUT;
-                const int tyy = pix / TWT, txx = pix - tyy * TWT;
-                const int gy = y0 + tyy, gx = x0 + txx;
-                v[k] = 0.0f;
-                if (idx < TOTAL && gy < Y && gx < X) v[k] = __ldg(g + (((size_t)b * Y + gy) * X + gx) * COUT + c);
-            }
+                for (int k = 0; k < CH; ++k) {
+                    const int idx = tid + (it0 + k) * 256;
+                    const int c = idx % COUT, pix = idx / COUT;
+                    const int tyy = pix / TWT, txx = pix - tyy * TWT;
+                    const int gy = y0 + tyy, gx = x0 + txx;
+                    v[k] = 0.0f;
+                    if (idx < TOTAL && gy < Y && gx < X) v[k] = __ldg(gb + ((size_t)gy * X + gx) * COUT + c);
+                }
 #pragma unroll
-            for (int k = 0; k < CH; ++k) {
-                const int idx = tid + (it0 + k) * 256;
-                if (idx < TOTAL) tg[(idx / COUT) * COUTP + idx % COUT] = v[k];
+                for (int k = 0; k < CH; ++k) {
+                    const int idx = tid + (it0 + k) * 256;
+                    if (idx < TOTAL) tg[(idx / COUT) * COUTP + idx % COUT] = v[k];
+                }
             }
         }
-    }
-    __syncthreads();
-    constexpr int E = 25 * CIN * COUT;
-    for (int e = tid; e < E + COUT; e += 256) {
-        float acc = 0.0f;
-        if (e < E) {
-            const int co = e % COUT, ci = (e / COUT) % CIN, tap = e / (COUT * CIN);
-            const int dy = tap / 5, dx = tap - dy * 5;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            const int e = tid + k * 256;
+            float s = 0.0f;
+            if (e < E) {
+                const int co = e % COUT, ci = (e / COUT) % CIN, tap = e / (COUT * CIN);
+                const int dy = tap / 5, dx = tap - dy * 5;
 #pragma unroll 1
-            for (int yy = 0; yy < TR; ++yy) {
-                const float* ip = tin + ((yy + dy) * PWT + dx) * CINP + ci;
-                const float* gp = tg + (yy * TWT) * COUTP + co;
+                for (int yy = 0; yy < TR; ++yy) {
+                    const float* ip = tin + ((yy + dy) * PWT + dx) * CINP + ci;
+                    const float* gp = tg + (yy * TWT) * COUTP + co;
 #pragma unroll 8
-                for (int xx = 0; xx < TWT; ++xx) acc = fmaf(ip[xx * CINP], gp[xx * COUTP], acc);
+                    for (int xx = 0; xx < TWT; ++xx) s = fmaf(ip[xx * CINP], gp[xx * COUTP], s);
+                }
+            } else if (e < E + COUT) {
+                const int co = e - E;
+                for (int pix = 0; pix < TR * TWT; ++pix) s += tg[pix * COUTP + co];
             }
-            atomicAdd(dW + e, acc);
-        } else {
-            const int co = e - E;
-            for (int pix = 0; pix < TR * TWT; ++pix) acc += tg[pix * COUTP + co];
-            atomicAdd(db + co, acc);
+            acc[k] += s;
         }
+    }
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+        const int e = tid + k * 256;
+        if (e < E) atomicAdd(dW + e, acc[k]);
+        else if (e < E + COUT) atomicAdd(db + (e - E), acc[k]);
     }
 }
 
 template <int CIN, int COUT>
-static int launch_wgrad_thin(cudaStream_t st, int B, int Y, int X, const float* in, const float* g, float* dW, float* db) {
+static int launch_wgrad_thin(cudaStream_t st, int steps, int B, int Y, int X, const float* in, size_t in_step_stride, const float* g,
+                             size_t g_step_stride, float* dW, float* db) {
     constexpr int CINP = (CIN % 2 == 0) ? CIN + 1 : CIN;
     constexpr int COUTP = (COUT % 2 == 0) ? COUT + 1 : COUT;
     const size_t smem = (size_t)(12 * 36 * CINP + 8 * 32 * COUTP) * sizeof(float);
@@ -461,9 +489,21 @@ static int launch_wgrad_thin(cudaStream_t st, int B, int Y, int X, const float* 
         SOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    kern<<<dim3(cdiv(X, 32), cdiv(Y, 8), B), 256, smem, st>>>(in, g, dW, db, B, Y, X);
+    const int ntiles = cdiv(X, 32) * cdiv(Y, 8) * B * steps;
+    const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;
+    kern<<<grid, 256, smem, st>>>(in, g, dW, db, steps, B, Y, X, in_step_stride, g_step_stride);
     SOL_LAUNCHED();
     return SOL_OK;
+}
+
+// thin-layer weight gradient accumulated INTO dW/db (atomics) over `steps` unrolled steps
+int launch_wgrad_thin_multi(cudaStream_t st, int steps, int B, int Y, int X, int Cin, int Cout, const float* in, size_t in_step_stride,
+                            const float* g, size_t g_step_stride, float* dW, float* db) {
+#define SOL_WTHIN(CI, CO) \
+    if (Cin == CI && Cout == CO) return launch_wgrad_thin<CI, CO>(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db);
+    SOL_WTHIN(3, 32) SOL_WTHIN(4, 32) SOL_WTHIN(2, 32) SOL_WTHIN(32, 2)
+#undef SOL_WTHIN
+    return fail(SOL_ERR_UNSUPPORTED, "wgrad: unsupported (Cin, Cout) pair");
 }
 
 size_t wgrad_workspace_floats(int Cin, int Cout) {
@@ -514,11 +554,7 @@ int launch_wgrad(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const 
         SOL_CUDA(cudaMemsetAsync(dW, 0, (size_t)25 * Cin * Cout * sizeof(float), st));
         SOL_CUDA(cudaMemsetAsync(db, 0, (size_t)Cout * sizeof(float), st));
     }
-#define SOL_WTHIN(CI, CO) \
-    if (Cin == CI && Cout == CO) return launch_wgrad_thin<CI, CO>(st, B, Y, X, in, g_out, dW, db);
-    SOL_WTHIN(3, 32) SOL_WTHIN(4, 32) SOL_WTHIN(2, 32) SOL_WTHIN(32, 2)
-#undef SOL_WTHIN
-    return fail(SOL_ERR_UNSUPPORTED, "wgrad: unsupported (Cin, Cout) pair");
+    return launch_wgrad_thin_multi(st, 1, B, Y, X, Cin, Cout, in, 0, g_out, 0, dW, db);
 }
 
 }  // namespace sol

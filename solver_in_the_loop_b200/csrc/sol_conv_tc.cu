@@ -264,8 +264,8 @@ EncodeTiledFn get_encode_tiled() {
 }  // namespace tc
 
 int g_tc_base_offset_mode = 0;   // measured on B200: the swizzle phase comes from the absolute address bits; base_offset stays 0
-int g_conv_path = 0;
-int g_wgrad_path = 0;
+int g_conv_path = 2;    // default: tcgen05 convolutions (1 = fp32 SIMT validation kernels)
+int g_wgrad_path = 2;   // default: deferred tcgen05 weight-gradient GEMM (1 = per-step fp32 SIMT)
 
 size_t tc_weights_floats() { return (size_t)2 * 25 * 32 * 32; }
 

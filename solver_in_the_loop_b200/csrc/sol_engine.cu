@@ -236,12 +236,12 @@ extern "C" int sol_set_option(const char* name, int value) {
     SOL_CHECK(name != nullptr, "sol_set_option: NULL name");
     if (strcmp(name, "conv_path") == 0) {
         SOL_CHECK(value >= 0 && value <= 2, "conv_path must be 0,1,2");
-        sol::g_conv_path = value;
+        sol::g_conv_path = value == 0 ? 2 : value;
         return SOL_OK;
     }
     if (strcmp(name, "wgrad_path") == 0) {
         SOL_CHECK(value >= 0 && value <= 2, "wgrad_path must be 0,1,2");
-        sol::g_wgrad_path = value;
+        sol::g_wgrad_path = value == 0 ? 2 : value;
         return SOL_OK;
     }
     if (strcmp(name, "tc_base_offset_mode") == 0) {
@@ -376,7 +376,7 @@ extern "C" size_t sol_conv5x5_wgrad_workspace(int Cin, int Cout) { return wgrad_
 extern "C" int sol_conv5x5_wgrad(void* stream, int B, int Y, int X, int Cin, int Cout, const float* in, const float* g_out, float* dW,
                                  float* db, int accumulate, float* partials) {
     SOL_CHECK(in && g_out && dW && db, "sol_conv5x5_wgrad: NULL pointer");
-    if (Cin == 32 && Cout == 32 && sol::g_wgrad_path == 2) {
+    if (Cin == 32 && Cout == 32 && sol::g_wgrad_path == 2 && Y % 16 == 0 && X % 8 == 0) {
         // tensor-core GEMM over the pixels of this one batch (the engine defers it over all unrolled steps)
         SOL_CHECK(partials != nullptr, "sol_conv5x5_wgrad: partials workspace required");
         cudaStream_t st = (cudaStream_t)stream;
@@ -385,9 +385,7 @@ extern "C" int sol_conv5x5_wgrad(void* stream, int B, int Y, int X, int Cin, int
         SOL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const size_t stride = (size_t)B * Y * X * 32;
         SOL_TRY(launch_wgrad_c32_tc(st, sms, 1, B, Y, X, in, stride, g_out, stride, partials, &nctas));
-        if (!accumulate) SOL_CUDA(cudaMemsetAsync(db, 0, 32 * sizeof(float), st));
-        SOL_TRY(launch_wgrad_finalize_n(st, nctas, partials, dW, db, accumulate));
-        return launch_colsum32(st, g_out, (size_t)B * Y * X, db);
+        return launch_wgrad_finalize_n(st, nctas, partials, dW, db, accumulate);
     }
     return launch_wgrad((cudaStream_t)stream, B, Y, X, Cin, Cout, in, g_out, dW, db, accumulate, partials, true);
 }
@@ -432,6 +430,9 @@ struct sol_unroll {
     float* wT;
     float *wprep_fwd, *wprep_bwd;   // [10 layers][2*25*32*32] pre-split tensor-core weights
     float* gst;        // deferred weight gradient: [10 layers][msteps][B,Y,X,32] output-gradient stash
+    float* g0_st;      // [msteps][B,Y,X,32] output gradient of layer 0
+    bool deferred_wgrad = false;   // decided per backward sweep: option wgrad_path == 2 and the grid tiles evenly (Y%16, X%8)
+    float* gcorr_st;   // [msteps][B,Y,X,2]  output gradient of layer 11
     size_t nA = 0;
     float* partials;   // [n_c32][WG_MAX_CTAS][25632]
     size_t partial_stride = 0;
@@ -494,6 +495,8 @@ int carve(sol_unroll* u, void* ws, size_t* total) {
     u->wprep_bwd = cv.take<float>(tc_weights_floats() * 10);
     u->nA = nA;
     u->gst = cv.take<float>(nA * 10 * c.msteps);
+    u->g0_st = cv.take<float>(nA * c.msteps);
+    u->gcorr_st = cv.take<float>(NC * 2 * c.msteps);
     u->partial_stride = wgrad_workspace_floats(32, 32);
     u->partials = cv.take<float>(u->partial_stride * 10);
     u->iters = cv.take<int>((size_t)2 * c.msteps * c.B);
@@ -542,7 +545,7 @@ int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, cons
     const std::vector<LayerDesc>& L = u->L;
     const float* wT = u->wT;
     const bool tc = sol::g_conv_path == 2;
-    const bool deferred = sol::g_wgrad_path == 2;   // weight gradients of the 32->32 layers in one GEMM per layer after the sweep
+    const bool deferred = u->deferred_wgrad;        // weight gradients in one GEMM per layer after the sweep
     // output-gradient tensor of layer l (1..10) for this step
     auto gout = [&](int l, float* fallback) -> float* {
         return deferred ? u->gst + ((size_t)(l - 1) * u->cfg.msteps + step) * u->nA : fallback;
@@ -550,7 +553,8 @@ int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, cons
     float* gS = gout(10, u->gbuf[0]);
     float* spare[3] = {u->gbuf[0], u->gbuf[1], u->gbuf[2]};
     // output layer (32 -> 2)
-    SOL_TRY(launch_wgrad(st, B, Y, X, 32, 2, s.acts[10], g_corr, gw + L[11].w_off, gw + L[11].b_off, 1, nullptr, false));
+    if (!deferred)
+        SOL_TRY(launch_wgrad(st, B, Y, X, 32, 2, s.acts[10], g_corr, gw + L[11].w_off, gw + L[11].b_off, 1, nullptr, false));
     SOL_TRY(launch_conv5x5(st, B, Y, X, 2, 32, g_corr, wT + L[11].w_off, nullptr, nullptr, s.acts[10], SOL_ACT_DLRELU, a, gS));
     for (int k = 5; k >= 1; --k) {
         const LayerDesc& l1 = L[2 * k - 1];
@@ -561,7 +565,7 @@ int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, cons
         float* fT = spare[0] == gS ? spare[1] : spare[0];
         float* gT = gout(2 * k - 1, fT);
         float* fN = (spare[0] != gS && spare[0] != gT) ? spare[0] : ((spare[1] != gS && spare[1] != gT) ? spare[1] : spare[2]);
-        float* gN = (k >= 2) ? gout(2 * k - 2, fN) : fN;
+        float* gN = (k >= 2) ? gout(2 * k - 2, fN) : (deferred ? u->g0_st + (size_t)step * u->nA : fN);
         // gS = d/d(a_{k-1} + conv_{2k}(t_k) + b)
         if (!deferred)
             SOL_TRY(launch_wgrad(st, B, Y, X, 32, 32, t_k, gS, nullptr, nullptr, !first, u->partials + u->partial_stride * (2 * k - 1), false));
@@ -574,7 +578,8 @@ int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, cons
         gS = gN;
     }
     // input layer (cin0 -> 32): gS is the gradient w.r.t. its pre-activation
-    SOL_TRY(launch_wgrad(st, B, Y, X, L[0].cin, 32, s.feat, gS, gw + L[0].w_off, gw + L[0].b_off, 1, nullptr, false));
+    if (!deferred)
+        SOL_TRY(launch_wgrad(st, B, Y, X, L[0].cin, 32, s.feat, gS, gw + L[0].w_off, gw + L[0].b_off, 1, nullptr, false));
     return launch_conv5x5(st, B, Y, X, 32, L[0].cin, gS, wT + L[0].w_off, nullptr, nullptr, nullptr, SOL_ACT_NONE, a, g_feat);
 }
 
@@ -618,6 +623,7 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
     const sol_unroll_cfg& c = u->cfg;
     const int B = c.B, m = c.msteps;
     SOL_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * u->nparams, st));
+    u->deferred_wgrad = (sol::g_wgrad_path == 2) && (p->Y % 16 == 0) && (p->X % 8 == 0);
     for (size_t l = 0; l < u->L.size(); ++l)
         SOL_TRY(launch_flip_weights(st, u->L[l].cin, u->L[l].cout, weights + u->L[l].w_off, u->wT + u->L[l].w_off));
     if (sol::g_conv_path == 2)
@@ -627,8 +633,9 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
     const float* Gx = u->stash[m - 1].gl_vx;
     for (int i = m - 1; i >= 0; --i) {
         StepStash& s = u->stash[i];
-        SOL_TRY(launch_corr_bwd(p, st, B, Gy, Gx, c.sig_vy, c.sig_vx, u->g_corr));
-        SOL_TRY(cnn_backward(u, st, weights, gw, s, u->g_corr, u->g_feat, i == m - 1, i));
+        float* g_corr = u->deferred_wgrad ? u->gcorr_st + (size_t)i * p->NC() * B * 2 : u->g_corr;
+        SOL_TRY(launch_corr_bwd(p, st, B, Gy, Gx, c.sig_vy, c.sig_vx, g_corr));
+        SOL_TRY(cnn_backward(u, st, weights, gw, s, g_corr, u->g_feat, i == m - 1, i));
         SOL_TRY(launch_feat_bwd(p, st, B, Gy, Gx, u->g_feat, c.cin0, c.sig_vy, c.sig_vx, u->H_vy, u->H_vx));
         SOL_TRY(launch_cg(p, st, B, 1, nullptr, nullptr, u->H_vy, u->H_vx, u->K_vy, u->K_vx, u->iters + (size_t)(m + i) * B));
         SOL_TRY(launch_advect_bwd(p, st, B, c.dt, s.vy1, s.vx1, u->K_vy, u->K_vx, u->H_vy, u->H_vx));
@@ -640,16 +647,20 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
             SOL_TRY(launch_diffuse_bc_bwd(p, st, B, re, c.dt, c.res, u->H_vy, u->H_vx, g_vy0, g_vx0, nullptr, nullptr));
         }
     }
-    if (sol::g_wgrad_path == 2) {
+    if (u->deferred_wgrad) {
         // deferred weight gradients: one tensor-core GEMM per layer over all msteps x B x Y x X pixels
         const size_t in_stride = (m > 1) ? (size_t)(u->stash[1].acts[0] - u->stash[0].acts[0]) : u->nA;
+        // thin layers: one persistent launch each over all steps (gw was zeroed at the start of the sweep)
+        SOL_TRY(launch_wgrad_thin_multi(st, m, B, p->Y, p->X, 32, 2, u->stash[0].acts[10], in_stride, u->gcorr_st, (size_t)p->NC() * B * 2,
+                                        gw + u->L[11].w_off, gw + u->L[11].b_off));
+        SOL_TRY(launch_wgrad_thin_multi(st, m, B, p->Y, p->X, u->L[0].cin, 32, u->stash[0].feat, in_stride, u->g0_st, u->nA,
+                                        gw + u->L[0].w_off, gw + u->L[0].b_off));
         for (int l = 1; l <= 10; ++l) {
             int nctas = 0;
             float* part = u->partials + u->partial_stride * (l - 1);
             const float* gl = u->gst + (size_t)(l - 1) * m * u->nA;
             SOL_TRY(launch_wgrad_c32_tc(st, p->sm_count, m, B, p->Y, p->X, u->stash[0].acts[l - 1], in_stride, gl, u->nA, part, &nctas));
             SOL_TRY(launch_wgrad_finalize_n(st, nctas, part, gw + u->L[l].w_off, gw + u->L[l].b_off, 0));
-            SOL_TRY(launch_colsum32(st, gl, (size_t)m * B * p->NC(), gw + u->L[l].b_off));
         }
         return SOL_OK;
     }

@@ -140,16 +140,18 @@ size_t wgrad_workspace_floats(int Cin, int Cout);
 int launch_wgrad(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const float* in, const float* g_out, float* dW, float* db,
                  int accumulate, float* partials, bool finalize);
 
+int launch_wgrad_thin_multi(cudaStream_t st, int steps, int B, int Y, int X, int Cin, int Cout, const float* in, size_t in_step_stride,
+                            const float* g, size_t g_step_stride, float* dW, float* db);
 int launch_wgrad_finalize_n(cudaStream_t st, int nctas, const float* partials, float* dW, float* db, int accumulate);
 
 // ---- deferred tensor-core weight gradient (sol_wgrad_tc.cu) ----
-extern int g_wgrad_path;            // 0 auto (= SIMT per step for now), 1 SIMT per step, 2 tcgen05 deferred over the whole sweep
+extern int g_wgrad_path;            // 1 SIMT per step, 2 tcgen05 deferred over the whole sweep (default; 0 = auto = 2)
 int launch_wgrad_c32_tc(cudaStream_t st, int sm_count, int steps, int B, int Y, int X, const float* in, size_t in_step_stride,
                         const float* g, size_t g_step_stride, float* part, int* nctas_out);
 int launch_colsum32(cudaStream_t st, const float* g, size_t npix, float* db);
 
 // ---- tensor-core convolution (sol_conv_tc.cu) ----
-extern int g_conv_path;             // 0 auto (= SIMT for now), 1 SIMT fp32, 2 tcgen05 3xTF32
+extern int g_conv_path;             // 1 SIMT fp32, 2 tcgen05 3xTF32 (default; option value 0 = auto = 2)
 extern int g_tc_base_offset_mode;
 size_t tc_weights_floats();
 int launch_prep_tc_weights(cudaStream_t st, const float* w, float* wprep);

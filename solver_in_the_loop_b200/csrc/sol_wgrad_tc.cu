@@ -154,6 +154,9 @@ k_wgrad_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     } else {
         // ================= splitter (warps 2..5), then accumulator dump =================
         const int tt = threadIdx.x - 64;
+        // bias gradient for free: thread tt always touches the same 16-byte chunk position (tt & 7) of rows
+        // with the same (row & 3), i.e. (32B-chunk swizzle) always the same 4 logical channels
+        float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
         int n = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++n) {
             const int s = n % WG_NSTAGE;
@@ -176,6 +179,7 @@ k_wgrad_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant
 #pragma unroll 4
             for (int i = tt; i < WG_G_BYTES / 16; i += 128) {
                 const float4 v = ghi[i];
+                bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w;
                 float4 h, l;
                 h.x = tf32_rn(v.x); l.x = tf32_rn(v.x - h.x);
                 h.y = tf32_rn(v.y); l.y = tf32_rn(v.y - h.y);
@@ -191,7 +195,17 @@ k_wgrad_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;
         float* part = a.part + (size_t)blockIdx.x * (25 * 32 * 32 + 32);
-        if (tt < 32) part[25 * 32 * 32 + tt] = 0.0f;     // bias slot: the bias gradient comes from k_colsum32
+        {   // bias slot: reduce the per-thread channel sums through shared memory (stage 0 is free now)
+            float* bsm = reinterpret_cast<float*>(gbase);
+            if (tt < 32) bsm[tt] = 0.0f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int row = tt >> 3, cphys = tt & 7;                       // G tile: 8 chunks of 16 B per pixel row
+            const int ch = ((((cphys >> 1) ^ (row & 3)) << 1) | (cphys & 1)) * 4;   // undo the 32-byte-chunk swizzle
+            atomicAdd(bsm + ch + 0, bsum.x); atomicAdd(bsm + ch + 1, bsum.y);
+            atomicAdd(bsm + ch + 2, bsum.z); atomicAdd(bsm + ch + 3, bsum.w);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tt < 32) part[25 * 32 * 32 + tt] = a.accumulate ? part[25 * 32 * 32 + tt] + bsm[tt] : bsm[tt];
+        }
 #pragma unroll 1
         for (int grp = 0; grp < WG_NGROUP; ++grp) {
             // M-block q of group grp -> tap
