@@ -17,12 +17,13 @@ for (Y, X) in [(128, 64), (256, 128)]:
         re, vy0, vx0, gy, gx, sig = bench.synth_batch(plan, engine, torch, B, 1, 0, 30)
         o = plan.step_fwd(re, vy0, vx0)
         ay, ax = plan.advect(o["vy1"], o["vx1"])
-        for cl, rows, pre in [(1, 8, 0), (1, 16, 0), (1, 8, 1), (1, 16, 1), (4, 8, 0), (8, 4, 0)]:
+        for cl, rows, pre in [(1, 8, 0), (1, 16, 0), (1, 8, 1), (1, 16, 1), (1, 8, 2), (1, 16, 2), (4, 8, 0), (8, 4, 0)]:
             if True:
                 try:
                     plan.set_cg(1e-5, 0.0, 2000, cl)
                     plan.set_option("cg_rows", rows)
-                    plan.set_option("cg_precond", pre)
+                    plan.set_option("cg_precond", 1 if pre else 0)
+                    plan.set_option("mg_variant", 2 if pre == 2 else 0)
                     for _ in range(3):
                         py, px, it = plan.project(ay, ax)
                     torch.cuda.synchronize()

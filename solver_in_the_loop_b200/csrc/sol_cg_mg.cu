@@ -454,6 +454,343 @@ __global__ void __launch_bounds__(NT, 1) k_cg_mg(const MgArgs a) {
     }
 }
 
+// =================================================================================================
+// v3: fully compile-time hierarchy for the reference aspect ratio (Y = 2X, X in {32, 64}).
+//
+// The generic kernel above spends most of its time in ~26 block-wide barrier steps per V-cycle on
+// coarse levels that have almost no work.  Here every coarse level L (XL x YL cells) is owned by a
+// shrinking GROUP of G_L = XL*YL/4 threads (column strips of 4 cells per thread): level 1 by 512
+// threads, level 2 by 128 (named barrier), level 3 by ONE warp (__syncwarp), and the coarsest
+// 8x4 level by the lanes of that warp (exact solve: 32 shuffled FMAs).  Group thread t of level L
+// computes the restricted residual of level-(L+1) cell t, so restriction needs no redistribution.
+// Threads outside a group wait at the group's join barrier.  All tile offsets are constexpr.
+// =================================================================================================
+namespace v3 {
+
+template <int XF, int YF, int NL>
+struct Map {                      // shared-memory offsets (floats)
+    __host__ __device__ static constexpr int tile(int l) { return ((YF >> l) + 2) * ((XF >> l) + 2); }
+    __host__ __device__ static constexpr int cells(int l) { return (YF >> l) * (XF >> l); }
+    static constexpr int T0 = 0, T1 = tile(0);
+    __host__ __device__ static constexpr int u0(int l) { int o = 2 * tile(0); for (int k = 1; k < l; ++k) o += 2 * tile(k); return o; }
+    __host__ __device__ static constexpr int u1(int l) { return u0(l) + tile(l); }
+    static constexpr int TILES_END = u0(NL - 1);
+    __host__ __device__ static constexpr int b(int l) { int o = TILES_END; for (int k = 1; k < l; ++k) o += cells(k); return o; }
+    __host__ __device__ static constexpr int dinv(int l) { int o = b(NL - 1) + cells(NL - 1); for (int k = 1; k < l; ++k) o += 2 * cells(k); return o; }
+    __host__ __device__ static constexpr int diag(int l) { return dinv(l) + cells(l); }
+    static constexpr int ZC = dinv(NL - 1);
+    static constexpr int RED = ZC + cells(NL - 1);
+    static constexpr int TOTAL = RED + 64;
+};
+
+template <int G, int NT, int ID>
+__device__ __forceinline__ void group_sync() {
+    if constexpr (G >= NT) __syncthreads();
+    else if constexpr (G > 32) asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(G) : "memory");
+    else __syncwarp();
+}
+
+// one damped-Jacobi sweep of the group's 4-cell strips: dst = src + dinv (b - A src); first: dst = dinv b
+template <int XL, bool FIRST>
+__device__ __forceinline__ void strip_sweep(const float* __restrict__ src, float* __restrict__ dst, const float* __restrict__ bb,
+                                            const float* __restrict__ dinv, const float* __restrict__ diag, int i, int j0) {
+    constexpr int P = XL + 2;
+    const float* s = src + (j0 + 1) * P + i + 1;
+    float* d = dst + (j0 + 1) * P + i + 1;
+    const int c0 = j0 * XL + i;
+    if (FIRST) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d[k * P] = dinv[c0 + k * XL] * bb[c0 + k * XL];
+    } else {
+        float zc[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) zc[k] = s[(k - 1) * P];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float nb = (zc[k] + zc[k + 2]) + (s[k * P - 1] + s[k * P + 1]);
+            const float z = zc[k + 1];
+            d[k * P] = fmaf(dinv[c0 + k * XL], bb[c0 + k * XL] - (nb - diag[c0 + k * XL] * z), z);
+        }
+    }
+}
+
+// residual of level-L cell (j,i) from tile u
+template <int XL>
+__device__ __forceinline__ float cell_residual(const float* __restrict__ u, const float* __restrict__ bb, const float* __restrict__ dinv,
+                                               const float* __restrict__ diag, int j, int i) {
+    constexpr int P = XL + 2;
+    const int c = j * XL + i, o = (j + 1) * P + i + 1;
+    const float nb = (u[o - P] + u[o + P]) + (u[o - 1] + u[o + 1]);
+    return (dinv[c] != 0.0f) ? bb[c] - (nb - diag[c] * u[o]) : 0.0f;
+}
+
+// V-cycle on levels L..NL-1, executed by the threads tid < G_L (all of them call this function)
+template <int XF, int YF, int NT, int NL, int L>
+__device__ __forceinline__ void coarse_cycle(float* smem, const float* __restrict__ cinv, int tid) {
+    using M = Map<XF, YF, NL>;
+    constexpr int XL = XF >> L, YL = YF >> L, G = XL * YL / 4, P = XL + 2;
+    constexpr int XN = XL / 2, PN = XN + 2;
+    constexpr bool NEXT_COARSEST = (L + 1 == NL - 1);
+    float* u0 = smem + M::u0(L);
+    float* u1 = smem + M::u1(L);
+    const float* bl = smem + M::b(L);
+    const float* dinv = smem + M::dinv(L);
+    const float* diag = smem + M::diag(L);
+    const int i = tid & (XL - 1), j0 = (tid / XL) * 4;
+    strip_sweep<XL, true>(u1, u0, bl, dinv, diag, i, j0);
+    group_sync<G, NT, L>();
+    strip_sweep<XL, false>(u0, u1, bl, dinv, diag, i, j0);
+    group_sync<G, NT, L>();
+    // restriction: group thread t owns next-level cell t
+    const int jc = tid / XN, ic = tid & (XN - 1);
+    float rsum = cell_residual<XL>(u1, bl, dinv, diag, 2 * jc, 2 * ic) + cell_residual<XL>(u1, bl, dinv, diag, 2 * jc, 2 * ic + 1) +
+                 cell_residual<XL>(u1, bl, dinv, diag, 2 * jc + 1, 2 * ic) + cell_residual<XL>(u1, bl, dinv, diag, 2 * jc + 1, 2 * ic + 1);
+    if constexpr (NEXT_COARSEST) {
+        // G == 32: this warp's lanes own the coarsest cells; exact solve z = cinv * b with shuffled b
+        static_assert(G == 32, "coarsest level must have 32 cells");
+        float zc = 0.0f;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) zc = fmaf(__ldg(cinv + tid * 32 + j), __shfl_sync(0xffffffffu, rsum, j), zc);
+        smem[M::ZC + tid] = zc;
+        __syncwarp();
+    } else {
+        const float* dinvn = smem + M::dinv(L + 1);
+        smem[M::b(L + 1) + tid] = (dinvn[tid] != 0.0f) ? rsum : 0.0f;
+        group_sync<G, NT, L>();
+        if (tid < G / 4) coarse_cycle<XF, YF, NT, NL, L + 1>(smem, cinv, tid);
+        group_sync<G, NT, L>();      // join: the sub-group's result is in its u0 tile
+    }
+    // prolong (u0 = u1 + P z_{L+1}) and post-smooth twice
+    {
+        const float* un = NEXT_COARSEST ? (smem + M::ZC) : (smem + M::u0(L + 1));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int j = j0 + k, o = (j + 1) * P + i + 1;
+            const float zn = NEXT_COARSEST ? un[(j >> 1) * XN + (i >> 1)] : un[((j >> 1) + 1) * PN + (i >> 1) + 1];
+            u0[o] = u1[o] + ((dinv[j * XL + i] != 0.0f) ? zn : 0.0f);
+        }
+    }
+    group_sync<G, NT, L>();
+    strip_sweep<XL, false>(u0, u1, bl, dinv, diag, i, j0);
+    group_sync<G, NT, L>();
+    strip_sweep<XL, false>(u1, u0, bl, dinv, diag, i, j0);
+    // the caller's join barrier publishes u0
+}
+
+}  // namespace v3
+
+template <int X, int R, int MODE, int NT>
+__global__ void __launch_bounds__(NT, 1) k_cg_mg3(const MgArgs a) {
+    extern __shared__ float smem[];
+    constexpr int Y = 2 * X;
+    constexpr int NL = (X == 64) ? 5 : 4;
+    using M = v3::Map<X, Y, NL>;
+    constexpr int PITCH = X + 2;
+    constexpr int TY = Y / R;
+    static_assert(X * TY == NT, "thread geometry");
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * X + tx;
+    constexpr int nwarps = NT / 32;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    float* red = smem + M::RED;
+
+    for (int k = tid; k < M::TILES_END; k += NT) smem[k] = 0.0f;
+#pragma unroll
+    for (int l = 1; l < NL - 1; ++l) {
+        const int n = (Y >> l) * (X >> l);
+        for (int c = tid; c < n; c += NT) {
+            smem[M::dinv(l) + c] = __ldg(a.dinv_g + a.coff[l] + c);
+            smem[M::diag(l) + c] = __ldg(a.diag_g + a.coff[l] + c);
+        }
+    }
+    const int j0 = ty * R;
+    constexpr size_t NC = (size_t)Y * X, NY = (size_t)(Y + 1) * X, NX = (size_t)Y * (X + 1);
+    float* const T0 = smem + M::T0 + (j0 + 1) * PITCH + tx + 1;
+    float* const T1 = smem + M::T1 + (j0 + 1) * PITCH + tx + 1;
+    const float* const dg = a.diag + j0 * X + tx;
+    int pp = 0;
+
+    float x[R], r[R], p[R], z[R];
+    unsigned act = 0u;
+    bool regular = true;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        const int c = (j0 + k) * X + tx;
+        const bool ak = a.active[c] != 0;
+        if (ak) act |= 1u << k;
+        regular = regular && ak && (a.diag[c] == 4.0f);
+        x[k] = 0.0f;
+    }
+    regular = __all_sync(0xffffffffu, regular);
+    if (MODE == 1) {
+        const float* vy = a.vy_in + (size_t)b * NY;
+        const float* vx = a.vx_in + (size_t)b * NX;
+        float vlo = a.my[j0 * X + tx] * vy[j0 * X + tx];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int j = j0 + k;
+            const float vhi = a.my[(j + 1) * X + tx] * vy[(j + 1) * X + tx];
+            const float xl = a.mx[j * (X + 1) + tx] * vx[j * (X + 1) + tx];
+            const float xr = a.mx[j * (X + 1) + tx + 1] * vx[j * (X + 1) + tx + 1];
+            r[k] = (vhi - vlo) + (xr - xl);
+            vlo = vhi;
+        }
+    } else {
+        const float* rhs = a.rhs + (size_t)b * NC;
+#pragma unroll
+        for (int k = 0; k < R; ++k) r[k] = ((act >> k) & 1u) ? rhs[(j0 + k) * X + tx] : 0.0f;
+    }
+    __syncthreads();
+
+    const float omega = a.omega;
+    const float dinv_reg = -0.25f * omega;
+    using FR = FineOps<X, R, true>;
+    using FG = FineOps<X, R, false>;
+    auto publish = [&](const float (&v)[R]) -> const float* {
+        float* t = pp ? T1 : T0;
+#pragma unroll
+        for (int k = 0; k < R; ++k) t[k * PITCH] = v[k];
+        __syncthreads();
+        pp ^= 1;
+        return t;
+    };
+    auto fine_smooth = [&]() {
+        const float* t = publish(z);
+        if (regular) FR::smooth(t, z, r, act, dg, dinv_reg, omega);
+        else FG::smooth(t, z, r, act, dg, dinv_reg, omega);
+    };
+    auto vcycle = [&]() {
+        if (regular) FR::smooth0(z, r, act, dg, dinv_reg, omega);
+        else FG::smooth0(z, r, act, dg, dinv_reg, omega);
+        fine_smooth();
+        {
+            const float* t = publish(z);
+            float* b1 = smem + M::b(1);
+            const float* dinv1 = smem + M::dinv(1);
+            constexpr int X1 = X / 2;
+#pragma unroll
+            for (int k = 0; k < R; k += 2) {
+                float s;
+                if (regular) s = FR::residual(t, z, r, k, act, dg) + FR::residual(t, z, r, k + 1, act, dg);
+                else s = FG::residual(t, z, r, k, act, dg) + FG::residual(t, z, r, k + 1, act, dg);
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                if ((tx & 1) == 0) {
+                    const int cc = ((j0 + k) >> 1) * X1 + (tx >> 1);
+                    b1[cc] = (dinv1[cc] != 0.0f) ? s : 0.0f;
+                }
+            }
+            __syncthreads();
+        }
+        constexpr int G1 = (Y / 2) * (X / 2) / 4;
+        if (tid < G1) v3::coarse_cycle<X, Y, NT, NL, 1>(smem, a.cinv, tid);
+        __syncthreads();     // join: level-1 result in its u0 tile
+        {
+            constexpr int X1 = X / 2, P1 = X1 + 2;
+            const float* u = smem + M::u0(1);
+#pragma unroll
+            for (int k = 0; k < R; k += 2) {
+                const float zn = u[(((j0 + k) >> 1) + 1) * P1 + (tx >> 1) + 1];
+                z[k] += (regular || ((act >> k) & 1u)) ? zn : 0.0f;
+                z[k + 1] += (regular || ((act >> (k + 1)) & 1u)) ? zn : 0.0f;
+            }
+        }
+        fine_smooth();
+        fine_smooth();
+    };
+
+    int par = 0;
+    float rmax = 0.0f;
+#pragma unroll
+    for (int k = 0; k < R; ++k) rmax = fmaxf(rmax, fabsf(r[k]));
+    rmax = block_max(rmax, red, par, warp, lane, nwarps);
+    const float tol = fmaxf(a.tol_abs, a.tol_rel * rmax);
+    int it = 0;
+    if (rmax > 0.0f && rmax >= tol && a.max_it > 0) {
+        vcycle();
+        float rz = 0.0f;
+#pragma unroll
+        for (int k = 0; k < R; ++k) { p[k] = z[k]; rz = fmaf(r[k], z[k], rz); }
+        rz = block_sum(rz, red, par, warp, lane, nwarps);
+        while (true) {
+            const float* t = publish(p);
+            float pq;
+            if (regular) pq = FR::apply(t, p, z, act, dg);
+            else pq = FG::apply(t, p, z, act, dg);
+            pq = block_sum(pq, red, par, warp, lane, nwarps);
+            const float alpha = (pq != 0.0f) ? __fdividef(rz, pq) : 0.0f;
+            rmax = 0.0f;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                x[k] = fmaf(alpha, p[k], x[k]);
+                r[k] = fmaf(-alpha, z[k], r[k]);
+                rmax = fmaxf(rmax, fabsf(r[k]));
+            }
+            rmax = block_max(rmax, red, par, warp, lane, nwarps);
+            ++it;
+            if (!(rmax > 0.0f && rmax >= tol) || it >= a.max_it) break;
+            vcycle();
+            float rz_new = 0.0f;
+#pragma unroll
+            for (int k = 0; k < R; ++k) rz_new = fmaf(r[k], z[k], rz_new);
+            rz_new = block_sum(rz_new, red, par, warp, lane, nwarps);
+            const float beta = (rz != 0.0f) ? __fdividef(rz_new, rz) : 0.0f;
+            rz = rz_new;
+#pragma unroll
+            for (int k = 0; k < R; ++k) p[k] = fmaf(beta, p[k], z[k]);
+        }
+    }
+    if (a.iters && tid == 0) a.iters[b] = it;
+
+    if (MODE == 0) {
+        const float* rhs = a.rhs + (size_t)b * NC;
+        float* po = a.p_out + (size_t)b * NC;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int c = (j0 + k) * X + tx;
+            po[c] = ((act >> k) & 1u) ? x[k] : -rhs[c] / a.diag[c];
+        }
+        return;
+    }
+    {
+        const float* t = publish(x);
+        const float* vy = a.vy_in + (size_t)b * NY;
+        const float* vx = a.vx_in + (size_t)b * NX;
+        float* vyo = a.vy_out + (size_t)b * NY;
+        float* vxo = a.vx_out + (size_t)b * NX;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int j = j0 + k;
+            const float pdn = (k > 0) ? x[k - 1] : t[(k - 1) * PITCH];
+            const float plf = t[k * PITCH - 1];
+            vyo[j * X + tx] = a.my[j * X + tx] * (vy[j * X + tx] - (x[k] - pdn));
+            vxo[j * (X + 1) + tx] = a.mx[j * (X + 1) + tx] * (vx[j * (X + 1) + tx] - (x[k] - plf));
+            if (tx == X - 1) vxo[j * (X + 1) + X] = a.mx[j * (X + 1) + X] * (vx[j * (X + 1) + X] + x[k]);
+        }
+        if (j0 + R == Y) vyo[Y * X + tx] = a.my[Y * X + tx] * (vy[Y * X + tx] + x[R - 1]);
+        if (a.p_out) {
+            float* po = a.p_out + (size_t)b * NC;
+#pragma unroll
+            for (int k = 0; k < R; ++k) po[(j0 + k) * X + tx] = x[k];
+        }
+    }
+}
+
+template <int X, int R, int MODE, int NT>
+static int launch_mg3_t(const MgArgs& a, cudaStream_t st) {
+    constexpr int NL = (X == 64) ? 5 : 4;
+    constexpr size_t smem_bytes = (size_t)v3::Map<X, 2 * X, NL>::TOTAL * sizeof(float);
+    auto kern = k_cg_mg3<X, R, MODE, NT>;
+    static bool attr_done = false;
+    if (smem_bytes > 48 * 1024 && !attr_done) {
+        SOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        attr_done = true;
+    }
+    kern<<<dim3(1, a.B, 1), dim3(X, 2 * X / R, 1), smem_bytes, st>>>(a);
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 template <int X, int R, int MODE, int NT>
 static int launch_mg_t(const MgArgs& a, cudaStream_t st, int TY, size_t smem_bytes) {
@@ -492,6 +829,17 @@ int launch_cg_mg(const sol_plan* p, cudaStream_t st, int B, int mode, const floa
     if ((R == 0 || p->cg_rows == 8) && p->Y % 8 == 0 && p->X * (p->Y / 8) <= 1024) R = 8;
     if (!R) return fail(SOL_ERR_UNSUPPORTED, "cg_mg: no thread geometry for this grid");
     const int TY = p->Y / R;
+    for (int l = 0; l < h.nlev; ++l) { a.LY[l] = h.LY[l]; a.LX[l] = h.LX[l]; a.coff[l] = h.coff[l]; }
+    if (p->mg_variant != 2 && p->Y == 2 * p->X && h.nlev == ((p->X == 64) ? 5 : 4) && h.LY[h.nlev - 1] * h.LX[h.nlev - 1] == 32) {
+        // compile-time hierarchy (v3)
+#define SOL_MG3_CASE(XX, RR, NTT)                                                  \
+        if (p->X == XX && R == RR) {                                               \
+            if (mode == 0) return launch_mg3_t<XX, RR, 0, NTT>(a, st);             \
+            return launch_mg3_t<XX, RR, 1, NTT>(a, st);                            \
+        }
+        SOL_MG3_CASE(64, 16, 512) SOL_MG3_CASE(64, 8, 1024) SOL_MG3_CASE(32, 16, 128) SOL_MG3_CASE(32, 8, 256)
+#undef SOL_MG3_CASE
+    }
     // shared-memory carve-up (floats)
     int off = 0;
     a.s_t0 = off; off += (p->Y + 2) * (p->X + 2);

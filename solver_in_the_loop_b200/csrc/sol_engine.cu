@@ -224,6 +224,11 @@ extern "C" int sol_plan_set_option(sol_plan* p, const char* name, int value) {
         p->cg_rows = value;
         return SOL_OK;
     }
+    if (strcmp(name, "mg_variant") == 0) {
+        SOL_CHECK(value == 0 || value == 2, "mg_variant must be 0 or 2");
+        p->mg_variant = value;
+        return SOL_OK;
+    }
     if (strcmp(name, "cg_precond") == 0) {
         SOL_CHECK(value == 0 || value == 1, "cg_precond must be 0 or 1");
         p->cg_precond = value;

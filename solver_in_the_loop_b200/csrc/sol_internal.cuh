@@ -89,6 +89,7 @@ struct sol_plan {
     int cg_rows = 0;   // rows per thread in the CG kernel (0 = auto)
     int cg_precond = 1; // 1 = multigrid-preconditioned CG when the grid supports it, 0 = plain CG (reference recurrences)
     sol_mg mg;
+    int mg_variant = 0; // 0 auto (compile-time hierarchy when Y == 2X), 2 = generic run-time hierarchy kernel
     size_t NY() const { return (size_t)(Y + 1) * X; }
     size_t NX() const { return (size_t)Y * (X + 1); }
     size_t NC() const { return (size_t)Y * X; }

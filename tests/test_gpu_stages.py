@@ -84,12 +84,13 @@ def test_advect(case, cuda_device):
     assert rel(iy, vyt.grad) < 1e-5 and rel(ix, vxt.grad) < 1e-5
 
 
-@pytest.mark.parametrize("cluster,precond", [(1, 1), (1, 0), (2, 0), (4, 0), (8, 0)],
-                         ids=["mgpcg", "cg", "cg-cluster2", "cg-cluster4", "cg-cluster8"])
+@pytest.mark.parametrize("cluster,precond", [(1, 1), (1, 2), (1, 0), (2, 0), (4, 0), (8, 0)],
+                         ids=["mgpcg", "mgpcg-generic", "cg", "cg-cluster2", "cg-cluster4", "cg-cluster8"])
 def test_pressure_solve_and_project(case, cuda_device, cluster, precond):
     c = case; plan = c["plan"]; geom = c["geom"]
     plan.set_cg(tol_abs=1e-7, tol_rel=1e-6, max_it=4000, cluster=cluster)
-    plan.set_option("cg_precond", precond)
+    plan.set_option("mg_variant", 2 if precond == 2 else 0)      # 2: run-time-hierarchy kernel, 0: compile-time hierarchy
+    plan.set_option("cg_precond", 1 if precond else 0)
     try:
         g = torch.Generator().manual_seed(4)
         vy = c["vy"] + 0.05 * torch.randn(c["vy"].shape, generator=g, dtype=torch.float64)
@@ -122,6 +123,7 @@ def test_pressure_solve_and_project(case, cuda_device, cluster, precond):
     finally:
         plan.set_cg(tol_abs=1e-7, tol_rel=1e-6, max_it=4000, cluster=0)
         plan.set_option("cg_precond", 1)
+        plan.set_option("mg_variant", 0)
 
 
 def test_reference_style_cg_iterations(case, cuda_device):
