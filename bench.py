@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--conv-path", type=int, default=0, help="0 auto, 1 fp32 SIMT, 2 tcgen05 3xTF32")
     ap.add_argument("--wgrad-path", type=int, default=0, help="0 auto, 1 per-step SIMT, 2 deferred tcgen05")
     ap.add_argument("--cg-rows", type=int, default=0)
+    ap.add_argument("--mg-variant", type=int, default=0, help="0 = compile-time-hierarchy multigrid kernel, 2 = run-time-hierarchy kernel")
     ap.add_argument("--cg-precond", type=int, default=1, help="1 = multigrid-preconditioned CG, 0 = the reference's plain CG")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-msteps", type=int, default=4, help="unroll length of the bounded CPU sample")
@@ -235,6 +236,7 @@ def main():
     plan = engine.Plan.karman(Y, X, B)
     plan.set_option("cg_rows", args.cg_rows)
     plan.set_option("cg_precond", args.cg_precond)
+    plan.set_option("mg_variant", args.mg_variant)
     plan.set_cg(tol_abs=1e-7, tol_rel=1e-6, max_it=4000, cluster=args.cluster)     # accurate solves for the spin-up
     re, vy0, vx0, gt_vy, gt_vx, sig = synth_batch(plan, engine, torch, B, m, rank, args.spin)
     if world > 1:   # identical normalisation on every rank (dataStats are global in the reference)

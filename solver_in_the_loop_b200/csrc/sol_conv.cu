@@ -7,7 +7,7 @@
 //                   register tile 8 pixels x 4 couts per thread, input tile + halo in shared
 //                   memory (float4 over cin), weights streamed through L1 (100 KB, L1-resident),
 //                   5-tap sliding window along x so each shared load feeds 20+ FMAs.
-//   k_conv5x5_thin  first / last layers (Cin or Cout <= 4)
+//   k_conv5x5_expand / k_conv5x5_reduce   first / last layers (Cin <= 4 -> 32, 32 -> Cout <= 4)
 //   k_wgrad_c32     weight gradient of the 32->32 layers: every thread owns 80 (tap,cin,cout)
 //                   accumulators in registers for the whole pixel range of its CTA; per-CTA partial
 //                   sums go to a private slot (no atomics, deterministic), reduced by
@@ -111,110 +111,210 @@ __global__ void __launch_bounds__(TH * 32, (TH <= 4 ? 3 : 2)) k_conv5x5_c32(cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// thin layers: one output pixel per thread, 16x16 tiles
+// thin layers.  Both kernels are issue-bound (shared-memory loads + FMAs), so the weights are read
+// as uniform 128-bit shared loads and tiles are small enough that the bench grid gives 192 CTAs.
 // ------------------------------------------------------------------------------------------------
-template <int CIN, int COUT>
-__global__ void __launch_bounds__(256) k_conv5x5_thin(const ConvArgs a) {
-    constexpr int T = 16, P = T + 4;
-    constexpr int CINP = (CIN % 2 == 0) ? CIN + 1 : CIN;   // odd pixel stride: conflict-free scalar reads
-    extern __shared__ float sm[];
-    float* tin = sm;                       // [P*P][CINP]
-    float* ws = sm + P * P * CINP;         // [25*CIN*COUT]
+// Cin <= 4 -> 32: one output pixel x 32 couts per thread, tile 32 (x) x 4 (y), one warp per tile row.
+// Input tile is planar [ci][8][36] (conflict-free scalar reads), weights [tap][ci][32] as float4.
+template <int CIN>
+__global__ void __launch_bounds__(128) k_conv5x5_expand(const ConvArgs a) {
+    constexpr int TW = 32, TH = 4, PW = TW + 4, PH = TH + 4, COUT = 32;
+    __shared__ float4 ws4[25 * CIN * 8];
+    __shared__ float tin[CIN * PH * PW];
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * T, y0 = blockIdx.y * T, b = blockIdx.z;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
     const float* inb = a.in + (size_t)b * a.Y * a.X * CIN;
-    // staging loops are fully unrolled (compile-time trip counts) so that every thread has all of its
-    // global loads in flight at once — a rolled loop exposes one L2 latency per iteration
-    if constexpr (CIN % 4 == 0) {
-        constexpr int NV = CIN / 4, TOTAL = P * P * NV, ITER = (TOTAL + 255) / 256;
-        float4 v[ITER];
-#pragma unroll
-        for (int it = 0; it < ITER; ++it) {
-            const int idx = tid + it * 256;
-            const int c4 = idx % NV, pix = idx / NV;
-            const int tyy = pix / P, txx = pix - tyy * P;
-            const int gy = y0 + tyy - 2, gx = x0 + txx - 2;
-            v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (idx < TOTAL && gy >= 0 && gy < a.Y && gx >= 0 && gx < a.X)
-                v[it] = __ldg(reinterpret_cast<const float4*>(inb + ((size_t)gy * a.X + gx) * CIN) + c4);
-        }
-#pragma unroll
-        for (int it = 0; it < ITER; ++it) {
-            const int idx = tid + it * 256;
-            if (idx < TOTAL) {
-                const int c4 = idx % NV, pix = idx / NV;
-                float* d = tin + pix * CINP + c4 * 4;
-                d[0] = v[it].x; d[1] = v[it].y; d[2] = v[it].z; d[3] = v[it].w;
-            }
-        }
-    } else {
-        constexpr int TOTAL = P * P * CIN, ITER = (TOTAL + 255) / 256;
+    {
+        // all global loads of a thread are issued before the first shared store (compile-time trip counts)
+        constexpr int TOTAL = PH * PW * CIN, ITER = (TOTAL + 127) / 128;
         float v[ITER];
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
-            const int idx = tid + it * 256;
-            const int c = idx % CIN, pix = idx / CIN;
-            const int tyy = pix / P, txx = pix - tyy * P;
-            const int gy = y0 + tyy - 2, gx = x0 + txx - 2;
+            const int idx = tid + it * 128;
+            const int row = idx / (PW * CIN), rem = idx - row * (PW * CIN);     // [row][px][ci] order = global order
+            const int px = rem / CIN;
+            const int gy = y0 + row - 2, gx = x0 + px - 2;
             v[it] = 0.0f;
-            if (idx < TOTAL && gy >= 0 && gy < a.Y && gx >= 0 && gx < a.X) v[it] = __ldg(inb + ((size_t)gy * a.X + gx) * CIN + c);
+            if (idx < TOTAL && gy >= 0 && gy < a.Y && gx >= 0 && gx < a.X) v[it] = __ldg(inb + ((size_t)gy * a.X + gx) * CIN + (rem - px * CIN));
         }
+        constexpr int TOTALW = 25 * CIN * 8, ITERW = (TOTALW + 127) / 128;
+        float4 wv[ITERW];
+        const float4* wg = reinterpret_cast<const float4*>(a.w);
+#pragma unroll
+        for (int it = 0; it < ITERW; ++it) { const int idx = tid + it * 128; wv[it] = (idx < TOTALW) ? __ldg(wg + idx) : make_float4(0.f, 0.f, 0.f, 0.f); }
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
-            const int idx = tid + it * 256;
-            if (idx < TOTAL) tin[(idx / CIN) * CINP + idx % CIN] = v[it];
+            const int idx = tid + it * 128;
+            if (idx < TOTAL) {
+                const int row = idx / (PW * CIN), rem = idx - row * (PW * CIN);
+                const int px = rem / CIN, ci = rem - px * CIN;
+                tin[(ci * PH + row) * PW + px] = v[it];
+            }
         }
-    }
-    {
-        constexpr int TOTALW = 25 * CIN * COUT, ITERW = (TOTALW + 255) / 256;
-        float wv[ITERW];
 #pragma unroll
-        for (int it = 0; it < ITERW; ++it) { const int idx = tid + it * 256; wv[it] = (idx < TOTALW) ? __ldg(a.w + idx) : 0.0f; }
-#pragma unroll
-        for (int it = 0; it < ITERW; ++it) { const int idx = tid + it * 256; if (idx < TOTALW) ws[idx] = wv[it]; }
+        for (int it = 0; it < ITERW; ++it) { const int idx = tid + it * 128; if (idx < TOTALW) ws4[idx] = wv[it]; }
     }
     __syncthreads();
-    const int tx = tid & 15, ty = tid >> 4;
+    const int tx = tid & 31, ty = tid >> 5;
     float acc[COUT];
 #pragma unroll
     for (int c = 0; c < COUT; ++c) acc[c] = 0.0f;
 #pragma unroll 1
-    for (int tap = 0; tap < 25; ++tap) {
-        const int dy = tap / 5, dx = tap - dy * 5;
-        const float* tp = tin + ((ty + dy) * P + tx + dx) * CINP;
-        const float* wp = ws + tap * CIN * COUT;
-#pragma unroll 4
-        for (int ci = 0; ci < CIN; ++ci) {
-            const float v = tp[ci];
+    for (int dy = 0; dy < 5; ++dy) {
 #pragma unroll
-            for (int c = 0; c < COUT; ++c) acc[c] = fmaf(v, wp[ci * COUT + c], acc[c]);
+        for (int dx = 0; dx < 5; ++dx) {
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) {
+                const float v = tin[(ci * PH + ty + dy) * PW + tx + dx];
+                const float4* wq = ws4 + ((dy * 5 + dx) * CIN + ci) * 8;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 w = wq[q];
+                    acc[4 * q + 0] = fmaf(v, w.x, acc[4 * q + 0]);
+                    acc[4 * q + 1] = fmaf(v, w.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(v, w.z, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(v, w.w, acc[4 * q + 3]);
+                }
+            }
         }
     }
     const int gy = y0 + ty, gx = x0 + tx;
     if (gy >= a.Y || gx >= a.X) return;
-    const size_t o = (((size_t)b * a.Y + gy) * a.X + gx) * COUT;
+    const size_t o4 = (((size_t)b * a.Y + gy) * a.X + gx) * 8;
+    float4* out4 = reinterpret_cast<float4*>(a.out) + o4;
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) {
-        float v = acc[c];
-        if (a.bias) v += __ldg(a.bias + c);
-        if (a.addend) v += __ldg(a.addend + o + c);
-        const float rf = (a.act == SOL_ACT_DLRELU) ? __ldg(a.ref + o + c) : 0.0f;
-        a.out[o + c] = apply_act(v, a.act, a.slope, rf);
+    for (int q = 0; q < 8; ++q) {
+        float4 f = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        if (a.bias) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias) + q);
+            f.x += bv.x; f.y += bv.y; f.z += bv.z; f.w += bv.w;
+        }
+        if (a.addend) {
+            const float4 ad = __ldg(reinterpret_cast<const float4*>(a.addend) + o4 + q);
+            f.x += ad.x; f.y += ad.y; f.z += ad.z; f.w += ad.w;
+        }
+        float4 rf = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.act == SOL_ACT_DLRELU) rf = __ldg(reinterpret_cast<const float4*>(a.ref) + o4 + q);
+        f.x = apply_act(f.x, a.act, a.slope, rf.x); f.y = apply_act(f.y, a.act, a.slope, rf.y);
+        f.z = apply_act(f.z, a.act, a.slope, rf.z); f.w = apply_act(f.w, a.act, a.slope, rf.w);
+        out4[q] = f;
     }
 }
 
-template <int CIN, int COUT>
-static int launch_thin(const ConvArgs& a, cudaStream_t st) {
-    constexpr int CINP = (CIN % 2 == 0) ? CIN + 1 : CIN;
-    const size_t smem = (size_t)(20 * 20 * CINP + 25 * CIN * COUT) * sizeof(float);
-    auto kern = k_conv5x5_thin<CIN, COUT>;
+// 32 -> Cout <= 4: tile 16 (x) x 8 (y), 128 threads.  Each half of the CTA reduces 16 of the 32 input
+// channels; a thread owns two vertically adjacent pixels so that one 6-row column of float4 inputs and
+// one set of weights feed 5 taps x 2 pixels.  The halves are summed through shared memory.
+template <int COUT>
+__global__ void __launch_bounds__(128) k_conv5x5_reduce(const ConvArgs a) {
+    constexpr int TW = 16, TH = 8, PW = TW + 4, PH = TH + 4, C = 32, PS = 36;   // PS: padded pixel stride (floats)
+    extern __shared__ float4 smem4[];
+    float* ws = reinterpret_cast<float*>(smem4);                 // [25][32][COUT]
+    float* tin = ws + 25 * C * COUT;                             // [PH*PW][PS]
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
+    const float* inb = a.in + (size_t)b * a.Y * a.X * C;
+    {
+        constexpr int TOTAL = PH * PW * 8, ITER = TOTAL / 128;   // 1920 float4 = 15 per thread
+        static_assert(TOTAL % 128 == 0, "staging geometry");
+        float4 v[ITER];
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int idx = tid + it * 128;
+            const int c4 = idx & 7, pix = idx >> 3;
+            const int row = pix / PW, px = pix - row * PW;
+            const int gy = y0 + row - 2, gx = x0 + px - 2;
+            v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gy >= 0 && gy < a.Y && gx >= 0 && gx < a.X) v[it] = __ldg(reinterpret_cast<const float4*>(inb + ((size_t)gy * a.X + gx) * C) + c4);
+        }
+        constexpr int TOTALW = 25 * C * COUT / 4, ITERW = (TOTALW + 127) / 128;
+        float4 wv[ITERW];
+        const float4* wg = reinterpret_cast<const float4*>(a.w);
+#pragma unroll
+        for (int it = 0; it < ITERW; ++it) { const int idx = tid + it * 128; wv[it] = (idx < TOTALW) ? __ldg(wg + idx) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int idx = tid + it * 128;
+            *reinterpret_cast<float4*>(tin + (idx >> 3) * PS + (idx & 7) * 4) = v[it];
+        }
+#pragma unroll
+        for (int it = 0; it < ITERW; ++it) { const int idx = tid + it * 128; if (idx < TOTALW) smem4[idx] = wv[it]; }
+    }
+    __syncthreads();
+    const int half = tid >> 6, t = tid & 63;
+    const int tx = t & 15, ty0 = (t >> 4) * 2;
+    float acc[2][COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) { acc[0][c] = 0.0f; acc[1][c] = 0.0f; }
+#pragma unroll 1
+    for (int dx = 0; dx < 5; ++dx) {
+#pragma unroll 1
+        for (int cq = 0; cq < 4; ++cq) {
+            const int c4 = half * 4 + cq;
+            float4 iv[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) iv[r] = *reinterpret_cast<const float4*>(tin + ((ty0 + r) * PW + tx + dx) * PS + c4 * 4);
+#pragma unroll
+            for (int dy = 0; dy < 5; ++dy) {
+                float wv[4 * COUT];                                  // [ci 0..3][co]
+                const float4* wq = reinterpret_cast<const float4*>(ws + ((dy * 5 + dx) * C + c4 * 4) * COUT);
+#pragma unroll
+                for (int q = 0; q < COUT; ++q) {
+                    const float4 w = wq[q];
+                    wv[4 * q] = w.x; wv[4 * q + 1] = w.y; wv[4 * q + 2] = w.z; wv[4 * q + 3] = w.w;
+                }
+#pragma unroll
+                for (int pz = 0; pz < 2; ++pz) {
+                    const float4 v = iv[dy + pz];
+#pragma unroll
+                    for (int co = 0; co < COUT; ++co)
+                        acc[pz][co] = fmaf(v.x, wv[co], fmaf(v.y, wv[COUT + co], fmaf(v.z, wv[2 * COUT + co], fmaf(v.w, wv[3 * COUT + co], acc[pz][co]))));
+                }
+            }
+        }
+    }
+    __syncthreads();                       // everyone is done with the input tile: reuse it for the half sums
+    float* red = tin;                      // [64][2*COUT]
+    if (half == 1) {
+#pragma unroll
+        for (int pz = 0; pz < 2; ++pz)
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) red[(pz * COUT + co) * 64 + t] = acc[pz][co];
+    }
+    __syncthreads();
+    if (half == 1) return;
+#pragma unroll
+    for (int pz = 0; pz < 2; ++pz) {
+        const int gy = y0 + ty0 + pz, gx = x0 + tx;
+        if (gy >= a.Y || gx >= a.X) continue;
+        const size_t o = (((size_t)b * a.Y + gy) * a.X + gx) * COUT;
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+            float v = acc[pz][co] + red[(pz * COUT + co) * 64 + t];
+            if (a.bias) v += __ldg(a.bias + co);
+            if (a.addend) v += __ldg(a.addend + o + co);
+            const float rf = (a.act == SOL_ACT_DLRELU) ? __ldg(a.ref + o + co) : 0.0f;
+            a.out[o + co] = apply_act(v, a.act, a.slope, rf);
+        }
+    }
+}
+
+template <int CIN>
+static int launch_expand(const ConvArgs& a, cudaStream_t st) {
+    k_conv5x5_expand<CIN><<<dim3(cdiv(a.X, 32), cdiv(a.Y, 4), a.B), 128, 0, st>>>(a);
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
+template <int COUT>
+static int launch_reduce(const ConvArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)(25 * 32 * COUT + 12 * 20 * 36) * sizeof(float);
+    auto kern = k_conv5x5_reduce<COUT>;
     static bool attr_done = false;   // one process per GPU: set once, outside any later graph capture
     if (smem > 48 * 1024 && !attr_done) {
         SOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    dim3 grid(cdiv(a.X, 16), cdiv(a.Y, 16), a.B);
-    kern<<<grid, 256, smem, st>>>(a);
+    kern<<<dim3(cdiv(a.X, 16), cdiv(a.Y, 8), a.B), 128, smem, st>>>(a);
     SOL_LAUNCHED();
     return SOL_OK;
 }
@@ -243,10 +343,14 @@ int launch_conv5x5(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, cons
         SOL_LAUNCHED();
         return SOL_OK;
     }
-#define SOL_THIN(CI, CO) \
-    if (Cin == CI && Cout == CO) return launch_thin<CI, CO>(a, st);
-    SOL_THIN(3, 32) SOL_THIN(4, 32) SOL_THIN(2, 32) SOL_THIN(32, 2) SOL_THIN(32, 3) SOL_THIN(32, 4)
-#undef SOL_THIN
+    if (((uintptr_t)in & 15) && Cin == 32) return fail(SOL_ERR_INVALID, "conv5x5: 32-channel input must be 16-byte aligned");
+    if (((uintptr_t)w & 15) || ((uintptr_t)out & 15 && Cout == 32)) return fail(SOL_ERR_INVALID, "conv5x5: weights / 32-channel output must be 16-byte aligned");
+    if (Cout == 32 && Cin == 2) return launch_expand<2>(a, st);
+    if (Cout == 32 && Cin == 3) return launch_expand<3>(a, st);
+    if (Cout == 32 && Cin == 4) return launch_expand<4>(a, st);
+    if (Cin == 32 && Cout == 2) return launch_reduce<2>(a, st);
+    if (Cin == 32 && Cout == 3) return launch_reduce<3>(a, st);
+    if (Cin == 32 && Cout == 4) return launch_reduce<4>(a, st);
     return fail(SOL_ERR_UNSUPPORTED, "conv5x5: unsupported (Cin, Cout) pair");
 }
 

@@ -49,9 +49,17 @@ struct TcArgs {
     int B, Y, X;
     int act;
     float slope;
+    long long* trace;       // diagnostics: 16 slots per CTA of clock64 phase stamps (null in production)
 };
 
 using namespace tc;
+
+__device__ __forceinline__ void tc_stamp(long long* trace, int slot) {
+    if (trace) {
+        const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        trace[cta * 16 + slot] = clock64();
+    }
+}
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2,
 // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
@@ -80,6 +88,13 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
     // tap).  Each CTA therefore starts at a different tap and wraps around.
     const int tap0 = (int)((blockIdx.x + blockIdx.y * gridDim.x + blockIdx.z * gridDim.x * gridDim.y) * 7u % 25u);
 
+    if (threadIdx.x == 0 && a.trace) {
+        const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        a.trace[cta * 16 + 0] = smid; a.trace[cta * 16 + 1] = (long long)gt;
+        tc_stamp(a.trace, 2);
+    }
     if (warp == 0 && lane == 0) {
         mbar_init(bar_afull, 1);
         mbar_init(bar_asplit, 128);
@@ -96,6 +111,7 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_acc = *tmem_slot;
+    if (threadIdx.x == 0) tc_stamp(a.trace, 3);      // set-up done (barriers, TMEM)
 
     if (warp == 0) {
         // ================= TMA producer (warp-uniform control flow, one elected lane issues) =================
@@ -130,6 +146,7 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
         const uint64_t dB = make_desc(s_b, 1024, 0);
         mbar_wait(bar_asplit, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (leader) tc_stamp(a.trace, 6);            // operands split, MMA may start
 #pragma unroll 1
         for (int n = 0; n < 25; ++n) {
             const int s = n % TC_STAGES;
@@ -138,6 +155,7 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
             mbar_wait(bar_bfull + 8 * s, ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (leader) {
+                if (n == 0) tc_stamp(a.trace, 7);    // first weight stage landed
                 const int dy = tap / 5, dx = tap - dy * 5;
                 const uint64_t a_off = (uint64_t)((dy * TC_HW + dx) * 8);            // 128 B rows in 16 B units
                 const uint64_t b_off = (uint64_t)(s * (2 * TC_B_BYTES / 16));
@@ -153,12 +171,13 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
             }
             __syncwarp();
         }
-        if (leader) umma_commit(bar_acc);            // accumulators complete
+        if (leader) { umma_commit(bar_acc); tc_stamp(a.trace, 8); }   // all MMAs issued
         __syncwarp();
     } else {
         // ================= splitter, then epilogue (warps 2..5 = 128 threads) =================
         const int t = threadIdx.x - 64;
         mbar_wait(bar_afull, 0);
+        if (t == 0) tc_stamp(a.trace, 4);            // halo tile landed
         float4* hi4 = reinterpret_cast<float4*>(gbase + TC_OFF_AHI);
         float4* lo4 = reinterpret_cast<float4*>(gbase + TC_OFF_ALO);
 #pragma unroll 4
@@ -174,10 +193,12 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
         mbar_arrive(bar_asplit);
+        if (t == 0) tc_stamp(a.trace, 5);            // split done (this thread)
 
         // ---- epilogue: TMEM lane = pixel row of the tile, 32 columns = cout ----
         mbar_wait(bar_acc, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (t == 0) tc_stamp(a.trace, 9);            // accumulators complete
         const int q = warp & 3;                 // this warp may touch TMEM lanes [32q, 32q+32)
         const int r = q * 32 + lane;            // accumulator row = pixel
         float acc[32];
@@ -228,8 +249,10 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
         }
     }
 
+    if (threadIdx.x == 64) tc_stamp(a.trace, 10);    // epilogue stores issued
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) tc_stamp(a.trace, 11);
     if (warp == 1) {
         __syncwarp();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -263,6 +286,7 @@ EncodeTiledFn get_encode_tiled() {
 }
 }  // namespace tc
 
+static long long* g_tc_trace = nullptr;
 int g_tc_base_offset_mode = 0;   // measured on B200: the swizzle phase comes from the absolute address bits; base_offset stays 0
 int g_conv_path = 2;    // default: tcgen05 convolutions (1 = fp32 SIMT validation kernels)
 int g_wgrad_path = 2;   // default: deferred tcgen05 weight-gradient GEMM (1 = per-step fp32 SIMT)
@@ -301,6 +325,7 @@ int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, con
     }
     TcArgs a;
     a.base_offset_mode = g_tc_base_offset_mode;
+    a.trace = g_tc_trace;
     a.bias = bias; a.addend = addend; a.ref = ref; a.out = out; a.B = B; a.Y = Y; a.X = X; a.act = act; a.slope = slope;
     static bool attr_done = false;
     if (!attr_done) {
@@ -328,3 +353,7 @@ int launch_conv5x5_c32_auto(cudaStream_t st, int B, int Y, int X, const float* i
 }
 
 }  // namespace sol
+
+// Diagnostics hook (not part of the public ABI): device buffer of 16 int64 per CTA that the tensor-core
+// convolution fills with clock64 phase stamps; pass null to switch tracing off.
+extern "C" void sol_debug_conv_trace(long long* buf) { sol::g_tc_trace = buf; }
