@@ -53,12 +53,20 @@ def parse():
     return ap.parse_args()
 
 
-def load_peaks():
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_conv5x5_c32_tc launch at the bench shape, from the committed
+# `ncu --set full` capture (None until a capture of the current kernel is committed under profiles/)
+CONV_TC_DRAM_BYTES = None
+CONV_TC_DRAM_SOURCE = None
+
+
+def load_peaks(key="hbm_gbs"):
+    """Roofline denominators: the driver-measured numbers, else the profiling recipe's fallback."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        if key in d:
+            return float(d[key]), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}[key], "fallback (B200_PROFILING.md)"
 
 
 # --------------------------------------------------------------------------------------------------
@@ -304,15 +312,43 @@ def main():
     torch.cuda.synchronize()
     t_solve = e4.elapsed_time(e5) / 1e3 / nrep
     K = float(it_k.float().mean())
-    alg_bytes = (40.0 * K + 8.0) * Y * X * B        # per cell per solve
+    precond = bool(args.cg_precond) and args.cluster <= 1
+    # algorithmic bytes per cell per solve: plain CG 40K+8; multigrid-preconditioned CG adds
+    # the V(2,2) cycle: 4 fine smoothing sweeps (16 B each) + residual/restrict/prolong (20 B) + coarse levels (1/3 of fine)
+    per_iter_bytes = 148.0 if precond else 40.0
+    alg_bytes = (per_iter_bytes * K + 8.0) * Y * X * B
     peak, peak_src = load_peaks()
     achieved = alg_bytes / t_solve / 1e9
 
+    # ------------------------------------------------------------------ 32->32 convolution kernel roofline (live, CUDA events)
+    t_conv = None
+    if args.conv_path != 1:
+        wl = torch.randn(5, 5, 32, 32, device=dev) * 0.03
+        bl = torch.randn(32, device=dev) * 0.1
+        ws = engine.conv5x5_split_weights(wl)
+        act_a = torch.randn(B, Y, X, 32, device=dev)
+        act_b = torch.empty_like(act_a)
+        for _ in range(4):
+            engine.conv5x5_c32_presplit(act_a, ws, bl, act=1, out=act_b)
+            engine.conv5x5_c32_presplit(act_b, ws, bl, act=1, out=act_a)
+        nconv = 100
+        torch.cuda.synchronize()
+        e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e6.record()
+        for _ in range(nconv // 2):      # dependent chain, ping-pong buffers, exactly like consecutive layers
+            engine.conv5x5_c32_presplit(act_a, ws, bl, act=1, out=act_b)
+            engine.conv5x5_c32_presplit(act_b, ws, bl, act=1, out=act_a)
+        e7.record()
+        torch.cuda.synchronize()
+        t_conv = e6.elapsed_time(e7) / 1e3 / nconv
+    conv_flops = 2.0 * 25 * 32 * 32 * B * Y * X           # algorithmic (fp32-equivalent) flops of one launch
+    tpeak, tpeak_src = load_peaks("bf16_tflops")
+
     # max over ranks
-    tt = torch.tensor([t_dev, t_e2e, t_solve], device=dev, dtype=torch.float64)
+    tt = torch.tensor([t_dev, t_e2e, t_solve, t_conv or 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_dev, t_e2e, t_solve_max = [float(x) for x in tt]
+    t_dev, t_e2e, t_solve_max, t_conv_max = [float(x) for x in tt]
 
     step_cells = m * B * Y * X * world
     value = step_cells * args.steps / t_dev
@@ -339,13 +375,38 @@ def main():
                     "ms_per_step": t_e2e / args.steps * 1e3, "wall_ms_per_step": t_e2e_wall / args.steps * 1e3},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "k_cg (fused projection: divergence + CG + gradient subtract)", "bound": "hbm",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_src, "cg_iters": K, "us_per_launch": t_solve * 1e6,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "CG state is register/SMEM-resident: DRAM traffic is ~20 B/cell regardless of K; "
-                                 "achieved = (40K+8) B/cell algorithmic bytes / CUDA-event launch time"},
+            "roofline": None,
         }
+        t_iter = t_dev / args.steps
+        solver_name = ("k_cg_mg3 (fused projection: divergence + multigrid-preconditioned CG + gradient subtract)" if precond
+                       else "k_cg (fused projection: divergence + CG + gradient subtract)")
+        roof_solver = {"kernel": solver_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                       "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "cg_iters": K,
+                       "us_per_launch": t_solve_max * 1e6, "algorithmic_bytes_per_launch": alg_bytes,
+                       "launches_per_step": 2 * m, "share_of_step": 2 * m * t_solve_max / t_iter,
+                       "note": "solver state is register/SMEM-resident (DRAM traffic ~20 B/cell regardless of K); achieved = "
+                               "(%gK+8) B/cell algorithmic bytes / CUDA-event launch time; one CTA per simulation, so at "
+                               "B=%d sims only %d of 148 SMs are busy (latency-bound; scripts/cg_bench.py reports B=148)" % (per_iter_bytes, B, B)}
+        if t_conv is not None:
+            tf = conv_flops / t_conv_max / 1e12
+            roof_conv = {"kernel": "k_conv5x5_c32_tc (tcgen05 3xTF32 implicit-GEMM 5x5 conv 32->32, fwd layers and data gradients)",
+                         "bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                         "traffic": CONV_TC_DRAM_BYTES, "traffic_source": CONV_TC_DRAM_SOURCE,
+                         "peak_source": tpeak_src + ", dense bf16 (tf32 issues at half that rate)", "us_per_launch": t_conv_max * 1e6,
+                         "algorithmic_flops_per_launch": conv_flops, "executed_tensor_tflops": 3.0 * tf,
+                         "launches_per_step": 20 * m, "share_of_step": 20 * m * t_conv_max / t_iter,
+                         "note": "achieved = 2*25*32*32 flop/pixel x B*Y*X pixels / CUDA-event launch time of a dependent "
+                                 "ping-pong chain; fp32-accurate 3xTF32 executes 3 tf32 MMAs per algorithmic product, so the "
+                                 "tensor pipe runs 3x the algorithmic rate at half the bf16 peak (ceiling = peak/6); "
+                                 "%d pixels = %d CTA tiles on 148 SMs: latency- not throughput-bound" % (B * Y * X, B * Y * X // 128)}
+        else:
+            roof_conv = None
+        if roof_conv is not None and roof_conv["share_of_step"] >= roof_solver["share_of_step"]:
+            line["roofline"] = roof_conv; line["roofline_pressure_solve"] = roof_solver
+        else:
+            line["roofline"] = roof_solver
+            if roof_conv is not None:
+                line["roofline_conv"] = roof_conv
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

@@ -138,6 +138,13 @@ int sol_burgers_step_bwd(sol_plan* plan, void* stream, int B, float dt, float vi
  * ref).  bias/addend/ref may be NULL. */
 int sol_conv5x5(void* stream, int B, int Y, int X, int Cin, int Cout, const float* in, const float* w,
                 const float* bias, const float* addend, const float* ref, int act, float slope, float* out);
+/* Tensor-core path of the 32->32 layers (same keras Conv2D, karman_train.py:107-133): the fp32 weights
+ * are split ONCE per optimiser step into their tf32 hi/lo operand layout (sol_conv5x5_split_floats()
+ * floats, 16-byte aligned) and reused by every unrolled step; sol_conv5x5() splits on every call. */
+size_t sol_conv5x5_split_floats(void);
+int sol_conv5x5_split_weights(void* stream, const float* w, float* wsplit);
+int sol_conv5x5_c32_presplit(void* stream, int B, int Y, int X, const float* in, const float* wsplit, const float* bias,
+                             const float* addend, const float* ref, int act, float slope, float* out);
 /* wT[5,5,Cout,Cin] = flip+transpose of w[5,5,Cin,Cout]: conv5x5(g_out; wT) is the data gradient */
 int sol_conv5x5_flip_weights(void* stream, int Cin, int Cout, const float* w, float* wT);
 /* dW[5,5,Cin,Cout] (+)= in (x) g_out, db[Cout] (+)= sum g_out.  partials: workspace of

@@ -53,6 +53,9 @@ SIGNATURES = {
     "sol_burgers_step": (_i, [_vp, _vp, _i, _f, _f] + [_vp] * 10),
     "sol_burgers_step_bwd": (_i, [_vp, _vp, _i, _f, _f] + [_vp] * 10),
     "sol_conv5x5": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp]),
+    "sol_conv5x5_split_floats": (_sz, []),
+    "sol_conv5x5_split_weights": (_i, [_vp, _vp, _vp]),
+    "sol_conv5x5_c32_presplit": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp]),
     "sol_conv5x5_flip_weights": (_i, [_vp, _i, _i, _vp, _vp]),
     "sol_conv5x5_wgrad_workspace": (_sz, [_i, _i]),
     "sol_conv5x5_wgrad": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),

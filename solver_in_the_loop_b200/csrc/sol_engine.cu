@@ -371,6 +371,20 @@ extern "C" int sol_conv5x5(void* stream, int B, int Y, int X, int Cin, int Cout,
     return launch_conv5x5((cudaStream_t)stream, B, Y, X, Cin, Cout, in, w, bias, addend, ref, act, slope, out);
 }
 
+extern "C" size_t sol_conv5x5_split_floats(void) { return tc_weights_floats(); }
+
+extern "C" int sol_conv5x5_split_weights(void* stream, const float* w, float* wsplit) {
+    SOL_CHECK(w && wsplit, "sol_conv5x5_split_weights: NULL pointer");
+    return launch_prep_tc_weights((cudaStream_t)stream, w, wsplit);
+}
+
+extern "C" int sol_conv5x5_c32_presplit(void* stream, int B, int Y, int X, const float* in, const float* wsplit, const float* bias,
+                                        const float* addend, const float* ref, int act, float slope, float* out) {
+    SOL_CHECK(in && wsplit && out && B >= 1 && Y >= 1 && X >= 1, "sol_conv5x5_c32_presplit: bad arguments");
+    SOL_CHECK(!(act == SOL_ACT_DLRELU && !ref), "sol_conv5x5_c32_presplit: SOL_ACT_DLRELU needs ref");
+    return launch_conv5x5_tc((cudaStream_t)stream, B, Y, X, in, wsplit, bias, addend, ref, act, slope, out);
+}
+
 extern "C" int sol_conv5x5_flip_weights(void* stream, int Cin, int Cout, const float* w, float* wT) {
     SOL_CHECK(w && wT && Cin >= 1 && Cout >= 1, "sol_conv5x5_flip_weights: bad arguments");
     return launch_flip_weights((cudaStream_t)stream, Cin, Cout, w, wT);

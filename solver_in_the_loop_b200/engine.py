@@ -213,6 +213,27 @@ def conv5x5(x: torch.Tensor, w: torch.Tensor, bias=None, addend=None, ref=None, 
     return out
 
 
+def conv5x5_split_weights(w: torch.Tensor) -> torch.Tensor:
+    """tf32 hi/lo operand layout of a [5,5,32,32] weight tensor for conv5x5_c32_presplit (tensor-core path)."""
+    lib = _lib.load()
+    assert tuple(w.shape) == (5, 5, 32, 32)
+    ws = torch.empty(lib.sol_conv5x5_split_floats(), device=w.device)
+    check(lib.sol_conv5x5_split_weights(_stream(), _ptr(w), _ptr(ws)))
+    return ws
+
+
+def conv5x5_c32_presplit(x: torch.Tensor, wsplit: torch.Tensor, bias=None, addend=None, ref=None, act=_lib.SOL_ACT_NONE,
+                         slope=LEAKY_ALPHA, out=None):
+    """32->32 layer on the tensor cores with weights split once by conv5x5_split_weights."""
+    lib = _lib.load()
+    B, Y, X, Cin = x.shape
+    assert Cin == 32
+    if out is None:
+        out = torch.empty(B, Y, X, 32, device=x.device)
+    check(lib.sol_conv5x5_c32_presplit(_stream(), B, Y, X, _ptr(x), _ptr(wsplit), _ptr(bias), _ptr(addend), _ptr(ref), act, slope, _ptr(out)))
+    return out
+
+
 def conv5x5_flip_weights(w: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     Cin, Cout = w.shape[2], w.shape[3]

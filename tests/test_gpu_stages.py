@@ -173,7 +173,7 @@ def test_step_forward_and_adjoint(case, cuda_device):
 # ---------------------------------------------------------------------------------------------------
 # convolutions
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("cin,cout", [(3, 32), (32, 32), (32, 2), (2, 32), (32, 3), (4, 32)])
+@pytest.mark.parametrize("cin,cout", [(3, 32), (32, 32), (32, 2), (2, 32), (32, 3), (4, 32), (32, 4)])
 @pytest.mark.parametrize("shape", [(2, 24, 32), (1, 20, 40)], ids=["2x24x32", "1x20x40"])
 def test_conv5x5(eng, cuda_device, cin, cout, shape):
     B, Y, X = shape
@@ -218,6 +218,22 @@ def test_conv5x5_tensor_core_path(eng, cuda_device, shape):
             assert rel(t0, base) < 3e-6
             assert rel(t1, torch.nn.functional.leaky_relu(base + add, 0.3)) < 3e-6
             assert rel(t2, (so._conv(x, w, None) + add) * torch.where(ref_t > 0, 1.0, 0.3)) < 3e-6
+    finally:
+        eng.set_option("conv_path", 0)
+
+
+def test_conv5x5_presplit_weights(eng, cuda_device):
+    """Weights split once (sol_conv5x5_split_weights) give the same result as the split-per-call entry point."""
+    g = torch.Generator().manual_seed(12)
+    x = dev(torch.randn(2, 24, 32, 32, generator=g, dtype=torch.float64), cuda_device)
+    w = dev(torch.randn(5, 5, 32, 32, generator=g, dtype=torch.float64) * 0.05, cuda_device)
+    b = dev(torch.randn(32, generator=g, dtype=torch.float64), cuda_device)
+    try:
+        eng.set_option("conv_path", 2)
+        ws = eng.conv5x5_split_weights(w)
+        o0 = eng.conv5x5(x, w, b, act=1)
+        o1 = eng.conv5x5_c32_presplit(x, ws, b, act=1)
+        assert torch.equal(o0, o1)
     finally:
         eng.set_option("conv_path", 0)
 
