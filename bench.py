@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--spin", type=int, default=200, help="spin-up solver steps for the synthetic wake")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cluster", type=int, default=0)
+    ap.add_argument("--pdl", type=int, default=1, help="1 = programmatic dependent launch of every kernel, 0 = plain stream order")
     ap.add_argument("--conv-path", type=int, default=0, help="0 auto, 1 fp32 SIMT, 2 tcgen05 3xTF32")
     ap.add_argument("--wgrad-path", type=int, default=0, help="0 auto, 1 per-step SIMT, 2 deferred tcgen05")
     ap.add_argument("--cg-rows", type=int, default=0)
@@ -240,6 +241,7 @@ def main():
     lib_launch0 = None
 
     engine.set_option("conv_path", args.conv_path)
+    engine.set_option("pdl", args.pdl)
     engine.set_option("wgrad_path", args.wgrad_path)
     plan = engine.Plan.karman(Y, X, B)
     plan.set_option("cg_rows", args.cg_rows)
@@ -326,18 +328,19 @@ def main():
         wl = torch.randn(5, 5, 32, 32, device=dev) * 0.03
         bl = torch.randn(32, device=dev) * 0.1
         ws = engine.conv5x5_split_weights(wl)
+        torch.cuda.synchronize()            # the split weights are settled before the chain starts
         act_a = torch.randn(B, Y, X, 32, device=dev)
         act_b = torch.empty_like(act_a)
         for _ in range(4):
-            engine.conv5x5_c32_presplit(act_a, ws, bl, act=1, out=act_b)
-            engine.conv5x5_c32_presplit(act_b, ws, bl, act=1, out=act_a)
+            engine.conv5x5_c32_presplit(act_a, ws, bl, act=1, out=act_b, weights_settled=True)
+            engine.conv5x5_c32_presplit(act_b, ws, bl, act=1, out=act_a, weights_settled=True)
         nconv = 100
         torch.cuda.synchronize()
         e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e6.record()
         for _ in range(nconv // 2):      # dependent chain, ping-pong buffers, exactly like consecutive layers
-            engine.conv5x5_c32_presplit(act_a, ws, bl, act=1, out=act_b)
-            engine.conv5x5_c32_presplit(act_b, ws, bl, act=1, out=act_a)
+            engine.conv5x5_c32_presplit(act_a, ws, bl, act=1, out=act_b, weights_settled=True)
+            engine.conv5x5_c32_presplit(act_b, ws, bl, act=1, out=act_a, weights_settled=True)
         e7.record()
         torch.cuda.synchronize()
         t_conv = e6.elapsed_time(e7) / 1e3 / nconv
@@ -370,7 +373,7 @@ def main():
                        "cg": "max|r|<1e-5 per sim, <=2000 it (reference stop rule)", "mean_cg_iters": [k_fwd, k_bwd],
                        "l2": "working set (activation stash %.2f GB/iter) exceeds the 126 MB L2; no explicit flush"
                              % (trainer.unroll.workspace.numel() / 1e9),
-                       "cuda_graph": not args.no_graph, "conv_path": args.conv_path, "wgrad_path": args.wgrad_path, "cg_precond": args.cg_precond, "loss": float(loss_host)},
+                       "cuda_graph": not args.no_graph, "conv_path": args.conv_path, "wgrad_path": args.wgrad_path, "cg_precond": args.cg_precond, "pdl": args.pdl, "loss": float(loss_host)},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": trainer.h2d_bytes_per_step(), "d2h_bytes_per_step": 4,
                     "ms_per_step": t_e2e / args.steps * 1e3, "wall_ms_per_step": t_e2e_wall / args.steps * 1e3},
             "gpu_launches": int(launches),

@@ -75,6 +75,8 @@ int sol_plan_set_option(sol_plan* plan, const char* name, int value);
 /* Process-wide knobs:
  *   "conv_path" 0 = auto, 1 = fp32 SIMT kernels, 2 = tcgen05 tensor-core kernels (3xTF32, fp32-accurate)
  *   "wgrad_path" 0 = auto, 1 = per-step fp32 SIMT weight gradients, 2 = deferred tcgen05 weight-gradient GEMM
+ *   "pdl" 1 (default) = kernels are launched with programmatic stream serialization (the prologue of a kernel
+ *         overlaps the tail of its predecessor on the stream), 0 = plain stream order
  *   "tc_base_offset_mode" (debug) how the UMMA shared-memory descriptors encode unaligned starts */
 int sol_set_option(const char* name, int value);
 
@@ -140,11 +142,14 @@ int sol_conv5x5(void* stream, int B, int Y, int X, int Cin, int Cout, const floa
                 const float* bias, const float* addend, const float* ref, int act, float slope, float* out);
 /* Tensor-core path of the 32->32 layers (same keras Conv2D, karman_train.py:107-133): the fp32 weights
  * are split ONCE per optimiser step into their tf32 hi/lo operand layout (sol_conv5x5_split_floats()
- * floats, 16-byte aligned) and reused by every unrolled step; sol_conv5x5() splits on every call. */
+ * floats, 16-byte aligned) and reused by every unrolled step; sol_conv5x5() splits on every call.
+ * weights_settled != 0 is the caller's guarantee that wsplit was complete before the PREVIOUS kernel of this
+ * stream was launched (e.g. split once per optimiser step): the kernel then prefetches the weights while its
+ * predecessor drains (programmatic dependent launch).  Pass 0 when in doubt. */
 size_t sol_conv5x5_split_floats(void);
 int sol_conv5x5_split_weights(void* stream, const float* w, float* wsplit);
 int sol_conv5x5_c32_presplit(void* stream, int B, int Y, int X, const float* in, const float* wsplit, const float* bias,
-                             const float* addend, const float* ref, int act, float slope, float* out);
+                             const float* addend, const float* ref, int act, float slope, float* out, int weights_settled);
 /* wT[5,5,Cout,Cin] = flip+transpose of w[5,5,Cin,Cout]: conv5x5(g_out; wT) is the data gradient */
 int sol_conv5x5_flip_weights(void* stream, int Cin, int Cout, const float* w, float* wT);
 /* dW[5,5,Cin,Cout] (+)= in (x) g_out, db[Cout] (+)= sum g_out.  partials: workspace of

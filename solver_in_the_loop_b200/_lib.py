@@ -55,7 +55,7 @@ SIGNATURES = {
     "sol_conv5x5": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp]),
     "sol_conv5x5_split_floats": (_sz, []),
     "sol_conv5x5_split_weights": (_i, [_vp, _vp, _vp]),
-    "sol_conv5x5_c32_presplit": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp]),
+    "sol_conv5x5_c32_presplit": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _i]),
     "sol_conv5x5_flip_weights": (_i, [_vp, _i, _i, _vp, _vp]),
     "sol_conv5x5_wgrad_workspace": (_sz, [_i, _i]),
     "sol_conv5x5_wgrad": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),

@@ -93,6 +93,7 @@ __device__ __forceinline__ void reduce_sm(float& s, float& m, float* wpart, floa
 // compile-time so that every shared-memory address in the iteration loop is base + immediate.
 template <int X, int R, int CL, int MODE, int NT>
 __global__ void __launch_bounds__(NT, 1) k_cg(const CgArgs a) {
+    pdl_sync();
     extern __shared__ float smem[];
     constexpr int PITCH = X + 2;
     const int Y = a.Y;

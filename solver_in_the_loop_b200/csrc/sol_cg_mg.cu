@@ -182,6 +182,7 @@ struct FineOps {
 
 template <int X, int R, int MODE, int NT>
 __global__ void __launch_bounds__(NT, 1) k_cg_mg(const MgArgs a) {
+    pdl_sync();
     extern __shared__ float smem[];
     constexpr int PITCH = X + 2;
     constexpr int LGX = (X == 32) ? 5 : 6;
@@ -581,6 +582,7 @@ __device__ __forceinline__ void coarse_cycle(float* smem, const float* __restric
 
 template <int X, int R, int MODE, int NT>
 __global__ void __launch_bounds__(NT, 1) k_cg_mg3(const MgArgs a) {
+    
     extern __shared__ float smem[];
     constexpr int Y = 2 * X;
     constexpr int NL = (X == 64) ? 5 : 4;
@@ -623,6 +625,7 @@ __global__ void __launch_bounds__(NT, 1) k_cg_mg3(const MgArgs a) {
         x[k] = 0.0f;
     }
     regular = __all_sync(0xffffffffu, regular);
+    pdl_sync();        // everything above reads only plan constants (masks, hierarchy)
     if (MODE == 1) {
         const float* vy = a.vy_in + (size_t)b * NY;
         const float* vx = a.vx_in + (size_t)b * NX;
@@ -786,7 +789,7 @@ static int launch_mg3_t(const MgArgs& a, cudaStream_t st) {
         SOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         attr_done = true;
     }
-    kern<<<dim3(1, a.B, 1), dim3(X, 2 * X / R, 1), smem_bytes, st>>>(a);
+    SOL_CUDA(launch_kernel(kern, dim3(1, a.B, 1), dim3(X, 2 * X / R, 1), smem_bytes, st, a));
     SOL_LAUNCHED();
     return SOL_OK;
 }
@@ -800,7 +803,7 @@ static int launch_mg_t(const MgArgs& a, cudaStream_t st, int TY, size_t smem_byt
         SOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         attr_smem = smem_bytes;
     }
-    kern<<<dim3(1, a.B, 1), dim3(X, TY, 1), smem_bytes, st>>>(a);
+    SOL_CUDA(launch_kernel(kern, dim3(1, a.B, 1), dim3(X, TY, 1), smem_bytes, st, a));
     SOL_LAUNCHED();
     return SOL_OK;
 }

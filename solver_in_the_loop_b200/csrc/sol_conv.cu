@@ -40,6 +40,7 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope, float 
 // ------------------------------------------------------------------------------------------------
 template <int TH>
 __global__ void __launch_bounds__(TH * 32, (TH <= 4 ? 3 : 2)) k_conv5x5_c32(const ConvArgs a) {
+    pdl_sync();
     constexpr int TW = 32, PW = TW + 4, PH = TH + 4, C = 32;
     extern __shared__ float4 tile4[];   // [PH][PW][8]
     const int tid = threadIdx.x;
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(TH * 32, (TH <= 4 ? 3 : 2)) k_conv5x5_c32(cons
 // Input tile is planar [ci][8][36] (conflict-free scalar reads), weights [tap][ci][32] as float4.
 template <int CIN>
 __global__ void __launch_bounds__(128) k_conv5x5_expand(const ConvArgs a) {
+    pdl_sync();
     constexpr int TW = 32, TH = 4, PW = TW + 4, PH = TH + 4, COUT = 32;
     __shared__ float4 ws4[25 * CIN * 8];
     __shared__ float tin[CIN * PH * PW];
@@ -206,6 +208,7 @@ __global__ void __launch_bounds__(128) k_conv5x5_expand(const ConvArgs a) {
 // one set of weights feed 5 taps x 2 pixels.  The halves are summed through shared memory.
 template <int COUT>
 __global__ void __launch_bounds__(128) k_conv5x5_reduce(const ConvArgs a) {
+    pdl_sync();
     constexpr int TW = 16, TH = 8, PW = TW + 4, PH = TH + 4, C = 32, PS = 36;   // PS: padded pixel stride (floats)
     extern __shared__ float4 smem4[];
     float* ws = reinterpret_cast<float*>(smem4);                 // [25][32][COUT]
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(128) k_conv5x5_reduce(const ConvArgs a) {
 
 template <int CIN>
 static int launch_expand(const ConvArgs& a, cudaStream_t st) {
-    k_conv5x5_expand<CIN><<<dim3(cdiv(a.X, 32), cdiv(a.Y, 4), a.B), 128, 0, st>>>(a);
+    SOL_CUDA(launch_kernel(k_conv5x5_expand<CIN>, dim3(cdiv(a.X, 32), cdiv(a.Y, 4), a.B), dim3(128), 0, st, a));
     SOL_LAUNCHED();
     return SOL_OK;
 }
@@ -314,7 +317,7 @@ static int launch_reduce(const ConvArgs& a, cudaStream_t st) {
         SOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    kern<<<dim3(cdiv(a.X, 16), cdiv(a.Y, 8), a.B), 128, smem, st>>>(a);
+    SOL_CUDA(launch_kernel(kern, dim3(cdiv(a.X, 16), cdiv(a.Y, 8), a.B), dim3(128), smem, st, a));
     SOL_LAUNCHED();
     return SOL_OK;
 }
@@ -335,10 +338,10 @@ int launch_conv5x5(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, cons
                 SOL_CUDA(cudaFuncSetAttribute(k_conv5x5_c32<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 attr_done = true;
             }
-            k_conv5x5_c32<8><<<dim3(cdiv(X, 32), cdiv(Y, 8), B), 256, smem, st>>>(a);
+            SOL_CUDA(launch_kernel(k_conv5x5_c32<8>, dim3(cdiv(X, 32), cdiv(Y, 8), B), dim3(256), smem, st, a));
         } else {
             const size_t smem = (size_t)8 * 36 * 8 * sizeof(float4);
-            k_conv5x5_c32<4><<<dim3(cdiv(X, 32), cdiv(Y, 4), B), 128, smem, st>>>(a);
+            SOL_CUDA(launch_kernel(k_conv5x5_c32<4>, dim3(cdiv(X, 32), cdiv(Y, 4), B), dim3(128), smem, st, a));
         }
         SOL_LAUNCHED();
         return SOL_OK;
@@ -358,6 +361,7 @@ int launch_conv5x5(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, cons
 // wT[tap][co][ci] = w[24 - tap][ci][co]
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_flip_weights(int Cin, int Cout, const float* __restrict__ w, float* __restrict__ wT) {
+    pdl_sync();
     const int n = 25 * Cin * Cout;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
         const int ci = idx % Cin;
@@ -369,7 +373,7 @@ __global__ void __launch_bounds__(256) k_flip_weights(int Cin, int Cout, const f
 
 int launch_flip_weights(cudaStream_t st, int Cin, int Cout, const float* w, float* wT) {
     const int n = 25 * Cin * Cout;
-    k_flip_weights<<<cdiv(n, 256), 256, 0, st>>>(Cin, Cout, w, wT);
+    SOL_CUDA(launch_kernel(k_flip_weights, dim3(cdiv(n, 256)), dim3(256), 0, st, Cin, Cout, w, wT));
     SOL_LAUNCHED();
     return SOL_OK;
 }
@@ -389,6 +393,7 @@ struct WgradArgs {
 };
 
 __global__ void __launch_bounds__(320, 1) k_wgrad_c32(const WgradArgs a) {
+    pdl_sync();
     extern __shared__ float4 wsm[];
     const int X = a.X, Y = a.Y;
     const int PWX = X + 4;
@@ -467,6 +472,7 @@ __global__ void __launch_bounds__(320, 1) k_wgrad_c32(const WgradArgs a) {
 
 __global__ void __launch_bounds__(256) k_wgrad_finalize(int nctas, const float* __restrict__ part, float* __restrict__ dW,
                                                         float* __restrict__ db, int accumulate) {
+    pdl_sync();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= WG_E) return;
     float s = 0.0f;
@@ -485,6 +491,7 @@ __global__ void __launch_bounds__(256) k_wgrad_finalize(int nctas, const float* 
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(256) k_wgrad_thin(const float* __restrict__ in, const float* __restrict__ g, float* dW, float* db,
                                                     int steps, int B, int Y, int X, size_t in_step_stride, size_t g_step_stride) {
+    pdl_sync();
     constexpr int TR = 8, TWT = 32, PR = TR + 4, PWT = TWT + 4;
     constexpr int CINP = (CIN % 2 == 0) ? CIN + 1 : CIN;
     constexpr int COUTP = (COUT % 2 == 0) ? COUT + 1 : COUT;
@@ -595,7 +602,7 @@ static int launch_wgrad_thin(cudaStream_t st, int steps, int B, int Y, int X, co
     }
     const int ntiles = cdiv(X, 32) * cdiv(Y, 8) * B * steps;
     const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;
-    kern<<<grid, 256, smem, st>>>(in, g, dW, db, steps, B, Y, X, in_step_stride, g_step_stride);
+    SOL_CUDA(launch_kernel(kern, grid, dim3(256), smem, st, in, g, dW, db, steps, B, Y, X, in_step_stride, g_step_stride));
     SOL_LAUNCHED();
     return SOL_OK;
 }
@@ -616,7 +623,7 @@ size_t wgrad_workspace_floats(int Cin, int Cout) {
 }
 
 int launch_wgrad_finalize_n(cudaStream_t st, int nctas, const float* partials, float* dW, float* db, int accumulate) {
-    k_wgrad_finalize<<<cdiv(WG_E, 256), 256, 0, st>>>(nctas, partials, dW, db, accumulate);
+    SOL_CUDA(launch_kernel(k_wgrad_finalize, dim3(cdiv(WG_E, 256)), dim3(256), 0, st, nctas, partials, dW, db, accumulate));
     SOL_LAUNCHED();
     return SOL_OK;
 }
@@ -644,11 +651,11 @@ int launch_wgrad(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const 
                 SOL_CUDA(cudaFuncSetAttribute(k_wgrad_c32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 attr_smem = smem;
             }
-            k_wgrad_c32<<<nctas, 320, smem, st>>>(a);
+            SOL_CUDA(launch_kernel(k_wgrad_c32, dim3(nctas), dim3(320), smem, st, a));
             SOL_LAUNCHED();
         }
         if (finalize) {
-            k_wgrad_finalize<<<cdiv(WG_E, 256), 256, 0, st>>>(nctas, partials, dW, db, accumulate);
+            SOL_CUDA(launch_kernel(k_wgrad_finalize, dim3(cdiv(WG_E, 256)), dim3(256), 0, st, nctas, partials, dW, db, accumulate));
             SOL_LAUNCHED();
         }
         return SOL_OK;

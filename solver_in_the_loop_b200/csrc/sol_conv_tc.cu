@@ -49,6 +49,7 @@ struct TcArgs {
     int B, Y, X;
     int act;
     float slope;
+    int weights_ready;      // 1: the split weights were complete before the previous kernel of the stream started
     long long* trace;       // diagnostics: 16 slots per CTA of clock64 phase stamps (null in production)
 };
 
@@ -70,6 +71,7 @@ constexpr uint32_t TC_IDESC64 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3)
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
 k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w, const TcArgs a) {
+    
     extern __shared__ uint8_t tc_smem_raw[];
     // 1024-byte alignment for the 128B swizzle atoms
     const uint32_t raw = smem_u32(tc_smem_raw);
@@ -116,12 +118,23 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
     if (warp == 0) {
         // ================= TMA producer (warp-uniform control flow, one elected lane issues) =================
         const bool leader = elect_one();
+        // Weights that were ready before the predecessor kernel started do not depend on it: fill the ring
+        // before waiting for the predecessor (programmatic dependent launch), then fetch the halo tile.
+        const int npre = a.weights_ready ? TC_STAGES : 0;
+        for (int n = 0; n < npre; ++n) {
+            int tap = tap0 + n; if (tap >= 25) tap -= 25;
+            if (leader) {
+                mbar_arrive_expect_tx(bar_bfull + 8 * n, 2 * TC_B_BYTES);
+                tma_load_2d(s_b + 2 * n * TC_B_BYTES, &map_w, bar_bfull + 8 * n, 0, tap * 64);
+            }
+        }
+        pdl_sync();
         if (leader) {
             mbar_arrive_expect_tx(bar_afull, TC_A_BYTES);
             tma_load_4d(s_ahi, &map_in, bar_afull, 0, x0 - 2, y0 - 2, b);
         }
 #pragma unroll 1
-        for (int n = 0; n < 25; ++n) {
+        for (int n = npre; n < 25; ++n) {
             const int s = n % TC_STAGES;
             const uint32_t ph = (uint32_t)(n / TC_STAGES) & 1u;
             int tap = tap0 + n; if (tap >= 25) tap -= 25;
@@ -140,6 +153,7 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
         // Accumulations into the same TMEM tile serialise on the MMA latency and the tensor core
         // accumulates with truncation, so two independent accumulator sets are used alternately and
         // summed with RN fp32 adds in the epilogue.
+        pdl_sync();
         const bool leader = elect_one();
         const uint64_t dA_hi = make_desc(s_ahi, TC_HW * 128, 0);
         const uint64_t dA_lo = make_desc(s_alo, TC_HW * 128, 0);
@@ -176,12 +190,15 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
     } else {
         // ================= splitter, then epilogue (warps 2..5 = 128 threads) =================
         const int t = threadIdx.x - 64;
+        pdl_sync();
         mbar_wait(bar_afull, 0);
         if (t == 0) tc_stamp(a.trace, 4);            // halo tile landed
         float4* hi4 = reinterpret_cast<float4*>(gbase + TC_OFF_AHI);
         float4* lo4 = reinterpret_cast<float4*>(gbase + TC_OFF_ALO);
-#pragma unroll 4
-        for (int i = t; i < TC_A_BYTES / 16; i += 128) {
+        static_assert(TC_A_BYTES / 16 % 128 == 0, "split geometry");
+#pragma unroll 5
+        for (int it = 0; it < TC_A_BYTES / 16 / 128; ++it) {      // 15 float4 per thread, 5 loads in flight
+            const int i = t + it * 128;
             const float4 v = hi4[i];
             float4 h, l;
             h.x = tf32_rn(v.x); l.x = tf32_rn(v.x - h.x);
@@ -196,14 +213,38 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
         if (t == 0) tc_stamp(a.trace, 5);            // split done (this thread)
 
         // ---- epilogue: TMEM lane = pixel row of the tile, 32 columns = cout ----
+        const int q = warp & 3;                 // this warp may touch TMEM lanes [32q, 32q+32)
+        const int r = q * 32 + lane;            // accumulator row = pixel
+        const int gy = y0 + (r >> 3), gx = x0 + (r & 7);
+        const bool inside = gy < a.Y && gx < a.X;
+        const size_t o = (((size_t)b * a.Y + gy) * a.X + gx) * 32;
+        // the residual / activation-reference rows are fetched while the tensor core is still busy
+        float4 ad[8], rf[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { ad[c] = make_float4(0.f, 0.f, 0.f, 0.f); rf[c] = make_float4(1.f, 1.f, 1.f, 1.f); }
+        if (inside) {
+            if (a.addend) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) ad[c] = __ldg(reinterpret_cast<const float4*>(a.addend + o) + c);
+            }
+            if (a.act == SOL_ACT_DLRELU) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) rf[c] = __ldg(reinterpret_cast<const float4*>(a.ref + o) + c);
+            }
+        }
+        if (a.bias) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias) + c);
+                ad[c].x += bv.x; ad[c].y += bv.y; ad[c].z += bv.z; ad[c].w += bv.w;
+            }
+        }
         mbar_wait(bar_acc, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (t == 0) tc_stamp(a.trace, 9);            // accumulators complete
-        const int q = warp & 3;                 // this warp may touch TMEM lanes [32q, 32q+32)
-        const int r = q * 32 + lane;            // accumulator row = pixel
         float acc[32];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
+        for (int c = 0; c < 8; ++c) { acc[4 * c] = ad[c].x; acc[4 * c + 1] = ad[c].y; acc[4 * c + 2] = ad[c].z; acc[4 * c + 3] = ad[c].w; }
 #pragma unroll 1
         for (int j = 0; j < 3 * TC_NSET; ++j) {       // per set: hh, hl, lh column blocks
             uint32_t v[32];
@@ -221,28 +262,17 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
 #pragma unroll
             for (int c = 0; c < 32; ++c) acc[c] += __uint_as_float(v[c]);
         }
-        const int gy = y0 + (r >> 3), gx = x0 + (r & 7);
-        if (gy < a.Y && gx < a.X) {
-            const size_t o = (((size_t)b * a.Y + gy) * a.X + gx) * 32;
+        if (inside) {
             float4* out4 = reinterpret_cast<float4*>(a.out + o);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 float4 f = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
-                if (a.bias) {
-                    const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias) + c);
-                    f.x += bv.x; f.y += bv.y; f.z += bv.z; f.w += bv.w;
-                }
-                if (a.addend) {
-                    const float4 ad = __ldg(reinterpret_cast<const float4*>(a.addend + o) + c);
-                    f.x += ad.x; f.y += ad.y; f.z += ad.z; f.w += ad.w;
-                }
                 if (a.act == SOL_ACT_LRELU) {
                     f.x = f.x > 0.f ? f.x : a.slope * f.x; f.y = f.y > 0.f ? f.y : a.slope * f.y;
                     f.z = f.z > 0.f ? f.z : a.slope * f.z; f.w = f.w > 0.f ? f.w : a.slope * f.w;
                 } else if (a.act == SOL_ACT_DLRELU) {
-                    const float4 rf = __ldg(reinterpret_cast<const float4*>(a.ref + o) + c);
-                    f.x = rf.x > 0.f ? f.x : a.slope * f.x; f.y = rf.y > 0.f ? f.y : a.slope * f.y;
-                    f.z = rf.z > 0.f ? f.z : a.slope * f.z; f.w = rf.w > 0.f ? f.w : a.slope * f.w;
+                    f.x = rf[c].x > 0.f ? f.x : a.slope * f.x; f.y = rf[c].y > 0.f ? f.y : a.slope * f.y;
+                    f.z = rf[c].z > 0.f ? f.z : a.slope * f.z; f.w = rf[c].w > 0.f ? f.w : a.slope * f.w;
                 }
                 out4[c] = f;
             }
@@ -262,6 +292,7 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
 
 // wprep[tap][hi|lo][n][k]: hi / lo halves of  Bt[tap][n][k] = w[tap][k][n]   (w: Keras [5,5,K=Cin,N=Cout])
 __global__ void __launch_bounds__(256) k_prep_tc_weights(const float* __restrict__ w, float* __restrict__ wprep) {
+    pdl_sync();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 25 * 32 * 32) return;
     const int k = idx & 31, n = (idx >> 5) & 31, tap = idx >> 10;
@@ -294,13 +325,13 @@ int g_wgrad_path = 2;   // default: deferred tcgen05 weight-gradient GEMM (1 = p
 size_t tc_weights_floats() { return (size_t)2 * 25 * 32 * 32; }
 
 int launch_prep_tc_weights(cudaStream_t st, const float* w, float* wprep) {
-    k_prep_tc_weights<<<cdiv(25 * 32 * 32, 256), 256, 0, st>>>(w, wprep);
+    SOL_CUDA(launch_kernel(k_prep_tc_weights, dim3(cdiv(25 * 32 * 32, 256)), dim3(256), 0, st, w, wprep));
     SOL_LAUNCHED();
     return SOL_OK;
 }
 
 int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, const float* wprep, const float* bias,
-                      const float* addend, const float* ref, int act, float slope, float* out) {
+                      const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready) {
     tc::EncodeTiledFn enc = tc::get_encode_tiled();
     if (!enc) return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     if (((uintptr_t)in & 15) || ((uintptr_t)wprep & 15)) return fail(SOL_ERR_INVALID, "conv tc: operands must be 16-byte aligned");
@@ -326,6 +357,7 @@ int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, con
     TcArgs a;
     a.base_offset_mode = g_tc_base_offset_mode;
     a.trace = g_tc_trace;
+    a.weights_ready = weights_ready ? 1 : 0;
     a.bias = bias; a.addend = addend; a.ref = ref; a.out = out; a.B = B; a.Y = Y; a.X = X; a.act = act; a.slope = slope;
     static bool attr_done = false;
     if (!attr_done) {
@@ -333,7 +365,7 @@ int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, con
         attr_done = true;
     }
     dim3 grid(cdiv(X, TC_TX), cdiv(Y, TC_TY), B);
-    k_conv5x5_c32_tc<<<grid, TC_THREADS, TC_SMEM, st>>>(map_in, map_w, a);
+    SOL_CUDA(launch_kernel(k_conv5x5_c32_tc, grid, dim3(TC_THREADS), TC_SMEM, st, map_in, map_w, a));
     SOL_LAUNCHED();
     return SOL_OK;
 }
@@ -342,6 +374,7 @@ int launch_conv5x5_c32_auto(cudaStream_t st, int B, int Y, int X, const float* i
                             const float* bias, const float* addend, const float* ref, int act, float slope, float* out) {
     if (g_conv_path != 2) return launch_conv5x5(st, B, Y, X, 32, 32, in, w, bias, addend, ref, act, slope, out);
     if (act == SOL_ACT_DLRELU && !ref) return fail(SOL_ERR_INVALID, "conv5x5: SOL_ACT_DLRELU needs ref");
+    const bool engine_weights = wprep != nullptr;   // the unrolled sweep splits all weights before its first step
     if (!wprep) {
         // stand-alone call: split the weights into a process-wide scratch buffer (stream-ordered reuse)
         static float* scratch = nullptr;
@@ -349,7 +382,7 @@ int launch_conv5x5_c32_auto(cudaStream_t st, int B, int Y, int X, const float* i
         SOL_TRY(launch_prep_tc_weights(st, w, scratch));
         wprep = scratch;
     }
-    return launch_conv5x5_tc(st, B, Y, X, in, wprep, bias, addend, ref, act, slope, out);
+    return launch_conv5x5_tc(st, B, Y, X, in, wprep, bias, addend, ref, act, slope, out, engine_weights);
 }
 
 }  // namespace sol

@@ -249,6 +249,10 @@ extern "C" int sol_set_option(const char* name, int value) {
         sol::g_wgrad_path = value == 0 ? 2 : value;
         return SOL_OK;
     }
+    if (strcmp(name, "pdl") == 0) {
+        sol::g_pdl = value ? 1 : 0;
+        return SOL_OK;
+    }
     if (strcmp(name, "tc_base_offset_mode") == 0) {
         sol::g_tc_base_offset_mode = value ? 1 : 0;
         return SOL_OK;
@@ -379,10 +383,10 @@ extern "C" int sol_conv5x5_split_weights(void* stream, const float* w, float* ws
 }
 
 extern "C" int sol_conv5x5_c32_presplit(void* stream, int B, int Y, int X, const float* in, const float* wsplit, const float* bias,
-                                        const float* addend, const float* ref, int act, float slope, float* out) {
+                                        const float* addend, const float* ref, int act, float slope, float* out, int weights_settled) {
     SOL_CHECK(in && wsplit && out && B >= 1 && Y >= 1 && X >= 1, "sol_conv5x5_c32_presplit: bad arguments");
     SOL_CHECK(!(act == SOL_ACT_DLRELU && !ref), "sol_conv5x5_c32_presplit: SOL_ACT_DLRELU needs ref");
-    return launch_conv5x5_tc((cudaStream_t)stream, B, Y, X, in, wsplit, bias, addend, ref, act, slope, out);
+    return launch_conv5x5_tc((cudaStream_t)stream, B, Y, X, in, wsplit, bias, addend, ref, act, slope, out, weights_settled != 0);
 }
 
 extern "C" int sol_conv5x5_flip_weights(void* stream, int Cin, int Cout, const float* w, float* wT) {

@@ -1,5 +1,6 @@
 // Internal declarations shared by the translation units of libsol_b200.so.
 #pragma once
+#include <utility>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -49,6 +50,29 @@ inline int fail(int code, const char* fmt, const char* a = "", const char* b = "
         sol::g_launches.fetch_add(1, std::memory_order_relaxed); \
         SOL_CUDA(cudaGetLastError());                    \
     } while (0)
+
+// Programmatic dependent launch: every kernel of this library is launched with programmatic stream
+// serialization, so its CTAs may become resident while the previous kernel of the stream is still
+// draining.  A kernel must therefore execute pdl_wait() before its first access to global memory that
+// another kernel reads or writes (pdl_sync() at the top, or later when there is launch-independent
+// prologue work), and triggers its own dependents only after that wait, which makes completion
+// transitive along the stream.  With the attribute off (option "pdl" = 0) both are no-ops.
+extern int g_pdl;
+template <typename... P, typename... A>
+inline cudaError_t launch_kernel(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
+#endif
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -157,7 +181,7 @@ extern int g_tc_base_offset_mode;
 size_t tc_weights_floats();
 int launch_prep_tc_weights(cudaStream_t st, const float* w, float* wprep);
 int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, const float* wprep, const float* bias,
-                      const float* addend, const float* ref, int act, float slope, float* out);
+                      const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready);
 // 32->32 layers: tensor-core path when enabled (wprep = pre-split weights or NULL for internal scratch), else SIMT
 int launch_conv5x5_c32_auto(cudaStream_t st, int B, int Y, int X, const float* in, const float* w, const float* wprep,
                             const float* bias, const float* addend, const float* ref, int act, float slope, float* out);

@@ -13,6 +13,7 @@ namespace sol {
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
+int g_pdl = 1;
 
 static inline int grid_for(size_t n, int threads, int sm_count) {
     size_t blocks = (n + threads - 1) / threads;
@@ -38,6 +39,7 @@ __global__ void __launch_bounds__(256) k_diffuse_bc(int B, int Y, int X, const f
                                                     const float* __restrict__ vy, const float* __restrict__ vx,
                                                     const float* __restrict__ bcm, const float* __restrict__ bcv,
                                                     float* __restrict__ vy_out, float* __restrict__ vx_out) {
+    pdl_sync();
     const int NY = (Y + 1) * X, NX = Y * (X + 1), NF = NY + NX;
     const size_t total = (size_t)B * NF;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -56,6 +58,7 @@ __global__ void __launch_bounds__(256) k_diffuse_bc_bwd(int B, int Y, int X, con
                                                         const float* __restrict__ bcm,
                                                         const float* __restrict__ add_y, const float* __restrict__ add_x,
                                                         float* __restrict__ gy_in, float* __restrict__ gx_in) {
+    pdl_sync();
     const int NY = (Y + 1) * X, NX = Y * (X + 1), NF = NY + NX;
     const size_t total = (size_t)B * NF;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -79,8 +82,8 @@ __global__ void __launch_bounds__(256) k_diffuse_bc_bwd(int B, int Y, int X, con
 int launch_diffuse_bc(const sol_plan* p, cudaStream_t st, int B, const float* re, float dt, float res,
                       const float* vy, const float* vx, float* vy_out, float* vx_out) {
     const size_t total = (size_t)B * (p->NY() + p->NX());
-    k_diffuse_bc<<<grid_for(total, 256, p->sm_count), 256, 0, st>>>(B, p->Y, p->X, re, dt * res * res, vy, vx, p->bc_mask_y,
-                                                                    p->bc_val_y, vy_out, vx_out);
+    SOL_CUDA(launch_kernel(k_diffuse_bc, dim3(grid_for(total, 256, p->sm_count)), dim3(256), 0, st, B, p->Y, p->X, re, dt * res * res, vy, vx, p->bc_mask_y,
+                                                                    p->bc_val_y, vy_out, vx_out));
     SOL_LAUNCHED();
     return SOL_OK;
 }
@@ -88,8 +91,8 @@ int launch_diffuse_bc(const sol_plan* p, cudaStream_t st, int B, const float* re
 int launch_diffuse_bc_bwd(const sol_plan* p, cudaStream_t st, int B, const float* re, float dt, float res,
                           const float* gy, const float* gx, float* gy_in, float* gx_in, const float* add_y, const float* add_x) {
     const size_t total = (size_t)B * (p->NY() + p->NX());
-    k_diffuse_bc_bwd<<<grid_for(total, 256, p->sm_count), 256, 0, st>>>(B, p->Y, p->X, re, dt * res * res, gy, gx, p->bc_mask_y,
-                                                                        add_y, add_x, gy_in, gx_in);
+    SOL_CUDA(launch_kernel(k_diffuse_bc_bwd, dim3(grid_for(total, 256, p->sm_count)), dim3(256), 0, st, B, p->Y, p->X, re, dt * res * res, gy, gx, p->bc_mask_y,
+                                                                        add_y, add_x, gy_in, gx_in));
     SOL_LAUNCHED();
     return SOL_OK;
 }
@@ -102,6 +105,7 @@ __global__ void __launch_bounds__(256) k_advect(int B, int Y, int X, float s, fl
                                                 const float* __restrict__ vx, const float* __restrict__ rho,
                                                 const float* __restrict__ inflow, float* __restrict__ vy_out,
                                                 float* __restrict__ vx_out, float* __restrict__ rho_out) {
+    pdl_sync();
     const int NY = (Y + 1) * X, NX = Y * (X + 1), NC = Y * X;
     const int NF = NY + NX + (rho ? NC : 0);
     const size_t total = (size_t)B * NF;
@@ -128,6 +132,7 @@ template <int WRAP>
 __global__ void __launch_bounds__(256) k_advect_bwd(int B, int Y, int X, float s, const float* __restrict__ vy,
                                                     const float* __restrict__ vx, const float* __restrict__ gy_out,
                                                     const float* __restrict__ gx_out, float* gy, float* gx) {
+    pdl_sync();
     const int NY = (Y + 1) * X, NX = Y * (X + 1), NF = NY + NX;
     const size_t total = (size_t)B * NF;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -153,9 +158,9 @@ int launch_advect(const sol_plan* p, cudaStream_t st, int B, float dt, const flo
     const float s = dt / p->dx;
     const int g = grid_for(total, 256, p->sm_count);
     if (p->boundary == SOL_BOUNDARY_PERIODIC)
-        k_advect<WRAP_PERIODIC><<<g, 256, 0, st>>>(B, p->Y, p->X, s, dt, vy, vx, nullptr, nullptr, vy_out, vx_out, nullptr);
+        SOL_CUDA(launch_kernel(k_advect<WRAP_PERIODIC>, g, dim3(256), 0, st, B, p->Y, p->X, s, dt, vy, vx, nullptr, nullptr, vy_out, vx_out, nullptr));
     else
-        k_advect<WRAP_REPLICATE><<<g, 256, 0, st>>>(B, p->Y, p->X, s, dt, vy, vx, rho, p->inflow, vy_out, vx_out, rho_out);
+        SOL_CUDA(launch_kernel(k_advect<WRAP_REPLICATE>, g, dim3(256), 0, st, B, p->Y, p->X, s, dt, vy, vx, rho, p->inflow, vy_out, vx_out, rho_out));
     SOL_LAUNCHED();
     return SOL_OK;
 }
@@ -168,9 +173,9 @@ int launch_advect_bwd(const sol_plan* p, cudaStream_t st, int B, float dt, const
     const float s = dt / p->dx;
     const int g = grid_for(total, 256, p->sm_count);
     if (p->boundary == SOL_BOUNDARY_PERIODIC)
-        k_advect_bwd<WRAP_PERIODIC><<<g, 256, 0, st>>>(B, p->Y, p->X, s, vy, vx, gy_out, gx_out, gy, gx);
+        SOL_CUDA(launch_kernel(k_advect_bwd<WRAP_PERIODIC>, g, dim3(256), 0, st, B, p->Y, p->X, s, vy, vx, gy_out, gx_out, gy, gx));
     else
-        k_advect_bwd<WRAP_REPLICATE><<<g, 256, 0, st>>>(B, p->Y, p->X, s, vy, vx, gy_out, gx_out, gy, gx);
+        SOL_CUDA(launch_kernel(k_advect_bwd<WRAP_REPLICATE>, g, dim3(256), 0, st, B, p->Y, p->X, s, vy, vx, gy_out, gx_out, gy, gx));
     SOL_LAUNCHED();
     return SOL_OK;
 }
@@ -180,6 +185,7 @@ int launch_advect_bwd(const sol_plan* p, cudaStream_t st, int B, float dt, const
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_divergence(int B, int Y, int X, const float* __restrict__ vy, const float* __restrict__ vx,
                                                     const float* __restrict__ my, const float* __restrict__ mx, float* __restrict__ d) {
+    pdl_sync();
     const int NY = (Y + 1) * X, NX = Y * (X + 1), NC = Y * X;
     const size_t total = (size_t)B * NC;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -192,7 +198,7 @@ __global__ void __launch_bounds__(256) k_divergence(int B, int Y, int X, const f
 
 int launch_divergence(const sol_plan* p, cudaStream_t st, int B, const float* vy, const float* vx, float* div) {
     const size_t total = (size_t)B * p->NC();
-    k_divergence<<<grid_for(total, 256, p->sm_count), 256, 0, st>>>(B, p->Y, p->X, vy, vx, p->face_my, p->face_mx, div);
+    SOL_CUDA(launch_kernel(k_divergence, dim3(grid_for(total, 256, p->sm_count)), dim3(256), 0, st, B, p->Y, p->X, vy, vx, p->face_my, p->face_mx, div));
     SOL_LAUNCHED();
     return SOL_OK;
 }
@@ -203,6 +209,7 @@ int launch_divergence(const sol_plan* p, cudaStream_t st, int B, const float* vy
 __global__ void __launch_bounds__(256) k_to_feature(int B, int Y, int X, const float* __restrict__ vy, const float* __restrict__ vx,
                                                     const float* __restrict__ re, float isy, float isx, float isr,
                                                     float* __restrict__ feat) {
+    pdl_sync();
     const int NY = (Y + 1) * X, NX = Y * (X + 1), NC = Y * X;
     const size_t total = (size_t)B * NC;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -219,7 +226,7 @@ __global__ void __launch_bounds__(256) k_to_feature(int B, int Y, int X, const f
 int launch_to_feature(const sol_plan* p, cudaStream_t st, int B, const float* vy, const float* vx, const float* re,
                       float sy, float sx, float sr, float* feat) {
     const size_t total = (size_t)B * p->NC();
-    k_to_feature<<<grid_for(total, 256, p->sm_count), 256, 0, st>>>(B, p->Y, p->X, vy, vx, re, 1.0f / sy, 1.0f / sx, 1.0f / sr, feat);
+    SOL_CUDA(launch_kernel(k_to_feature, dim3(grid_for(total, 256, p->sm_count)), dim3(256), 0, st, B, p->Y, p->X, vy, vx, re, 1.0f / sy, 1.0f / sx, 1.0f / sr, feat));
     SOL_LAUNCHED();
     return SOL_OK;
 }
@@ -237,6 +244,7 @@ __global__ void __launch_bounds__(256) k_correct_loss(int B, int Y, int X, const
                                                       const float* __restrict__ gt_vy, const float* __restrict__ gt_vx, float inv_m,
                                                       float* __restrict__ vy_out, float* __restrict__ vx_out,
                                                       float* __restrict__ gl_vy, float* __restrict__ gl_vx, float* loss) {
+    pdl_sync();
     const int NY = (Y + 1) * X, NX = Y * (X + 1), NF = NY + NX, NC = Y * X;
     const size_t total = (size_t)B * NF;
     float part = 0.0f;
@@ -284,14 +292,15 @@ int launch_correct_loss(const sol_plan* p, cudaStream_t st, int B, const float* 
     const size_t total = (size_t)B * (p->NY() + p->NX());
     int g = grid_for(total, 256, p->sm_count);
     if (g > p->sm_count) g = p->sm_count;   // few atomics on the loss scalar
-    k_correct_loss<<<g, 256, 0, st>>>(B, p->Y, p->X, vy, vx, corr, sy, sx, gt_vy, gt_vx, inv_m, vy_out, vx_out, gl_vy, gl_vx,
-                                      gt_vy ? loss : nullptr);
+    SOL_CUDA(launch_kernel(k_correct_loss, g, dim3(256), 0, st, B, p->Y, p->X, vy, vx, corr, sy, sx, gt_vy, gt_vx, inv_m, vy_out, vx_out, gl_vy, gl_vx,
+                                      gt_vy ? loss : nullptr));
     SOL_LAUNCHED();
     return SOL_OK;
 }
 
 __global__ void __launch_bounds__(256) k_corr_bwd(int B, int Y, int X, const float* __restrict__ Gy, const float* __restrict__ Gx,
                                                   float sy, float sx, float* __restrict__ g_corr) {
+    pdl_sync();
     const int NY = (Y + 1) * X, NX = Y * (X + 1), NC = Y * X;
     const size_t total = (size_t)B * NC;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -307,7 +316,7 @@ __global__ void __launch_bounds__(256) k_corr_bwd(int B, int Y, int X, const flo
 
 int launch_corr_bwd(const sol_plan* p, cudaStream_t st, int B, const float* Gy, const float* Gx, float sy, float sx, float* g_corr) {
     const size_t total = (size_t)B * p->NC();
-    k_corr_bwd<<<grid_for(total, 256, p->sm_count), 256, 0, st>>>(B, p->Y, p->X, Gy, Gx, sy, sx, g_corr);
+    SOL_CUDA(launch_kernel(k_corr_bwd, dim3(grid_for(total, 256, p->sm_count)), dim3(256), 0, st, B, p->Y, p->X, Gy, Gx, sy, sx, g_corr));
     SOL_LAUNCHED();
     return SOL_OK;
 }
@@ -315,6 +324,7 @@ int launch_corr_bwd(const sol_plan* p, cudaStream_t st, int B, const float* Gy, 
 __global__ void __launch_bounds__(256) k_feat_bwd(int B, int Y, int X, const float* __restrict__ Gy, const float* __restrict__ Gx,
                                                   const float* __restrict__ g_feat, int cfeat, float isy, float isx,
                                                   float* __restrict__ Gy_out, float* __restrict__ Gx_out) {
+    pdl_sync();
     const int NY = (Y + 1) * X, NX = Y * (X + 1), NF = NY + NX, NC = Y * X;
     const size_t total = (size_t)B * NF;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -337,7 +347,7 @@ __global__ void __launch_bounds__(256) k_feat_bwd(int B, int Y, int X, const flo
 int launch_feat_bwd(const sol_plan* p, cudaStream_t st, int B, const float* Gy, const float* Gx, const float* g_feat, int cfeat,
                     float sy, float sx, float* Gy_out, float* Gx_out) {
     const size_t total = (size_t)B * (p->NY() + p->NX());
-    k_feat_bwd<<<grid_for(total, 256, p->sm_count), 256, 0, st>>>(B, p->Y, p->X, Gy, Gx, g_feat, cfeat, 1.0f / sy, 1.0f / sx, Gy_out, Gx_out);
+    SOL_CUDA(launch_kernel(k_feat_bwd, dim3(grid_for(total, 256, p->sm_count)), dim3(256), 0, st, B, p->Y, p->X, Gy, Gx, g_feat, cfeat, 1.0f / sy, 1.0f / sx, Gy_out, Gx_out));
     SOL_LAUNCHED();
     return SOL_OK;
 }
@@ -350,6 +360,7 @@ int launch_feat_bwd(const sol_plan* p, cudaStream_t st, int B, const float* Gy, 
 __global__ void __launch_bounds__(256) k_burgers_diffuse(int H, int W, size_t stride, float amount, const float* __restrict__ ker,
                                                          const float* __restrict__ v, const float* __restrict__ f, float dtf,
                                                          float* __restrict__ out) {
+    pdl_sync();
     extern __shared__ float sm[];
     float* sv = sm;            // [H*W]
     float* sk = sm + H * W;    // [H*W]
@@ -390,9 +401,9 @@ int launch_burgers_diffuse(const sol_plan* p, cudaStream_t st, int B, float amou
         SOL_CUDA(cudaFuncSetAttribute(k_burgers_diffuse, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    k_burgers_diffuse<<<B, 256, smy, st>>>(p->Y + 1, p->X, p->NY(), amount, ky, vy, fy, dtf, vy_out);
+    SOL_CUDA(launch_kernel(k_burgers_diffuse, dim3(B), dim3(256), smy, st, p->Y + 1, p->X, p->NY(), amount, ky, vy, fy, dtf, vy_out));
     SOL_LAUNCHED();
-    k_burgers_diffuse<<<B, 256, smx, st>>>(p->Y, p->X + 1, p->NX(), amount, kx, vx, fx, dtf, vx_out);
+    SOL_CUDA(launch_kernel(k_burgers_diffuse, dim3(B), dim3(256), smx, st, p->Y, p->X + 1, p->NX(), amount, kx, vx, fx, dtf, vx_out));
     SOL_LAUNCHED();
     return SOL_OK;
 }
@@ -402,6 +413,7 @@ int launch_burgers_diffuse(const sol_plan* p, cudaStream_t st, int B, float amou
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_adam(size_t n, float* __restrict__ theta, const float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ v, float lr_t, float b1, float b2, float eps, float gscale) {
+    pdl_sync();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float gi = g[i] * gscale;
         const float mi = b1 * m[i] + (1.0f - b1) * gi;
@@ -413,7 +425,7 @@ __global__ void __launch_bounds__(256) k_adam(size_t n, float* __restrict__ thet
 
 int launch_adam(cudaStream_t st, size_t n, float* theta, const float* g, float* m, float* v, float lr_t, float b1, float b2,
                 float eps, float gscale) {
-    k_adam<<<grid_for(n, 256, 148), 256, 0, st>>>(n, theta, g, m, v, lr_t, b1, b2, eps, gscale);
+    SOL_CUDA(launch_kernel(k_adam, dim3(grid_for(n, 256, 148)), dim3(256), 0, st, n, theta, g, m, v, lr_t, b1, b2, eps, gscale));
     SOL_LAUNCHED();
     return SOL_OK;
 }

@@ -56,6 +56,7 @@ struct WgTcArgs {
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
 k_wgrad_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_g, const WgTcArgs a) {
+    pdl_sync();
     extern __shared__ uint8_t wg_smem_raw[];
     const uint32_t raw = smem_u32(wg_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -243,6 +244,7 @@ k_wgrad_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant
 
 // db[co] (+)= sum over pixels of g[pix][co]
 __global__ void __launch_bounds__(256) k_colsum32(const float* __restrict__ g, size_t npix, float* db) {
+    pdl_sync();
     const int c4 = threadIdx.x & 7;          // 4 channels per thread
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     for (size_t p = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3); p < npix; p += (size_t)gridDim.x * 32) {
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(256) k_colsum32(const float* __restrict__ g, s
 }
 
 int launch_colsum32(cudaStream_t st, const float* g, size_t npix, float* db) {
-    k_colsum32<<<148, 256, 0, st>>>(g, npix, db);
+    SOL_CUDA(launch_kernel(k_colsum32, dim3(148), dim3(256), 0, st, g, npix, db));
     SOL_LAUNCHED();
     return SOL_OK;
 }
@@ -304,7 +306,7 @@ int launch_wgrad_c32_tc(cudaStream_t st, int sm_count, int steps, int B, int Y, 
         SOL_CUDA(cudaFuncSetAttribute(k_wgrad_c32_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
         attr_done = true;
     }
-    k_wgrad_c32_tc<<<nctas, WG_THREADS, WG_SMEM, st>>>(map_in, map_g, a);
+    SOL_CUDA(launch_kernel(k_wgrad_c32_tc, dim3(nctas), dim3(WG_THREADS), WG_SMEM, st, map_in, map_g, a));
     SOL_LAUNCHED();
     if (nctas_out) *nctas_out = nctas;
     return SOL_OK;

@@ -223,14 +223,16 @@ def conv5x5_split_weights(w: torch.Tensor) -> torch.Tensor:
 
 
 def conv5x5_c32_presplit(x: torch.Tensor, wsplit: torch.Tensor, bias=None, addend=None, ref=None, act=_lib.SOL_ACT_NONE,
-                         slope=LEAKY_ALPHA, out=None):
-    """32->32 layer on the tensor cores with weights split once by conv5x5_split_weights."""
+                         slope=LEAKY_ALPHA, out=None, weights_settled=False):
+    """32->32 layer on the tensor cores with weights split once by conv5x5_split_weights.  weights_settled=True
+    promises that wsplit was complete before the previous kernel on this stream was launched."""
     lib = _lib.load()
     B, Y, X, Cin = x.shape
     assert Cin == 32
     if out is None:
         out = torch.empty(B, Y, X, 32, device=x.device)
-    check(lib.sol_conv5x5_c32_presplit(_stream(), B, Y, X, _ptr(x), _ptr(wsplit), _ptr(bias), _ptr(addend), _ptr(ref), act, slope, _ptr(out)))
+    check(lib.sol_conv5x5_c32_presplit(_stream(), B, Y, X, _ptr(x), _ptr(wsplit), _ptr(bias), _ptr(addend), _ptr(ref), act, slope, _ptr(out),
+                                       1 if weights_settled else 0))
     return out
 
 
