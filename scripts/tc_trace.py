@@ -13,7 +13,7 @@ from solver_in_the_loop_b200 import _lib, engine  # noqa: E402
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 lib = _lib.load()
-lib.sol_debug_conv_trace.argtypes = [ctypes.c_void_p]
+lib.sol_debug_conv_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
 lib.sol_debug_conv_trace.restype = None
 B, Y, X = 3, 128, 64
 x = torch.randn(B, Y, X, 32, device=dev); w = torch.randn(5, 5, 32, 32, device=dev) * 0.05; b = torch.randn(32, device=dev)
@@ -23,10 +23,10 @@ for _ in range(5):
     y = engine.conv5x5(x, w, b, act=1)
 torch.cuda.synchronize()
 tr = torch.zeros(nct, 16, dtype=torch.int64, device=dev)
-lib.sol_debug_conv_trace(ctypes.c_void_p(tr.data_ptr()))
+lib.sol_debug_conv_trace(ctypes.c_void_p(tr.data_ptr()), 1)
 x2 = engine.conv5x5(y, w, b, act=1)     # chained like the network
 torch.cuda.synchronize()
-lib.sol_debug_conv_trace(None)
+lib.sol_debug_conv_trace(None, 0)
 t = tr.cpu().numpy()
 names = {2: "start", 3: "setup", 4: "halo landed", 5: "split done", 6: "mma may start", 7: "first weights", 8: "mmas issued",
          9: "acc complete", 10: "stores issued", 11: "cta end"}

@@ -12,7 +12,7 @@
 //                   accumulators in registers for the whole pixel range of its CTA; per-CTA partial
 //                   sums go to a private slot (no atomics, deterministic), reduced by
 //                   k_wgrad_finalize once per optimiser step.
-//   k_wgrad_thin    weight gradient of the thin layers (atomics; tiny)
+//   k_wgrad_expand / k_wgrad_reduce   weight gradients of the thin layers (register-tiled, persistent)
 #include "sol_internal.cuh"
 
 namespace sol {
@@ -482,127 +482,294 @@ __global__ void __launch_bounds__(256) k_wgrad_finalize(int nctas, const float* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// weight gradient, thin layers (atomics into dW / db)
-// ------------------------------------------------------------------------------------------------
-// Persistent over tiles of (possibly many) images: every thread keeps its (tap,cin,cout) entries in
-// registers across all tiles of its CTA and issues one atomic per entry at the end.  Image z = step*B + b
-// lives at in + step*in_step_stride + b*Y*X*CIN (and likewise for g), so the same kernel serves the
+// weight gradient of the thin layers, persistent over the tiles of `steps` x B images.  Image (step, b)
+// lives at in + step*in_step_stride + b*Y*X*CIN (and likewise for g), so the same kernels serve the
 // per-step call (steps = 1) and the deferred call over the whole unrolled sweep.
-template <int CIN, int COUT>
-__global__ void __launch_bounds__(256) k_wgrad_thin(const float* __restrict__ in, const float* __restrict__ g, float* dW, float* db,
-                                                    int steps, int B, int Y, int X, size_t in_step_stride, size_t g_step_stride) {
+// Register-tiled outer products: a thread owns 40 accumulators (5 dx taps x 8 values) and walks along x
+// with a 5-deep sliding window, so one new input value and one g vector feed 40 FMAs.  240 threads =
+// NOWN owners x P row groups; the row groups are summed through shared memory, then one atomicAdd per
+// weight and CTA.
+// ------------------------------------------------------------------------------------------------
+template <int CIN>
+__global__ void __launch_bounds__(256, 2) k_wgrad_expand(const float* __restrict__ in, const float* __restrict__ g, float* dW, float* db,
+                                                         int steps, int B, int Y, int X, size_t in_step_stride, size_t g_step_stride) {
     pdl_sync();
-    constexpr int TR = 8, TWT = 32, PR = TR + 4, PWT = TWT + 4;
-    constexpr int CINP = (CIN % 2 == 0) ? CIN + 1 : CIN;
-    constexpr int COUTP = (COUT % 2 == 0) ? COUT + 1 : COUT;
-    constexpr int E = 25 * CIN * COUT;
-    constexpr int NE = (E + COUT + 255) / 256;
-    extern __shared__ float sm[];
-    float* tin = sm;                          // [PR*PWT][CINP]
-    float* tg = sm + PR * PWT * CINP;         // [TR*TWT][COUTP]
+    constexpr int COUT = 32;
+    constexpr int NOWN = 5 * CIN * 4;              // owner = (dy, ci, cout octet)
+    constexpr int P = 240 / NOWN;                  // row groups: 6 / 4 / 3 for CIN = 2 / 3 / 4
+    constexpr int TR = 2 * P, TW = 32, PR = TR + 4, PW = TW + 4;
+    static_assert(NOWN * P == 240, "thread geometry");
+    extern __shared__ float4 wg_sm4[];
+    float* tg = reinterpret_cast<float*>(wg_sm4);  // [TR*TW][32]
+    float* tin = tg + TR * TW * COUT;              // [CIN][PR][PW] planar
     const int tid = threadIdx.x;
-    const int tiles_x = (X + TWT - 1) / TWT, tiles_y = (Y + TR - 1) / TR;
+    const bool worker = tid < 240;
+    const int pg = tid / NOWN, own = tid - pg * NOWN;
+    const int cq = own & 3, ci = (own >> 2) % CIN, dy = own / (4 * CIN);
+    const int tiles_x = (X + TW - 1) / TW, tiles_y = (Y + TR - 1) / TR;
     const int tiles_img = tiles_x * tiles_y;
     const int ntiles = tiles_img * steps * B;
-    float acc[NE];
+    float acc[5][8];
 #pragma unroll
-    for (int k = 0; k < NE; ++k) acc[k] = 0.0f;
+    for (int d = 0; d < 5; ++d)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[d][j] = 0.0f;
+    float dbacc0 = 0.0f, dbacc1 = 0.0f;            // threads 240..255: bias gradient of couts 2(tid-240), +1
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int img = tile / tiles_img, rem = tile - img * tiles_img;
         const int tyi = rem / tiles_x, txi = rem - tyi * tiles_x;
         const int step = img / B, b = img - step * B;
-        const int x0 = txi * TWT, y0 = tyi * TR;
+        const int x0 = txi * TW, y0 = tyi * TR;
         const float* inb = in + (size_t)step * in_step_stride + (size_t)b * Y * X * CIN;
         const float* gb = g + (size_t)step * g_step_stride + (size_t)b * Y * X * COUT;
         __syncthreads();     // previous tile fully consumed
         {
-            constexpr int TOTAL = PR * PWT * CIN, ITER = (TOTAL + 255) / 256, CH = 8;
-#pragma unroll 1
-            for (int it0 = 0; it0 < ITER; it0 += CH) {      // chunks of 8 loads in flight
-                float v[CH];
+            constexpr int TOTG = TR * TW * 8, ITG = TOTG / 256;       // float4 loads of g: TR per thread
+            static_assert(TOTG % 256 == 0, "g staging geometry");
+            float4 v[ITG];
 #pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    const int idx = tid + (it0 + k) * 256;
-                    const int c = idx % CIN, pix = idx / CIN;
-                    const int tyy = pix / PWT, txx = pix - tyy * PWT;
-                    const int gy = y0 + tyy - 2, gx = x0 + txx - 2;
-                    v[k] = 0.0f;
-                    if (idx < TOTAL && gy >= 0 && gy < Y && gx >= 0 && gx < X) v[k] = __ldg(inb + ((size_t)gy * X + gx) * CIN + c);
-                }
-#pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    const int idx = tid + (it0 + k) * 256;
-                    if (idx < TOTAL) tin[(idx / CIN) * CINP + idx % CIN] = v[k];
-                }
+            for (int k = 0; k < ITG; ++k) {
+                const int idx = tid + k * 256;
+                const int c4 = idx & 7, pix = idx >> 3;
+                const int gy = y0 + pix / TW, gx = x0 + (pix & (TW - 1));
+                v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gy < Y && gx < X) v[k] = __ldg(reinterpret_cast<const float4*>(gb + ((size_t)gy * X + gx) * COUT) + c4);
             }
-        }
-        {
-            constexpr int TOTAL = TR * TWT * COUT, ITER = (TOTAL + 255) / 256, CH = 8;
-#pragma unroll 1
-            for (int it0 = 0; it0 < ITER; it0 += CH) {
-                float v[CH];
+            constexpr int TOTI = PR * PW * CIN, ITI = (TOTI + 255) / 256;
+            float u[ITI];
 #pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    const int idx = tid + (it0 + k) * 256;
-                    const int c = idx % COUT, pix = idx / COUT;
-                    const int tyy = pix / TWT, txx = pix - tyy * TWT;
-                    const int gy = y0 + tyy, gx = x0 + txx;
-                    v[k] = 0.0f;
-                    if (idx < TOTAL && gy < Y && gx < X) v[k] = __ldg(gb + ((size_t)gy * X + gx) * COUT + c);
-                }
+            for (int k = 0; k < ITI; ++k) {
+                const int idx = tid + k * 256;
+                const int row = idx / (PW * CIN), r2 = idx - row * (PW * CIN);
+                const int px = r2 / CIN;
+                const int gy = y0 + row - 2, gx = x0 + px - 2;
+                u[k] = 0.0f;
+                if (idx < TOTI && gy >= 0 && gy < Y && gx >= 0 && gx < X) u[k] = __ldg(inb + ((size_t)gy * X + gx) * CIN + (r2 - px * CIN));
+            }
 #pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    const int idx = tid + (it0 + k) * 256;
-                    if (idx < TOTAL) tg[(idx / COUT) * COUTP + idx % COUT] = v[k];
+            for (int k = 0; k < ITG; ++k) wg_sm4[tid + k * 256] = v[k];
+#pragma unroll
+            for (int k = 0; k < ITI; ++k) {
+                const int idx = tid + k * 256;
+                if (idx < TOTI) {
+                    const int row = idx / (PW * CIN), r2 = idx - row * (PW * CIN);
+                    const int px = r2 / CIN;
+                    tin[((r2 - px * CIN) * PR + row) * PW + px] = u[k];
                 }
             }
         }
         __syncthreads();
-#pragma unroll
-        for (int k = 0; k < NE; ++k) {
-            const int e = tid + k * 256;
-            float s = 0.0f;
-            if (e < E) {
-                const int co = e % COUT, ci = (e / COUT) % CIN, tap = e / (COUT * CIN);
-                const int dy = tap / 5, dx = tap - dy * 5;
+        if (worker) {
 #pragma unroll 1
-                for (int yy = 0; yy < TR; ++yy) {
-                    const float* ip = tin + ((yy + dy) * PWT + dx) * CINP + ci;
-                    const float* gp = tg + (yy * TWT) * COUTP + co;
-#pragma unroll 8
-                    for (int xx = 0; xx < TWT; ++xx) s = fmaf(ip[xx * CINP], gp[xx * COUTP], s);
+            for (int rr = 0; rr < 2; ++rr) {
+                const int y = pg * 2 + rr;
+                const float* irow = tin + (ci * PR + y + dy) * PW;
+                const float4* grow = reinterpret_cast<const float4*>(tg + (size_t)y * TW * COUT + cq * 8);
+                float w0 = irow[0], w1 = irow[1], w2 = irow[2], w3 = irow[3];
+#pragma unroll 4
+                for (int x = 0; x < TW; ++x) {
+                    const float w4 = irow[x + 4];
+                    const float4 ga = grow[x * 8], gc = grow[x * 8 + 1];
+                    const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gc.x, gc.y, gc.z, gc.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        acc[0][j] = fmaf(w0, gv[j], acc[0][j]);
+                        acc[1][j] = fmaf(w1, gv[j], acc[1][j]);
+                        acc[2][j] = fmaf(w2, gv[j], acc[2][j]);
+                        acc[3][j] = fmaf(w3, gv[j], acc[3][j]);
+                        acc[4][j] = fmaf(w4, gv[j], acc[4][j]);
+                    }
+                    w0 = w1; w1 = w2; w2 = w3; w3 = w4;
                 }
-            } else if (e < E + COUT) {
-                const int co = e - E;
-                for (int pix = 0; pix < TR * TWT; ++pix) s += tg[pix * COUTP + co];
             }
-            acc[k] += s;
+        } else {
+            const int co = 2 * (tid - 240);
+#pragma unroll 4
+            for (int pix = 0; pix < TR * TW; ++pix) {
+                const float2 t2 = *reinterpret_cast<const float2*>(tg + pix * COUT + co);
+                dbacc0 += t2.x; dbacc1 += t2.y;
+            }
         }
     }
+    // sum the row groups: groups 1..P-1 park their accumulators in shared memory, group 0 adds and publishes
+    __syncthreads();
+    float* red = reinterpret_cast<float*>(wg_sm4);           // [(P-1)][40][NOWN]
+    static_assert((P - 1) * 40 * NOWN <= TR * TW * COUT + CIN * PR * PW, "reduction buffer must fit the tiles");
+    if (worker && pg > 0) {
 #pragma unroll
-    for (int k = 0; k < NE; ++k) {
-        const int e = tid + k * 256;
-        if (e < E) atomicAdd(dW + e, acc[k]);
-        else if (e < E + COUT) atomicAdd(db + (e - E), acc[k]);
+        for (int d = 0; d < 5; ++d)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) red[((pg - 1) * 40 + d * 8 + j) * NOWN + own] = acc[d][j];
+    }
+    __syncthreads();
+    if (worker && pg == 0) {
+#pragma unroll
+        for (int d = 0; d < 5; ++d)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float s = acc[d][j];
+#pragma unroll
+                for (int q = 0; q < P - 1; ++q) s += red[(q * 40 + d * 8 + j) * NOWN + own];
+                atomicAdd(dW + ((dy * 5 + d) * CIN + ci) * COUT + cq * 8 + j, s);
+            }
+    } else if (!worker) {
+        atomicAdd(db + 2 * (tid - 240), dbacc0);
+        atomicAdd(db + 2 * (tid - 240) + 1, dbacc1);
     }
 }
 
-template <int CIN, int COUT>
-static int launch_wgrad_thin(cudaStream_t st, int steps, int B, int Y, int X, const float* in, size_t in_step_stride, const float* g,
-                             size_t g_step_stride, float* dW, float* db) {
-    constexpr int CINP = (CIN % 2 == 0) ? CIN + 1 : CIN;
-    constexpr int COUTP = (COUT % 2 == 0) ? COUT + 1 : COUT;
-    const size_t smem = (size_t)(12 * 36 * CINP + 8 * 32 * COUTP) * sizeof(float);
-    auto kern = k_wgrad_thin<CIN, COUT>;
+// 32 -> COUT <= 2: owner = (dy, cin quad), 40 accumulators = 5 dx x 4 cin x COUT
+template <int COUT>
+__global__ void __launch_bounds__(256, 2) k_wgrad_reduce(const float* __restrict__ in, const float* __restrict__ g, float* dW, float* db,
+                                                         int steps, int B, int Y, int X, size_t in_step_stride, size_t g_step_stride) {
+    pdl_sync();
+    static_assert(COUT == 2, "accumulator tile is written for two output channels");
+    constexpr int CIN = 32, NOWN = 40, P = 6, TR = 2 * P, TW = 32, PR = TR + 4, PW = TW + 4, PS = 36;   // PS: padded pixel stride
+    extern __shared__ float4 wg_sm4[];
+    float* tin = reinterpret_cast<float*>(wg_sm4);   // [PR*PW][PS]
+    float* tg = tin + PR * PW * PS;                  // [TR*TW][COUT]
+    const int tid = threadIdx.x;
+    const bool worker = tid < 240;
+    const int pg = tid / NOWN, own = tid - pg * NOWN;
+    const int c4 = own & 7, dy = own >> 3;
+    const int tiles_x = (X + TW - 1) / TW, tiles_y = (Y + TR - 1) / TR;
+    const int tiles_img = tiles_x * tiles_y;
+    const int ntiles = tiles_img * steps * B;
+    float acc[5][4][COUT];
+#pragma unroll
+    for (int d = 0; d < 5; ++d)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { acc[d][k][0] = 0.0f; acc[d][k][1] = 0.0f; }
+    float dbacc = 0.0f;                              // threads 240, 241: bias gradient
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int img = tile / tiles_img, rem = tile - img * tiles_img;
+        const int tyi = rem / tiles_x, txi = rem - tyi * tiles_x;
+        const int step = img / B, b = img - step * B;
+        const int x0 = txi * TW, y0 = tyi * TR;
+        const float* inb = in + (size_t)step * in_step_stride + (size_t)b * Y * X * CIN;
+        const float* gb = g + (size_t)step * g_step_stride + (size_t)b * Y * X * COUT;
+        __syncthreads();
+        {
+            constexpr int TOTI = PR * PW * 8, CH = 6;                  // 4608 float4 = 18 per thread, 6 in flight
+            static_assert(TOTI % (256 * CH) == 0, "input staging geometry");
+#pragma unroll 1
+            for (int it0 = 0; it0 < TOTI / 256; it0 += CH) {
+                float4 v[CH];
+#pragma unroll
+                for (int k = 0; k < CH; ++k) {
+                    const int idx = tid + (it0 + k) * 256;
+                    const int q4 = idx & 7, pix = idx >> 3;
+                    const int row = pix / PW, px = pix - row * PW;
+                    const int gy = y0 + row - 2, gx = x0 + px - 2;
+                    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (gy >= 0 && gy < Y && gx >= 0 && gx < X) v[k] = __ldg(reinterpret_cast<const float4*>(inb + ((size_t)gy * X + gx) * CIN) + q4);
+                }
+#pragma unroll
+                for (int k = 0; k < CH; ++k) {
+                    const int idx = tid + (it0 + k) * 256;
+                    *reinterpret_cast<float4*>(tin + (idx >> 3) * PS + (idx & 7) * 4) = v[k];
+                }
+            }
+            constexpr int TOTG = TR * TW * COUT, ITG = TOTG / 256;     // 768 floats = 3 per thread
+            static_assert(TOTG % 256 == 0, "g staging geometry");
+#pragma unroll
+            for (int k = 0; k < ITG; ++k) {
+                const int idx = tid + k * 256;
+                const int pix = idx / COUT;
+                const int gy = y0 + pix / TW, gx = x0 + (pix & (TW - 1));
+                tg[idx] = (gy < Y && gx < X) ? __ldg(gb + ((size_t)gy * X + gx) * COUT + (idx - pix * COUT)) : 0.0f;
+            }
+        }
+        __syncthreads();
+        if (worker) {
+#pragma unroll 1
+            for (int rr = 0; rr < 2; ++rr) {
+                const int y = pg * 2 + rr;
+                const float* irow = tin + (size_t)((y + dy) * PW) * PS + c4 * 4;
+                const float2* grow = reinterpret_cast<const float2*>(tg + y * TW * COUT);
+                float4 w0 = *reinterpret_cast<const float4*>(irow), w1 = *reinterpret_cast<const float4*>(irow + PS),
+                       w2 = *reinterpret_cast<const float4*>(irow + 2 * PS), w3 = *reinterpret_cast<const float4*>(irow + 3 * PS);
+#pragma unroll 4
+                for (int x = 0; x < TW; ++x) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(irow + (x + 4) * PS);
+                    const float2 gv = grow[x];
+                    const float4 ww[5] = {w0, w1, w2, w3, w4};
+#pragma unroll
+                    for (int d = 0; d < 5; ++d) {
+                        acc[d][0][0] = fmaf(ww[d].x, gv.x, acc[d][0][0]); acc[d][0][1] = fmaf(ww[d].x, gv.y, acc[d][0][1]);
+                        acc[d][1][0] = fmaf(ww[d].y, gv.x, acc[d][1][0]); acc[d][1][1] = fmaf(ww[d].y, gv.y, acc[d][1][1]);
+                        acc[d][2][0] = fmaf(ww[d].z, gv.x, acc[d][2][0]); acc[d][2][1] = fmaf(ww[d].z, gv.y, acc[d][2][1]);
+                        acc[d][3][0] = fmaf(ww[d].w, gv.x, acc[d][3][0]); acc[d][3][1] = fmaf(ww[d].w, gv.y, acc[d][3][1]);
+                    }
+                    w0 = w1; w1 = w2; w2 = w3; w3 = w4;
+                }
+            }
+        } else if (tid < 240 + COUT) {
+#pragma unroll 4
+            for (int pix = 0; pix < TR * TW; ++pix) dbacc += tg[pix * COUT + (tid - 240)];
+        }
+    }
+    __syncthreads();
+    float* red = tin;                                  // [(P-1)][40][NOWN]
+    static_assert((P - 1) * 40 * NOWN <= PR * PW * PS, "reduction buffer must fit the input tile");
+    if (worker && pg > 0) {
+#pragma unroll
+        for (int d = 0; d < 5; ++d)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) red[((pg - 1) * 40 + (d * 4 + k) * COUT + co) * NOWN + own] = acc[d][k][co];
+    }
+    __syncthreads();
+    if (worker && pg == 0) {
+#pragma unroll
+        for (int d = 0; d < 5; ++d)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) {
+                    float s = acc[d][k][co];
+#pragma unroll
+                    for (int q = 0; q < P - 1; ++q) s += red[(q * 40 + (d * 4 + k) * COUT + co) * NOWN + own];
+                    atomicAdd(dW + ((dy * 5 + d) * CIN + c4 * 4 + k) * COUT + co, s);
+                }
+    } else if (!worker && tid < 240 + COUT) {
+        atomicAdd(db + (tid - 240), dbacc);
+    }
+}
+
+template <int CIN>
+static int launch_wgrad_expand(cudaStream_t st, int steps, int B, int Y, int X, const float* in, size_t in_step_stride, const float* g,
+                               size_t g_step_stride, float* dW, float* db) {
+    constexpr int P = 240 / (20 * CIN), TR = 2 * P;
+    const size_t smem = (size_t)(TR * 32 * 32 + CIN * (TR + 4) * 36) * sizeof(float);
+    auto kern = k_wgrad_expand<CIN>;
     static bool attr_done = false;
     if (smem > 48 * 1024 && !attr_done) {
         SOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    const int ntiles = cdiv(X, 32) * cdiv(Y, 8) * B * steps;
+    const int ntiles = cdiv(X, 32) * cdiv(Y, TR) * B * steps;
     const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;
-    SOL_CUDA(launch_kernel(kern, grid, dim3(256), smem, st, in, g, dW, db, steps, B, Y, X, in_step_stride, g_step_stride));
+    SOL_CUDA(launch_kernel(kern, dim3(grid), dim3(256), smem, st, in, g, dW, db, steps, B, Y, X, in_step_stride, g_step_stride));
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
+static int launch_wgrad_reduce2(cudaStream_t st, int steps, int B, int Y, int X, const float* in, size_t in_step_stride, const float* g,
+                                size_t g_step_stride, float* dW, float* db) {
+    const size_t smem = (size_t)(16 * 36 * 36 + 12 * 32 * 2) * sizeof(float);
+    auto kern = k_wgrad_reduce<2>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const int ntiles = cdiv(X, 32) * cdiv(Y, 12) * B * steps;
+    const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;
+    SOL_CUDA(launch_kernel(kern, dim3(grid), dim3(256), smem, st, in, g, dW, db, steps, B, Y, X, in_step_stride, g_step_stride));
     SOL_LAUNCHED();
     return SOL_OK;
 }
@@ -610,10 +777,12 @@ static int launch_wgrad_thin(cudaStream_t st, int steps, int B, int Y, int X, co
 // thin-layer weight gradient accumulated INTO dW/db (atomics) over `steps` unrolled steps
 int launch_wgrad_thin_multi(cudaStream_t st, int steps, int B, int Y, int X, int Cin, int Cout, const float* in, size_t in_step_stride,
                             const float* g, size_t g_step_stride, float* dW, float* db) {
-#define SOL_WTHIN(CI, CO) \
-    if (Cin == CI && Cout == CO) return launch_wgrad_thin<CI, CO>(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db);
-    SOL_WTHIN(3, 32) SOL_WTHIN(4, 32) SOL_WTHIN(2, 32) SOL_WTHIN(32, 2)
-#undef SOL_WTHIN
+    if (((uintptr_t)in & 15) && Cin == 32) return fail(SOL_ERR_INVALID, "wgrad: 32-channel input must be 16-byte aligned");
+    if (((uintptr_t)g & 15) && Cout == 32) return fail(SOL_ERR_INVALID, "wgrad: 32-channel gradient must be 16-byte aligned");
+    if (Cout == 32 && Cin == 2) return launch_wgrad_expand<2>(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db);
+    if (Cout == 32 && Cin == 3) return launch_wgrad_expand<3>(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db);
+    if (Cout == 32 && Cin == 4) return launch_wgrad_expand<4>(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db);
+    if (Cin == 32 && Cout == 2) return launch_wgrad_reduce2(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db);
     return fail(SOL_ERR_UNSUPPORTED, "wgrad: unsupported (Cin, Cout) pair");
 }
 

@@ -50,7 +50,8 @@ struct TcArgs {
     int act;
     float slope;
     int weights_ready;      // 1: the split weights were complete before the previous kernel of the stream started
-    long long* trace;       // diagnostics: 16 slots per CTA of clock64 phase stamps (null in production)
+    long long* trace;       // diagnostics: 16 slots per CTA of clock64 phase stamps (null in production), already offset
+                            // to this launch's block of gridsize x 16 slots
 };
 
 using namespace tc;
@@ -129,6 +130,11 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
             }
         }
         pdl_sync();
+        if (leader && a.trace) {
+            const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+            unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            a.trace[cta * 16 + 13] = (long long)gt;      // dependency on the previous kernel resolved
+        }
         if (leader) {
             mbar_arrive_expect_tx(bar_afull, TC_A_BYTES);
             tma_load_4d(s_ahi, &map_in, bar_afull, 0, x0 - 2, y0 - 2, b);
@@ -282,7 +288,12 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
     if (threadIdx.x == 64) tc_stamp(a.trace, 10);    // epilogue stores issued
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (threadIdx.x == 0) tc_stamp(a.trace, 11);
+    if (threadIdx.x == 0 && a.trace) {
+        const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        a.trace[cta * 16 + 12] = (long long)gt;
+        tc_stamp(a.trace, 11);
+    }
     if (warp == 1) {
         __syncwarp();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -318,6 +329,7 @@ EncodeTiledFn get_encode_tiled() {
 }  // namespace tc
 
 static long long* g_tc_trace = nullptr;
+static int g_tc_trace_cap = 0, g_tc_trace_seq = 0;     // capacity in launches, launches traced so far
 int g_tc_base_offset_mode = 0;   // measured on B200: the swizzle phase comes from the absolute address bits; base_offset stays 0
 int g_conv_path = 2;    // default: tcgen05 convolutions (1 = fp32 SIMT validation kernels)
 int g_wgrad_path = 2;   // default: deferred tcgen05 weight-gradient GEMM (1 = per-step fp32 SIMT)
@@ -356,7 +368,11 @@ int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, con
     }
     TcArgs a;
     a.base_offset_mode = g_tc_base_offset_mode;
-    a.trace = g_tc_trace;
+    a.trace = nullptr;
+    if (g_tc_trace && g_tc_trace_seq < g_tc_trace_cap) {
+        a.trace = g_tc_trace + (size_t)g_tc_trace_seq * cdiv(X, TC_TX) * cdiv(Y, TC_TY) * B * 16;
+        ++g_tc_trace_seq;
+    }
     a.weights_ready = weights_ready ? 1 : 0;
     a.bias = bias; a.addend = addend; a.ref = ref; a.out = out; a.B = B; a.Y = Y; a.X = X; a.act = act; a.slope = slope;
     static bool attr_done = false;
@@ -387,6 +403,9 @@ int launch_conv5x5_c32_auto(cudaStream_t st, int B, int Y, int X, const float* i
 
 }  // namespace sol
 
-// Diagnostics hook (not part of the public ABI): device buffer of 16 int64 per CTA that the tensor-core
-// convolution fills with clock64 phase stamps; pass null to switch tracing off.
-extern "C" void sol_debug_conv_trace(long long* buf) { sol::g_tc_trace = buf; }
+// Diagnostics hook (not part of the public ABI): device buffer of `launches` x gridsize x 16 int64 that the next
+// `launches` tensor-core convolution launches (also when captured into a CUDA graph) fill with clock64 /
+// globaltimer phase stamps; pass null to switch tracing off.
+extern "C" void sol_debug_conv_trace(long long* buf, int launches) {
+    sol::g_tc_trace = buf; sol::g_tc_trace_cap = launches; sol::g_tc_trace_seq = 0;
+}

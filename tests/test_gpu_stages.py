@@ -238,9 +238,10 @@ def test_conv5x5_presplit_weights(eng, cuda_device):
         eng.set_option("conv_path", 0)
 
 
-@pytest.mark.parametrize("cin,cout", [(3, 32), (32, 32), (32, 2)])
-def test_conv5x5_gradients(eng, cuda_device, cin, cout):
-    B, Y, X = 2, 24, 32
+@pytest.mark.parametrize("cin,cout", [(3, 32), (32, 32), (32, 2), (2, 32), (4, 32)])
+@pytest.mark.parametrize("shape", [(2, 24, 32), (1, 20, 40)], ids=["2x24x32", "1x20x40"])
+def test_conv5x5_gradients(eng, cuda_device, cin, cout, shape):
+    B, Y, X = shape
     g = torch.Generator().manual_seed(7)
     x = torch.randn(B, Y, X, cin, generator=g, dtype=torch.float64).requires_grad_()
     w = (torch.randn(5, 5, cin, cout, generator=g, dtype=torch.float64) * 0.1).requires_grad_()
