@@ -18,6 +18,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--msteps", type=int, default=4)
 ap.add_argument("--pdl", type=int, default=1)
 ap.add_argument("--graph", type=int, default=1)
+ap.add_argument("--chain", type=int, default=1)
 a = ap.parse_args()
 torch.cuda.set_device(0)
 dev = torch.device("cuda", 0)
@@ -25,6 +26,7 @@ lib = _lib.load()
 lib.sol_debug_conv_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
 lib.sol_debug_conv_trace.restype = None
 engine.set_option("pdl", a.pdl)
+engine.set_option("conv_chain", a.chain)
 B, Y, X, m = 3, 128, 64, a.msteps
 plan = engine.Plan.karman(Y, X, B)
 plan.set_cg(1e-7, 1e-6, 4000, 0)
@@ -43,7 +45,7 @@ lib.sol_debug_conv_trace(None, 0)
 d = tr.cpu().numpy()
 start = d[:, :, 1].min(axis=1); end = d[:, :, 12].max(axis=1)
 rel_first = d[:, :, 13].min(axis=1); rel_last = d[:, :, 13].max(axis=1)      # dependency resolved (after griddepcontrol.wait)
-print("pdl %d graph %d: %d conv launches" % (a.pdl, a.graph, nl))
+print("pdl %d chain %d graph %d: %d conv launches" % (a.pdl, a.chain, a.graph, nl))
 period = (end[1:] - end[:-1]) / 1e3
 adj = period < 22.0              # directly consecutive conv layers (other kernels in between give longer periods)
 print("end(i+1) - end(i) between directly consecutive conv launches: n=%d mean %.2f us  min %.2f  max %.2f" %

@@ -49,6 +49,8 @@ struct TcArgs {
     int B, Y, X;
     int act;
     float slope;
+    const int* dep_flags;   // tile-completion flags of the producer launch of `in` (nullptr: whole-grid dependency)
+    int* out_flags;         // this launch's tile-completion flags (nullptr: none)
     int weights_ready;      // 1: the split weights were complete before the previous kernel of the stream started
     long long* trace;       // diagnostics: 16 slots per CTA of clock64 phase stamps (null in production), already offset
                             // to this launch's block of gridsize x 16 slots
@@ -71,7 +73,8 @@ constexpr uint32_t TC_IDESC64 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3)
 }  // namespace
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
-k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w, const TcArgs a) {
+k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
+                 const __grid_constant__ CUtensorMap map_out, const TcArgs a) {
     
     extern __shared__ uint8_t tc_smem_raw[];
     // 1024-byte alignment for the 128B swizzle atoms
@@ -129,7 +132,24 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
                 tma_load_2d(s_b + 2 * n * TC_B_BYTES, &map_w, bar_bfull + 8 * n, 0, tap * 64);
             }
         }
-        pdl_sync();
+        if (a.dep_flags) {
+            // tile-level dependency: the halo covers this tile and its (up to 8) neighbours in the producer launch
+            if (lane < 9) {
+                const int nx = (int)blockIdx.x + lane % 3 - 1, ny = (int)blockIdx.y + lane / 3 - 1;
+                if (nx >= 0 && nx < (int)gridDim.x && ny >= 0 && ny < (int)gridDim.y) {
+                    const int* f = a.dep_flags + nx + (int)gridDim.x * (ny + (int)gridDim.y * (int)blockIdx.z);
+                    int v;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                        if (!v) __nanosleep(100);
+                    } while (!v);
+                }
+            }
+            __syncwarp();
+            asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy stores of the producer tiles -> TMA reads
+        } else {
+            pdl_wait();
+        }
         if (leader && a.trace) {
             const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
             unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -159,7 +179,7 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
         // Accumulations into the same TMEM tile serialise on the MMA latency and the tensor core
         // accumulates with truncation, so two independent accumulator sets are used alternately and
         // summed with RN fp32 adds in the epilogue.
-        pdl_sync();
+        if (!a.dep_flags) pdl_wait();
         const bool leader = elect_one();
         const uint64_t dA_hi = make_desc(s_ahi, TC_HW * 128, 0);
         const uint64_t dA_lo = make_desc(s_alo, TC_HW * 128, 0);
@@ -196,8 +216,11 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
     } else {
         // ================= splitter, then epilogue (warps 2..5 = 128 threads) =================
         const int t = threadIdx.x - 64;
-        pdl_sync();
+        if (!a.dep_flags) pdl_wait();
         mbar_wait(bar_afull, 0);
+        // The next kernel of the stream may become resident from here on: this CTA no longer reads its input from
+        // global memory, and every producer tile under its halo is complete (the first launch_dependents of a CTA counts).
+        if (t == 0) pdl_trigger();
         if (t == 0) tc_stamp(a.trace, 4);            // halo tile landed
         float4* hi4 = reinterpret_cast<float4*>(gbase + TC_OFF_AHI);
         float4* lo4 = reinterpret_cast<float4*>(gbase + TC_OFF_ALO);
@@ -268,8 +291,11 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
 #pragma unroll
             for (int c = 0; c < 32; ++c) acc[c] += __uint_as_float(v[c]);
         }
-        if (inside) {
-            float4* out4 = reinterpret_cast<float4*>(a.out + o);
+        // Output tile -> shared memory (the A_lo tile is free once the accumulators are complete) in the 128B-swizzled
+        // layout of the output tensor map, then ONE bulk tensor store per CTA: full 128-byte lines instead of 16-byte
+        // pieces per thread, clipped at the image border by the TMA unit.
+        {
+            uint8_t* stage = gbase + TC_OFF_ALO + r * 128;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 float4 f = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
@@ -280,7 +306,23 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
                     f.x = rf[c].x > 0.f ? f.x : a.slope * f.x; f.y = rf[c].y > 0.f ? f.y : a.slope * f.y;
                     f.z = rf[c].z > 0.f ? f.z : a.slope * f.z; f.w = rf[c].w > 0.f ? f.w : a.slope * f.w;
                 }
-                out4[c] = f;
+                *reinterpret_cast<float4*>(stage + ((c ^ (r & 7)) << 4)) = f;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> bulk store reads
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (t == 0) {
+            tma_store_4d(&map_out, s_alo, 0, x0, y0, b);
+            tma_store_commit();
+            if (a.out_flags) {
+                // publish the tile for the chained consumer launch: the bulk store is complete, then the flag is released
+                tma_store_wait_all();
+                asm volatile("fence.proxy.async;" ::: "memory");
+                __threadfence();
+                int* f = a.out_flags + blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(1) : "memory");
+            } else {
+                tma_store_wait_read();       // shared memory must stay valid until the bulk store has read it
             }
         }
     }
@@ -330,9 +372,12 @@ EncodeTiledFn get_encode_tiled() {
 
 static long long* g_tc_trace = nullptr;
 static int g_tc_trace_cap = 0, g_tc_trace_seq = 0;     // capacity in launches, launches traced so far
+int g_conv_chain = 0;   // measured slower than whole-kernel PDL edges at 192 tiles (late CTA residency); kept as an option
 int g_tc_base_offset_mode = 0;   // measured on B200: the swizzle phase comes from the absolute address bits; base_offset stays 0
 int g_conv_path = 2;    // default: tcgen05 convolutions (1 = fp32 SIMT validation kernels)
 int g_wgrad_path = 2;   // default: deferred tcgen05 weight-gradient GEMM (1 = per-step fp32 SIMT)
+
+int tc_tiles_per_launch(int B, int Y, int X) { return cdiv(X, TC_TX) * cdiv(Y, TC_TY) * B; }
 
 size_t tc_weights_floats() { return (size_t)2 * 25 * 32 * 32; }
 
@@ -343,11 +388,13 @@ int launch_prep_tc_weights(cudaStream_t st, const float* w, float* wprep) {
 }
 
 int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, const float* wprep, const float* bias,
-                      const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready) {
+                      const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready,
+                      const int* dep_flags, int* out_flags) {
     tc::EncodeTiledFn enc = tc::get_encode_tiled();
     if (!enc) return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     if (((uintptr_t)in & 15) || ((uintptr_t)wprep & 15)) return fail(SOL_ERR_INVALID, "conv tc: operands must be 16-byte aligned");
-    alignas(64) CUtensorMap map_in, map_w;
+    if ((uintptr_t)out & 15) return fail(SOL_ERR_INVALID, "conv tc: output must be 16-byte aligned");
+    alignas(64) CUtensorMap map_in, map_w, map_out;
     {
         cuuint64_t dims[4] = {32, (cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)B};
         cuuint64_t strides[3] = {128, (cuuint64_t)X * 128, (cuuint64_t)Y * X * 128};
@@ -356,6 +403,10 @@ int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, con
         CUresult r = enc(&map_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled(activations) failed");
+        cuuint32_t obox[4] = {32, TC_TX, TC_TY, 1};
+        r = enc(&map_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)out, dims, strides, obox, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled(output) failed");
     }
     {
         cuuint64_t dims[2] = {32, 1600};
@@ -374,6 +425,7 @@ int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, con
         ++g_tc_trace_seq;
     }
     a.weights_ready = weights_ready ? 1 : 0;
+    a.dep_flags = dep_flags; a.out_flags = out_flags;
     a.bias = bias; a.addend = addend; a.ref = ref; a.out = out; a.B = B; a.Y = Y; a.X = X; a.act = act; a.slope = slope;
     static bool attr_done = false;
     if (!attr_done) {
@@ -381,7 +433,7 @@ int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, con
         attr_done = true;
     }
     dim3 grid(cdiv(X, TC_TX), cdiv(Y, TC_TY), B);
-    SOL_CUDA(launch_kernel(k_conv5x5_c32_tc, grid, dim3(TC_THREADS), TC_SMEM, st, map_in, map_w, a));
+    SOL_CUDA(launch_kernel(k_conv5x5_c32_tc, grid, dim3(TC_THREADS), TC_SMEM, st, map_in, map_w, map_out, a));
     SOL_LAUNCHED();
     return SOL_OK;
 }

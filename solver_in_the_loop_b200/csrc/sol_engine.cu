@@ -249,6 +249,10 @@ extern "C" int sol_set_option(const char* name, int value) {
         sol::g_wgrad_path = value == 0 ? 2 : value;
         return SOL_OK;
     }
+    if (strcmp(name, "conv_chain") == 0) {
+        sol::g_conv_chain = value ? 1 : 0;
+        return SOL_OK;
+    }
     if (strcmp(name, "pdl") == 0) {
         sol::g_pdl = value ? 1 : 0;
         return SOL_OK;
@@ -452,6 +456,10 @@ struct sol_unroll {
     float *g_corr, *g_feat, *gbuf[3];
     float* wT;
     float *wprep_fwd, *wprep_bwd;   // [10 layers][2*25*32*32] pre-split tensor-core weights
+    int* tc_flags;     // tile-completion flags of the tensor-core conv launches of one sweep: [10*msteps][tiles]
+    int tc_tiles = 0;  // tiles per launch
+    int tc_seq = 0;    // next flag block (host-side cursor, reset at the start of each sweep)
+    const int* tc_prev = nullptr;   // flags of the conv launch directly preceding on the stream (nullptr: something else ran)
     float* gst;        // deferred weight gradient: [10 layers][msteps][B,Y,X,32] output-gradient stash
     float* g0_st;      // [msteps][B,Y,X,32] output gradient of layer 0
     bool deferred_wgrad = false;   // decided per backward sweep: option wgrad_path == 2 and the grid tiles evenly (Y%16, X%8)
@@ -516,6 +524,8 @@ int carve(sol_unroll* u, void* ws, size_t* total) {
     u->wT = cv.take<float>(u->nparams);
     u->wprep_fwd = cv.take<float>(tc_weights_floats() * 10);
     u->wprep_bwd = cv.take<float>(tc_weights_floats() * 10);
+    u->tc_tiles = tc_tiles_per_launch(u->cfg.B, u->plan->Y, u->plan->X);
+    u->tc_flags = cv.take<int>((size_t)10 * u->cfg.msteps * u->tc_tiles);
     u->nA = nA;
     u->gst = cv.take<float>(nA * 10 * c.msteps);
     u->g0_st = cv.take<float>(nA * c.msteps);
@@ -538,6 +548,26 @@ int check_cfg(const sol_plan* p, const sol_unroll_cfg* c) {
     return SOL_OK;
 }
 
+// A 32->32 layer of the sweep.  Directly consecutive tensor-core launches are chained by per-tile completion
+// flags instead of the whole-grid dependency: a tile of layer n+1 starts as soon as the (up to 9) tiles of
+// layer n under its halo are stored.  Output buffers of chained launches never alias what a live
+// predecessor reads (the forward stash and the deferred-gradient stash are write-once per sweep).
+int chained_conv(sol_unroll* u, cudaStream_t st, const float* in, const float* w, const float* wprep, const float* bias, const float* addend,
+                 const float* ref, int act, float slope, float* out) {
+    const sol_plan* p = u->plan;
+    const int B = u->cfg.B, Y = p->Y, X = p->X;
+    const bool chain = sol::g_conv_path == 2 && sol::g_pdl && sol::g_conv_chain && wprep && u->tc_seq < 10 * u->cfg.msteps;
+    if (!chain) {
+        u->tc_prev = nullptr;
+        return launch_conv5x5_c32_auto(st, B, Y, X, in, w, wprep, bias, addend, ref, act, slope, out);
+    }
+    int* mine = u->tc_flags + (size_t)u->tc_seq * u->tc_tiles;
+    ++u->tc_seq;
+    const int* dep = u->tc_prev;
+    u->tc_prev = mine;
+    return launch_conv5x5_tc(st, B, Y, X, in, wprep, bias, addend, ref, act, slope, out, true, dep, mine);
+}
+
 // ---- CNN forward / backward over the stash of one step (model_mars_moon, karman_train.py:101-138)
 int cnn_forward(sol_unroll* u, cudaStream_t st, const float* w, const StepStash& s, float* corr) {
     const sol_plan* p = u->plan;
@@ -546,6 +576,7 @@ int cnn_forward(sol_unroll* u, cudaStream_t st, const float* w, const StepStash&
     const std::vector<LayerDesc>& L = u->L;
     const bool tc = sol::g_conv_path == 2;
     SOL_TRY(launch_conv5x5(st, B, Y, X, L[0].cin, 32, s.feat, w + L[0].w_off, w + L[0].b_off, nullptr, nullptr, SOL_ACT_LRELU, a, s.acts[0]));
+    u->tc_prev = nullptr;
     for (int k = 1; k <= 5; ++k) {
         const LayerDesc& l1 = L[2 * k - 1];
         const LayerDesc& l2 = L[2 * k];
@@ -554,9 +585,10 @@ int cnn_forward(sol_unroll* u, cudaStream_t st, const float* w, const StepStash&
         float* a_k = s.acts[2 * k];
         const float* p1 = tc ? u->wprep_fwd + tc_weights_floats() * (2 * k - 2) : nullptr;
         const float* p2 = tc ? u->wprep_fwd + tc_weights_floats() * (2 * k - 1) : nullptr;
-        SOL_TRY(launch_conv5x5_c32_auto(st, B, Y, X, a_prev, w + l1.w_off, p1, w + l1.b_off, nullptr, nullptr, SOL_ACT_LRELU, a, t_k));
-        SOL_TRY(launch_conv5x5_c32_auto(st, B, Y, X, t_k, w + l2.w_off, p2, w + l2.b_off, a_prev, nullptr, SOL_ACT_LRELU, a, a_k));
+        SOL_TRY(chained_conv(u, st, a_prev, w + l1.w_off, p1, w + l1.b_off, nullptr, nullptr, SOL_ACT_LRELU, a, t_k));
+        SOL_TRY(chained_conv(u, st, t_k, w + l2.w_off, p2, w + l2.b_off, a_prev, nullptr, SOL_ACT_LRELU, a, a_k));
     }
+    u->tc_prev = nullptr;
     return launch_conv5x5(st, B, Y, X, 32, 2, s.acts[10], w + L[11].w_off, w + L[11].b_off, nullptr, nullptr, SOL_ACT_NONE, a, corr);
 }
 
@@ -579,6 +611,7 @@ int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, cons
     if (!deferred)
         SOL_TRY(launch_wgrad(st, B, Y, X, 32, 2, s.acts[10], g_corr, gw + L[11].w_off, gw + L[11].b_off, 1, nullptr, false));
     SOL_TRY(launch_conv5x5(st, B, Y, X, 2, 32, g_corr, wT + L[11].w_off, nullptr, nullptr, s.acts[10], SOL_ACT_DLRELU, a, gS));
+    u->tc_prev = nullptr;
     for (int k = 5; k >= 1; --k) {
         const LayerDesc& l1 = L[2 * k - 1];
         const LayerDesc& l2 = L[2 * k];
@@ -590,16 +623,21 @@ int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, cons
         float* fN = (spare[0] != gS && spare[0] != gT) ? spare[0] : ((spare[1] != gS && spare[1] != gT) ? spare[1] : spare[2]);
         float* gN = (k >= 2) ? gout(2 * k - 2, fN) : (deferred ? u->g0_st + (size_t)step * u->nA : fN);
         // gS = d/d(a_{k-1} + conv_{2k}(t_k) + b)
-        if (!deferred)
+        if (!deferred) {
             SOL_TRY(launch_wgrad(st, B, Y, X, 32, 32, t_k, gS, nullptr, nullptr, !first, u->partials + u->partial_stride * (2 * k - 1), false));
+            u->tc_prev = nullptr;
+        }
         const float* p2 = tc ? u->wprep_bwd + tc_weights_floats() * (2 * k - 1) : nullptr;
         const float* p1 = tc ? u->wprep_bwd + tc_weights_floats() * (2 * k - 2) : nullptr;
-        SOL_TRY(launch_conv5x5_c32_auto(st, B, Y, X, gS, wT + l2.w_off, p2, nullptr, nullptr, t_k, SOL_ACT_DLRELU, a, gT));
-        if (!deferred)
+        SOL_TRY(chained_conv(u, st, gS, wT + l2.w_off, p2, nullptr, nullptr, t_k, SOL_ACT_DLRELU, a, gT));
+        if (!deferred) {
             SOL_TRY(launch_wgrad(st, B, Y, X, 32, 32, a_prev, gT, nullptr, nullptr, !first, u->partials + u->partial_stride * (2 * k - 2), false));
-        SOL_TRY(launch_conv5x5_c32_auto(st, B, Y, X, gT, wT + l1.w_off, p1, nullptr, gS, a_prev, SOL_ACT_DLRELU, a, gN));
+            u->tc_prev = nullptr;
+        }
+        SOL_TRY(chained_conv(u, st, gT, wT + l1.w_off, p1, nullptr, gS, a_prev, SOL_ACT_DLRELU, a, gN));
         gS = gN;
     }
+    u->tc_prev = nullptr;
     // input layer (cin0 -> 32): gS is the gradient w.r.t. its pre-activation
     if (!deferred)
         SOL_TRY(launch_wgrad(st, B, Y, X, L[0].cin, 32, s.feat, gS, gw + L[0].w_off, gw + L[0].b_off, 1, nullptr, false));
@@ -616,9 +654,12 @@ int do_forward(sol_unroll* u, cudaStream_t st, const float* weights, const float
     SOL_CUDA(cudaMemcpyAsync(u->re_buf, re, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
     re = u->re_buf;
     if (gt_vy) SOL_CUDA(cudaMemsetAsync(loss_steps, 0, sizeof(float) * m, st));
-    if (sol::g_conv_path == 2)
+    if (sol::g_conv_path == 2) {
         for (int l = 1; l <= 10; ++l)
             SOL_TRY(launch_prep_tc_weights(st, weights + u->L[l].w_off, u->wprep_fwd + tc_weights_floats() * (l - 1)));
+        SOL_CUDA(cudaMemsetAsync(u->tc_flags, 0, sizeof(int) * (size_t)10 * m * u->tc_tiles, st));
+    }
+    u->tc_seq = 0; u->tc_prev = nullptr;
     const float* cvy = vy0; const float* cvx = vx0; const float* crho = dens ? rho0 : nullptr;
     for (int i = 0; i < m; ++i) {
         StepStash& s = u->stash[i];
@@ -649,9 +690,12 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
     u->deferred_wgrad = (sol::g_wgrad_path == 2) && (p->Y % 16 == 0) && (p->X % 8 == 0);
     for (size_t l = 0; l < u->L.size(); ++l)
         SOL_TRY(launch_flip_weights(st, u->L[l].cin, u->L[l].cout, weights + u->L[l].w_off, u->wT + u->L[l].w_off));
-    if (sol::g_conv_path == 2)
+    if (sol::g_conv_path == 2) {
         for (int l = 1; l <= 10; ++l)
             SOL_TRY(launch_prep_tc_weights(st, u->wT + u->L[l].w_off, u->wprep_bwd + tc_weights_floats() * (l - 1)));
+        SOL_CUDA(cudaMemsetAsync(u->tc_flags, 0, sizeof(int) * (size_t)10 * m * u->tc_tiles, st));
+    }
+    u->tc_seq = 0; u->tc_prev = nullptr;
     const float* Gy = u->stash[m - 1].gl_vy;
     const float* Gx = u->stash[m - 1].gl_vx;
     for (int i = m - 1; i >= 0; --i) {

@@ -181,7 +181,10 @@ extern int g_tc_base_offset_mode;
 size_t tc_weights_floats();
 int launch_prep_tc_weights(cudaStream_t st, const float* w, float* wprep);
 int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, const float* wprep, const float* bias,
-                      const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready);
+                      const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready,
+                      const int* dep_flags = nullptr, int* out_flags = nullptr);
+int tc_tiles_per_launch(int B, int Y, int X);
+extern int g_conv_chain;
 // 32->32 layers: tensor-core path when enabled (wprep = pre-split weights or NULL for internal scratch), else SIMT
 int launch_conv5x5_c32_auto(cudaStream_t st, int B, int Y, int X, const float* in, const float* w, const float* wprep,
                             const float* bias, const float* addend, const float* ref, int act, float slope, float* out);
