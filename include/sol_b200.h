@@ -75,6 +75,8 @@ int sol_plan_set_option(sol_plan* plan, const char* name, int value);
 /* Process-wide knobs:
  *   "conv_path" 0 = auto, 1 = fp32 SIMT kernels, 2 = tcgen05 tensor-core kernels (3xTF32, fp32-accurate)
  *   "wgrad_path" 0 = auto, 1 = per-step fp32 SIMT weight gradients, 2 = deferred tcgen05 weight-gradient GEMM
+ *   "wgrad_overlap" 1 (default) = the deferred weight-gradient GEMMs of already finished steps run on a side stream
+ *         while an adjoint pressure solve keeps only B SMs busy, 0 = all of them after the adjoint sweep
  *   "conv_chain" 1 = consecutive tensor-core conv layers of the unrolled sweep are chained by per-tile
  *         completion flags (a tile starts when the tiles under its halo are stored), 0 (default) = whole-kernel dependencies
  *   "pdl" 1 (default) = kernels are launched with programmatic stream serialization (the prologue of a kernel

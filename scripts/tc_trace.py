@@ -29,7 +29,7 @@ torch.cuda.synchronize()
 lib.sol_debug_conv_trace(None, 0)
 t = tr.cpu().numpy()
 names = {2: "start", 3: "setup", 4: "halo landed", 5: "split done", 6: "mma may start", 7: "first weights", 8: "mmas issued",
-         9: "acc complete", 10: "stores issued", 11: "cta end"}
+         9: "acc complete", 10: "stores issued"}
 gt0 = t[:, 1].min()
 print("CTAs %d, SMs used %d, CTAs/SM max %d" % (nct, len(set(t[:, 0])), np.bincount(t[:, 0]).max()))
 print("kernel span by globaltimer (start of first CTA -> start of last): %.2f us" % ((t[:, 1].max() - gt0) / 1e3))
@@ -39,6 +39,6 @@ for multi in (False, True):
     if not sel.any():
         continue
     print("== SMs with %s CTA (%d CTAs)" % ("2" if multi else "1", sel.sum()))
-    for k in range(3, 12):
+    for k in range(3, 11):
         d = (t[sel, k] - t[sel, 2]) / 1.965e3
         print("  %-16s mean %6.2f us  min %6.2f  max %6.2f" % (names[k], d.mean(), d.min(), d.max()))

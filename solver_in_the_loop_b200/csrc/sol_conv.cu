@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(256, 2) k_wgrad_reduce(const float* __restrict
 
 template <int CIN>
 static int launch_wgrad_expand(cudaStream_t st, int steps, int B, int Y, int X, const float* in, size_t in_step_stride, const float* g,
-                               size_t g_step_stride, float* dW, float* db) {
+                               size_t g_step_stride, float* dW, float* db, int max_ctas) {
     constexpr int P = 240 / (20 * CIN), TR = 2 * P;
     const size_t smem = (size_t)(TR * 32 * 32 + CIN * (TR + 4) * 36) * sizeof(float);
     auto kern = k_wgrad_expand<CIN>;
@@ -752,14 +752,15 @@ static int launch_wgrad_expand(cudaStream_t st, int steps, int B, int Y, int X, 
         attr_done = true;
     }
     const int ntiles = cdiv(X, 32) * cdiv(Y, TR) * B * steps;
-    const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;
+    const int cap = max_ctas > 0 ? max_ctas : 2 * 148;
+    const int grid = ntiles < cap ? ntiles : cap;
     SOL_CUDA(launch_kernel(kern, dim3(grid), dim3(256), smem, st, in, g, dW, db, steps, B, Y, X, in_step_stride, g_step_stride));
     SOL_LAUNCHED();
     return SOL_OK;
 }
 
 static int launch_wgrad_reduce2(cudaStream_t st, int steps, int B, int Y, int X, const float* in, size_t in_step_stride, const float* g,
-                                size_t g_step_stride, float* dW, float* db) {
+                                size_t g_step_stride, float* dW, float* db, int max_ctas) {
     const size_t smem = (size_t)(16 * 36 * 36 + 12 * 32 * 2) * sizeof(float);
     auto kern = k_wgrad_reduce<2>;
     static bool attr_done = false;
@@ -768,7 +769,8 @@ static int launch_wgrad_reduce2(cudaStream_t st, int steps, int B, int Y, int X,
         attr_done = true;
     }
     const int ntiles = cdiv(X, 32) * cdiv(Y, 12) * B * steps;
-    const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;
+    const int cap = max_ctas > 0 ? max_ctas : 2 * 148;
+    const int grid = ntiles < cap ? ntiles : cap;
     SOL_CUDA(launch_kernel(kern, dim3(grid), dim3(256), smem, st, in, g, dW, db, steps, B, Y, X, in_step_stride, g_step_stride));
     SOL_LAUNCHED();
     return SOL_OK;
@@ -776,13 +778,13 @@ static int launch_wgrad_reduce2(cudaStream_t st, int steps, int B, int Y, int X,
 
 // thin-layer weight gradient accumulated INTO dW/db (atomics) over `steps` unrolled steps
 int launch_wgrad_thin_multi(cudaStream_t st, int steps, int B, int Y, int X, int Cin, int Cout, const float* in, size_t in_step_stride,
-                            const float* g, size_t g_step_stride, float* dW, float* db) {
+                            const float* g, size_t g_step_stride, float* dW, float* db, int max_ctas) {
     if (((uintptr_t)in & 15) && Cin == 32) return fail(SOL_ERR_INVALID, "wgrad: 32-channel input must be 16-byte aligned");
     if (((uintptr_t)g & 15) && Cout == 32) return fail(SOL_ERR_INVALID, "wgrad: 32-channel gradient must be 16-byte aligned");
-    if (Cout == 32 && Cin == 2) return launch_wgrad_expand<2>(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db);
-    if (Cout == 32 && Cin == 3) return launch_wgrad_expand<3>(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db);
-    if (Cout == 32 && Cin == 4) return launch_wgrad_expand<4>(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db);
-    if (Cin == 32 && Cout == 2) return launch_wgrad_reduce2(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db);
+    if (Cout == 32 && Cin == 2) return launch_wgrad_expand<2>(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db, max_ctas);
+    if (Cout == 32 && Cin == 3) return launch_wgrad_expand<3>(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db, max_ctas);
+    if (Cout == 32 && Cin == 4) return launch_wgrad_expand<4>(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db, max_ctas);
+    if (Cin == 32 && Cout == 2) return launch_wgrad_reduce2(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db, max_ctas);
     return fail(SOL_ERR_UNSUPPORTED, "wgrad: unsupported (Cin, Cout) pair");
 }
 

@@ -327,15 +327,14 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
         }
     }
 
-    if (threadIdx.x == 64) tc_stamp(a.trace, 10);    // epilogue stores issued
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (threadIdx.x == 0 && a.trace) {
+    if (threadIdx.x == 64 && a.trace) {              // the thread that issued the bulk store: end of this CTA's useful work
         const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
         unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         a.trace[cta * 16 + 12] = (long long)gt;
-        tc_stamp(a.trace, 11);
+        tc_stamp(a.trace, 10);
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
     if (warp == 1) {
         __syncwarp();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

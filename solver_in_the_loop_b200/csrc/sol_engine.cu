@@ -249,6 +249,10 @@ extern "C" int sol_set_option(const char* name, int value) {
         sol::g_wgrad_path = value == 0 ? 2 : value;
         return SOL_OK;
     }
+    if (strcmp(name, "wgrad_overlap") == 0) {
+        sol::g_wgrad_overlap = value ? 1 : 0;
+        return SOL_OK;
+    }
     if (strcmp(name, "conv_chain") == 0) {
         sol::g_conv_chain = value ? 1 : 0;
         return SOL_OK;
@@ -480,6 +484,8 @@ struct sol_unroll {
     // stream, which cannot be captured); fork/join with events keeps the caller's stream ordering
     cudaStream_t gstream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t sstream = nullptr;                    // side stream: weight-gradient GEMMs in the shadow of the adjoint solves
+    cudaEvent_t ev_wfork = nullptr, ev_wjoin = nullptr;
 };
 
 namespace {
@@ -696,6 +702,74 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
         SOL_CUDA(cudaMemsetAsync(u->tc_flags, 0, sizeof(int) * (size_t)10 * m * u->tc_tiles, st));
     }
     u->tc_seq = 0; u->tc_prev = nullptr;
+    // ---- deferred weight gradients: work items (layer, step range) over the stashed activations / output gradients.
+    // While an adjoint pressure solve occupies B SMs for ~100 us, the other SMs are idle: items whose steps are already
+    // complete run there on a side stream (option "wgrad_overlap"), the remainder after the sweep.
+    struct WgItem { int layer, step0, nsteps; };
+    bool started[12] = {false};
+    const size_t in_stride = (m > 1) ? (size_t)(u->stash[1].acts[0] - u->stash[0].acts[0]) : u->nA;
+    const int tiles_step = (p->X / 8) * (p->Y / 16) * B;
+    const bool overlap = u->deferred_wgrad && sol::g_wgrad_overlap && B + 17 <= p->sm_count;
+    const int sm_budget = overlap ? p->sm_count - B - 1 : p->sm_count;        // SMs left beside the solve's B CTAs
+    const int nct32 = tiles_step < sm_budget ? tiles_step : sm_budget;          // fixed per sweep: the partial-sum slots must line up
+    if (overlap && !u->sstream) {
+        SOL_CUDA(cudaStreamCreateWithFlags(&u->sstream, cudaStreamNonBlocking));
+        SOL_CUDA(cudaEventCreateWithFlags(&u->ev_wfork, cudaEventDisableTiming));
+        SOL_CUDA(cudaEventCreateWithFlags(&u->ev_wjoin, cudaEventDisableTiming));
+    }
+    auto launch_item = [&](cudaStream_t s, const WgItem& it) -> int {
+        const int l = it.layer;
+        if (l == 11)
+            return launch_wgrad_thin_multi(s, it.nsteps, B, p->Y, p->X, 32, 2, u->stash[it.step0].acts[10], in_stride,
+                                           u->gcorr_st + (size_t)it.step0 * p->NC() * B * 2, (size_t)p->NC() * B * 2, gw + u->L[11].w_off,
+                                           gw + u->L[11].b_off, 2 * sm_budget);
+        if (l == 0)
+            return launch_wgrad_thin_multi(s, it.nsteps, B, p->Y, p->X, u->L[0].cin, 32, u->stash[it.step0].feat, in_stride,
+                                           u->g0_st + (size_t)it.step0 * u->nA, u->nA, gw + u->L[0].w_off, gw + u->L[0].b_off, 2 * sm_budget);
+        int nctas = 0;
+        SOL_TRY(launch_wgrad_c32_tc(s, nct32, it.nsteps, B, p->Y, p->X, u->stash[it.step0].acts[l - 1], in_stride,
+                                    u->gst + ((size_t)(l - 1) * m + it.step0) * u->nA, u->nA, u->partials + u->partial_stride * (l - 1), &nctas,
+                                    started[l] ? 1 : 0));
+        started[l] = true;
+        return nctas == nct32 ? SOL_OK : fail(SOL_ERR_CUDA, "deferred wgrad: CTA count changed between chunks");
+    };
+    // Greedy schedule: done[l] = steps >= done[l] of layer l are already issued.  In the window of step i the steps
+    // >= i are complete; the layer with the largest backlog gets an item as long as its estimated time fits what is
+    // left of the window (cost model in us, measured on B200: a launch costs ~15 us of prologue + partial-sum flush
+    // + launch gap, a round of nct32 128-pixel tiles ~7.5 us; the thin layers ~7 us per step and 192 tiles).
+    int done[12];
+    for (int l = 0; l < 12; ++l) done[l] = m;
+    auto item_cost = [&](int l, int n) -> float {
+        if (l == 0 || l == 11) return 4.0f + 7.0f * (float)n * (float)tiles_step / 192.0f;
+        return 15.0f + 7.5f * (float)(((long)tiles_step * n + nct32 - 1) / nct32);
+    };
+    const float window_us = 110.0f * (float)(p->Y * p->X) / 8192.0f;      // adjoint solve + advection adjoint on this grid
+    auto fill_window = [&](cudaStream_t s, int i, float budget) -> int {
+        float left = budget;
+        bool any = false;
+        for (;;) {
+            // small items are mostly launch overhead: a layer waits until 3 steps (thin layers: 2) have piled up
+            int best = -1, backlog = 0;
+            for (int l = 0; l < 12; ++l) {
+                const int bl = done[l] - i, nmin = (l == 0 || l == 11) ? 2 : 3;
+                if (bl >= nmin && bl > backlog) { backlog = bl; best = l; }
+            }
+            if (best < 0) break;
+            int n = backlog;
+            while (n > 0 && item_cost(best, n) > left) --n;
+            if (n == 0) {
+                if (any) break;
+                n = 1;                                  // always make progress: one step of the fullest layer
+            }
+            SOL_TRY(launch_item(s, WgItem{best, done[best] - n, n}));
+            done[best] -= n;
+            left -= item_cost(best, n);
+            any = true;
+            if (left <= 0.0f) break;
+        }
+        return SOL_OK;
+    };
+
     const float* Gy = u->stash[m - 1].gl_vy;
     const float* Gx = u->stash[m - 1].gl_vx;
     for (int i = m - 1; i >= 0; --i) {
@@ -704,8 +778,17 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
         SOL_TRY(launch_corr_bwd(p, st, B, Gy, Gx, c.sig_vy, c.sig_vx, g_corr));
         SOL_TRY(cnn_backward(u, st, weights, gw, s, g_corr, u->g_feat, i == m - 1, i));
         SOL_TRY(launch_feat_bwd(p, st, B, Gy, Gx, u->g_feat, c.cin0, c.sig_vy, c.sig_vx, u->H_vy, u->H_vx));
+        bool joined = true;
+        if (overlap && i > 0) {     // the items of the last window would only delay the end of the sweep: they are merged below
+            SOL_CUDA(cudaEventRecord(u->ev_wfork, st));
+            SOL_CUDA(cudaStreamWaitEvent(u->sstream, u->ev_wfork, 0));
+            SOL_TRY(fill_window(u->sstream, i, window_us));
+            SOL_CUDA(cudaEventRecord(u->ev_wjoin, u->sstream));
+            joined = false;
+        }
         SOL_TRY(launch_cg(p, st, B, 1, nullptr, nullptr, u->H_vy, u->H_vx, u->K_vy, u->K_vx, u->iters + (size_t)(m + i) * B));
         SOL_TRY(launch_advect_bwd(p, st, B, c.dt, s.vy1, s.vx1, u->K_vy, u->K_vx, u->H_vy, u->H_vx));
+        if (!joined) SOL_CUDA(cudaStreamWaitEvent(st, u->ev_wjoin, 0));
         if (i > 0) {
             float* ny = u->G_vy[i & 1]; float* nx = u->G_vx[i & 1];
             SOL_TRY(launch_diffuse_bc_bwd(p, st, B, re, c.dt, c.res, u->H_vy, u->H_vx, ny, nx, u->stash[i - 1].gl_vy, u->stash[i - 1].gl_vx));
@@ -715,20 +798,12 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
         }
     }
     if (u->deferred_wgrad) {
-        // deferred weight gradients: one tensor-core GEMM per layer over all msteps x B x Y x X pixels
-        const size_t in_stride = (m > 1) ? (size_t)(u->stash[1].acts[0] - u->stash[0].acts[0]) : u->nA;
-        // thin layers: one persistent launch each over all steps (gw was zeroed at the start of the sweep)
-        SOL_TRY(launch_wgrad_thin_multi(st, m, B, p->Y, p->X, 32, 2, u->stash[0].acts[10], in_stride, u->gcorr_st, (size_t)p->NC() * B * 2,
-                                        gw + u->L[11].w_off, gw + u->L[11].b_off));
-        SOL_TRY(launch_wgrad_thin_multi(st, m, B, p->Y, p->X, u->L[0].cin, 32, u->stash[0].feat, in_stride, u->g0_st, u->nA,
-                                        gw + u->L[0].w_off, gw + u->L[0].b_off));
-        for (int l = 1; l <= 10; ++l) {
-            int nctas = 0;
-            float* part = u->partials + u->partial_stride * (l - 1);
-            const float* gl = u->gst + (size_t)(l - 1) * m * u->nA;
-            SOL_TRY(launch_wgrad_c32_tc(st, p->sm_count, m, B, p->Y, p->X, u->stash[0].acts[l - 1], in_stride, gl, u->nA, part, &nctas));
-            SOL_TRY(launch_wgrad_finalize_n(st, nctas, part, gw + u->L[l].w_off, gw + u->L[l].b_off, 0));
-        }
+        // what the solve windows did not absorb: ONE launch per layer over its remaining steps [0, done[l]), then the
+        // per-layer reduction of the CTA partial sums
+        for (int l = 0; l <= 11; ++l)
+            if (done[l] > 0) { SOL_TRY(launch_item(st, WgItem{l, 0, done[l]})); done[l] = 0; }
+        for (int l = 1; l <= 10; ++l)
+            SOL_TRY(launch_wgrad_finalize_n(st, nct32, u->partials + u->partial_stride * (l - 1), gw + u->L[l].w_off, gw + u->L[l].b_off, 0));
         return SOL_OK;
     }
     for (int l = 1; l <= 10; ++l)
@@ -774,6 +849,9 @@ extern "C" int sol_unroll_destroy(sol_unroll* u) {
     if (u->ev_fork) cudaEventDestroy(u->ev_fork);
     if (u->ev_join) cudaEventDestroy(u->ev_join);
     if (u->gstream) cudaStreamDestroy(u->gstream);
+    if (u->ev_wfork) cudaEventDestroy(u->ev_wfork);
+    if (u->ev_wjoin) cudaEventDestroy(u->ev_wjoin);
+    if (u->sstream) cudaStreamDestroy(u->sstream);
     delete u;
     return SOL_OK;
 }

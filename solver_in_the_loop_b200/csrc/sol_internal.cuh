@@ -166,13 +166,13 @@ int launch_wgrad(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const 
                  int accumulate, float* partials, bool finalize);
 
 int launch_wgrad_thin_multi(cudaStream_t st, int steps, int B, int Y, int X, int Cin, int Cout, const float* in, size_t in_step_stride,
-                            const float* g, size_t g_step_stride, float* dW, float* db);
+                            const float* g, size_t g_step_stride, float* dW, float* db, int max_ctas = 0);
 int launch_wgrad_finalize_n(cudaStream_t st, int nctas, const float* partials, float* dW, float* db, int accumulate);
 
 // ---- deferred tensor-core weight gradient (sol_wgrad_tc.cu) ----
 extern int g_wgrad_path;            // 1 SIMT per step, 2 tcgen05 deferred over the whole sweep (default; 0 = auto = 2)
 int launch_wgrad_c32_tc(cudaStream_t st, int sm_count, int steps, int B, int Y, int X, const float* in, size_t in_step_stride,
-                        const float* g, size_t g_step_stride, float* part, int* nctas_out);
+                        const float* g, size_t g_step_stride, float* part, int* nctas_out, int accumulate = 0);
 int launch_colsum32(cudaStream_t st, const float* g, size_t npix, float* db);
 
 // ---- tensor-core convolution (sol_conv_tc.cu) ----
@@ -185,6 +185,7 @@ int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, con
                       const int* dep_flags = nullptr, int* out_flags = nullptr);
 int tc_tiles_per_launch(int B, int Y, int X);
 extern int g_conv_chain;
+extern int g_wgrad_overlap;
 // 32->32 layers: tensor-core path when enabled (wprep = pre-split weights or NULL for internal scratch), else SIMT
 int launch_conv5x5_c32_auto(cudaStream_t st, int B, int Y, int X, const float* in, const float* w, const float* wprep,
                             const float* bias, const float* addend, const float* ref, int act, float slope, float* out);

@@ -273,8 +273,10 @@ int launch_colsum32(cudaStream_t st, const float* g, size_t npix, float* db) {
 // in: activations of `steps` unrolled steps, image (step, b) at in + step*in_step_stride + b*Y*X*32 floats;
 // g:  output gradients, image (step, b) at g + step*g_step_stride + b*Y*X*32.
 // part: sm_count x (25*32*32+32) floats; dW = sum over CTAs (k_wgrad_finalize).
+int g_wgrad_overlap = 1;    // deferred weight-gradient GEMMs run beside the adjoint pressure solves (see sol_engine.cu)
+
 int launch_wgrad_c32_tc(cudaStream_t st, int sm_count, int steps, int B, int Y, int X, const float* in, size_t in_step_stride,
-                        const float* g, size_t g_step_stride, float* part, int* nctas_out) {
+                        const float* g, size_t g_step_stride, float* part, int* nctas_out, int accumulate) {
     tc::EncodeTiledFn enc = tc::get_encode_tiled();
     if (!enc) return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     if (X % WG_TX || Y % WG_TY) return fail(SOL_ERR_UNSUPPORTED, "wgrad tc: needs X % 8 == 0 and Y % 16 == 0");
@@ -297,7 +299,7 @@ int launch_wgrad_c32_tc(cudaStream_t st, int sm_count, int steps, int B, int Y, 
             return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled(wgrad gradients) failed");
     }
     WgTcArgs a;
-    a.part = part; a.tiles_x = X / WG_TX; a.tiles_y = Y / WG_TY; a.images = steps * B; a.B = B; a.accumulate = 0;
+    a.part = part; a.tiles_x = X / WG_TX; a.tiles_y = Y / WG_TY; a.images = steps * B; a.B = B; a.accumulate = accumulate;
     const int ntiles = a.tiles_x * a.tiles_y * a.images;
     int nctas = sm_count < 148 ? sm_count : 148;
     if (nctas > ntiles) nctas = ntiles;

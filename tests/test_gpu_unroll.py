@@ -31,21 +31,28 @@ def _setup(Y, X, B, m, device, use_graph=False, spin=25):
     return engine, geom, rho, vy, vx, re, gty, gtx, sig, params, plan, un, w
 
 
-@pytest.fixture(params=[(1, 1, 1, 0), (2, 1, 1, 0), (2, 2, 1, 0), (2, 2, 1, 1), (2, 2, 0, 0)],
-                ids=["simt", "tcgen05-conv", "tcgen05-conv+wgrad", "tcgen05-conv+wgrad-tilechain", "tcgen05-conv+wgrad-nopdl"])
+_PATHS = {
+    # id: (conv_path, wgrad_path, pdl, conv_chain, wgrad_overlap)
+    "simt": (1, 1, 1, 0, 1),
+    "tcgen05-conv": (2, 1, 1, 0, 1),
+    "tcgen05-conv+wgrad": (2, 2, 1, 0, 1),
+    "tcgen05-conv+wgrad-tilechain": (2, 2, 1, 1, 1),
+    "tcgen05-conv+wgrad-serial": (2, 2, 1, 0, 0),
+    "tcgen05-conv+wgrad-nopdl": (2, 2, 0, 0, 1),
+}
+
+
+@pytest.fixture(params=list(_PATHS.values()), ids=list(_PATHS.keys()))
 def conv_path(request):
-    """(conv_path, wgrad_path, pdl, conv_chain): kernel families, plain vs programmatic-dependent stream order,
-    whole-kernel vs tile-flag dependencies between consecutive tensor-core conv layers."""
+    """Kernel families (SIMT / tcgen05), plain vs programmatic-dependent stream order, whole-kernel vs tile-flag
+    dependencies between consecutive conv layers, weight gradients beside the adjoint solves vs after the sweep."""
     from solver_in_the_loop_b200 import engine
-    engine.set_option("conv_path", request.param[0])
-    engine.set_option("wgrad_path", request.param[1])
-    engine.set_option("pdl", request.param[2])
-    engine.set_option("conv_chain", request.param[3])
+    names = ("conv_path", "wgrad_path", "pdl", "conv_chain", "wgrad_overlap")
+    for n, v in zip(names, request.param):
+        engine.set_option(n, v)
     yield request.param
-    engine.set_option("conv_path", 0)
-    engine.set_option("wgrad_path", 0)
-    engine.set_option("pdl", 1)
-    engine.set_option("conv_chain", 0)
+    for n, v in zip(names, (0, 0, 1, 0, 1)):
+        engine.set_option(n, v)
 
 
 @pytest.mark.parametrize("Y,X,B,m", [(64, 32, 2, 2), (128, 64, 3, 2)], ids=["64x32m2", "128x64m2"])
