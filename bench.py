@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--conv-chain", type=int, default=0, help="1 = consecutive tensor-core conv layers chained by tile flags")
     ap.add_argument("--wgrad-overlap", type=int, default=1, help="1 = deferred weight-gradient GEMMs run beside the adjoint solves")
+    ap.add_argument("--wgrad-window-us", type=int, default=-1, help="tuning: time budget of one adjoint-solve window (us at 128x64)")
     ap.add_argument("--pdl", type=int, default=1, help="1 = programmatic dependent launch of every kernel, 0 = plain stream order")
     ap.add_argument("--conv-path", type=int, default=0, help="0 auto, 1 fp32 SIMT, 2 tcgen05 3xTF32")
     ap.add_argument("--wgrad-path", type=int, default=0, help="0 auto, 1 per-step SIMT, 2 deferred tcgen05")
@@ -246,6 +247,8 @@ def main():
     engine.set_option("pdl", args.pdl)
     engine.set_option("conv_chain", args.conv_chain)
     engine.set_option("wgrad_overlap", args.wgrad_overlap)
+    if args.wgrad_window_us >= 0:
+        engine.set_option("wgrad_window_us", args.wgrad_window_us)
     engine.set_option("wgrad_path", args.wgrad_path)
     plan = engine.Plan.karman(Y, X, B)
     plan.set_option("cg_rows", args.cg_rows)

@@ -77,6 +77,7 @@ int sol_plan_set_option(sol_plan* plan, const char* name, int value);
  *   "wgrad_path" 0 = auto, 1 = per-step fp32 SIMT weight gradients, 2 = deferred tcgen05 weight-gradient GEMM
  *   "wgrad_overlap" 1 (default) = the deferred weight-gradient GEMMs of already finished steps run on a side stream
  *         while an adjoint pressure solve keeps only B SMs busy, 0 = all of them after the adjoint sweep
+ *   "wgrad_window_us" (tuning) time budget of one such window at 128x64, default 110
  *   "conv_chain" 1 = consecutive tensor-core conv layers of the unrolled sweep are chained by per-tile
  *         completion flags (a tile starts when the tiles under its halo are stored), 0 (default) = whole-kernel dependencies
  *   "pdl" 1 (default) = kernels are launched with programmatic stream serialization (the prologue of a kernel

@@ -623,6 +623,7 @@ __global__ void __launch_bounds__(NT, 1) k_cg_mg3(const MgArgs a) {
         if (ak) act |= 1u << k;
         regular = regular && ak && (a.diag[c] == 4.0f);
         x[k] = 0.0f;
+        p[k] = 0.0f;
     }
     regular = __all_sync(0xffffffffu, regular);
     pdl_sync();        // everything above reads only plan constants (masks, hierarchy)
@@ -698,8 +699,8 @@ __global__ void __launch_bounds__(NT, 1) k_cg_mg3(const MgArgs a) {
                 z[k + 1] += (regular || ((act >> (k + 1)) & 1u)) ? zn : 0.0f;
             }
         }
-        fine_smooth();
-        fine_smooth();
+#pragma unroll 1
+        for (int sweep = 0; sweep < 2; ++sweep) fine_smooth();     // post-smoothing (one inlined copy)
     };
 
     int par = 0;
@@ -710,12 +711,21 @@ __global__ void __launch_bounds__(NT, 1) k_cg_mg3(const MgArgs a) {
     const float tol = fmaxf(a.tol_abs, a.tol_rel * rmax);
     int it = 0;
     if (rmax > 0.0f && rmax >= tol && a.max_it > 0) {
-        vcycle();
+        // preconditioned CG with ONE inlined copy of the V-cycle (the kernel has to fit the instruction cache)
         float rz = 0.0f;
-#pragma unroll
-        for (int k = 0; k < R; ++k) { p[k] = z[k]; rz = fmaf(r[k], z[k], rz); }
-        rz = block_sum(rz, red, par, warp, lane, nwarps);
+        bool first = true;
+#pragma unroll 1
         while (true) {
+            vcycle();
+            float rz_new = 0.0f;
+#pragma unroll
+            for (int k = 0; k < R; ++k) rz_new = fmaf(r[k], z[k], rz_new);
+            rz_new = block_sum(rz_new, red, par, warp, lane, nwarps);
+            const float beta = (first || rz == 0.0f) ? 0.0f : __fdividef(rz_new, rz);
+            first = false;
+            rz = rz_new;
+#pragma unroll
+            for (int k = 0; k < R; ++k) p[k] = fmaf(beta, p[k], z[k]);
             const float* t = publish(p);
             float pq;
             if (regular) pq = FR::apply(t, p, z, act, dg);
@@ -732,15 +742,6 @@ __global__ void __launch_bounds__(NT, 1) k_cg_mg3(const MgArgs a) {
             rmax = block_max(rmax, red, par, warp, lane, nwarps);
             ++it;
             if (!(rmax > 0.0f && rmax >= tol) || it >= a.max_it) break;
-            vcycle();
-            float rz_new = 0.0f;
-#pragma unroll
-            for (int k = 0; k < R; ++k) rz_new = fmaf(r[k], z[k], rz_new);
-            rz_new = block_sum(rz_new, red, par, warp, lane, nwarps);
-            const float beta = (rz != 0.0f) ? __fdividef(rz_new, rz) : 0.0f;
-            rz = rz_new;
-#pragma unroll
-            for (int k = 0; k < R; ++k) p[k] = fmaf(beta, p[k], z[k]);
         }
     }
     if (a.iters && tid == 0) a.iters[b] = it;

@@ -249,6 +249,11 @@ extern "C" int sol_set_option(const char* name, int value) {
         sol::g_wgrad_path = value == 0 ? 2 : value;
         return SOL_OK;
     }
+    if (strcmp(name, "wgrad_window_us") == 0) {
+        SOL_CHECK(value >= 0 && value <= 10000, "wgrad_window_us out of range");
+        sol::g_wgrad_window_us = value;
+        return SOL_OK;
+    }
     if (strcmp(name, "wgrad_overlap") == 0) {
         sol::g_wgrad_overlap = value ? 1 : 0;
         return SOL_OK;
@@ -743,7 +748,8 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
         if (l == 0 || l == 11) return 4.0f + 7.0f * (float)n * (float)tiles_step / 192.0f;
         return 15.0f + 7.5f * (float)(((long)tiles_step * n + nct32 - 1) / nct32);
     };
-    const float window_us = 110.0f * (float)(p->Y * p->X) / 8192.0f;      // adjoint solve + advection adjoint on this grid
+    // adjoint solve + advection adjoint on this grid (option "wgrad_window_us" overrides the 128x64 figure)
+    const float window_us = (float)sol::g_wgrad_window_us * (float)(p->Y * p->X) / 8192.0f;
     auto fill_window = [&](cudaStream_t s, int i, float budget) -> int {
         float left = budget;
         bool any = false;

@@ -186,6 +186,7 @@ int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, con
 int tc_tiles_per_launch(int B, int Y, int X);
 extern int g_conv_chain;
 extern int g_wgrad_overlap;
+extern int g_wgrad_window_us;
 // 32->32 layers: tensor-core path when enabled (wprep = pre-split weights or NULL for internal scratch), else SIMT
 int launch_conv5x5_c32_auto(cudaStream_t st, int B, int Y, int X, const float* in, const float* w, const float* wprep,
                             const float* bias, const float* addend, const float* ref, int act, float slope, float* out);

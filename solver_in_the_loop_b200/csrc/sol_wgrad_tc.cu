@@ -273,6 +273,7 @@ int launch_colsum32(cudaStream_t st, const float* g, size_t npix, float* db) {
 // in: activations of `steps` unrolled steps, image (step, b) at in + step*in_step_stride + b*Y*X*32 floats;
 // g:  output gradients, image (step, b) at g + step*g_step_stride + b*Y*X*32.
 // part: sm_count x (25*32*32+32) floats; dW = sum over CTAs (k_wgrad_finalize).
+int g_wgrad_window_us = 110;   // time budget of one solve window at 128x64 (scaled with the cell count)
 int g_wgrad_overlap = 1;    // deferred weight-gradient GEMMs run beside the adjoint pressure solves (see sol_engine.cu)
 
 int launch_wgrad_c32_tc(cudaStream_t st, int sm_count, int steps, int B, int Y, int X, const float* in, size_t in_step_stride,
