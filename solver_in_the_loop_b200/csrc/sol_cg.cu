@@ -338,11 +338,16 @@ static bool cg_geometry(int Y, int X, int want_cl, int want_r, int& CL, int& R, 
     return false;
 }
 
+bool cg_fuses(const sol_plan* p) {
+    return p->boundary == SOL_BOUNDARY_OPEN && p->cg_precond && p->cluster <= 1 && mg3_selected(p);
+}
+
 int launch_cg(const sol_plan* p, cudaStream_t st, int B, int mode, const float* rhs, float* p_out, const float* vy,
-              const float* vx, float* vy_out, float* vx_out, int* iters) {
+              const float* vx, float* vy_out, float* vx_out, int* iters, const CgFuse* fuse) {
     if (p->boundary != SOL_BOUNDARY_OPEN) return fail(SOL_ERR_UNSUPPORTED, "pressure solve requires an OPEN-boundary plan");
     if (p->cg_precond && p->cluster <= 1 && mg_supported(p))
-        return launch_cg_mg(p, st, B, mode, rhs, p_out, vy, vx, vy_out, vx_out, iters);
+        return launch_cg_mg(p, st, B, mode, rhs, p_out, vy, vx, vy_out, vx_out, iters, fuse);
+    if (fuse && (fuse->feat_out || fuse->gfeat_in)) return fail(SOL_ERR_UNSUPPORTED, "cg: fused feature I/O is not available for this solver variant (see cg_fuses)");
     CgArgs a;
     a.Y = p->Y; a.X = p->X; a.B = B;
     a.diag = p->diag; a.active = p->active; a.my = p->face_my; a.mx = p->face_mx;

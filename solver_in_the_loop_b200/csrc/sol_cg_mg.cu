@@ -46,6 +46,8 @@ struct MgArgs {
     int coff[MG_MAX_LEVELS];      // offset of level l (>= 1) in dinv_g / diag_g
     const float* dinv_g;          // -omega/diag (0 on solid cells), levels 1..nlev-2
     const float* diag_g;
+    // fused feature output / feature-gradient input (CgFuse), compile-time-hierarchy kernel only
+    float* feat_out; const float* re; float isy, isx, isr; const float* gfeat_in; int cfeat;
     const float* cinv;            // coarsest inverse [Nc*Nc]
     float omega;
     // shared-memory offsets (floats)
@@ -627,16 +629,26 @@ __global__ void __launch_bounds__(NT, 1) k_cg_mg3(const MgArgs a) {
     }
     regular = __all_sync(0xffffffffu, regular);
     pdl_sync();        // everything above reads only plan constants (masks, hierarchy)
+    // incoming velocity (MODE 1), optionally plus the feature gradient of the correction network (fused feat_bwd)
+    const float* gfb = (MODE == 1 && a.gfeat_in) ? a.gfeat_in + (size_t)b * NC * a.cfeat : nullptr;
+    auto in_y = [&](int j, int i) -> float {
+        float v = a.vy_in[(size_t)b * NY + j * X + i];
+        if (gfb && j < Y) v = fmaf(gfb[((size_t)j * X + i) * a.cfeat], a.isy, v);
+        return v;
+    };
+    auto in_x = [&](int j, int i) -> float {
+        float v = a.vx_in[(size_t)b * NX + j * (X + 1) + i];
+        if (gfb && i < X) v = fmaf(gfb[((size_t)j * X + i) * a.cfeat + 1], a.isx, v);
+        return v;
+    };
     if (MODE == 1) {
-        const float* vy = a.vy_in + (size_t)b * NY;
-        const float* vx = a.vx_in + (size_t)b * NX;
-        float vlo = a.my[j0 * X + tx] * vy[j0 * X + tx];
+        float vlo = a.my[j0 * X + tx] * in_y(j0, tx);
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             const int j = j0 + k;
-            const float vhi = a.my[(j + 1) * X + tx] * vy[(j + 1) * X + tx];
-            const float xl = a.mx[j * (X + 1) + tx] * vx[j * (X + 1) + tx];
-            const float xr = a.mx[j * (X + 1) + tx + 1] * vx[j * (X + 1) + tx + 1];
+            const float vhi = a.my[(j + 1) * X + tx] * in_y(j + 1, tx);
+            const float xl = a.mx[j * (X + 1) + tx] * in_x(j, tx);
+            const float xr = a.mx[j * (X + 1) + tx + 1] * in_x(j, tx + 1);
             r[k] = (vhi - vlo) + (xr - xl);
             vlo = vhi;
         }
@@ -758,20 +770,26 @@ __global__ void __launch_bounds__(NT, 1) k_cg_mg3(const MgArgs a) {
     }
     {
         const float* t = publish(x);
-        const float* vy = a.vy_in + (size_t)b * NY;
-        const float* vx = a.vx_in + (size_t)b * NX;
         float* vyo = a.vy_out + (size_t)b * NY;
         float* vxo = a.vx_out + (size_t)b * NX;
+        float* fo = a.feat_out ? a.feat_out + (size_t)b * NC * a.cfeat : nullptr;     // fused to_feature of the projected velocity
+        const float fre = fo ? a.re[b] * a.isr : 0.0f;
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             const int j = j0 + k;
             const float pdn = (k > 0) ? x[k - 1] : t[(k - 1) * PITCH];
             const float plf = t[k * PITCH - 1];
-            vyo[j * X + tx] = a.my[j * X + tx] * (vy[j * X + tx] - (x[k] - pdn));
-            vxo[j * (X + 1) + tx] = a.mx[j * (X + 1) + tx] * (vx[j * (X + 1) + tx] - (x[k] - plf));
-            if (tx == X - 1) vxo[j * (X + 1) + X] = a.mx[j * (X + 1) + X] * (vx[j * (X + 1) + X] + x[k]);
+            const float oy = a.my[j * X + tx] * (in_y(j, tx) - (x[k] - pdn));
+            const float ox = a.mx[j * (X + 1) + tx] * (in_x(j, tx) - (x[k] - plf));
+            vyo[j * X + tx] = oy;
+            vxo[j * (X + 1) + tx] = ox;
+            if (tx == X - 1) vxo[j * (X + 1) + X] = a.mx[j * (X + 1) + X] * (in_x(j, X) + x[k]);
+            if (fo) {
+                float* f = fo + ((size_t)j * X + tx) * a.cfeat;
+                f[0] = oy * a.isy; f[1] = ox * a.isx; f[2] = fre;
+            }
         }
-        if (j0 + R == Y) vyo[Y * X + tx] = a.my[Y * X + tx] * (vy[Y * X + tx] + x[R - 1]);
+        if (j0 + R == Y) vyo[Y * X + tx] = a.my[Y * X + tx] * (in_y(Y, tx) + x[R - 1]);
         if (a.p_out) {
             float* po = a.p_out + (size_t)b * NC;
 #pragma unroll
@@ -818,8 +836,14 @@ bool mg_supported(const sol_plan* p) {
     return false;
 }
 
+bool mg3_selected(const sol_plan* p) {
+    const sol_mg& h = p->mg;
+    return mg_supported(p) && p->mg_variant != 2 && p->Y == 2 * p->X && h.nlev == ((p->X == 64) ? 5 : 4) &&
+           h.LY[h.nlev - 1] * h.LX[h.nlev - 1] == 32;
+}
+
 int launch_cg_mg(const sol_plan* p, cudaStream_t st, int B, int mode, const float* rhs, float* p_out, const float* vy,
-                 const float* vx, float* vy_out, float* vx_out, int* iters) {
+                 const float* vx, float* vy_out, float* vx_out, int* iters, const CgFuse* fuse) {
     const sol_mg& h = p->mg;
     MgArgs a;
     memset(&a, 0, sizeof(a));
@@ -834,7 +858,13 @@ int launch_cg_mg(const sol_plan* p, cudaStream_t st, int B, int mode, const floa
     if (!R) return fail(SOL_ERR_UNSUPPORTED, "cg_mg: no thread geometry for this grid");
     const int TY = p->Y / R;
     for (int l = 0; l < h.nlev; ++l) { a.LY[l] = h.LY[l]; a.LX[l] = h.LX[l]; a.coff[l] = h.coff[l]; }
-    if (p->mg_variant != 2 && p->Y == 2 * p->X && h.nlev == ((p->X == 64) ? 5 : 4) && h.LY[h.nlev - 1] * h.LX[h.nlev - 1] == 32) {
+    if (fuse && (fuse->feat_out || fuse->gfeat_in)) {
+        if (!mg3_selected(p) || mode != 1) return fail(SOL_ERR_UNSUPPORTED, "cg_mg: fused feature I/O needs the compile-time-hierarchy kernel (see cg_fuses)");
+        if (fuse->cfeat < 3 && fuse->feat_out) return fail(SOL_ERR_UNSUPPORTED, "cg_mg: fused feature output needs >= 3 feature channels");
+        a.feat_out = fuse->feat_out; a.re = fuse->re; a.isy = fuse->isy; a.isx = fuse->isx; a.isr = fuse->isr;
+        a.gfeat_in = fuse->gfeat_in; a.cfeat = fuse->cfeat;
+    }
+    if (mg3_selected(p)) {
         // compile-time hierarchy (v3)
 #define SOL_MG3_CASE(XX, RR, NTT)                                                  \
         if (p->X == XX && R == RR) {                                               \

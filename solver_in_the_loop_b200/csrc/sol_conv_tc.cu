@@ -103,7 +103,7 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
     }
     if (warp == 0 && lane == 0) {
         mbar_init(bar_afull, 1);
-        mbar_init(bar_asplit, 128);
+        mbar_init(bar_asplit, TC_THREADS);
         mbar_init(bar_acc, 1);
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -119,12 +119,12 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
     const uint32_t tmem_acc = *tmem_slot;
     if (threadIdx.x == 0) tc_stamp(a.trace, 3);      // set-up done (barriers, TMEM)
 
+    const int npre = a.weights_ready ? TC_STAGES : 0;
     if (warp == 0) {
-        // ================= TMA producer (warp-uniform control flow, one elected lane issues) =================
+        // ================= TMA producer, part 1 (warp-uniform control flow, one elected lane issues) =================
         const bool leader = elect_one();
         // Weights that were ready before the predecessor kernel started do not depend on it: fill the ring
         // before waiting for the predecessor (programmatic dependent launch), then fetch the halo tile.
-        const int npre = a.weights_ready ? TC_STAGES : 0;
         for (int n = 0; n < npre; ++n) {
             int tap = tap0 + n; if (tap >= 25) tap -= 25;
             if (leader) {
@@ -159,6 +159,40 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
             mbar_arrive_expect_tx(bar_afull, TC_A_BYTES);
             tma_load_4d(s_ahi, &map_in, bar_afull, 0, x0 - 2, y0 - 2, b);
         }
+    } else if (!a.dep_flags) {
+        pdl_wait();
+    }
+
+    // ================= operand split by ALL warps: hi = rn_tf32(x) in place, lo = rn_tf32(x - hi) =================
+    mbar_wait(bar_afull, 0);
+    // The next kernel of the stream may become resident from here on: this CTA no longer reads its input from
+    // global memory, and every producer tile under its halo is complete (the first launch_dependents of a CTA counts).
+    if (threadIdx.x == 64) pdl_trigger();
+    if (threadIdx.x == 64) tc_stamp(a.trace, 4);            // halo tile landed
+    {
+        float4* hi4 = reinterpret_cast<float4*>(gbase + TC_OFF_AHI);
+        float4* lo4 = reinterpret_cast<float4*>(gbase + TC_OFF_ALO);
+        static_assert(TC_A_BYTES / 16 % TC_THREADS == 0, "split geometry");
+#pragma unroll 5
+        for (int it = 0; it < TC_A_BYTES / 16 / TC_THREADS; ++it) {      // 10 float4 per thread, 5 loads in flight
+            const int i = (int)threadIdx.x + it * TC_THREADS;
+            const float4 v = hi4[i];
+            float4 h, l;
+            h.x = tf32_rn(v.x); l.x = tf32_rn(v.x - h.x);
+            h.y = tf32_rn(v.y); l.y = tf32_rn(v.y - h.y);
+            h.z = tf32_rn(v.z); l.z = tf32_rn(v.z - h.z);
+            h.w = tf32_rn(v.w); l.w = tf32_rn(v.w - h.w);
+            hi4[i] = h;
+            lo4[i] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
+        mbar_arrive(bar_asplit);
+    }
+    if (threadIdx.x == 64) tc_stamp(a.trace, 5);            // split done (this thread)
+
+    if (warp == 0) {
+        // ================= TMA producer, part 2: keep the weight ring full =================
+        const bool leader = elect_one();
 #pragma unroll 1
         for (int n = npre; n < 25; ++n) {
             const int s = n % TC_STAGES;
@@ -179,7 +213,6 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
         // Accumulations into the same TMEM tile serialise on the MMA latency and the tensor core
         // accumulates with truncation, so two independent accumulator sets are used alternately and
         // summed with RN fp32 adds in the epilogue.
-        if (!a.dep_flags) pdl_wait();
         const bool leader = elect_one();
         const uint64_t dA_hi = make_desc(s_ahi, TC_HW * 128, 0);
         const uint64_t dA_lo = make_desc(s_alo, TC_HW * 128, 0);
@@ -216,31 +249,6 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
     } else {
         // ================= splitter, then epilogue (warps 2..5 = 128 threads) =================
         const int t = threadIdx.x - 64;
-        if (!a.dep_flags) pdl_wait();
-        mbar_wait(bar_afull, 0);
-        // The next kernel of the stream may become resident from here on: this CTA no longer reads its input from
-        // global memory, and every producer tile under its halo is complete (the first launch_dependents of a CTA counts).
-        if (t == 0) pdl_trigger();
-        if (t == 0) tc_stamp(a.trace, 4);            // halo tile landed
-        float4* hi4 = reinterpret_cast<float4*>(gbase + TC_OFF_AHI);
-        float4* lo4 = reinterpret_cast<float4*>(gbase + TC_OFF_ALO);
-        static_assert(TC_A_BYTES / 16 % 128 == 0, "split geometry");
-#pragma unroll 5
-        for (int it = 0; it < TC_A_BYTES / 16 / 128; ++it) {      // 15 float4 per thread, 5 loads in flight
-            const int i = t + it * 128;
-            const float4 v = hi4[i];
-            float4 h, l;
-            h.x = tf32_rn(v.x); l.x = tf32_rn(v.x - h.x);
-            h.y = tf32_rn(v.y); l.y = tf32_rn(v.y - h.y);
-            h.z = tf32_rn(v.z); l.z = tf32_rn(v.z - h.z);
-            h.w = tf32_rn(v.w); l.w = tf32_rn(v.w - h.w);
-            hi4[i] = h;
-            lo4[i] = l;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
-        mbar_arrive(bar_asplit);
-        if (t == 0) tc_stamp(a.trace, 5);            // split done (this thread)
-
         // ---- epilogue: TMEM lane = pixel row of the tile, 32 columns = cout ----
         const int q = warp & 3;                 // this warp may touch TMEM lanes [32q, 32q+32)
         const int r = q * 32 + lane;            // accumulator row = pixel
@@ -274,9 +282,8 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
         float acc[32];
 #pragma unroll
         for (int c = 0; c < 8; ++c) { acc[4 * c] = ad[c].x; acc[4 * c + 1] = ad[c].y; acc[4 * c + 2] = ad[c].z; acc[4 * c + 3] = ad[c].w; }
-#pragma unroll 1
-        for (int j = 0; j < 3 * TC_NSET; ++j) {       // per set: hh, hl, lh column blocks
-            uint32_t v[32];
+        // six 32-column blocks (per set: hh, hl, lh), two loads in flight per wait
+        auto tmem_ld32 = [&](uint32_t (&v)[32], int j) {
             const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + 32u * (uint32_t)j;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -287,9 +294,15 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                 : "r"(taddr));
+        };
+#pragma unroll 1
+        for (int j = 0; j < 3 * TC_NSET; j += 2) {
+            uint32_t v0[32], v1[32];
+            tmem_ld32(v0, j);
+            tmem_ld32(v1, j + 1);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int c = 0; c < 32; ++c) acc[c] += __uint_as_float(v[c]);
+            for (int c = 0; c < 32; ++c) acc[c] += __uint_as_float(v0[c]) + __uint_as_float(v1[c]);
         }
         // Output tile -> shared memory (the A_lo tile is free once the accumulators are complete) in the 128B-swizzled
         // layout of the output tensor map, then ONE bulk tensor store per CTA: full 128-byte lines instead of 16-byte

@@ -249,6 +249,14 @@ extern "C" int sol_set_option(const char* name, int value) {
         sol::g_wgrad_path = value == 0 ? 2 : value;
         return SOL_OK;
     }
+    if (strcmp(name, "fuse_solver_io") == 0) {
+        sol::g_fuse_solver_io = value ? 1 : 0;
+        return SOL_OK;
+    }
+    if (strcmp(name, "fuse_small") == 0) {
+        sol::g_fuse_small = value ? 1 : 0;
+        return SOL_OK;
+    }
     if (strcmp(name, "wgrad_window_us") == 0) {
         SOL_CHECK(value >= 0 && value <= 10000, "wgrad_window_us out of range");
         sol::g_wgrad_window_us = value;
@@ -672,6 +680,7 @@ int do_forward(sol_unroll* u, cudaStream_t st, const float* weights, const float
     }
     u->tc_seq = 0; u->tc_prev = nullptr;
     const float* cvy = vy0; const float* cvx = vx0; const float* crho = dens ? rho0 : nullptr;
+    const bool fuse_io = sol::g_fuse_solver_io && cg_fuses(p);
     for (int i = 0; i < m; ++i) {
         StepStash& s = u->stash[i];
         float* nvy = pred_vy ? pred_vy + (size_t)i * NY : ((i & 1) ? u->sB_vy : u->sA_vy);
@@ -679,8 +688,13 @@ int do_forward(sol_unroll* u, cudaStream_t st, const float* weights, const float
         float* nrho = dens ? (pred_rho ? pred_rho + (size_t)i * NC : ((i & 1) ? u->rhoB : u->rhoA)) : nullptr;
         SOL_TRY(launch_diffuse_bc(p, st, B, re, c.dt, c.res, cvy, cvx, s.vy1, s.vx1));
         SOL_TRY(launch_advect(p, st, B, c.dt, s.vy1, s.vx1, crho, u->vy2, u->vx2, nrho));
-        SOL_TRY(launch_cg(p, st, B, 1, nullptr, nullptr, u->vy2, u->vx2, u->vy3, u->vx3, u->iters + (size_t)i * B));
-        SOL_TRY(launch_to_feature(p, st, B, u->vy3, u->vx3, re, c.sig_vy, c.sig_vx, c.sig_ext, s.feat));
+        if (fuse_io && c.cin0 == 3) {      // the projection kernel also writes the CNN features of the projected velocity
+            CgFuse f; f.feat_out = s.feat; f.re = re; f.isy = 1.0f / c.sig_vy; f.isx = 1.0f / c.sig_vx; f.isr = 1.0f / c.sig_ext; f.cfeat = 3;
+            SOL_TRY(launch_cg(p, st, B, 1, nullptr, nullptr, u->vy2, u->vx2, u->vy3, u->vx3, u->iters + (size_t)i * B, &f));
+        } else {
+            SOL_TRY(launch_cg(p, st, B, 1, nullptr, nullptr, u->vy2, u->vx2, u->vy3, u->vx3, u->iters + (size_t)i * B));
+            SOL_TRY(launch_to_feature(p, st, B, u->vy3, u->vx3, re, c.sig_vy, c.sig_vx, c.sig_ext, s.feat));
+        }
         SOL_TRY(cnn_forward(u, st, weights, s, u->corr));
         SOL_TRY(launch_correct_loss(p, st, B, u->vy3, u->vx3, u->corr, c.sig_vy, c.sig_vx, gt_vy ? gt_vy + (size_t)i * NY : nullptr,
                                     gt_vx ? gt_vx + (size_t)i * NX : nullptr, 1.0f / (float)m, nvy, nvx, s.gl_vy, s.gl_vx,
@@ -778,12 +792,14 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
 
     const float* Gy = u->stash[m - 1].gl_vy;
     const float* Gx = u->stash[m - 1].gl_vx;
+    const bool fuse_io = sol::g_fuse_solver_io && cg_fuses(p);
+    bool corr_ready = false;
     for (int i = m - 1; i >= 0; --i) {
         StepStash& s = u->stash[i];
         float* g_corr = u->deferred_wgrad ? u->gcorr_st + (size_t)i * p->NC() * B * 2 : u->g_corr;
-        SOL_TRY(launch_corr_bwd(p, st, B, Gy, Gx, c.sig_vy, c.sig_vx, g_corr));
+        if (!corr_ready) SOL_TRY(launch_corr_bwd(p, st, B, Gy, Gx, c.sig_vy, c.sig_vx, g_corr));   // else: written by diffuse_bc_bwd of step i+1
         SOL_TRY(cnn_backward(u, st, weights, gw, s, g_corr, u->g_feat, i == m - 1, i));
-        SOL_TRY(launch_feat_bwd(p, st, B, Gy, Gx, u->g_feat, c.cin0, c.sig_vy, c.sig_vx, u->H_vy, u->H_vx));
+        if (!fuse_io) SOL_TRY(launch_feat_bwd(p, st, B, Gy, Gx, u->g_feat, c.cin0, c.sig_vy, c.sig_vx, u->H_vy, u->H_vx));
         bool joined = true;
         if (overlap && i > 0) {     // the items of the last window would only delay the end of the sweep: they are merged below
             SOL_CUDA(cudaEventRecord(u->ev_wfork, st));
@@ -792,12 +808,21 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
             SOL_CUDA(cudaEventRecord(u->ev_wjoin, u->sstream));
             joined = false;
         }
-        SOL_TRY(launch_cg(p, st, B, 1, nullptr, nullptr, u->H_vy, u->H_vx, u->K_vy, u->K_vx, u->iters + (size_t)(m + i) * B));
+        if (fuse_io) {      // the adjoint projection adds the feature gradient to the incoming velocity gradient itself
+            CgFuse f; f.gfeat_in = u->g_feat; f.isy = 1.0f / c.sig_vy; f.isx = 1.0f / c.sig_vx; f.cfeat = c.cin0;
+            SOL_TRY(launch_cg(p, st, B, 1, nullptr, nullptr, Gy, Gx, u->K_vy, u->K_vx, u->iters + (size_t)(m + i) * B, &f));
+        } else {
+            SOL_TRY(launch_cg(p, st, B, 1, nullptr, nullptr, u->H_vy, u->H_vx, u->K_vy, u->K_vx, u->iters + (size_t)(m + i) * B));
+        }
         SOL_TRY(launch_advect_bwd(p, st, B, c.dt, s.vy1, s.vx1, u->K_vy, u->K_vx, u->H_vy, u->H_vx));
         if (!joined) SOL_CUDA(cudaStreamWaitEvent(st, u->ev_wjoin, 0));
         if (i > 0) {
             float* ny = u->G_vy[i & 1]; float* nx = u->G_vx[i & 1];
-            SOL_TRY(launch_diffuse_bc_bwd(p, st, B, re, c.dt, c.res, u->H_vy, u->H_vx, ny, nx, u->stash[i - 1].gl_vy, u->stash[i - 1].gl_vx));
+            float* gc_next = nullptr;       // fused corr_bwd of step i-1
+            if (sol::g_fuse_small) gc_next = u->deferred_wgrad ? u->gcorr_st + (size_t)(i - 1) * p->NC() * B * 2 : u->g_corr;
+            SOL_TRY(launch_diffuse_bc_bwd(p, st, B, re, c.dt, c.res, u->H_vy, u->H_vx, ny, nx, u->stash[i - 1].gl_vy, u->stash[i - 1].gl_vx,
+                                          gc_next, c.sig_vy, c.sig_vx));
+            corr_ready = gc_next != nullptr;
             Gy = ny; Gx = nx;
         } else if (g_vy0 && g_vx0) {
             SOL_TRY(launch_diffuse_bc_bwd(p, st, B, re, c.dt, c.res, u->H_vy, u->H_vx, g_vy0, g_vx0, nullptr, nullptr));

@@ -125,7 +125,8 @@ namespace sol {
 int launch_diffuse_bc(const sol_plan* p, cudaStream_t st, int B, const float* re, float dt, float res,
                       const float* vy, const float* vx, float* vy_out, float* vx_out);
 int launch_diffuse_bc_bwd(const sol_plan* p, cudaStream_t st, int B, const float* re, float dt, float res,
-                          const float* gy, const float* gx, float* gy_in, float* gx_in, const float* add_y, const float* add_x);
+                          const float* gy, const float* gx, float* gy_in, float* gx_in, const float* add_y, const float* add_x,
+                          float* g_corr = nullptr, float sy = 1.0f, float sx = 1.0f);
 int launch_advect(const sol_plan* p, cudaStream_t st, int B, float dt, const float* vy, const float* vx, const float* rho,
                   float* vy_out, float* vx_out, float* rho_out);
 int launch_advect_bwd(const sol_plan* p, cudaStream_t st, int B, float dt, const float* vy, const float* vx,
@@ -149,13 +150,25 @@ int launch_adam(cudaStream_t st, size_t n, float* theta, const float* g, float* 
                 float eps, float gscale);
 
 // ---- pressure projection (sol_cg.cu) ----
+// Optional work fused into the projection kernel (only the compile-time-hierarchy multigrid kernel implements it,
+// see cg_fuses()): the CNN feature tensor of the projected velocity (to_feature, karman_train.py:77-86,416-420) as an
+// extra output, and the feature gradient added to the incoming velocity gradient (adjoint of the same op) as input.
+struct CgFuse {
+    float* feat_out = nullptr;          // [B,Y,X,cfeat]: (vy_out[j,i]/sig_y, vx_out[j,i]/sig_x, re[b]/sig_r)
+    const float* re = nullptr;
+    float isy = 0.f, isx = 0.f, isr = 0.f;
+    const float* gfeat_in = nullptr;    // [B,Y,X,cfeat]: vy_in[j,i] += gfeat[...,0]*isy (j < Y), vx_in[j,i] += gfeat[...,1]*isx (i < X)
+    int cfeat = 3;
+};
+bool cg_fuses(const sol_plan* p);
 int launch_cg(const sol_plan* p, cudaStream_t st, int B, int mode, const float* rhs, float* p_out, const float* vy,
-              const float* vx, float* vy_out, float* vx_out, int* iters);
+              const float* vx, float* vy_out, float* vx_out, int* iters, const CgFuse* fuse = nullptr);
 
 // ---- multigrid-preconditioned CG (sol_cg_mg.cu) ----
 bool mg_supported(const sol_plan* p);
 int launch_cg_mg(const sol_plan* p, cudaStream_t st, int B, int mode, const float* rhs, float* p_out, const float* vy,
-                 const float* vx, float* vy_out, float* vx_out, int* iters);
+                 const float* vx, float* vy_out, float* vx_out, int* iters, const CgFuse* fuse = nullptr);
+bool mg3_selected(const sol_plan* p);
 
 // ---- convolutions (sol_conv.cu) ----
 int launch_conv5x5(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const float* in, const float* w, const float* bias,
@@ -185,6 +198,8 @@ int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, con
                       const int* dep_flags = nullptr, int* out_flags = nullptr);
 int tc_tiles_per_launch(int B, int Y, int X);
 extern int g_conv_chain;
+extern int g_fuse_small;
+extern int g_fuse_solver_io;
 extern int g_wgrad_overlap;
 extern int g_wgrad_window_us;
 // 32->32 layers: tensor-core path when enabled (wprep = pre-split weights or NULL for internal scratch), else SIMT

@@ -14,6 +14,9 @@ namespace sol {
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
 int g_pdl = 1;
+int g_fuse_small = 1;        // fold corr_bwd (correction-gradient scaling) into diffuse_bc_bwd
+int g_fuse_solver_io = 0;    // fold to_feature / feat_bwd into the projection kernel: measured SLOWER (the extra loads and stores
+                             // run on the solve's B CTAs instead of the whole machine), kept for one-simulation-per-SM batches
 
 static inline int grid_for(size_t n, int threads, int sm_count) {
     size_t blocks = (n + threads - 1) / threads;
@@ -57,7 +60,8 @@ __global__ void __launch_bounds__(256) k_diffuse_bc_bwd(int B, int Y, int X, con
                                                         const float* __restrict__ gy, const float* __restrict__ gx,
                                                         const float* __restrict__ bcm,
                                                         const float* __restrict__ add_y, const float* __restrict__ add_x,
-                                                        float* __restrict__ gy_in, float* __restrict__ gx_in) {
+                                                        float* __restrict__ gy_in, float* __restrict__ gx_in,
+                                                        float* __restrict__ g_corr, float sy, float sx) {
     pdl_sync();
     const int NY = (Y + 1) * X, NX = Y * (X + 1), NF = NY + NX;
     const size_t total = (size_t)B * NF;
@@ -70,11 +74,14 @@ __global__ void __launch_bounds__(256) k_diffuse_bc_bwd(int B, int Y, int X, con
             float v = diffuse_bc_bwd_cell(gy + (size_t)b * NY, Y + 1, X, f.j, f.i, alpha, bcm);
             if (add_y) v += add_y[o];
             gy_in[o] = v;
+            // fused corr_bwd of the step that consumes this gradient: g_corr[b,j,i,0] = sigma_y * G_y[b,j,i]
+            if (g_corr && f.j < Y) g_corr[((size_t)b * Y * X + f.j * X + f.i) * 2 + 0] = sy * v;
         } else {
             const size_t o = (size_t)b * NX + f.j * (X + 1) + f.i;
             float v = diffuse_bc_bwd_cell(gx + (size_t)b * NX, Y, X + 1, f.j, f.i, alpha, nullptr);
             if (add_x) v += add_x[o];
             gx_in[o] = v;
+            if (g_corr && f.i < X) g_corr[((size_t)b * Y * X + f.j * X + f.i) * 2 + 1] = sx * v;
         }
     }
 }
@@ -89,10 +96,11 @@ int launch_diffuse_bc(const sol_plan* p, cudaStream_t st, int B, const float* re
 }
 
 int launch_diffuse_bc_bwd(const sol_plan* p, cudaStream_t st, int B, const float* re, float dt, float res,
-                          const float* gy, const float* gx, float* gy_in, float* gx_in, const float* add_y, const float* add_x) {
+                          const float* gy, const float* gx, float* gy_in, float* gx_in, const float* add_y, const float* add_x,
+                          float* g_corr, float sy, float sx) {
     const size_t total = (size_t)B * (p->NY() + p->NX());
     SOL_CUDA(launch_kernel(k_diffuse_bc_bwd, dim3(grid_for(total, 256, p->sm_count)), dim3(256), 0, st, B, p->Y, p->X, re, dt * res * res, gy, gx, p->bc_mask_y,
-                                                                        add_y, add_x, gy_in, gx_in));
+                                                                        add_y, add_x, gy_in, gx_in, g_corr, sy, sx));
     SOL_LAUNCHED();
     return SOL_OK;
 }

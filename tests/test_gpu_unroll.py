@@ -32,13 +32,13 @@ def _setup(Y, X, B, m, device, use_graph=False, spin=25):
 
 
 _PATHS = {
-    # id: (conv_path, wgrad_path, pdl, conv_chain, wgrad_overlap)
-    "simt": (1, 1, 1, 0, 1),
-    "tcgen05-conv": (2, 1, 1, 0, 1),
-    "tcgen05-conv+wgrad": (2, 2, 1, 0, 1),
-    "tcgen05-conv+wgrad-tilechain": (2, 2, 1, 1, 1),
-    "tcgen05-conv+wgrad-serial": (2, 2, 1, 0, 0),
-    "tcgen05-conv+wgrad-nopdl": (2, 2, 0, 0, 1),
+    # id: (conv_path, wgrad_path, pdl, conv_chain, wgrad_overlap, fuse_small, fuse_solver_io)
+    "simt": (1, 1, 1, 0, 1, 1, 0),
+    "tcgen05-conv": (2, 1, 1, 0, 1, 1, 0),
+    "tcgen05-conv+wgrad": (2, 2, 1, 0, 1, 1, 0),
+    "tcgen05-conv+wgrad-tilechain-solverio": (2, 2, 1, 1, 1, 1, 1),
+    "tcgen05-conv+wgrad-serial-unfused": (2, 2, 1, 0, 0, 0, 0),
+    "tcgen05-conv+wgrad-nopdl": (2, 2, 0, 0, 1, 1, 0),
 }
 
 
@@ -47,11 +47,11 @@ def conv_path(request):
     """Kernel families (SIMT / tcgen05), plain vs programmatic-dependent stream order, whole-kernel vs tile-flag
     dependencies between consecutive conv layers, weight gradients beside the adjoint solves vs after the sweep."""
     from solver_in_the_loop_b200 import engine
-    names = ("conv_path", "wgrad_path", "pdl", "conv_chain", "wgrad_overlap")
+    names = ("conv_path", "wgrad_path", "pdl", "conv_chain", "wgrad_overlap", "fuse_small", "fuse_solver_io")
     for n, v in zip(names, request.param):
         engine.set_option(n, v)
     yield request.param
-    for n, v in zip(names, (0, 0, 1, 0, 1)):
+    for n, v in zip(names, (0, 0, 1, 0, 1, 1, 0)):
         engine.set_option(n, v)
 
 
