@@ -61,8 +61,10 @@ def parse():
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_conv5x5_c32_tc launch at the bench shape, from the committed
 # `ncu --set full` capture (None until a capture of the current kernel is committed under profiles/)
-CONV_TC_DRAM_BYTES = None
-CONV_TC_DRAM_SOURCE = None
+CONV_TC_DRAM_BYTES = 4.95e6
+CONV_TC_DRAM_SOURCE = ("profiles/r01_b_ncu_top.md: mean of 8 launches, dram read 3.4-6.5 MB + write 0 (the 3.1 MB output tile stays in the "
+                       "126 MB L2 under ncu's replay); algorithmic: 3.15 MB in + 3.15 MB out + 0.2 MB weights")
+CG_MG_DRAM_BYTES = 0.42e6   # profiles/r01_b_ncu_top.md: k_cg_mg3 reads 0.42 MB, writes stay in L2 (compulsory: 20 B/cell = 0.49 MB)
 
 
 def load_peaks(key="hbm_gbs"):
@@ -395,7 +397,7 @@ def main():
         solver_name = ("k_cg_mg3 (fused projection: divergence + multigrid-preconditioned CG + gradient subtract)" if precond
                        else "k_cg (fused projection: divergence + CG + gradient subtract)")
         roof_solver = {"kernel": solver_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                       "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "cg_iters": K,
+                       "frac": achieved / peak, "traffic": CG_MG_DRAM_BYTES if (precond and (Y, X, B) == (128, 64, 3)) else None, "peak_source": peak_src, "cg_iters": K,
                        "us_per_launch": t_solve_max * 1e6, "algorithmic_bytes_per_launch": alg_bytes,
                        "launches_per_step": 2 * m, "share_of_step": 2 * m * t_solve_max / t_iter,
                        "note": "solver state is register/SMEM-resident (DRAM traffic ~20 B/cell regardless of K); achieved = "
@@ -405,7 +407,7 @@ def main():
             tf = conv_flops / t_conv_max / 1e12
             roof_conv = {"kernel": "k_conv5x5_c32_tc (tcgen05 3xTF32 implicit-GEMM 5x5 conv 32->32, fwd layers and data gradients)",
                          "bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
-                         "traffic": CONV_TC_DRAM_BYTES, "traffic_source": CONV_TC_DRAM_SOURCE,
+                         "traffic": CONV_TC_DRAM_BYTES if (Y, X, B) == (128, 64, 3) else None, "traffic_source": CONV_TC_DRAM_SOURCE,
                          "peak_source": tpeak_src + ", dense bf16 (tf32 issues at half that rate)", "us_per_launch": t_conv_max * 1e6,
                          "algorithmic_flops_per_launch": conv_flops, "executed_tensor_tflops": 3.0 * tf,
                          "launches_per_step": 20 * m, "share_of_step": 20 * m * t_conv_max / t_iter,

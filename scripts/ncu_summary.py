@@ -12,9 +12,11 @@ METRICS = [
     ("launch__registers_per_thread", "regs", 1.0),
     ("dram__bytes_read.sum", "dram rd", None),
     ("dram__bytes_write.sum", "dram wr", None),
-    ("lts__t_bytes.sum", "L2 bytes", None),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %", 1.0),
+    ("lts__t_sector_hit_rate.pct", "L2 hit %", 1.0),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM %", 1.0),
-    ("sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe % (active)", 1.0),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe % (active)", 1.0),
+    ("sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "tmem pipe %", 1.0),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU %", 1.0),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %", 1.0),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy %", 1.0),

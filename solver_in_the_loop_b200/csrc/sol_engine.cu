@@ -488,10 +488,14 @@ struct sol_unroll {
     float* re_buf;     // private copy of Re[B]: the adjoint sweep must not depend on the caller keeping `re` alive
     bool forward_done = false, have_loss = false;
     const float* last_re = nullptr;
+    // Burgers scene (PERIODIC plans, sol_unroll_set_burgers): viscosity, real-space diffusion kernels, per-step forces
+    bool burgers_set = false;
+    float visc = 0.1f, sig_fy = 1.f, sig_fx = 1.f;
+    const float *bk_y = nullptr, *bk_x = nullptr, *bf_vy = nullptr, *bf_vx = nullptr;
     unsigned long long graph_kernels = 0;
     // CUDA graph cache
     cudaGraphExec_t gexec = nullptr;
-    const void* gkey[9] = {nullptr};
+    const void* gkey[13] = {nullptr};
     int warm = 0;
     // graph work runs on a private non-blocking stream (the caller's may be the legacy default
     // stream, which cannot be captured); fork/join with events keeps the caller's stream ordering
@@ -561,9 +565,11 @@ int check_cfg(const sol_plan* p, const sol_unroll_cfg* c) {
     SOL_CHECK(p && c, "unroll: NULL plan / cfg");
     SOL_CHECK(c->msteps >= 1 && c->B >= 1 && c->B <= p->B_max, "unroll: bad msteps / batch");
     SOL_CHECK(c->sig_vy > 0.f && c->sig_vx > 0.f && c->sig_ext > 0.f, "unroll: sigmas must be positive");
-    SOL_CHECK(c->cin0 == 3, "unroll: karman features have 3 channels (vy, vx, Re)");
+    if (p->boundary == SOL_BOUNDARY_OPEN)
+        SOL_CHECK(c->cin0 == 3, "unroll: karman features have 3 channels (vy, vx, Re)");
+    else
+        SOL_CHECK(c->cin0 == 4 || c->cin0 == 2, "unroll: burgers features have 4 channels (vy, vx, fy, fx) or 2 (--noforce)");
     if (c->model != SOL_MODEL_MARS_MOON) return fail(SOL_ERR_UNSUPPORTED, "unroll: only model_mars_moon is implemented on the GPU path");
-    if (p->boundary != SOL_BOUNDARY_OPEN) return fail(SOL_ERR_UNSUPPORTED, "unroll: karman (OPEN) plans only");
     return SOL_OK;
 }
 
@@ -670,8 +676,15 @@ int do_forward(sol_unroll* u, cudaStream_t st, const float* weights, const float
     const int B = c.B, m = c.msteps;
     const size_t NY = p->NY() * B, NX = p->NX() * B, NC = p->NC() * B;
     const bool dens = c.with_density && rho0 != nullptr;
-    SOL_CUDA(cudaMemcpyAsync(u->re_buf, re, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
-    re = u->re_buf;
+    const bool burgers = p->boundary == SOL_BOUNDARY_PERIODIC;
+    if (burgers) {
+        SOL_CHECK(u->burgers_set, "unroll: PERIODIC plan without sol_unroll_set_burgers()");
+        SOL_CHECK(!dens, "unroll: the burgers scene has no marker density");
+    } else {
+        SOL_CHECK(re != nullptr, "unroll: Re[B] required for the karman scene");
+        SOL_CUDA(cudaMemcpyAsync(u->re_buf, re, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
+        re = u->re_buf;
+    }
     if (gt_vy) SOL_CUDA(cudaMemsetAsync(loss_steps, 0, sizeof(float) * m, st));
     if (sol::g_conv_path == 2) {
         for (int l = 1; l <= 10; ++l)
@@ -686,6 +699,23 @@ int do_forward(sol_unroll* u, cudaStream_t st, const float* weights, const float
         float* nvy = pred_vy ? pred_vy + (size_t)i * NY : ((i & 1) ? u->sB_vy : u->sA_vy);
         float* nvx = pred_vx ? pred_vx + (size_t)i * NX : ((i & 1) ? u->sB_vx : u->sA_vx);
         float* nrho = dens ? (pred_rho ? pred_rho + (size_t)i * NC : ((i & 1) ? u->rhoB : u->rhoA)) : nullptr;
+        if (burgers) {
+            // BurgersTest.step_with_f (burgers_train.py:178-187, 382-396): advect -> diffuse(nu*dt) -> + dt*f_i; the stash
+            // keeps the step's INPUT velocity (what the advection adjoint needs)
+            const float* fy = u->bf_vy ? u->bf_vy + (size_t)i * NY : nullptr;
+            const float* fx = u->bf_vx ? u->bf_vx + (size_t)i * NX : nullptr;
+            SOL_CUDA(cudaMemcpyAsync(s.vy1, cvy, sizeof(float) * NY, cudaMemcpyDeviceToDevice, st));
+            SOL_CUDA(cudaMemcpyAsync(s.vx1, cvx, sizeof(float) * NX, cudaMemcpyDeviceToDevice, st));
+            SOL_TRY(launch_advect(p, st, B, c.dt, s.vy1, s.vx1, nullptr, u->vy2, u->vx2, nullptr));
+            SOL_TRY(launch_burgers_diffuse(p, st, B, u->visc * c.dt, u->bk_y, u->bk_x, u->vy2, u->vx2, fy, fx, c.dt, u->vy3, u->vx3));
+            SOL_TRY(launch_to_feature_burgers(p, st, B, u->vy3, u->vx3, fy, fx, c.sig_vy, c.sig_vx, u->sig_fy, u->sig_fx, c.cin0, s.feat));
+            SOL_TRY(cnn_forward(u, st, weights, s, u->corr));
+            SOL_TRY(launch_correct_loss(p, st, B, u->vy3, u->vx3, u->corr, c.sig_vy, c.sig_vx, gt_vy ? gt_vy + (size_t)i * NY : nullptr,
+                                        gt_vx ? gt_vx + (size_t)i * NX : nullptr, 1.0f / (float)m, nvy, nvx, s.gl_vy, s.gl_vx,
+                                        gt_vy ? loss_steps + i : nullptr));
+            cvy = nvy; cvx = nvx;
+            continue;
+        }
         SOL_TRY(launch_diffuse_bc(p, st, B, re, c.dt, c.res, cvy, cvx, s.vy1, s.vx1));
         SOL_TRY(launch_advect(p, st, B, c.dt, s.vy1, s.vx1, crho, u->vy2, u->vx2, nrho));
         if (fuse_io && c.cin0 == 3) {      // the projection kernel also writes the CNN features of the projected velocity
@@ -728,7 +758,8 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
     bool started[12] = {false};
     const size_t in_stride = (m > 1) ? (size_t)(u->stash[1].acts[0] - u->stash[0].acts[0]) : u->nA;
     const int tiles_step = (p->X / 8) * (p->Y / 16) * B;
-    const bool overlap = u->deferred_wgrad && sol::g_wgrad_overlap && B + 17 <= p->sm_count;
+    const bool burgers = p->boundary == SOL_BOUNDARY_PERIODIC;      // no pressure solve, hence no solve windows
+    const bool overlap = u->deferred_wgrad && sol::g_wgrad_overlap && B + 17 <= p->sm_count && !burgers;
     const int sm_budget = overlap ? p->sm_count - B - 1 : p->sm_count;        // SMs left beside the solve's B CTAs
     const int nct32 = tiles_step < sm_budget ? tiles_step : sm_budget;          // fixed per sweep: the partial-sum slots must line up
     if (overlap && !u->sstream) {
@@ -792,7 +823,7 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
 
     const float* Gy = u->stash[m - 1].gl_vy;
     const float* Gx = u->stash[m - 1].gl_vx;
-    const bool fuse_io = sol::g_fuse_solver_io && cg_fuses(p);
+    const bool fuse_io = sol::g_fuse_solver_io && !burgers && cg_fuses(p);
     bool corr_ready = false;
     for (int i = m - 1; i >= 0; --i) {
         StepStash& s = u->stash[i];
@@ -800,6 +831,23 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
         if (!corr_ready) SOL_TRY(launch_corr_bwd(p, st, B, Gy, Gx, c.sig_vy, c.sig_vx, g_corr));   // else: written by diffuse_bc_bwd of step i+1
         SOL_TRY(cnn_backward(u, st, weights, gw, s, g_corr, u->g_feat, i == m - 1, i));
         if (!fuse_io) SOL_TRY(launch_feat_bwd(p, st, B, Gy, Gx, u->g_feat, c.cin0, c.sig_vy, c.sig_vx, u->H_vy, u->H_vx));
+        if (burgers) {
+            // adjoint of advect -> diffuse (+ dt*f: no state dependence); the periodic diffusion operator is symmetric
+            SOL_TRY(launch_burgers_diffuse(p, st, B, u->visc * c.dt, u->bk_y, u->bk_x, u->H_vy, u->H_vx, nullptr, nullptr, 0.f, u->K_vy, u->K_vx));
+            SOL_TRY(launch_advect_bwd(p, st, B, c.dt, s.vy1, s.vx1, u->K_vy, u->K_vx, u->H_vy, u->H_vx));
+            if (i > 0) {
+                float* ny = u->G_vy[i & 1]; float* nx = u->G_vx[i & 1];
+                float* gc_next = nullptr;
+                if (sol::g_fuse_small) gc_next = u->deferred_wgrad ? u->gcorr_st + (size_t)(i - 1) * p->NC() * B * 2 : u->g_corr;
+                SOL_TRY(launch_add_faces(p, st, B, u->H_vy, u->H_vx, u->stash[i - 1].gl_vy, u->stash[i - 1].gl_vx, ny, nx, gc_next, c.sig_vy,
+                                         c.sig_vx));
+                corr_ready = gc_next != nullptr;
+                Gy = ny; Gx = nx;
+            } else if (g_vy0 && g_vx0) {
+                SOL_TRY(launch_add_faces(p, st, B, u->H_vy, u->H_vx, nullptr, nullptr, g_vy0, g_vx0));
+            }
+            continue;
+        }
         bool joined = true;
         if (overlap && i > 0) {     // the items of the last window would only delay the end of the sweep: they are merged below
             SOL_CUDA(cudaEventRecord(u->ev_wfork, st));
@@ -890,7 +938,7 @@ extern "C" int sol_unroll_destroy(sol_unroll* u) {
 extern "C" int sol_unroll_forward(sol_unroll* u, void* stream, const float* weights, const float* re, const float* rho0, const float* vy0,
                                   const float* vx0, const float* gt_vy, const float* gt_vx, float* loss_steps, float* pred_vy,
                                   float* pred_vx, float* pred_rho) {
-    SOL_CHECK(u && weights && re && vy0 && vx0, "sol_unroll_forward: NULL pointer");
+    SOL_CHECK(u && weights && vy0 && vx0, "sol_unroll_forward: NULL pointer");
     SOL_CHECK((gt_vy == nullptr) == (gt_vx == nullptr), "sol_unroll_forward: gt_vy and gt_vx go together");
     SOL_CHECK(!gt_vy || loss_steps, "sol_unroll_forward: loss_steps required with ground truth");
     SOL_CHECK((pred_vy == nullptr) == (pred_vx == nullptr), "sol_unroll_forward: pred_vy and pred_vx go together");
@@ -905,9 +953,9 @@ extern "C" int sol_unroll_backward(sol_unroll* u, void* stream, const float* wei
 
 extern "C" int sol_unroll_train_iter(sol_unroll* u, void* stream, const float* weights, const float* re, const float* rho0, const float* vy0,
                                      const float* vx0, const float* gt_vy, const float* gt_vx, float* loss_steps, float* grad_weights) {
-    SOL_CHECK(u && weights && re && vy0 && vx0 && gt_vy && gt_vx && loss_steps && grad_weights, "sol_unroll_train_iter: NULL pointer");
+    SOL_CHECK(u && weights && vy0 && vx0 && gt_vy && gt_vx && loss_steps && grad_weights, "sol_unroll_train_iter: NULL pointer");
     cudaStream_t caller = (cudaStream_t)stream;
-    const void* key[9] = {weights, re, rho0, vy0, vx0, gt_vy, gt_vx, loss_steps, grad_weights};
+    const void* key[13] = {weights, re, rho0, vy0, vx0, gt_vy, gt_vx, loss_steps, grad_weights, u->bk_y, u->bk_x, u->bf_vy, u->bf_vx};
     if (!u->cfg.use_graph) {
         SOL_TRY(do_forward(u, caller, weights, re, rho0, vy0, vx0, gt_vy, gt_vx, loss_steps, nullptr, nullptr, nullptr));
         return do_backward(u, caller, weights, u->re_buf, grad_weights, nullptr, nullptr);
@@ -959,6 +1007,20 @@ extern "C" int sol_unroll_train_iter(sol_unroll* u, void* stream, const float* w
     SOL_CUDA(cudaGraphLaunch(u->gexec, st));
     sol::g_launches.fetch_add(u->graph_kernels, std::memory_order_relaxed);
     return join();
+}
+
+extern "C" int sol_unroll_set_burgers(sol_unroll* u, float viscosity, const float* diff_kernel_y, const float* diff_kernel_x,
+                                      const float* f_vy, const float* f_vx, float sig_fy, float sig_fx) {
+    SOL_CHECK(u != nullptr, "sol_unroll_set_burgers: NULL unroll");
+    SOL_CHECK(u->plan->boundary == SOL_BOUNDARY_PERIODIC, "sol_unroll_set_burgers: PERIODIC plans only");
+    SOL_CHECK((diff_kernel_y == nullptr) == (diff_kernel_x == nullptr) && (f_vy == nullptr) == (f_vx == nullptr),
+              "sol_unroll_set_burgers: kernels / forces come in pairs");
+    SOL_CHECK(viscosity >= 0.f, "sol_unroll_set_burgers: negative viscosity");
+    if (u->cfg.cin0 == 4) SOL_CHECK(f_vy != nullptr && sig_fy > 0.f && sig_fx > 0.f, "sol_unroll_set_burgers: 4 feature channels need forces and positive force sigmas");
+    u->visc = viscosity; u->bk_y = diff_kernel_y; u->bk_x = diff_kernel_x; u->bf_vy = f_vy; u->bf_vx = f_vx;
+    u->sig_fy = sig_fy; u->sig_fx = sig_fx;
+    u->burgers_set = true;
+    return SOL_OK;
 }
 
 extern "C" int sol_unroll_cg_iters(sol_unroll* u, const int** dev_iters, int* count) {

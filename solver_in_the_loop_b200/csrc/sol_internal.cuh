@@ -134,6 +134,12 @@ int launch_advect_bwd(const sol_plan* p, cudaStream_t st, int B, float dt, const
 int launch_divergence(const sol_plan* p, cudaStream_t st, int B, const float* vy, const float* vx, float* div);
 int launch_to_feature(const sol_plan* p, cudaStream_t st, int B, const float* vy, const float* vx, const float* re,
                       float sy, float sx, float sr, float* feat);
+// Burgers features: [vy, vx (, fy, fx)][:Y,:X]/sigma (burgers_train.py:75-82, 398-415); cfeat = 2 (--noforce) or 4
+int launch_to_feature_burgers(const sol_plan* p, cudaStream_t st, int B, const float* vy, const float* vx, const float* fy, const float* fx,
+                              float sy, float sx, float sfy, float sfx, int cfeat, float* feat);
+// G_out = G + add (add_* may be NULL); optional fused corr_bwd output g_corr = sigma * G_out[:Y,:X]
+int launch_add_faces(const sol_plan* p, cudaStream_t st, int B, const float* gy, const float* gx, const float* add_y, const float* add_x,
+                     float* gy_out, float* gx_out, float* g_corr = nullptr, float sy = 1.0f, float sx = 1.0f);
 // v_out = v + sigma*corr (zero on the far row/col); optional loss + loss gradient
 int launch_correct_loss(const sol_plan* p, cudaStream_t st, int B, const float* vy, const float* vx, const float* corr,
                         float sy, float sx, const float* gt_vy, const float* gt_vx, float inv_m,

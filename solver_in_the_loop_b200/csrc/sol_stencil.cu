@@ -239,6 +239,72 @@ int launch_to_feature(const sol_plan* p, cudaStream_t st, int B, const float* vy
     return SOL_OK;
 }
 
+// Burgers features (burgers_train.py:75-82, 398-415): [vy, vx (, fy, fx)][:Y,:X] / sigma, channel-last
+__global__ void __launch_bounds__(256) k_to_feature_burgers(int B, int Y, int X, const float* __restrict__ vy, const float* __restrict__ vx,
+                                                            const float* __restrict__ fy, const float* __restrict__ fx, float isy, float isx,
+                                                            float isfy, float isfx, int cfeat, float* __restrict__ feat) {
+    pdl_sync();
+    const int NY = (Y + 1) * X, NX = Y * (X + 1), NC = Y * X;
+    const size_t total = (size_t)B * NC;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(idx / NC);
+        const int rem = (int)(idx - (size_t)b * NC);
+        const int j = rem / X, i = rem - j * X;
+        float* f = feat + idx * cfeat;
+        const size_t oy = (size_t)b * NY + j * X + i, ox = (size_t)b * NX + j * (X + 1) + i;
+        f[0] = vy[oy] * isy;
+        f[1] = vx[ox] * isx;
+        if (cfeat >= 4) {
+            f[2] = fy[oy] * isfy;
+            f[3] = fx[ox] * isfx;
+        }
+    }
+}
+
+int launch_to_feature_burgers(const sol_plan* p, cudaStream_t st, int B, const float* vy, const float* vx, const float* fy, const float* fx,
+                              float sy, float sx, float sfy, float sfx, int cfeat, float* feat) {
+    const size_t total = (size_t)B * p->NC();
+    SOL_CUDA(launch_kernel(k_to_feature_burgers, dim3(grid_for(total, 256, p->sm_count)), dim3(256), 0, st, B, p->Y, p->X, vy, vx, fy, fx,
+                           1.0f / sy, 1.0f / sx, 1.0f / sfy, 1.0f / sfx, cfeat, feat));
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
+// G_out = G + add (the loss gradient of the previous step joins the state gradient); optionally also the fused corr_bwd
+// of the step that consumes it: g_corr[b,j,i,:] = sigma * G_out[:Y,:X]
+__global__ void __launch_bounds__(256) k_add_faces(int B, int Y, int X, const float* __restrict__ gy, const float* __restrict__ gx,
+                                                   const float* __restrict__ add_y, const float* __restrict__ add_x,
+                                                   float* __restrict__ gy_out, float* __restrict__ gx_out, float* __restrict__ g_corr,
+                                                   float sy, float sx) {
+    pdl_sync();
+    const int NY = (Y + 1) * X, NX = Y * (X + 1), NF = NY + NX;
+    const size_t total = (size_t)B * NF;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(idx / NF);
+        const FaceIdx f = decode_face((int)(idx - (size_t)b * NF), NY, X);
+        if (f.comp == 0) {
+            const size_t o = (size_t)b * NY + f.j * X + f.i;
+            const float v = gy[o] + (add_y ? add_y[o] : 0.0f);
+            gy_out[o] = v;
+            if (g_corr && f.j < Y) g_corr[((size_t)b * Y * X + f.j * X + f.i) * 2 + 0] = sy * v;
+        } else {
+            const size_t o = (size_t)b * NX + f.j * (X + 1) + f.i;
+            const float v = gx[o] + (add_x ? add_x[o] : 0.0f);
+            gx_out[o] = v;
+            if (g_corr && f.i < X) g_corr[((size_t)b * Y * X + f.j * X + f.i) * 2 + 1] = sx * v;
+        }
+    }
+}
+
+int launch_add_faces(const sol_plan* p, cudaStream_t st, int B, const float* gy, const float* gx, const float* add_y, const float* add_x,
+                     float* gy_out, float* gx_out, float* g_corr, float sy, float sx) {
+    const size_t total = (size_t)B * (p->NY() + p->NX());
+    SOL_CUDA(launch_kernel(k_add_faces, dim3(grid_for(total, 256, p->sm_count)), dim3(256), 0, st, B, p->Y, p->X, gy, gx, add_y, add_x, gy_out,
+                           gx_out, g_corr, sy, sx));
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
