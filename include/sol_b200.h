@@ -205,6 +205,15 @@ int sol_unroll_backward(sol_unroll* u, void* stream, const float* weights, float
 int sol_unroll_train_iter(sol_unroll* u, void* stream, const float* weights, const float* re,
                           const float* rho0, const float* vy0, const float* vx0,
                           const float* gt_vy, const float* gt_vx, float* loss_steps, float* grad_weights);
+/* Burgers scene of an unroll created on a PERIODIC plan (burgers/burgers_train.py:379-437): every unrolled step is
+ * BurgersTest.step_with_f (:178-187, advect -> diffuse(viscosity*dt) -> + dt*f_i) followed by the correction net on
+ * to_feature([v],[f_i])/[std_v, std_f] (:75-82, 398-415; cfg.cin0 = 4) or to_feature_noforce (:84-90; cfg.cin0 = 2,
+ * f_* = NULL means step() without forcing).  diff_kernel_{y,x} as in sol_burgers_step (NULL: explicit 5-point);
+ * f_vy [m,B,Y+1,X], f_vx [m,B,Y,X+1] device arrays that must stay valid while the unroll is used.  cfg.sig_vy/sig_vx
+ * are the velocity std (features, output scaling and loss), sig_fy/sig_fx the force std; `re` of the sol_unroll_*
+ * calls is ignored (may be NULL).  Must be called before the first forward. */
+int sol_unroll_set_burgers(sol_unroll* u, float viscosity, const float* diff_kernel_y, const float* diff_kernel_x,
+                           const float* f_vy, const float* f_vx, float sig_fy, float sig_fx);
 /* device pointer to int[2*msteps*B] CG iteration counts: [0..m*B) forward, [m*B..2mB) adjoint */
 int sol_unroll_cg_iters(sol_unroll* u, const int** dev_iters, int* count);
 

@@ -551,3 +551,70 @@ def burgers_step(vy, vx, dt, dx, viscosity=0.1, fy=None, fx=None, switches: Swit
     if fy is not None:
         vy3 = vy3 + dt * fy; vx3 = vx3 + dt * fx
     return vy3, vx3
+
+
+def burgers_to_feature(vy, vx, fy, fx, sig_v, sig_f):
+    """burgers_train.py:75-90 + normalisation :398-415: [vy, vx (, fy, fx)][:, :-1, :-1] / std, channel-last.
+    fy is None: to_feature_noforce."""
+    Y, X = vx.shape[1], vy.shape[2]
+    ch = [vy[:, :Y, :] / sig_v[0], vx[:, :, :X] / sig_v[1]]
+    if fy is not None:
+        ch += [fy[:, :Y, :] / sig_f[0], fx[:, :, :X] / sig_f[1]]
+    return torch.stack(ch, dim=-1)
+
+
+def burgers_unrolled_loss(params, vy0, vx0, f_vy, f_vx, gt_vy, gt_vx, dx, dt, sig_v, sig_f, msteps, viscosity=0.1,
+                          model="mars_moon", switches: Switches = DEFAULT_SWITCHES, return_states=False):
+    """burgers_train.py:379-437: msteps x (step_with_f -> CNN on [v, f_i]/std -> to_staggered*std_v -> add), per-step
+    tf.nn.l2_loss of (gt - v)/std_v, total = sum / msteps.  f_vy/f_vx [m,B,..] or None (--noforce: plain step and
+    velocity-only features)."""
+    vy, vx = vy0, vx0
+    losses, states = [], []
+    for i in range(msteps):
+        fy = None if f_vy is None else f_vy[i]
+        fx = None if f_vx is None else f_vx[i]
+        vy, vx = burgers_step(vy, vx, dt, dx, viscosity, fy, fx, switches)
+        corr = cnn_forward(params, burgers_to_feature(vy, vx, fy, fx, sig_v, sig_f), model)
+        vy, vx = apply_correction(vy, vx, corr, sig_v)
+        losses.append(0.5 * (((gt_vy[i] - vy) / sig_v[0]) ** 2).sum() + 0.5 * (((gt_vx[i] - vx) / sig_v[1]) ** 2).sum())
+        if return_states:
+            states.append((vy, vx))
+    loss = sum(losses) / msteps
+    return (loss, losses, states) if return_states else (loss, losses)
+
+
+def make_burgers_case(R=32, B=1, msteps=1, L=32.0, dt=0.1, seed=0, dtype=torch.float64, noise=0.01, force=True):
+    """Deterministic synthetic Burgers case at the reference's SOL settings (burgers/Makefile:75-77: -l 32, --dt 0.1,
+    32x32 after 4x down-sampling): smooth random periodic velocity and forcing (sums of a few sine modes, the shape
+    burgers.py:89-121 generates), ground truth = uncorrected trajectory + noise.
+    Returns (dx, vy0, vx0, f_vy, f_vx, gt_vy, gt_vx, sig_v, sig_f)."""
+    g = torch.Generator().manual_seed(seed)
+    dx = L / R
+
+    def smooth(shape, amp):
+        H, W = shape[-2:]
+        yy = torch.arange(H, dtype=torch.float64).reshape(H, 1) / H
+        xx = torch.arange(W, dtype=torch.float64).reshape(1, W) / W
+        out = torch.zeros(shape, dtype=torch.float64)
+        for _ in range(4):
+            ky, kx = [int(k) for k in torch.randint(-2, 3, (2,), generator=g)]
+            ph = torch.rand(shape[:-2] + (1, 1), generator=g, dtype=torch.float64) * 2 * math.pi
+            a = (torch.rand(shape[:-2] + (1, 1), generator=g, dtype=torch.float64) * 2 - 1) * amp
+            out = out + a * torch.sin(2 * math.pi * (ky * yy + kx * xx) + ph)
+        return out
+
+    vy = smooth((B, R + 1, R), 1.0)
+    vx = smooth((B, R, R + 1), 1.0)
+    f_vy = smooth((msteps, B, R + 1, R), 0.5) if force else None
+    f_vx = smooth((msteps, B, R, R + 1), 0.5) if force else None
+    gy, gx = [], []
+    y2, x2 = vy, vx
+    with torch.no_grad():
+        for i in range(msteps):
+            y2, x2 = burgers_step(y2, x2, dt, dx, 0.1, None if f_vy is None else f_vy[i], None if f_vx is None else f_vx[i])
+            gy.append(y2 + noise * torch.randn(y2.shape, generator=g, dtype=torch.float64))
+            gx.append(x2 + noise * torch.randn(x2.shape, generator=g, dtype=torch.float64))
+    sig_v = (float(vy.std()) + 1e-3, float(vx.std()) + 1e-3)
+    sig_f = (float(f_vy.std()) + 1e-3, float(f_vx.std()) + 1e-3) if force else (1.0, 1.0)
+    c = lambda t: None if t is None else t.to(dtype)
+    return dx, c(vy), c(vx), c(f_vy), c(f_vx), c(torch.stack(gy)), c(torch.stack(gx)), sig_v, sig_f

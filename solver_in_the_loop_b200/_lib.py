@@ -67,6 +67,7 @@ SIGNATURES = {
     "sol_unroll_forward": (_i, [_vp] * 13),
     "sol_unroll_backward": (_i, [_vp] * 6),
     "sol_unroll_train_iter": (_i, [_vp] * 11),
+    "sol_unroll_set_burgers": (_i, [_vp, _f, _vp, _vp, _vp, _vp, _f, _f]),
     "sol_unroll_cg_iters": (_i, [_vp, C.POINTER(_vp), C.POINTER(_i)]),
     "sol_adam_tf1": (_i, [_vp, _sz, _vp, _vp, _vp, _vp, _i, _f, _f, _f, _f, _f]),
 }

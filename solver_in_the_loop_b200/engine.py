@@ -288,6 +288,13 @@ class Unroll:
         self.nparams = model_param_count(model, cin0)
         self.loss_steps = torch.zeros(self.msteps, device=plan.device)
 
+    def set_burgers(self, viscosity: float = 0.1, ky=None, kx=None, f_vy=None, f_vx=None, sig_f: Sequence[float] = (1.0, 1.0)):
+        """Burgers scene of an unroll on a periodic plan (burgers/burgers_train.py:379-437): diffusion kernels as in
+        Plan.burgers_step, per-step forces f_vy [m,B,Y+1,X] / f_vx [m,B,Y,X+1] (None with cin0 = 2: --noforce)."""
+        self._burgers_keep = (ky, kx, f_vy, f_vx)       # the library keeps the raw pointers
+        check(self.lib.sol_unroll_set_burgers(self.handle, float(viscosity), _ptr(ky), _ptr(kx), _ptr(f_vy), _ptr(f_vx),
+                                              float(sig_f[0]), float(sig_f[1])))
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.sol_unroll_destroy(self.handle)

@@ -48,17 +48,17 @@ def lr_schedule(epoch: int, current_lr: float) -> float:
 class SolTrainer:
     def __init__(self, plan: engine.Plan, msteps: int, batch: int, sig: Sequence[float], lr: float = 1e-4,
                  weights: Optional[torch.Tensor] = None, seed: int = 0, dt: float = 1.0, use_graph: bool = True,
-                 clip_grad: bool = False, process_group=None, with_density: bool = False):
+                 clip_grad: bool = False, process_group=None, with_density: bool = False, cin0: int = 3):
         self.plan, self.msteps, self.batch = plan, int(msteps), int(batch)
         self.lr, self.clip_grad = float(lr), bool(clip_grad)
         self.pg = process_group
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
-        self.unroll = engine.Unroll(plan, msteps, batch, sig, dt=dt, with_density=with_density, use_graph=use_graph)
+        self.unroll = engine.Unroll(plan, msteps, batch, sig, dt=dt, cin0=cin0, with_density=with_density, use_graph=use_graph)
         n = self.unroll.nparams
         dev = plan.device
-        w0 = glorot_uniform_params(seed=seed) if weights is None else weights
+        w0 = glorot_uniform_params(cin0=cin0, seed=seed) if weights is None else weights
         self.weights = w0.to(device=dev, dtype=torch.float32).contiguous().clone()
         # flat all-reduce bucket: [gradients | per-step losses]
         self.bucket = torch.zeros(n + self.msteps, device=dev)
@@ -124,3 +124,49 @@ class SolTrainer:
 
     def load_state_dict(self, sd):
         self.weights.copy_(sd["weights"]); self.adam_m.copy_(sd["adam_m"]); self.adam_v.copy_(sd["adam_v"]); self.t = int(sd["t"])
+
+
+class BurgersTrainer(SolTrainer):
+    """The unrolled training iteration of burgers/burgers_train.py:379-437 (sess.run at :487): msteps x
+    (BurgersTest.step_with_f -> correction net on [v, f_i]/std -> add), l2 loss on v/std_v, TF1 Adam.
+
+    ``sig_v`` / ``sig_f``: dataStats['std'][0] / [1] (velocity / force std per component, y first).
+    ``noforce=True`` is the --noforce variant (features = velocity only, plain ``step``).
+    """
+
+    def __init__(self, plan: engine.Plan, msteps: int, batch: int, sig_v: Sequence[float], sig_f: Sequence[float] = (1.0, 1.0),
+                 viscosity: float = 0.1, dt: float = 0.1, noforce: bool = False, spectral_diffusion: bool = True, **kw):
+        if plan.boundary != _lib.SOL_BOUNDARY_PERIODIC:
+            raise engine.SolError("BurgersTrainer needs a periodic plan (Plan.periodic)")
+        super().__init__(plan, msteps, batch, (sig_v[0], sig_v[1], 1.0), dt=dt, cin0=2 if noforce else 4, **kw)
+        dev = plan.device
+        self.noforce = bool(noforce)
+        self.ky = self.kx = None
+        if spectral_diffusion:
+            from .phi_compat import periodic_diffusion_kernel
+            self.ky = periodic_diffusion_kernel(plan.Y + 1, plan.X, viscosity * dt, dev)
+            self.kx = periodic_diffusion_kernel(plan.Y, plan.X + 1, viscosity * dt, dev)
+        # persistent force buffers: the library keeps their addresses (they are part of the CUDA-graph key)
+        self.f_vy = None if noforce else torch.zeros(self.msteps, self.batch, plan.Y + 1, plan.X, device=dev)
+        self.f_vx = None if noforce else torch.zeros(self.msteps, self.batch, plan.Y, plan.X + 1, device=dev)
+        self.unroll.set_burgers(viscosity, self.ky, self.kx, self.f_vy, self.f_vx, sig_f)
+
+    def train_step(self, vy0, vx0, f_vy, f_vx, gt_vy, gt_vx, lr: Optional[float] = None) -> torch.Tensor:
+        if not self.noforce:
+            self.f_vy.copy_(f_vy, non_blocking=True)
+            self.f_vx.copy_(f_vx, non_blocking=True)
+        return SolTrainer.train_step(self, None, vy0, vx0, gt_vy, gt_vx, lr=lr)
+
+    def train_step_host(self, vy0, vx0, f_vy, f_vx, gt_vy, gt_vx, lr: Optional[float] = None) -> float:
+        """Host-fed variant: the feed_dict of burgers_train.py:482-486 (state, forces, ground truth) -> loss."""
+        srcs = [vy0, vx0, gt_vy, gt_vx]
+        if self._dev_in is None:
+            self._dev_in = [torch.empty(s.shape, dtype=torch.float32, device=self.plan.device) for s in srcs]
+            self._loss_pin = torch.empty((), dtype=torch.float32).pin_memory()
+        for s, d in zip(srcs, self._dev_in):
+            d.copy_(s, non_blocking=True)
+        d = self._dev_in
+        loss = self.train_step(d[0], d[1], f_vy, f_vx, d[2], d[3], lr=lr)
+        self._loss_pin.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self._loss_pin)
