@@ -15,7 +15,7 @@ torch.cuda.set_device(dev)
 lib = _lib.load()
 lib.sol_debug_conv_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
 lib.sol_debug_conv_trace.restype = None
-B, Y, X = 3, 128, 64
+B, Y, X = (int(sys.argv[1]) if len(sys.argv) > 1 else 3), 128, 64
 x = torch.randn(B, Y, X, 32, device=dev); w = torch.randn(5, 5, 32, 32, device=dev) * 0.05; b = torch.randn(32, device=dev)
 engine.set_option("conv_path", 2)
 nct = (X // 8) * (Y // 16) * B

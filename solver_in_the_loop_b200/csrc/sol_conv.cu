@@ -322,6 +322,123 @@ static int launch_reduce(const ConvArgs& a, cudaStream_t st) {
     return SOL_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// any other (Cin, Cout) — the layers of model_mercury (karman_train.py:92-99: 32 -> 64 -> 2) and their data
+// gradients.  Tile 16 (x) x 8 (y) pixels, one pixel per thread, 8 couts per pass in registers; the input tile +
+// halo sits in shared memory as [PH][PW][Cin], weights are warp-uniform 128-bit loads.  Plain fp32 FMAs.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_conv5x5_generic(const ConvArgs a, int Cin, int Cout) {
+    pdl_sync();
+    constexpr int TW = 16, TH = 8, PW = TW + 4, PH = TH + 4;
+    extern __shared__ float gen_tile[];      // [PH*PW][Cin + 1]  (+1: conflict-free across the 16 pixels of a row)
+    const int CP = Cin + 1;
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
+    const float* inb = a.in + (size_t)b * a.Y * a.X * Cin;
+    for (int idx = tid; idx < PH * PW * Cin; idx += 128) {
+        const int c = idx % Cin, pix = idx / Cin;
+        const int tyy = pix / PW, txx = pix - tyy * PW;
+        const int gy = y0 + tyy - 2, gx = x0 + txx - 2;
+        float v = 0.0f;
+        if (gy >= 0 && gy < a.Y && gx >= 0 && gx < a.X) v = __ldg(inb + ((size_t)gy * a.X + gx) * Cin + c);
+        gen_tile[pix * CP + c] = v;
+    }
+    __syncthreads();
+    const int px = tid & 15, py = tid >> 4;
+    const int gy = y0 + py, gx = x0 + px;
+    const bool inside = gy < a.Y && gx < a.X;
+    const size_t opix = ((size_t)b * a.Y + gy) * a.X + gx;
+    for (int co0 = 0; co0 < Cout; co0 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+        const int nco = Cout - co0 < 8 ? Cout - co0 : 8;
+        for (int tap = 0; tap < 25; ++tap) {
+            const int dy = tap / 5, dx = tap - dy * 5;
+            const float* tp = gen_tile + ((py + dy) * PW + px + dx) * CP;
+            const float* wp = a.w + (size_t)tap * Cin * Cout + co0;
+            if (nco == 8 && (Cout & 3) == 0) {
+                for (int ci = 0; ci < Cin; ++ci) {
+                    const float v = tp[ci];
+                    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp + (size_t)ci * Cout));
+                    const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + (size_t)ci * Cout) + 1);
+                    acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+                    acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+                }
+            } else {
+                for (int ci = 0; ci < Cin; ++ci) {
+                    const float v = tp[ci];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (k < nco) acc[k] = fmaf(v, __ldg(wp + (size_t)ci * Cout + k), acc[k]);
+                }
+            }
+        }
+        if (inside) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (k >= nco) break;
+                const size_t o = opix * Cout + co0 + k;
+                float v = acc[k];
+                if (a.bias) v += __ldg(a.bias + co0 + k);
+                if (a.addend) v += __ldg(a.addend + o);
+                const float rf = (a.act == SOL_ACT_DLRELU) ? __ldg(a.ref + o) : 0.0f;
+                a.out[o] = apply_act(v, a.act, a.slope, rf);
+            }
+        }
+    }
+}
+
+static int launch_conv_generic(const ConvArgs& a, cudaStream_t st, int Cin, int Cout) {
+    const size_t smem = (size_t)12 * 20 * (Cin + 1) * sizeof(float);
+    if (smem > 200 * 1024) return fail(SOL_ERR_UNSUPPORTED, "conv5x5: too many input channels for the generic kernel");
+    static size_t attr_smem = 48 * 1024;
+    if (smem > attr_smem) {
+        SOL_CUDA(cudaFuncSetAttribute(k_conv5x5_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    SOL_CUDA(launch_kernel(k_conv5x5_generic, dim3(cdiv(a.X, 16), cdiv(a.Y, 8), a.B), dim3(128), smem, st, a, Cin, Cout));
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
+// weight gradient for any (Cin, Cout): one CTA per (tap, cin); thread = (cout, pixel group), the pixel groups stride
+// over the image rows and are summed through shared memory in a fixed order (deterministic, no atomics); the CTA of
+// the centre tap and cin 0 also sums the bias gradient.
+__global__ void __launch_bounds__(256) k_wgrad_generic(const float* __restrict__ in, const float* __restrict__ g, float* __restrict__ dW,
+                                                       float* __restrict__ db, int B, int Y, int X, int Cin, int Cout, int CP, int accumulate) {
+    pdl_sync();
+    __shared__ float red[2][256];
+    const int tap = blockIdx.x / Cin, ci = blockIdx.x - tap * Cin;
+    const int dy = tap / 5 - 2, dx = tap % 5 - 2;
+    const bool do_bias = (tap == 12 && ci == 0);
+    const int co = threadIdx.x % CP, pg = threadIdx.x / CP, P = 256 / CP;
+    float acc = 0.0f, bacc = 0.0f;
+    if (co < Cout) {
+        for (int row = pg; row < B * Y; row += P) {
+            const int b = row / Y, y = row - b * Y;
+            const int yy = y + dy;
+            const bool rowok = yy >= 0 && yy < Y;
+            const float* gr = g + (size_t)row * X * Cout + co;
+            const float* ir = in + (((size_t)b * Y + yy) * X + dx) * Cin + ci;
+            for (int x = 0; x < X; ++x) {
+                const float gv = __ldg(gr + (size_t)x * Cout);
+                const int xx = x + dx;
+                if (rowok && xx >= 0 && xx < X) acc = fmaf(__ldg(ir + (size_t)x * Cin), gv, acc);
+                bacc += gv;
+            }
+        }
+    }
+    red[0][threadIdx.x] = acc; red[1][threadIdx.x] = bacc;
+    __syncthreads();
+    if (pg == 0 && co < Cout) {
+        for (int q = 1; q < P; ++q) { acc += red[0][q * CP + co]; bacc += red[1][q * CP + co]; }
+        const size_t o = ((size_t)tap * Cin + ci) * Cout + co;
+        dW[o] = accumulate ? dW[o] + acc : acc;
+        if (do_bias) db[co] = accumulate ? db[co] + bacc : bacc;
+    }
+}
+
 int launch_conv5x5(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const float* in, const float* w, const float* bias,
                    const float* addend, const float* ref, int act, float slope, float* out) {
     ConvArgs a;
@@ -354,7 +471,7 @@ int launch_conv5x5(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, cons
     if (Cin == 32 && Cout == 2) return launch_reduce<2>(a, st);
     if (Cin == 32 && Cout == 3) return launch_reduce<3>(a, st);
     if (Cin == 32 && Cout == 4) return launch_reduce<4>(a, st);
-    return fail(SOL_ERR_UNSUPPORTED, "conv5x5: unsupported (Cin, Cout) pair");
+    return launch_conv_generic(a, st, Cin, Cout);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -832,6 +949,15 @@ int launch_wgrad(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const 
         return SOL_OK;
     }
     if (!in) return SOL_OK;   // finalize-only call on a thin layer: nothing to do
+    const bool thin = (Cout == 32 && Cin >= 2 && Cin <= 4) || (Cin == 32 && Cout == 2);
+    if (!thin) {
+        int CP = 32;
+        while (CP < Cout) CP *= 2;
+        if (CP > 256) return fail(SOL_ERR_UNSUPPORTED, "wgrad: more than 256 output channels");
+        SOL_CUDA(launch_kernel(k_wgrad_generic, dim3(25 * Cin), dim3(256), 0, st, in, g_out, dW, db, B, Y, X, Cin, Cout, CP, accumulate));
+        SOL_LAUNCHED();
+        return SOL_OK;
+    }
     if (!accumulate) {
         SOL_CUDA(cudaMemsetAsync(dW, 0, (size_t)25 * Cin * Cout * sizeof(float), st));
         SOL_CUDA(cudaMemsetAsync(db, 0, (size_t)Cout * sizeof(float), st));

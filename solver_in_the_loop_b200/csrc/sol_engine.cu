@@ -523,13 +523,19 @@ int carve(sol_unroll* u, void* ws, size_t* total) {
     const sol_unroll_cfg& c = u->cfg;
     const size_t B = c.B, NC = p->NC() * B, NY = p->NY() * B, NX = p->NX() * B;
     const size_t nA = NC * 32;
+    const bool mercury = c.model == SOL_MODEL_MERCURY;
     Carver cv(ws);
     u->stash.resize(c.msteps);
     for (int i = 0; i < c.msteps; ++i) {
         StepStash& s = u->stash[i];
         s.vy1 = cv.take<float>(NY); s.vx1 = cv.take<float>(NX);
         s.feat = cv.take<float>(NC * c.cin0);
-        for (int k = 0; k < 11; ++k) s.acts[k] = cv.take<float>(nA);
+        if (mercury) {     // model_mercury: relu(conv 32), relu(conv 64)
+            s.acts[0] = cv.take<float>(NC * 32); s.acts[1] = cv.take<float>(NC * 64);
+            for (int k = 2; k < 11; ++k) s.acts[k] = nullptr;
+        } else {
+            for (int k = 0; k < 11; ++k) s.acts[k] = cv.take<float>(nA);
+        }
         s.gl_vy = cv.take<float>(NY); s.gl_vx = cv.take<float>(NX);
     }
     u->sA_vy = cv.take<float>(NY); u->sA_vx = cv.take<float>(NX);
@@ -543,18 +549,24 @@ int carve(sol_unroll* u, void* ws, size_t* total) {
     u->K_vy = cv.take<float>(NY); u->K_vx = cv.take<float>(NX);
     u->g_corr = cv.take<float>(NC * 2);
     u->g_feat = cv.take<float>(NC * c.cin0);
-    for (int k = 0; k < 3; ++k) u->gbuf[k] = cv.take<float>(nA);
     u->wT = cv.take<float>(u->nparams);
-    u->wprep_fwd = cv.take<float>(tc_weights_floats() * 10);
-    u->wprep_bwd = cv.take<float>(tc_weights_floats() * 10);
-    u->tc_tiles = tc_tiles_per_launch(u->cfg.B, u->plan->Y, u->plan->X);
-    u->tc_flags = cv.take<int>((size_t)10 * u->cfg.msteps * u->tc_tiles);
     u->nA = nA;
-    u->gst = cv.take<float>(nA * 10 * c.msteps);
-    u->g0_st = cv.take<float>(nA * c.msteps);
-    u->gcorr_st = cv.take<float>(NC * 2 * c.msteps);
-    u->partial_stride = wgrad_workspace_floats(32, 32);
-    u->partials = cv.take<float>(u->partial_stride * 10);
+    if (mercury) {      // per-step SIMT weight gradients, no tensor-core operand buffers, no deferred-gradient stash
+        u->gbuf[0] = cv.take<float>(NC * 64); u->gbuf[1] = cv.take<float>(nA); u->gbuf[2] = nullptr;
+        u->wprep_fwd = u->wprep_bwd = nullptr; u->tc_flags = nullptr; u->tc_tiles = 0;
+        u->gst = u->g0_st = u->gcorr_st = u->partials = nullptr; u->partial_stride = 0;
+    } else {
+        for (int k = 0; k < 3; ++k) u->gbuf[k] = cv.take<float>(nA);
+        u->wprep_fwd = cv.take<float>(tc_weights_floats() * 10);
+        u->wprep_bwd = cv.take<float>(tc_weights_floats() * 10);
+        u->tc_tiles = tc_tiles_per_launch(u->cfg.B, u->plan->Y, u->plan->X);
+        u->tc_flags = cv.take<int>((size_t)10 * u->cfg.msteps * u->tc_tiles);
+        u->gst = cv.take<float>(nA * 10 * c.msteps);
+        u->g0_st = cv.take<float>(nA * c.msteps);
+        u->gcorr_st = cv.take<float>(NC * 2 * c.msteps);
+        u->partial_stride = wgrad_workspace_floats(32, 32);
+        u->partials = cv.take<float>(u->partial_stride * 10);
+    }
     u->iters = cv.take<int>((size_t)2 * c.msteps * c.B);
     u->re_buf = cv.take<float>(c.B);
     *total = align_up(cv.off, 256);
@@ -569,7 +581,7 @@ int check_cfg(const sol_plan* p, const sol_unroll_cfg* c) {
         SOL_CHECK(c->cin0 == 3, "unroll: karman features have 3 channels (vy, vx, Re)");
     else
         SOL_CHECK(c->cin0 == 4 || c->cin0 == 2, "unroll: burgers features have 4 channels (vy, vx, fy, fx) or 2 (--noforce)");
-    if (c->model != SOL_MODEL_MARS_MOON) return fail(SOL_ERR_UNSUPPORTED, "unroll: only model_mars_moon is implemented on the GPU path");
+    SOL_CHECK(c->model == SOL_MODEL_MARS_MOON || c->model == SOL_MODEL_MERCURY, "unroll: unknown model");
     return SOL_OK;
 }
 
@@ -599,6 +611,11 @@ int cnn_forward(sol_unroll* u, cudaStream_t st, const float* w, const StepStash&
     const int B = u->cfg.B, Y = p->Y, X = p->X;
     const float a = 0.3f;   // keras LeakyReLU default
     const std::vector<LayerDesc>& L = u->L;
+    if (u->cfg.model == SOL_MODEL_MERCURY) {     // karman_train.py:92-99: conv32+relu, conv64+relu, conv2 (relu = leaky slope 0)
+        SOL_TRY(launch_conv5x5(st, B, Y, X, L[0].cin, 32, s.feat, w + L[0].w_off, w + L[0].b_off, nullptr, nullptr, SOL_ACT_LRELU, 0.0f, s.acts[0]));
+        SOL_TRY(launch_conv5x5(st, B, Y, X, 32, 64, s.acts[0], w + L[1].w_off, w + L[1].b_off, nullptr, nullptr, SOL_ACT_LRELU, 0.0f, s.acts[1]));
+        return launch_conv5x5(st, B, Y, X, 64, 2, s.acts[1], w + L[2].w_off, w + L[2].b_off, nullptr, nullptr, SOL_ACT_NONE, 0.0f, corr);
+    }
     const bool tc = sol::g_conv_path == 2;
     SOL_TRY(launch_conv5x5(st, B, Y, X, L[0].cin, 32, s.feat, w + L[0].w_off, w + L[0].b_off, nullptr, nullptr, SOL_ACT_LRELU, a, s.acts[0]));
     u->tc_prev = nullptr;
@@ -624,6 +641,16 @@ int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, cons
     const float a = 0.3f;
     const std::vector<LayerDesc>& L = u->L;
     const float* wT = u->wT;
+    if (u->cfg.model == SOL_MODEL_MERCURY) {
+        // weight gradients accumulate straight into gw (zeroed at the start of the sweep), step by step
+        float* g64 = u->gbuf[0]; float* g32 = u->gbuf[1];
+        SOL_TRY(launch_wgrad(st, B, Y, X, 64, 2, s.acts[1], g_corr, gw + L[2].w_off, gw + L[2].b_off, 1, nullptr, false));
+        SOL_TRY(launch_conv5x5(st, B, Y, X, 2, 64, g_corr, wT + L[2].w_off, nullptr, nullptr, s.acts[1], SOL_ACT_DLRELU, 0.0f, g64));
+        SOL_TRY(launch_wgrad(st, B, Y, X, 32, 64, s.acts[0], g64, gw + L[1].w_off, gw + L[1].b_off, 1, nullptr, false));
+        SOL_TRY(launch_conv5x5(st, B, Y, X, 64, 32, g64, wT + L[1].w_off, nullptr, nullptr, s.acts[0], SOL_ACT_DLRELU, 0.0f, g32));
+        SOL_TRY(launch_wgrad(st, B, Y, X, L[0].cin, 32, s.feat, g32, gw + L[0].w_off, gw + L[0].b_off, 1, nullptr, false));
+        return launch_conv5x5(st, B, Y, X, 32, L[0].cin, g32, wT + L[0].w_off, nullptr, nullptr, nullptr, SOL_ACT_NONE, 0.0f, g_feat);
+    }
     const bool tc = sol::g_conv_path == 2;
     const bool deferred = u->deferred_wgrad;        // weight gradients in one GEMM per layer after the sweep
     // output-gradient tensor of layer l (1..10) for this step
@@ -686,7 +713,8 @@ int do_forward(sol_unroll* u, cudaStream_t st, const float* weights, const float
         re = u->re_buf;
     }
     if (gt_vy) SOL_CUDA(cudaMemsetAsync(loss_steps, 0, sizeof(float) * m, st));
-    if (sol::g_conv_path == 2) {
+    const bool mars = c.model == SOL_MODEL_MARS_MOON;
+    if (sol::g_conv_path == 2 && mars) {
         for (int l = 1; l <= 10; ++l)
             SOL_TRY(launch_prep_tc_weights(st, weights + u->L[l].w_off, u->wprep_fwd + tc_weights_floats() * (l - 1)));
         SOL_CUDA(cudaMemsetAsync(u->tc_flags, 0, sizeof(int) * (size_t)10 * m * u->tc_tiles, st));
@@ -742,10 +770,11 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
     const sol_unroll_cfg& c = u->cfg;
     const int B = c.B, m = c.msteps;
     SOL_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * u->nparams, st));
-    u->deferred_wgrad = (sol::g_wgrad_path == 2) && (p->Y % 16 == 0) && (p->X % 8 == 0);
+    const bool mars = c.model == SOL_MODEL_MARS_MOON;
+    u->deferred_wgrad = mars && (sol::g_wgrad_path == 2) && (p->Y % 16 == 0) && (p->X % 8 == 0);
     for (size_t l = 0; l < u->L.size(); ++l)
         SOL_TRY(launch_flip_weights(st, u->L[l].cin, u->L[l].cout, weights + u->L[l].w_off, u->wT + u->L[l].w_off));
-    if (sol::g_conv_path == 2) {
+    if (sol::g_conv_path == 2 && mars) {
         for (int l = 1; l <= 10; ++l)
             SOL_TRY(launch_prep_tc_weights(st, u->wT + u->L[l].w_off, u->wprep_bwd + tc_weights_floats() * (l - 1)));
         SOL_CUDA(cudaMemsetAsync(u->tc_flags, 0, sizeof(int) * (size_t)10 * m * u->tc_tiles, st));
@@ -885,6 +914,7 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
             SOL_TRY(launch_wgrad_finalize_n(st, nct32, u->partials + u->partial_stride * (l - 1), gw + u->L[l].w_off, gw + u->L[l].b_off, 0));
         return SOL_OK;
     }
+    if (!mars) return SOL_OK;      // model_mercury accumulated into gw step by step
     for (int l = 1; l <= 10; ++l)
         SOL_TRY(launch_wgrad(st, B, p->Y, p->X, 32, 32, nullptr, nullptr, gw + u->L[l].w_off, gw + u->L[l].b_off, 0,
                              u->partials + u->partial_stride * (l - 1), true));

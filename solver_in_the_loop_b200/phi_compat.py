@@ -295,11 +295,12 @@ class CorrectionModel:
 
     LAYERS = [(3, 32)] + [(32, 32)] * 10 + [(32, 2)]
 
-    def __init__(self, weights: Optional[Sequence] = None, cin0: int = 3, seed: int = 0, device=None):
-        from .trainer import glorot_uniform_params
-        self.layers = [(cin0, 32)] + [(32, 32)] * 10 + [(32, 2)]
+    def __init__(self, weights: Optional[Sequence] = None, cin0: int = 3, seed: int = 0, device=None, model: str = "mars_moon"):
+        from .trainer import glorot_uniform_params, model_layers
+        self.model = model
+        self.layers = model_layers(model, cin0)
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.flat = glorot_uniform_params(cin0=cin0, seed=seed).to(dev)
+        self.flat = glorot_uniform_params(model, cin0=cin0, seed=seed).to(dev)
         if weights is not None:
             self.set_weights(weights)
 
@@ -322,6 +323,10 @@ class CorrectionModel:
         x = x.to(dtype=torch.float32).contiguous()
         v = self._views()
         L = _lib.SOL_ACT_LRELU
+        if self.model == "mercury":      # karman_train.py:92-99: relu = leaky with slope 0
+            a = engine.conv5x5(x, v[0], v[1], act=L, slope=0.0)
+            a = engine.conv5x5(a, v[2], v[3], act=L, slope=0.0)
+            return engine.conv5x5(a, v[4], v[5])
         a = engine.conv5x5(x, v[0], v[1], act=L)
         for k in range(1, 6):
             t = engine.conv5x5(a, v[2 * (2 * k - 1)], v[2 * (2 * k - 1) + 1], act=L)
@@ -342,6 +347,12 @@ class CorrectionModel:
 def model_mars_moon(tensor_in=None, **kw):
     cin0 = 3 if tensor_in is None else int(tensor_in.shape[-1])
     return CorrectionModel(cin0=cin0, **kw)
+
+
+def model_mercury(tensor_in=None, **kw):
+    """karman_train.py:92-99: Conv2D(32, relu) -> Conv2D(64, relu) -> Conv2D(2)."""
+    cin0 = 3 if tensor_in is None else int(tensor_in.shape[-1])
+    return CorrectionModel(cin0=cin0, model="mercury", **kw)
 
 
 # ---- Burgers (burgers/burgers_train.py:172-187) ------------------------------------------------------
@@ -410,3 +421,56 @@ class BurgersTest:
         oy, ox = plan.burgers_step(v.velocity._vy.contiguous(), v.velocity._vx.contiguous(), float(dt), self.viscosity, ky, kx,
                                    f.velocity._vy.contiguous(), f.velocity._vx.contiguous())
         return v.copied_with(velocity=StaggeredGrid([oy, ox], v.velocity.box))
+
+
+# ---- PhiFlow-2 flavoured surface (karman-2d-phi2/karman_train.py:149-196) ---------------------------
+class KarmanFlowPhi2:
+    """``KarmanFlow(domain).step(density_in, velocity_in, re, res, ...) -> [density, velocity]`` — the signature of the
+    PhiFlow-2 rewrite of the scene, on the same CUDA kernels.  The two in-repo differences of that script to the
+    PhiFlow-1 one are honoured: viscosity is ``diffuse.explicit(velocity, dt*res^2/re, dt)`` in PHYSICAL units
+    (:169; mapped onto the kernel's index-space alpha = dt^2*res^2/(re*dx^2)) and the inflow is added BEFORE the
+    advection (:182).  Everything PhiFlow-2 does inside ``make_incompressible`` / ``semi_lagrangian`` is not pinned
+    by code in the reference repository: this class is a signature-compatible surface, not a parity
+    target.  ``domain`` is a phi_compat.Domain; density / velocity are CenteredGrid / StaggeredGrid look-alikes."""
+
+    def __init__(self, domain: Domain):
+        self.domain = domain
+        Y, X = domain.resolution
+        vn = np.zeros((Y + 1, X), dtype=np.float32)      # karman-2d-phi2/karman_train.py:153-159
+        vn[0:2, 0:X - 1] = 1.0
+        vn[:, 0:1] = 1.0
+        vn[:, -1:] = 1.0
+        self.vel_yBc, self.vel_yBcMask = vn, vn.copy()
+        self.solve_info = {}
+        self._plans = {}
+
+    def _plan(self, B, dev) -> Plan:
+        key = (B, str(dev))
+        if key not in self._plans:
+            Y, X = self.domain.resolution
+            dx = float(self.domain.dx[1])
+            lo = self.domain.box.lower
+            CY, CX = np.meshgrid(lo[0] + (np.arange(Y) + 0.5) * dx, lo[1] + (np.arange(X) + 0.5) * dx, indexing="ij")
+            solid = ((CY - 50.0) ** 2 + (CX - 50.0) ** 2) <= 10.0 ** 2                      # Sphere([50,50],10), :162
+            self._inflow = torch.as_tensor(((CY >= 5) & (CY <= 10) & (CX >= 25) & (CX <= 75)).astype(np.float32), device=dev)   # Box[5:10,25:75], :161
+            plan = Plan(Y, X, B, dx, _lib.SOL_BOUNDARY_OPEN, solid, None, self.vel_yBcMask, self.vel_yBc, device=dev)
+            plan.set_cg(tol_abs=1e-5, tol_rel=0.0, max_it=2000, cluster=0)
+            self._plans[key] = plan
+        return self._plans[key]
+
+    def step(self, density_in, velocity_in, re, res, buoyancy_factor=0, dt=1.0, make_input_divfree=False, make_output_divfree=True):
+        if buoyancy_factor != 0 or make_input_divfree or not make_output_divfree:
+            raise SolError("only buoyancy_factor=0, make_input_divfree=False, make_output_divfree=True (the script's settings) are implemented")
+        vy, vx = velocity_in._vy.float().contiguous(), velocity_in._vx.float().contiguous()
+        B, dev = vy.shape[0], vy.device
+        plan = self._plan(B, dev)
+        re_t = torch.as_tensor(np.asarray(re.detach().cpu() if isinstance(re, torch.Tensor) else re, dtype=np.float32).reshape(-1), device=dev)
+        if re_t.numel() == 1 and B > 1:
+            re_t = re_t.expand(B)
+        dx = float(self.domain.dx[1])
+        # alpha = dt * (dt*res^2/re) / dx^2  ==  dt * res_eff^2 / re   with   res_eff = res * sqrt(dt) / dx
+        res_eff = float(res) * float(np.sqrt(dt)) / dx
+        rho = (density_in._t.float() + self._inflow).contiguous()          # inflow before advection
+        out = plan.step_fwd(re_t.contiguous(), vy, vx, rho=rho, dt=float(dt), res=res_eff)
+        self.solve_info = {"pressure": CenteredGrid(out["p"], self.domain.box), "iterations": out["iters"]}
+        return [CenteredGrid(out["rho"], self.domain.box), StaggeredGrid([out["vy"], out["vx"]], self.domain.box)]

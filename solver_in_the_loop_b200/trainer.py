@@ -17,16 +17,20 @@ import torch
 from . import _lib, engine
 
 
+def model_layers(model: str = "mars_moon", cin0: int = 3):
+    """(Cin, Cout) of the Conv2D layers of model_mars_moon / model_mercury (karman_train.py:92-138)."""
+    if model == "mars_moon":
+        return [(cin0, 32)] + [(32, 32)] * 10 + [(32, 2)]
+    if model == "mercury":
+        return [(cin0, 32), (32, 64), (64, 2)]
+    raise ValueError(model)
+
+
 def glorot_uniform_params(model: str = "mars_moon", cin0: int = 3, seed: int = 0) -> torch.Tensor:
     """Keras Conv2D default init (glorot_uniform kernels, zero biases), flat Keras-ordered fp32
     buffer (karman_train.py:101-138)."""
     import math
-    if model == "mars_moon":
-        layers = [(cin0, 32)] + [(32, 32)] * 10 + [(32, 2)]
-    elif model == "mercury":
-        layers = [(cin0, 32), (32, 64), (64, 2)]
-    else:
-        raise ValueError(model)
+    layers = model_layers(model, cin0)
     g = torch.Generator().manual_seed(seed)
     parts = []
     for ci, co in layers:
@@ -48,17 +52,20 @@ def lr_schedule(epoch: int, current_lr: float) -> float:
 class SolTrainer:
     def __init__(self, plan: engine.Plan, msteps: int, batch: int, sig: Sequence[float], lr: float = 1e-4,
                  weights: Optional[torch.Tensor] = None, seed: int = 0, dt: float = 1.0, use_graph: bool = True,
-                 clip_grad: bool = False, process_group=None, with_density: bool = False, cin0: int = 3):
+                 clip_grad: bool = False, process_group=None, with_density: bool = False, cin0: int = 3, model: str = "mars_moon"):
         self.plan, self.msteps, self.batch = plan, int(msteps), int(batch)
         self.lr, self.clip_grad = float(lr), bool(clip_grad)
         self.pg = process_group
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
-        self.unroll = engine.Unroll(plan, msteps, batch, sig, dt=dt, cin0=cin0, with_density=with_density, use_graph=use_graph)
+        self.model = model
+        model_id = {"mars_moon": _lib.SOL_MODEL_MARS_MOON, "mercury": _lib.SOL_MODEL_MERCURY}[model]      # --model (karman_train.py:33)
+        self.unroll = engine.Unroll(plan, msteps, batch, sig, dt=dt, model=model_id, cin0=cin0, with_density=with_density,
+                                    use_graph=use_graph)
         n = self.unroll.nparams
         dev = plan.device
-        w0 = glorot_uniform_params(cin0=cin0, seed=seed) if weights is None else weights
+        w0 = glorot_uniform_params(model, cin0=cin0, seed=seed) if weights is None else weights
         self.weights = w0.to(device=dev, dtype=torch.float32).contiguous().clone()
         # flat all-reduce bucket: [gradients | per-step losses]
         self.bucket = torch.zeros(n + self.msteps, device=dev)
@@ -87,7 +94,7 @@ class SolTrainer:
     def _clip_by_norm(self, clip: float):
         """tf.clip_by_norm(grad, 1e-3) per variable (karman_train.py:452-454)."""
         o = 0
-        for ci, co in [(self.unroll.cfg.cin0, 32)] + [(32, 32)] * 10 + [(32, 2)]:
+        for ci, co in model_layers(self.model, self.unroll.cfg.cin0):
             for n in (25 * ci * co, co):
                 g = self.grad[o:o + n]
                 nrm = g.norm()

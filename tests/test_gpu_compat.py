@@ -55,3 +55,37 @@ def test_reference_apply_loop(cuda_device):
         print("apply step", i, e)
         assert e[0] < 1e-5 and e[1] < 1e-4 and e[2] < 1e-4
     assert st.velocity.staggered_tensor().shape == (1, 2 * res + 1, res + 1, 2)
+
+
+def test_phi2_flavoured_surface(cuda_device):
+    """karman-2d-phi2/karman_train.py:149-196 signature: step(density_in, velocity_in, re, res, ...) -> [density, velocity];
+    physical-units viscosity and inflow-before-advection, checked against the oracle with the matching switches."""
+    from solver_in_the_loop_b200.phi_compat import OPEN, CenteredGrid, Domain, KarmanFlowPhi2, StaggeredGrid, box
+    res, L, B, dt = 32, 100, 2, 1.0
+    dm = Domain(resolution=[2 * res, res], box=box[0:2 * L, 0:L], boundaries=OPEN)
+    geom = so.KarmanGeom(2 * res, res, L)
+    rho, vy, vx = so.warm_start(geom, B)
+    re = torch.tensor([1.6e5, 6.4e5], dtype=torch.float64)
+    for _ in range(5):
+        rho, vy, vx = so.karman_step(rho, vy, vx, re, geom)
+    sim = KarmanFlowPhi2(dm)
+    sim._plan(B, cuda_device).set_cg(tol_abs=1e-7, tol_rel=1e-6, max_it=4000)
+    f = lambda t: t.to(cuda_device, torch.float32)
+    den, vel = sim.step(CenteredGrid(f(rho), dm.box), StaggeredGrid([f(vy), f(vx)], dm.box), re=re, res=res, dt=dt)
+    # oracle: alpha = dt^2 res^2/(re dx^2) == karman_step with res_eff = res*sqrt(dt)/dx; inflow added before the advection
+    dx = L / res
+    r_rho, r_vy, r_vx = so.karman_step(rho, vy, vx, re, geom, dt=dt, res=res * dt ** 0.5 / dx, switches=so.Switches(inflow_after_advect=False))
+    assert rel(vel._vy, r_vy) < 2e-5 and rel(vel._vx, r_vx) < 2e-4 and rel(den._t, r_rho) < 2e-5
+    assert vel.staggered_tensor().shape == (B, 2 * res + 1, res + 1, 2) and sim.solve_info["pressure"].data.shape == (B, 2 * res, res, 1)
+
+
+def test_model_mercury_predict(cuda_device):
+    from solver_in_the_loop_b200.phi_compat import model_mercury
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 24, 16, 3, generator=g)
+    m = model_mercury(x, seed=1)
+    ws = [torch.as_tensor(w).double() for w in m.get_weights()]
+    ws[1] = 0.1 * torch.randn(32, generator=g, dtype=torch.float64); ws[3] = 0.1 * torch.randn(64, generator=g, dtype=torch.float64)
+    m.set_weights([w.numpy() for w in ws])
+    ref = so.cnn_forward(ws, x.double(), model="mercury")
+    assert rel(m.predict(x.to(cuda_device)), ref) < 5e-6

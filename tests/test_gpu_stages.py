@@ -170,10 +170,31 @@ def test_step_forward_and_adjoint(case, cuda_device):
     assert rel(iy, vyt.grad) < 2e-5 and rel(ix, vxt.grad) < 2e-5
 
 
+def test_step_256x128_cluster_cg(cuda_device, eng):
+    """BASELINE config 4 grid (karman-2d 256x128 = the reference's hi-res data grid, karman-2d/Makefile:20-23): one solver
+    step forward + adjoint vs the oracle; the pressure solve runs on a thread-block cluster per simulation (DSMEM halos)."""
+    Y, X, B = 256, 128, 2
+    geom, rho, vy, vx, re, gty, gtx, sig = so.make_case(Y=Y, X=X, B=B, msteps=1, spin=6)
+    plan = eng.Plan.karman(Y, X, B)
+    plan.set_cg(tol_abs=1e-7, tol_rel=1e-6, max_it=6000, cluster=0)
+    vyt = vy.clone().requires_grad_(); vxt = vx.clone().requires_grad_()
+    rrho, ry, rx, aux = so.karman_step(rho, vyt, vxt, re, geom, return_aux=True)
+    out = plan.step_fwd(dev(re, cuda_device), dev(vy, cuda_device), dev(vx, cuda_device), rho=dev(rho, cuda_device))
+    print("256x128 step rel", rel(out["vy"], ry), rel(out["vx"], rx), rel(out["rho"], rrho), rel(out["p"], aux["p"]), out["iters"].tolist())
+    assert rel(out["vy"], ry) < 2e-5 and rel(out["vx"], rx) < 2e-4 and rel(out["rho"], rrho) < 1e-5
+    g = torch.Generator().manual_seed(5)
+    gy = torch.randn(ry.shape, generator=g, dtype=torch.float64); gx = torch.randn(rx.shape, generator=g, dtype=torch.float64)
+    ((ry * gy).sum() + (rx * gx).sum()).backward()
+    iy, ix, it = plan.step_bwd(dev(re, cuda_device), out["vy1"], out["vx1"], dev(gy, cuda_device), dev(gx, cuda_device))
+    print("256x128 step bwd rel", rel(iy, vyt.grad), rel(ix, vxt.grad), it.tolist())
+    assert rel(iy, vyt.grad) < 5e-5 and rel(ix, vxt.grad) < 5e-5
+    plan.close()
+
+
 # ---------------------------------------------------------------------------------------------------
 # convolutions
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("cin,cout", [(3, 32), (32, 32), (32, 2), (2, 32), (32, 3), (4, 32), (32, 4)])
+@pytest.mark.parametrize("cin,cout", [(3, 32), (32, 32), (32, 2), (2, 32), (32, 3), (4, 32), (32, 4), (32, 64), (64, 2), (2, 64), (64, 32)])
 @pytest.mark.parametrize("shape", [(2, 24, 32), (1, 20, 40)], ids=["2x24x32", "1x20x40"])
 def test_conv5x5(eng, cuda_device, cin, cout, shape):
     B, Y, X = shape
@@ -238,7 +259,7 @@ def test_conv5x5_presplit_weights(eng, cuda_device):
         eng.set_option("conv_path", 0)
 
 
-@pytest.mark.parametrize("cin,cout", [(3, 32), (32, 32), (32, 2), (2, 32), (4, 32)])
+@pytest.mark.parametrize("cin,cout", [(3, 32), (32, 32), (32, 2), (2, 32), (4, 32), (32, 64), (64, 2)])
 @pytest.mark.parametrize("shape", [(2, 24, 32), (1, 20, 40)], ids=["2x24x32", "1x20x40"])
 def test_conv5x5_gradients(eng, cuda_device, cin, cout, shape):
     B, Y, X = shape

@@ -120,3 +120,37 @@ def test_full_size_properties(cuda_device):
     assert torch.isfinite(ls).all() and torch.isfinite(g).all()
     assert int(it.max()) < 2000 and int(it.min()) >= 1
     assert float(g.abs().max()) > 0
+
+
+def test_model_mercury_unrolled_parity(cuda_device):
+    """--model mercury (karman_train.py:92-99: Conv2D 32/relu -> 64/relu -> 2): forward states, losses and weight
+    gradients of the unrolled iteration vs the oracle, eager and CUDA-graph."""
+    from solver_in_the_loop_b200 import _lib, engine
+    Y, X, B, m = 64, 32, 2, 2
+    geom, rho, vy, vx, re, gty, gtx, sig = so.make_case(Y=Y, X=X, B=B, msteps=m, spin=25)
+    params = so.init_params(model="mercury", seed=0)
+    for k in range(1, len(params), 2):
+        params[k] = 0.01 * torch.randn(params[k].shape, generator=torch.Generator().manual_seed(k), dtype=torch.float64)
+    pr = [p.clone().requires_grad_() for p in params]
+    loss, losses, states = so.unrolled_loss(pr, rho, vy, vx, re, gty, gtx, geom, sig, m, model="mercury", return_states=True)
+    loss.backward()
+    gref = so.flatten_params([p.grad for p in pr])
+    plan = engine.Plan.karman(Y, X, B)
+    plan.set_cg(tol_abs=1e-7, tol_rel=1e-6, max_it=4000, cluster=0)
+    d = lambda t: dev(t, cuda_device)
+    w = d(so.flatten_params(params))
+    un = engine.Unroll(plan, m, B, sig, model=_lib.SOL_MODEL_MERCURY)
+    assert un.nparams == so.param_count("mercury") == w.numel()
+    ls, pv, px, _ = un.forward(w, d(re), d(vy), d(vx), d(gty), d(gtx), return_pred=True)
+    for i in range(m):
+        assert rel(pv[i], states[i][1]) < 2e-5 and rel(px[i], states[i][2]) < 2e-4
+        assert abs(float(ls[i]) - float(losses[i])) < 1e-4 * abs(float(losses[i]))
+    gw = un.backward(w)
+    print("mercury grad rel", rel(gw, gref))
+    assert rel(gw, gref) < 1e-4
+    un_g = engine.Unroll(plan, m, B, sig, model=_lib.SOL_MODEL_MERCURY, use_graph=True)
+    g1 = torch.zeros_like(gw)
+    for _ in range(4):
+        l1 = un_g.train_iter(w, d(re), d(vy), d(vx), d(gty), d(gtx), g1).clone()
+    torch.cuda.synchronize()
+    assert rel(l1, ls) < 1e-6 and rel(g1, gw) < 1e-5
