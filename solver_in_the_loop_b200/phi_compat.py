@@ -341,7 +341,10 @@ class CorrectionModel:
     @classmethod
     def load(cls, path, **kw):
         z = np.load(path)
-        return cls(weights=[z["arr_%d" % i] for i in range(len(z.files))], **kw)
+        ws = [z["arr_%d" % i] for i in range(len(z.files))]
+        kw.setdefault("cin0", int(ws[0].shape[2]))                        # 3 karman, 4 / 2 burgers
+        kw.setdefault("model", "mercury" if len(ws) == 6 else "mars_moon")
+        return cls(weights=ws, **kw)
 
 
 def model_mars_moon(tensor_in=None, **kw):
@@ -356,6 +359,19 @@ def model_mercury(tensor_in=None, **kw):
 
 
 # ---- Burgers (burgers/burgers_train.py:172-187) ------------------------------------------------------
+def burgers_to_feature(smokestates, forcestates):
+    """burgers_train.py:75-82 ``to_feature(smokestates, forcestates)``: [vy, vx, fy, fx][:, :-1, :-1] channel-last (the karman
+    script's ``to_feature(state, Re)`` has the same name but another signature, hence the prefix here)."""
+    return torch.cat([s.velocity.staggered_tensor()[:, :-1, :-1, 0:2] for s in smokestates] +
+                     [f.velocity.staggered_tensor()[:, :-1, :-1, 0:2] for f in forcestates], dim=-1)
+
+
+def to_feature_noforce(smokestates):
+    """burgers_train.py:84-90."""
+    return torch.cat([s.velocity.staggered_tensor()[:, :-1, :-1, 0:2] for s in smokestates], dim=-1)
+
+
+
 def periodic_diffusion_kernel(H: int, W: int, amount: float, device) -> torch.Tensor:
     """Real-space circular kernel of PhiFlow's periodic diffuse(): ifft2(exp(-(2 pi |k|)^2 amount))
     on an [H, W] component array (a scene constant, like the masks of a karman plan)."""

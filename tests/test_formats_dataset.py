@@ -62,3 +62,33 @@ def test_dataset_epoch_logic_matches_reference(tmp_path):
     assert vy0.shape == (2, 5, 2) and vx0.shape == (2, 4, 3) and gy.shape == (2, 2, 5, 2) and re.dtype == np.float32
     ds.nextStep(); ds.nextBatch()
     assert ds.batchIdx == 2 and ds.stepIdx == 0
+
+
+def test_burgers_dataset_matches_reference_logic(tmp_path):
+    """burgers/burgers_train.py:189-337: (velocity, force) frame pairs, SMAC resolution - 1, per-component stds, and the
+    struct-of-arrays view BurgersTrainer consumes (state = frame 0, forces = frames 0..m-1, ground truth = frames 1..m)."""
+    from solver_in_the_loop_b200.dataset import BurgersPhifDataset
+    root = str(tmp_path / "bset")
+    rng = np.random.default_rng(5)
+    frames, sims, m = 6, 2, 2
+    raw = {}
+    for s in range(sims):
+        sd = formats.sim_dir(root, s)
+        for f in range(frames):
+            for name in ("velo", "forc"):
+                a = rng.standard_normal((1, 9, 9, 2)).astype(np.float32)
+                raw[(s, f, name)] = a
+                formats.write_zipped_array(os.path.join(sd, "%s_%06d.npz" % (name, f)), a)
+    ds = BurgersPhifDataset(root, frames, num_sims=sims, batch_size=2, print_fn=lambda *_: None, scale=2)
+    assert list(ds.resolution) == [4, 4] and ds.numOfBatchs == 1
+    lo = formats.downsample(raw[(0, 0, "velo")], 2, True)
+    assert np.allclose(ds.dataPreloaded[ds.dataSims[0]][0][0], lo)
+    allv0 = np.concatenate([np.abs(formats.downsample(raw[(s, f, "velo")], 2, True)[..., 0]).reshape(-1) for s in range(sims) for f in range(frames)])
+    assert np.isclose(ds.dataStats["std"][0][0], np.std(allv0))
+    random.seed(1)
+    ds.newEpoch(exclude_tail=m)
+    v, f = ds.getData(consecutive_frames=m)
+    assert len(v) == m + 1 and len(f) == m + 1 and v[0].shape == (2, 5, 5, 2)
+    vy0, vx0, fy, fx, gy, gx = BurgersPhifDataset.to_soa([v, f])
+    assert vy0.shape == (2, 5, 4) and vx0.shape == (2, 4, 5) and fy.shape == (m, 2, 5, 4) and gx.shape == (m, 2, 4, 5)
+    assert np.array_equal(gy[0], v[1][:, :, :-1, 0]) and np.array_equal(fx[1], f[1][:, :-1, :, 1]) and np.array_equal(vy0, v[0][:, :, :-1, 0])

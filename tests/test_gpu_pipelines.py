@@ -1,0 +1,55 @@
+"""The reference's Makefile pipelines end to end on the GPU through the CLI drop-ins (same flags as karman.py /
+karman_train.py / karman_apply.py / burgers_train.py / burgers_apply.py): data generation -> SOL training -> apply
+(karman-2d/Makefile:20-23, 78-80, 119-128; burgers/Makefile:75-77), at toy sizes."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sol_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+def test_karman_generate_train_apply(cuda_device, tmp_path):
+    from solver_in_the_loop_b200 import formats
+    from solver_in_the_loop_b200.scripts import karman, karman_apply, karman_train
+    data, tf, run = str(tmp_path / "data"), str(tmp_path / "tf"), str(tmp_path / "run")
+    for k, re in enumerate((1.6e5, 3.2e5)):      # two hi-res simulations (128x64 -> down-sampled 2x to 64x32)
+        karman.main(["-o", data, "-r", "64", "-l", "100", "--re", str(re), "-t", "14", "--skipsteps", "5", "--sim-index", str(k)])
+    frames = sorted(glob.glob(data + "/sim_000000/velo_0*.npz"))
+    assert len(frames) == 8 and formats.read_zipped_array(frames[0]).shape == (1, 129, 65, 2)
+    for model in ("mars_moon", "mercury"):
+        out = tf + "_" + model
+        karman_train.main(["--train", data, "--tf", out, "-s", "2", "-n", "2", "-b", "2", "-t", "8", "-m", "2", "-e", "1", "--lr", "1e-4",
+                           "-l", "100", "--model", model, "--seed", "0"])
+        assert os.path.isfile(out + "/model.npz") and os.path.isfile(out + "/dataStats.pickle")
+        st = karman_apply.main(["-o", run + "_" + model, "-r", "32", "-l", "100", "--re", "3.2e5", "-t", "6", "-s", "2",
+                                "--initvH", frames[0], "--stats", out + "/dataStats.pickle", "--model", out + "/model.npz"])
+        v = st.velocity.staggered_tensor()
+        assert v.shape == (1, 65, 33, 2) and torch.isfinite(v).all()
+        assert len(glob.glob(run + "_" + model + "/sim_000000/velTf_0*.npz")) == 6
+
+
+def test_burgers_train_apply(cuda_device, tmp_path):
+    from solver_in_the_loop_b200 import formats
+    from solver_in_the_loop_b200.scripts import burgers_apply, burgers_train
+    data, tf, run = str(tmp_path / "bdata"), str(tmp_path / "btf"), str(tmp_path / "brun")
+    R, frames, dt = 64, 6, 0.1
+    for s in range(2):       # "hi-res" 64x64 trajectories from the oracle, down-sampled 2x by the dataset
+        dx, vy, vx, fy, fx, gy, gx, sv, sf = so.make_burgers_case(R=R, B=1, msteps=frames, L=32.0, dt=dt, seed=s, noise=0.0)
+        vys = [vy] + [g for g in gy]; vxs = [vx] + [g for g in gx]
+        for f in range(frames):
+            sd = formats.sim_dir(data, s)
+            formats.write_zipped_array(os.path.join(sd, "velo_%06d.npz" % f), formats.pack_staggered(vys[f].numpy(), vxs[f].numpy()).astype(np.float32))
+            formats.write_zipped_array(os.path.join(sd, "forc_%06d.npz" % f), formats.pack_staggered(fy[f].numpy(), fx[f].numpy()).astype(np.float32))
+    tr = burgers_train.main(["--train", data, "--tf", tf, "-s", "2", "-n", "2", "-b", "2", "-t", str(frames), "-m", "2", "-e", "2", "--dt", str(dt),
+                             "-l", "32", "--lr", "1e-4", "--seed", "0"])
+    assert tr.t == 2 * (frames - 2) and os.path.isfile(tf + "/model.npz") and os.path.isfile(tf + "/model_epoch0001.pt")
+    st = burgers_apply.main(["-o", run, "-r", "32", "-l", "32", "--dt", str(dt), "-t", "5", "-s", "2", "--initvH", data + "/sim_000000/velo_000000.npz",
+                             "--loadfH", data + "/sim_000000/forc_0*.npz", "--stats", tf + "/dataStats.pickle", "--model", tf + "/model.npz"])
+    v = st.velocity.staggered_tensor()
+    assert v.shape == (1, 33, 33, 2) and torch.isfinite(v).all()
+    assert len(glob.glob(run + "/sim_000000/velTf_0*.npz")) == 5
