@@ -197,6 +197,13 @@ int sol_unroll_forward(sol_unroll* u, void* stream, const float* weights, const 
                        const float* rho0, const float* vy0, const float* vx0,
                        const float* gt_vy, const float* gt_vx, float* loss_steps,
                        float* pred_vy, float* pred_vx, float* pred_rho);
+/* forward-only rollout — the loop of karman_apply.py:138-151 / burgers_apply.py:129-151: nsteps x (step -> correction net -> add),
+ * every corrected frame written to pred_vy [nsteps,B,Y+1,X] / pred_vx [nsteps,B,Y,X+1] (/ pred_rho [nsteps,B,Y,X] with rho0 and
+ * cfg.with_density).  nsteps is independent of cfg.msteps (no adjoint stash is kept; sol_unroll_backward is invalid afterwards).
+ * Burgers unrolls: the force arrays registered with sol_unroll_set_burgers must hold nsteps frames. */
+int sol_unroll_rollout(sol_unroll* u, void* stream, const float* weights, const float* re,
+                       const float* rho0, const float* vy0, const float* vx0, int nsteps,
+                       float* pred_vy, float* pred_vx, float* pred_rho);
 /* adjoint sweep of the last forward: grad_weights (flat, Keras order) = d(sum_i loss_i / m)/d(weights);
  * g_vy0/g_vx0 (optional) receive the gradient w.r.t. the initial velocity. */
 int sol_unroll_backward(sol_unroll* u, void* stream, const float* weights, float* grad_weights,

@@ -65,6 +65,7 @@ SIGNATURES = {
     "sol_unroll_create": (_i, [_vp, C.POINTER(UnrollCfg), _vp, _sz, C.POINTER(_vp)]),
     "sol_unroll_destroy": (_i, [_vp]),
     "sol_unroll_forward": (_i, [_vp] * 13),
+    "sol_unroll_rollout": (_i, [_vp] * 7 + [_i] + [_vp] * 3),
     "sol_unroll_backward": (_i, [_vp] * 6),
     "sol_unroll_train_iter": (_i, [_vp] * 11),
     "sol_unroll_set_burgers": (_i, [_vp, _f, _vp, _vp, _vp, _vp, _f, _f]),

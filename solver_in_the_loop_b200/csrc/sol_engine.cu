@@ -696,11 +696,14 @@ int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, cons
     return launch_conv5x5(st, B, Y, X, 32, L[0].cin, gS, wT + L[0].w_off, nullptr, nullptr, nullptr, SOL_ACT_NONE, a, g_feat);
 }
 
+// nsteps_override > 0: forward-only rollout of that many frames which recycles the stash of step 0 (no adjoint afterwards)
 int do_forward(sol_unroll* u, cudaStream_t st, const float* weights, const float* re, const float* rho0, const float* vy0, const float* vx0,
-               const float* gt_vy, const float* gt_vx, float* loss_steps, float* pred_vy, float* pred_vx, float* pred_rho) {
+               const float* gt_vy, const float* gt_vx, float* loss_steps, float* pred_vy, float* pred_vx, float* pred_rho,
+               int nsteps_override = 0) {
     sol_plan* p = u->plan;
     const sol_unroll_cfg& c = u->cfg;
-    const int B = c.B, m = c.msteps;
+    const bool ring = nsteps_override > 0;
+    const int B = c.B, m = ring ? nsteps_override : c.msteps;
     const size_t NY = p->NY() * B, NX = p->NX() * B, NC = p->NC() * B;
     const bool dens = c.with_density && rho0 != nullptr;
     const bool burgers = p->boundary == SOL_BOUNDARY_PERIODIC;
@@ -717,13 +720,15 @@ int do_forward(sol_unroll* u, cudaStream_t st, const float* weights, const float
     if (sol::g_conv_path == 2 && mars) {
         for (int l = 1; l <= 10; ++l)
             SOL_TRY(launch_prep_tc_weights(st, weights + u->L[l].w_off, u->wprep_fwd + tc_weights_floats() * (l - 1)));
-        SOL_CUDA(cudaMemsetAsync(u->tc_flags, 0, sizeof(int) * (size_t)10 * m * u->tc_tiles, st));
+        SOL_CUDA(cudaMemsetAsync(u->tc_flags, 0, sizeof(int) * (size_t)10 * c.msteps * u->tc_tiles, st));
     }
-    u->tc_seq = 0; u->tc_prev = nullptr;
+    u->tc_seq = ring ? 10 * c.msteps : 0;      // a rollout never chains conv launches by tile flags (the flag blocks are per unrolled step)
+    u->tc_prev = nullptr;
     const float* cvy = vy0; const float* cvx = vx0; const float* crho = dens ? rho0 : nullptr;
     const bool fuse_io = sol::g_fuse_solver_io && cg_fuses(p);
     for (int i = 0; i < m; ++i) {
-        StepStash& s = u->stash[i];
+        StepStash& s = u->stash[ring ? 0 : i];
+        int* it_slot = u->iters + (size_t)(ring ? 0 : i) * B;
         float* nvy = pred_vy ? pred_vy + (size_t)i * NY : ((i & 1) ? u->sB_vy : u->sA_vy);
         float* nvx = pred_vx ? pred_vx + (size_t)i * NX : ((i & 1) ? u->sB_vx : u->sA_vx);
         float* nrho = dens ? (pred_rho ? pred_rho + (size_t)i * NC : ((i & 1) ? u->rhoB : u->rhoA)) : nullptr;
@@ -748,9 +753,9 @@ int do_forward(sol_unroll* u, cudaStream_t st, const float* weights, const float
         SOL_TRY(launch_advect(p, st, B, c.dt, s.vy1, s.vx1, crho, u->vy2, u->vx2, nrho));
         if (fuse_io && c.cin0 == 3) {      // the projection kernel also writes the CNN features of the projected velocity
             CgFuse f; f.feat_out = s.feat; f.re = re; f.isy = 1.0f / c.sig_vy; f.isx = 1.0f / c.sig_vx; f.isr = 1.0f / c.sig_ext; f.cfeat = 3;
-            SOL_TRY(launch_cg(p, st, B, 1, nullptr, nullptr, u->vy2, u->vx2, u->vy3, u->vx3, u->iters + (size_t)i * B, &f));
+            SOL_TRY(launch_cg(p, st, B, 1, nullptr, nullptr, u->vy2, u->vx2, u->vy3, u->vx3, it_slot, &f));
         } else {
-            SOL_TRY(launch_cg(p, st, B, 1, nullptr, nullptr, u->vy2, u->vx2, u->vy3, u->vx3, u->iters + (size_t)i * B));
+            SOL_TRY(launch_cg(p, st, B, 1, nullptr, nullptr, u->vy2, u->vx2, u->vy3, u->vx3, it_slot));
             SOL_TRY(launch_to_feature(p, st, B, u->vy3, u->vx3, re, c.sig_vy, c.sig_vx, c.sig_ext, s.feat));
         }
         SOL_TRY(cnn_forward(u, st, weights, s, u->corr));
@@ -759,9 +764,9 @@ int do_forward(sol_unroll* u, cudaStream_t st, const float* weights, const float
                                     gt_vy ? loss_steps + i : nullptr));
         cvy = nvy; cvx = nvx; crho = nrho;
     }
-    u->forward_done = true;
+    u->forward_done = !ring;
     u->last_re = u->re_buf;
-    u->have_loss = gt_vy != nullptr;
+    u->have_loss = !ring && gt_vy != nullptr;
     return SOL_OK;
 }
 
@@ -973,6 +978,13 @@ extern "C" int sol_unroll_forward(sol_unroll* u, void* stream, const float* weig
     SOL_CHECK(!gt_vy || loss_steps, "sol_unroll_forward: loss_steps required with ground truth");
     SOL_CHECK((pred_vy == nullptr) == (pred_vx == nullptr), "sol_unroll_forward: pred_vy and pred_vx go together");
     return do_forward(u, (cudaStream_t)stream, weights, re, rho0, vy0, vx0, gt_vy, gt_vx, loss_steps, pred_vy, pred_vx, pred_rho);
+}
+
+extern "C" int sol_unroll_rollout(sol_unroll* u, void* stream, const float* weights, const float* re, const float* rho0, const float* vy0,
+                                  const float* vx0, int nsteps, float* pred_vy, float* pred_vx, float* pred_rho) {
+    SOL_CHECK(u && weights && vy0 && vx0 && pred_vy && pred_vx && nsteps >= 1, "sol_unroll_rollout: bad arguments");
+    SOL_CHECK(pred_rho == nullptr || (rho0 != nullptr && u->cfg.with_density), "sol_unroll_rollout: pred_rho needs rho0 and cfg.with_density");
+    return do_forward(u, (cudaStream_t)stream, weights, re, rho0, vy0, vx0, nullptr, nullptr, nullptr, pred_vy, pred_vx, pred_rho, nsteps);
 }
 
 extern "C" int sol_unroll_backward(sol_unroll* u, void* stream, const float* weights, float* grad_weights, float* g_vy0, float* g_vx0) {

@@ -317,6 +317,17 @@ class Unroll:
                                           _ptr(gt_vy), _ptr(gt_vx), _ptr(self.loss_steps), _ptr(pv), _ptr(px), _ptr(pr)))
         return (self.loss_steps, pv, px, pr) if return_pred else self.loss_steps
 
+    def rollout(self, weights, re, vy0, vx0, nsteps: int, rho0=None):
+        """Forward-only rollout of nsteps corrected frames (karman_apply.py:138-151) in ONE library call: returns
+        (vy [n,B,Y+1,X], vx [n,B,Y,X+1], rho [n,B,Y,X] or None)."""
+        dev, p = self.plan.device, self.plan
+        pv = torch.empty(nsteps, self.B, p.Y + 1, p.X, device=dev)
+        px = torch.empty(nsteps, self.B, p.Y, p.X + 1, device=dev)
+        pr = torch.empty(nsteps, self.B, p.Y, p.X, device=dev) if (rho0 is not None and self.cfg.with_density) else None
+        check(self.lib.sol_unroll_rollout(self.handle, _stream(), _ptr(weights), _ptr(re), _ptr(rho0), _ptr(vy0), _ptr(vx0), int(nsteps),
+                                          _ptr(pv), _ptr(px), _ptr(pr)))
+        return pv, px, pr
+
     def backward(self, weights, grad_out=None, want_input_grad=False):
         g = torch.empty(self.nparams, device=self.plan.device) if grad_out is None else grad_out
         gy = gx = None

@@ -23,6 +23,7 @@ def parse(argv=None):
     ap.add_argument("-t", "--simsteps", default=500, type=int); ap.add_argument("-s", "--scale", default=4, type=int)
     ap.add_argument("--stats", default=None, help="dataStats.pickle of the training run")
     ap.add_argument("--model", default=None, help="model.npz (Keras-ordered weights)")
+    ap.add_argument("--fused", action="store_true", help="run all frames in ONE library call (sol_unroll_rollout) instead of the eager loop")
     return ap.parse_args(argv)
 
 
@@ -64,6 +65,19 @@ def main(argv=None):
 
     write(0)
     simulator = KarmanFlow()
+    if p["fused"]:
+        from .. import _lib, engine
+        n = p["simsteps"] - 1
+        plan = simulator._plan(st, velBCy, velBCyMask)
+        model_id = _lib.SOL_MODEL_MERCURY if model.model == "mercury" else _lib.SOL_MODEL_MARS_MOON
+        un = engine.Unroll(plan, 1, 1, (float(std_out[0]), float(std_out[1]), float(std_in[2])), model=model_id, with_density=True)
+        re_t = torch.full((1,), float(p["re"]), device="cuda")
+        pv, px, pr = un.rollout(model.flat, re_t, st.velocity._vy.contiguous(), st.velocity._vx.contiguous(), n, rho0=st.density._t.contiguous())
+        for i in range(1, p["simsteps"]):
+            vel = StaggeredGrid([pv[i - 1], px[i - 1]], st.velocity.box)
+            st = st.copied_with(density=pr[i - 1], velocity=vel)
+            write(i)          # corTf is not materialised by the fused rollout (the correction is applied in-kernel)
+        return st
     for i in range(1, p["simsteps"]):
         st = simulator.step(st, re=p["re"], res=res, velBCy=velBCy, velBCyMask=velBCyMask)
         inputf = to_feature([st], p["re"]) / std_in

@@ -31,6 +31,11 @@ def test_karman_generate_train_apply(cuda_device, tmp_path):
         v = st.velocity.staggered_tensor()
         assert v.shape == (1, 65, 33, 2) and torch.isfinite(v).all()
         assert len(glob.glob(run + "_" + model + "/sim_000000/velTf_0*.npz")) == 6
+        # the same rollout in one library call (sol_unroll_rollout)
+        st2 = karman_apply.main(["-r", "32", "-l", "100", "--re", "3.2e5", "-t", "6", "-s", "2", "--initvH", frames[0],
+                                 "--stats", out + "/dataStats.pickle", "--model", out + "/model.npz", "--fused"])
+        v2 = st2.velocity.staggered_tensor()
+        assert float((v2 - v).norm() / v.norm()) < 1e-5
 
 
 def test_burgers_train_apply(cuda_device, tmp_path):

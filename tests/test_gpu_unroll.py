@@ -154,3 +154,19 @@ def test_model_mercury_unrolled_parity(cuda_device):
         l1 = un_g.train_iter(w, d(re), d(vy), d(vx), d(gty), d(gtx), g1).clone()
     torch.cuda.synchronize()
     assert rel(l1, ls) < 1e-6 and rel(g1, gw) < 1e-5
+
+
+def test_rollout_matches_unrolled_forward(cuda_device):
+    """sol_unroll_rollout (the karman_apply.py:138-151 loop in one call, stash recycled) == the unrolled forward's
+    corrected states, for a rollout longer than the unroll's msteps."""
+    Y, X, B, m = 64, 32, 2, 5
+    engine, geom, rho, vy, vx, re, gty, gtx, sig, params, plan, un, w = _setup(Y, X, B, m, cuda_device)
+    d = lambda t: dev(t, cuda_device)
+    w = w * 0.2
+    _, pv, px, prho = un.forward(w, d(re), d(vy), d(vx), rho0=d(rho), return_pred=True)
+    short = engine.Unroll(plan, 2, B, sig, with_density=True)
+    rv, rx, rr = short.rollout(w, d(re), d(vy), d(vx), m, rho0=d(rho))
+    torch.cuda.synchronize()
+    assert rel(rv, pv) < 1e-6 and rel(rx, px) < 1e-6 and rel(rr, prho) < 1e-6
+    with pytest.raises(engine.SolError):
+        short.backward(w)          # a rollout keeps no adjoint stash
