@@ -75,10 +75,10 @@ int sol_plan_set_option(sol_plan* plan, const char* name, int value);
 /* Process-wide knobs:
  *   "conv_path" 0 = auto, 1 = fp32 SIMT kernels, 2 = tcgen05 tensor-core kernels (3xTF32, fp32-accurate)
  *   "wgrad_path" 0 = auto, 1 = per-step fp32 SIMT weight gradients, 2 = deferred tcgen05 weight-gradient GEMM
- *   "fuse_small" 1 (default) = the correction-gradient scaling (adjoint of "velocity + correction") is folded into the
- *         diffusion adjoint of the following step, 0 = separate kernel
- *   "fuse_solver_io" 1 = to_feature and its adjoint are folded into the projection kernel (2 launches fewer per step;
- *         slower at 3 simulations per GPU because the work moves onto the solve's B CTAs), 0 (default) = separate kernels
+ *   "fuse_small" 1 = the correction-gradient scaling (adjoint of "velocity + correction") is folded into the
+ *         diffusion adjoint of the following step, 0 (default: measured faster) = separate kernel
+ *   "fuse_solver_io" 1 (default) = to_feature and its adjoint are folded into the projection kernel (2 launches fewer per
+ *         step) where the solver variant supports it, 0 = separate kernels
  *   "wgrad_overlap" 1 (default) = the deferred weight-gradient GEMMs of already finished steps run on a side stream
  *         while an adjoint pressure solve keeps only B SMs busy, 0 = all of them after the adjoint sweep
  *   "wgrad_window_us" (tuning) time budget of one such window at 128x64, default 110

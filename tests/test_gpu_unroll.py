@@ -39,6 +39,7 @@ _PATHS = {
     "tcgen05-conv+wgrad-tilechain-solverio": (2, 2, 1, 1, 1, 1, 1),
     "tcgen05-conv+wgrad-serial-unfused": (2, 2, 1, 0, 0, 0, 0),
     "tcgen05-conv+wgrad-nopdl": (2, 2, 0, 0, 1, 1, 0),
+    "defaults(tcgen05,solverio,unfused-small)": (2, 2, 1, 0, 1, 0, 1),
 }
 
 
@@ -51,7 +52,7 @@ def conv_path(request):
     for n, v in zip(names, request.param):
         engine.set_option(n, v)
     yield request.param
-    for n, v in zip(names, (0, 0, 1, 0, 1, 1, 0)):
+    for n, v in zip(names, (0, 0, 1, 0, 1, 0, 1)):      # back to the library defaults
         engine.set_option(n, v)
 
 
