@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--conv-chain", type=int, default=0, help="1 = consecutive tensor-core conv layers chained by tile flags")
+    ap.add_argument("--conv-stack", type=int, default=0, help="1 = the ten 32->32 layers of a sweep in one persistent launch")
     ap.add_argument("--wgrad-overlap", type=int, default=1, help="1 = deferred weight-gradient GEMMs run beside the adjoint solves")
     ap.add_argument("--wgrad-window-us", type=int, default=-1, help="tuning: time budget of one adjoint-solve window (us at 128x64)")
     ap.add_argument("--fuse-small", type=int, default=0, help="1 = corr_bwd folded into the diffusion adjoint")
@@ -250,6 +251,7 @@ def main():
     engine.set_option("conv_path", args.conv_path)
     engine.set_option("pdl", args.pdl)
     engine.set_option("conv_chain", args.conv_chain)
+    engine.set_option("conv_stack", args.conv_stack)
     engine.set_option("wgrad_overlap", args.wgrad_overlap)
     engine.set_option("fuse_small", args.fuse_small)
     engine.set_option("fuse_solver_io", args.fuse_solver_io)
@@ -414,7 +416,7 @@ def main():
                        "cg": "max|r|<1e-5 per sim, <=2000 it (reference stop rule)", "mean_cg_iters": [k_fwd, k_bwd],
                        "l2": "working set (activation stash %.2f GB/iter) exceeds the 126 MB L2; no explicit flush"
                              % (trainer.unroll.workspace.numel() / 1e9),
-                       "cuda_graph": not args.no_graph, "conv_path": args.conv_path, "wgrad_path": args.wgrad_path, "cg_precond": args.cg_precond, "pdl": args.pdl, "conv_chain": args.conv_chain, "wgrad_overlap": args.wgrad_overlap, "fuse_small": args.fuse_small, "fuse_solver_io": args.fuse_solver_io, "loss": float(loss_host)},
+                       "cuda_graph": not args.no_graph, "conv_path": args.conv_path, "wgrad_path": args.wgrad_path, "cg_precond": args.cg_precond, "pdl": args.pdl, "conv_chain": args.conv_chain, "conv_stack": args.conv_stack, "wgrad_overlap": args.wgrad_overlap, "fuse_small": args.fuse_small, "fuse_solver_io": args.fuse_solver_io, "loss": float(loss_host)},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": trainer.h2d_bytes_per_step(), "d2h_bytes_per_step": 4,
                     "ms_per_step": t_e2e / args.steps * 1e3, "wall_ms_per_step": t_e2e_wall / args.steps * 1e3},
             "gpu_launches": int(launches),

@@ -79,6 +79,8 @@ int sol_plan_set_option(sol_plan* plan, const char* name, int value);
  *         diffusion adjoint of the following step, 0 (default: measured faster) = separate kernel
  *   "fuse_solver_io" 1 (default) = to_feature and its adjoint are folded into the projection kernel (2 launches fewer per
  *         step) where the solver variant supports it, 0 = separate kernels
+ *   "conv_stack" 1 = the ten consecutive 32->32 layers of a sweep run as ONE persistent tensor-core launch with per-tile
+ *         flags between layers (when all its CTAs are co-resident; measured slower), 0 (default) = one launch per layer
  *   "wgrad_overlap" 1 (default) = the deferred weight-gradient GEMMs of already finished steps run on a side stream
  *         while an adjoint pressure solve keeps only B SMs busy, 0 = all of them after the adjoint sweep
  *   "wgrad_window_us" (tuning) time budget of one such window at 128x64, default 110

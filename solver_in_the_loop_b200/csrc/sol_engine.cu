@@ -270,6 +270,10 @@ extern "C" int sol_set_option(const char* name, int value) {
         sol::g_conv_chain = value ? 1 : 0;
         return SOL_OK;
     }
+    if (strcmp(name, "conv_stack") == 0) {
+        sol::g_conv_stack = value ? 1 : 0;
+        return SOL_OK;
+    }
     if (strcmp(name, "pdl") == 0) {
         sol::g_pdl = value ? 1 : 0;
         return SOL_OK;
@@ -619,6 +623,18 @@ int cnn_forward(sol_unroll* u, cudaStream_t st, const float* w, const StepStash&
     const bool tc = sol::g_conv_path == 2;
     SOL_TRY(launch_conv5x5(st, B, Y, X, L[0].cin, 32, s.feat, w + L[0].w_off, w + L[0].b_off, nullptr, nullptr, SOL_ACT_LRELU, a, s.acts[0]));
     u->tc_prev = nullptr;
+    if (tc && sol::g_conv_stack && u->tc_seq + 10 <= 10 * u->cfg.msteps && conv_stack_fits(B, Y, X)) {
+        // the ten 32->32 layers in ONE persistent launch (per-tile flags between layers)
+        ConvStackLayer ls[10];
+        for (int k = 1; k <= 5; ++k) {
+            ls[2 * k - 2] = ConvStackLayer{s.acts[2 * k - 2], s.acts[2 * k - 1], w + L[2 * k - 1].b_off, nullptr, nullptr, SOL_ACT_LRELU, 2 * k - 2};
+            ls[2 * k - 1] = ConvStackLayer{s.acts[2 * k - 1], s.acts[2 * k], w + L[2 * k].b_off, s.acts[2 * k - 2], nullptr, SOL_ACT_LRELU, 2 * k - 1};
+        }
+        int* flags = u->tc_flags + (size_t)u->tc_seq * u->tc_tiles;
+        u->tc_seq += 10;
+        SOL_TRY(launch_conv_stack(st, B, Y, X, 10, ls, u->wprep_fwd, 10, a, flags));
+        return launch_conv5x5(st, B, Y, X, 32, 2, s.acts[10], w + L[11].w_off, w + L[11].b_off, nullptr, nullptr, SOL_ACT_NONE, a, corr);
+    }
     for (int k = 1; k <= 5; ++k) {
         const LayerDesc& l1 = L[2 * k - 1];
         const LayerDesc& l2 = L[2 * k];
@@ -664,6 +680,22 @@ int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, cons
         SOL_TRY(launch_wgrad(st, B, Y, X, 32, 2, s.acts[10], g_corr, gw + L[11].w_off, gw + L[11].b_off, 1, nullptr, false));
     SOL_TRY(launch_conv5x5(st, B, Y, X, 2, 32, g_corr, wT + L[11].w_off, nullptr, nullptr, s.acts[10], SOL_ACT_DLRELU, a, gS));
     u->tc_prev = nullptr;
+    if (tc && deferred && sol::g_conv_stack && u->tc_seq + 10 <= 10 * u->cfg.msteps && conv_stack_fits(B, Y, X)) {
+        // the ten data-gradient layers in ONE persistent launch; every output gradient goes to its write-once stash slot
+        ConvStackLayer ls[10];
+        int n = 0;
+        for (int k = 5; k >= 1; --k) {
+            float* gT = gout(2 * k - 1, nullptr);
+            float* gN = (k >= 2) ? gout(2 * k - 2, nullptr) : u->g0_st + (size_t)step * u->nA;
+            ls[n++] = ConvStackLayer{gS, gT, nullptr, nullptr, s.acts[2 * k - 1], SOL_ACT_DLRELU, 2 * k - 1};
+            ls[n++] = ConvStackLayer{gT, gN, nullptr, gS, s.acts[2 * k - 2], SOL_ACT_DLRELU, 2 * k - 2};
+            gS = gN;
+        }
+        int* flags = u->tc_flags + (size_t)u->tc_seq * u->tc_tiles;
+        u->tc_seq += 10;
+        SOL_TRY(launch_conv_stack(st, B, Y, X, 10, ls, u->wprep_bwd, 10, a, flags));
+        return launch_conv5x5(st, B, Y, X, 32, L[0].cin, gS, wT + L[0].w_off, nullptr, nullptr, nullptr, SOL_ACT_NONE, a, g_feat);
+    }
     for (int k = 5; k >= 1; --k) {
         const LayerDesc& l1 = L[2 * k - 1];
         const LayerDesc& l2 = L[2 * k];

@@ -203,6 +203,18 @@ int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, con
                       const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready,
                       const int* dep_flags = nullptr, int* out_flags = nullptr);
 int tc_tiles_per_launch(int B, int Y, int X);
+// persistent stack of consecutive 32->32 layers (one launch, per-tile flags between layers)
+struct ConvStackLayer {
+    const float* in; float* out;
+    const float* bias; const float* addend; const float* ref;
+    int act;
+    int weight_index;       // which [25][hi|lo][32][32] block of the pre-split weight array
+};
+extern int g_conv_stack;
+bool conv_stack_fits(int B, int Y, int X);
+// flags: int[nlayers * tc_tiles_per_launch(B,Y,X)], zero before the launch; wprep_all: wprep_layers consecutive pre-split weight blocks
+int launch_conv_stack(cudaStream_t st, int B, int Y, int X, int nlayers, const ConvStackLayer* layers, const float* wprep_all,
+                      int wprep_layers, float slope, int* flags);
 extern int g_conv_chain;
 extern int g_fuse_small;
 extern int g_fuse_solver_io;
