@@ -441,6 +441,7 @@ def main():
                          "peak_source": tpeak_src + ", dense bf16 (tf32 issues at half that rate)", "us_per_launch": t_conv_max * 1e6,
                          "algorithmic_flops_per_launch": conv_flops, "executed_tensor_tflops": 3.0 * tf,
                          "launches_per_step": 20 * m, "share_of_step": 20 * m * t_conv_max / t_iter,
+                         "frac_of_formulation_ceiling": tf / (tpeak / 6.0),
                          "note": "achieved = 2*25*32*32 flop/pixel x B*Y*X pixels / CUDA-event launch time of a dependent "
                                  "ping-pong chain; fp32-accurate 3xTF32 executes 3 tf32 MMAs per algorithmic product, so the "
                                  "tensor pipe runs 3x the algorithmic rate at half the bf16 peak (ceiling = peak/6); "
