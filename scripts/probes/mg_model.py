@@ -203,3 +203,57 @@ if __name__ == "__main__":
                                    "bilinear V(2,2) scale 0.7": ((0.8, 0.8), (0.8, 0.8), 0.7), "bilinear V(1,1) scale 0.7": ((0.8,), (0.8,), 0.7)}.items():
         its = [pcg_b(H, d, pre, post, scale=sc)[1] for d in rhs]
         print("%-32s iterations %s" % (name, its), flush=True)
+
+
+# ---- variant: red-black Gauss-Seidel smoothing (symmetric: R,B before / B,R after) ----
+def rb_halfsweep(L, u, b, color, om=1.0):
+    Yl, Xl = u.shape
+    jj, ii = np.meshgrid(np.arange(Yl), np.arange(Xl), indexing="ij")
+    m = ((jj + ii) % 2 == color) & L["act"]
+    a = L["act"]
+    p = np.zeros((Yl + 2, Xl + 2)); p[1:-1, 1:-1] = u * a
+    nb = p[:-2, 1:-1] + p[2:, 1:-1] + p[1:-1, :-2] + p[1:-1, 2:]
+    unew = (nb - b) / L["diag"]
+    out = u.copy()
+    out[m] = (1 - om) * u[m] + om * unew[m]
+    return out
+
+
+def vcycle_rb(H, l, b, nu, om=1.0):
+    L = H[l]
+    if l == len(H) - 1:
+        return (L["inv"] @ b.reshape(-1)).reshape(b.shape)
+    u = np.zeros_like(b)
+    for _ in range(nu):
+        u = rb_halfsweep(L, u, b, 0, om); u = rb_halfsweep(L, u, b, 1, om)
+    r = (b - applyA(L, u)) * L["act"]
+    rc = (r[0::2, 0::2] + r[0::2, 1::2] + r[1::2, 0::2] + r[1::2, 1::2]) * H[l + 1]["act"]
+    ec = vcycle_rb(H, l + 1, rc, nu, om)
+    u = u + np.kron(ec, np.ones((2, 2))) * L["act"]
+    for _ in range(nu):
+        u = rb_halfsweep(L, u, b, 1, om); u = rb_halfsweep(L, u, b, 0, om)
+    return u
+
+
+def pcg_rb(H, d, nu, tol=1e-5, om=1.0, maxit=100):
+    L = H[0]
+    x = np.zeros_like(d); r = d * L["act"]; p = np.zeros_like(d); rz = 0.0
+    it = 0
+    while np.abs(r).max() >= tol and it < maxit:
+        z = vcycle_rb(H, 0, r, nu, om)
+        rzn = (r * z).sum()
+        beta = 0.0 if it == 0 else rzn / rz
+        rz = rzn
+        p = z + beta * p
+        q = applyA(L, p)
+        alpha = rz / (p * q).sum()
+        x += alpha * p; r -= alpha * q
+        it += 1
+    return x, it
+
+
+if __name__ == "__main__":
+    for nu in (1, 2):
+        for om in (1.0, 1.15):
+            its = [pcg_rb(H, d, nu, om=om)[1] for d in rhs]
+            print("RB-GS V(%d,%d) omega=%.2f          iterations %s" % (nu, nu, om, its), flush=True)
