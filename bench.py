@@ -361,7 +361,9 @@ def main():
         t_full = e8.elapsed_time(e9) / 1e3 / nrep
         K_f = float(it_f.float().mean())
         ach_f = (per_iter_bytes * K_f + 8.0) * Y * X * nsm / t_full / 1e9
+        ach_cg = (40.0 * K_f + 8.0) * Y * X * nsm / t_full / 1e9       # the same launch counted with the plain-CG byte model of SURVEY 8d
         full = {"sims": nsm, "us_per_launch": t_full * 1e6, "cg_iters": K_f, "achieved": ach_f, "unit": "GB/s", "frac": ach_f / peak,
+                "achieved_plain_cg_byte_model": ach_cg, "frac_plain_cg_byte_model": ach_cg / peak,
                 "note": "one simulation per SM: same kernel, same per-launch latency, every SM busy"}
         plan_f.close()
 
