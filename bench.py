@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--cg-rows", type=int, default=0)
     ap.add_argument("--mg-variant", type=int, default=0, help="0 = compile-time-hierarchy multigrid kernel, 2 = run-time-hierarchy kernel")
     ap.add_argument("--cg-precond", type=int, default=1, help="1 = multigrid-preconditioned CG, 0 = the reference's plain CG")
+    ap.add_argument("--direct-solve", type=int, default=1, help="1 = direct projection (fast Poisson + capacitance correction) where supported")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-msteps", type=int, default=4, help="unroll length of the bounded CPU sample")
     return ap.parse_args()
@@ -262,6 +263,7 @@ def main():
     plan.set_option("cg_rows", args.cg_rows)
     plan.set_option("cg_precond", args.cg_precond)
     plan.set_option("mg_variant", args.mg_variant)
+    plan.set_option("direct_solve", args.direct_solve)
     plan.set_cg(tol_abs=1e-7, tol_rel=1e-6, max_it=4000, cluster=args.cluster)     # accurate solves for the spin-up
     re, vy0, vx0, gt_vy, gt_vx, sig = synth_batch(plan, engine, torch, B, m, rank, args.spin)
     if world > 1:   # identical normalisation on every rank (dataStats are global in the reference)
@@ -330,10 +332,15 @@ def main():
     t_solve = e4.elapsed_time(e5) / 1e3 / nrep
     K = float(it_k.float().mean())
     precond = bool(args.cg_precond) and args.cluster <= 1
+    direct = bool(args.direct_solve) and args.cluster <= 1 and (Y, X) in ((128, 64), (64, 32)) and K == 0.0
     # algorithmic bytes per cell per solve: plain CG 40K+8; multigrid-preconditioned CG adds
     # the V(2,2) cycle: 4 fine smoothing sweeps (16 B each) + residual/restrict/prolong (20 B) + coarse levels (1/3 of fine)
     per_iter_bytes = 148.0 if precond else 40.0
-    alg_bytes = (per_iter_bytes * K + 8.0) * Y * X * B
+    # direct projection: per simulation the compulsory field traffic (20 B/cell) + the precomputed operators it streams
+    # (transform matrices Sy, Sx, 1/lambda; capacitance matrix M; correction basis W: ~164 changed rows x N), all L2-resident
+    KCH = 164 if (Y, X) == (128, 64) else 84
+    direct_bytes_per_sim = 20.0 * Y * X + 4.0 * (Y * Y + X * X + Y * X) + 4.0 * KCH * KCH + 4.0 * KCH * Y * X
+    alg_bytes = direct_bytes_per_sim * B if direct else (per_iter_bytes * K + 8.0) * Y * X * B
     peak, peak_src = load_peaks()
     achieved = alg_bytes / t_solve / 1e9
 
@@ -346,6 +353,7 @@ def main():
         plan_f.set_option("cg_rows", args.cg_rows)
         plan_f.set_option("cg_precond", args.cg_precond)
         plan_f.set_option("mg_variant", args.mg_variant)
+        plan_f.set_option("direct_solve", args.direct_solve)
         plan_f.set_cg(tol_abs=1e-5, tol_rel=0.0, max_it=2000, cluster=args.cluster)
         rep = (nsm + B - 1) // B
         fy = adv_y.repeat(rep, 1, 1)[:nsm].contiguous(); fx = adv_x.repeat(rep, 1, 1)[:nsm].contiguous()
@@ -360,8 +368,8 @@ def main():
         torch.cuda.synchronize()
         t_full = e8.elapsed_time(e9) / 1e3 / nrep
         K_f = float(it_f.float().mean())
-        ach_f = (per_iter_bytes * K_f + 8.0) * Y * X * nsm / t_full / 1e9
-        ach_cg = (40.0 * K_f + 8.0) * Y * X * nsm / t_full / 1e9       # the same launch counted with the plain-CG byte model of SURVEY 8d
+        ach_f = (direct_bytes_per_sim * nsm if direct else (per_iter_bytes * K_f + 8.0) * Y * X * nsm) / t_full / 1e9
+        ach_cg = (40.0 * max(K_f, 0.0) + 8.0) * Y * X * nsm / t_full / 1e9       # the same launch counted with the plain-CG byte model of SURVEY 8d
         full = {"sims": nsm, "us_per_launch": t_full * 1e6, "cg_iters": K_f, "achieved": ach_f, "unit": "GB/s", "frac": ach_f / peak,
                 "achieved_plain_cg_byte_model": ach_cg, "frac_plain_cg_byte_model": ach_cg / peak,
                 "note": "one simulation per SM: same kernel, same per-launch latency, every SM busy"}
@@ -415,10 +423,11 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "karman-2d %dx%d SOL-32: msteps=%d, %d sims/GPU, Re in reference Makefile set" % (Y, X, m, B),
                        "global_batch": B * world, "parallelism": "dp%d over simulations, 1 all-reduce/step" % world,
-                       "cg": "max|r|<1e-5 per sim, <=2000 it (reference stop rule)", "mean_cg_iters": [k_fwd, k_bwd],
+                       "cg": ("direct projection (exact solve, no iterations)" if (k_fwd == 0.0 and args.direct_solve) else
+                              "max|r|<1e-5 per sim, <=2000 it (reference stop rule)"), "mean_cg_iters": [k_fwd, k_bwd],
                        "l2": "working set (activation stash %.2f GB/iter) exceeds the 126 MB L2; no explicit flush"
                              % (trainer.unroll.workspace.numel() / 1e9),
-                       "cuda_graph": not args.no_graph, "conv_path": args.conv_path, "wgrad_path": args.wgrad_path, "cg_precond": args.cg_precond, "pdl": args.pdl, "conv_chain": args.conv_chain, "conv_stack": args.conv_stack, "wgrad_overlap": args.wgrad_overlap, "fuse_small": args.fuse_small, "fuse_solver_io": args.fuse_solver_io, "loss": float(loss_host)},
+                       "cuda_graph": not args.no_graph, "conv_path": args.conv_path, "wgrad_path": args.wgrad_path, "cg_precond": args.cg_precond, "direct_solve": args.direct_solve, "pdl": args.pdl, "conv_chain": args.conv_chain, "conv_stack": args.conv_stack, "wgrad_overlap": args.wgrad_overlap, "fuse_small": args.fuse_small, "fuse_solver_io": args.fuse_solver_io, "loss": float(loss_host)},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": trainer.h2d_bytes_per_step(), "d2h_bytes_per_step": 4,
                     "ms_per_step": t_e2e / args.steps * 1e3, "wall_ms_per_step": t_e2e_wall / args.steps * 1e3},
             "gpu_launches": int(launches),
@@ -428,13 +437,18 @@ def main():
         t_iter = t_dev / args.steps
         solver_name = ("k_cg_mg3 (fused projection: divergence + multigrid-preconditioned CG + gradient subtract)" if precond
                        else "k_cg (fused projection: divergence + CG + gradient subtract)")
+        if direct:
+            solver_name = "k_direct_solve + k_direct_apply (direct projection: divergence -> DST fast Poisson solve -> capacitance correction -> gradient subtract)"
         roof_solver = {"kernel": solver_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                       "frac": achieved / peak, "traffic": CG_MG_DRAM_BYTES if (precond and (Y, X, B) == (128, 64, 3)) else None, "peak_source": peak_src, "cg_iters": K,
+                       "frac": achieved / peak, "traffic": CG_MG_DRAM_BYTES if (precond and not direct and (Y, X, B) == (128, 64, 3)) else None, "peak_source": peak_src, "cg_iters": K,
                        "us_per_launch": t_solve_max * 1e6, "algorithmic_bytes_per_launch": alg_bytes,
                        "launches_per_step": 2 * m, "share_of_step": 2 * m * t_solve_max / t_iter, "machine_filling_batch": full,
-                       "note": "solver state is register/SMEM-resident (DRAM traffic ~20 B/cell regardless of K); achieved = "
-                               "(%gK+8) B/cell algorithmic bytes / CUDA-event launch time; one CTA per simulation, so at "
-                               "B=%d sims only %d of 148 SMs are busy (latency-bound; scripts/cg_bench.py reports B=148)" % (per_iter_bytes, B, B)}
+                       "note": ("direct solve, no iterations: per simulation one CTA does the four small dense transforms (3.1 MFMA, fp32 FMA "
+                                "issue-bound on one SM) and the whole machine applies the capacitance correction; achieved = field + "
+                                "operator bytes streamed (L2-resident) / CUDA-event time of the two launches") if direct else
+                               ("solver state is register/SMEM-resident (DRAM traffic ~20 B/cell regardless of K); achieved = "
+                                "(%gK+8) B/cell algorithmic bytes / CUDA-event launch time; one CTA per simulation, so at "
+                                "B=%d sims only %d of 148 SMs are busy (latency-bound; scripts/cg_bench.py reports B=148)" % (per_iter_bytes, B, B))}
         if t_conv is not None:
             tf = conv_flops / t_conv_max / 1e12
             roof_conv = {"kernel": "k_conv5x5_c32_tc (tcgen05 3xTF32 implicit-GEMM 5x5 conv 32->32, fwd layers and data gradients)",

@@ -25,6 +25,7 @@ ap.add_argument("--conv-path", type=int, default=0)
 ap.add_argument("--wgrad-path", type=int, default=0)
 ap.add_argument("--cg-rows", type=int, default=0)
 ap.add_argument("--cg-precond", type=int, default=1)
+ap.add_argument("--direct-solve", type=int, default=1)
 a = ap.parse_args()
 torch.cuda.set_device(0)
 engine.set_option("conv_path", a.conv_path)
@@ -32,6 +33,7 @@ engine.set_option("wgrad_path", a.wgrad_path)
 plan = engine.Plan.karman(a.Y, a.X, a.batch)
 plan.set_option("cg_rows", a.cg_rows)
 plan.set_option("cg_precond", a.cg_precond)
+plan.set_option("direct_solve", a.direct_solve)
 plan.set_cg(1e-7, 1e-6, 4000, a.cluster)
 re, vy0, vx0, gy, gx, sig = bench.synth_batch(plan, engine, torch, a.batch, a.msteps, 0, a.spin)
 plan.set_cg(1e-5, 0.0, 2000, a.cluster)

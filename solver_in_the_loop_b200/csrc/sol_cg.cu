@@ -338,13 +338,26 @@ static bool cg_geometry(int Y, int X, int want_cl, int want_r, int& CL, int& R, 
     return false;
 }
 
+// The direct solver is built on first use (host precomputation, a fraction of a second) — never during a stream capture,
+// where the iterative path is used instead (the engine's first call with a set of buffers is always eager).
+bool direct_active(const sol_plan* p) {
+    if (!p->direct_solve || p->boundary != SOL_BOUNDARY_OPEN || p->cluster > 1 || !direct_supported(p)) return false;
+    if (!p->dir.tried) {
+        sol_plan* mp = const_cast<sol_plan*>(p);
+        if (direct_build(mp) != SOL_OK) { direct_free(mp); mp->dir.tried = true; }
+    }
+    return p->dir.valid;
+}
+
 bool cg_fuses(const sol_plan* p) {
+    if (direct_active(p)) return true;
     return p->boundary == SOL_BOUNDARY_OPEN && p->cg_precond && p->cluster <= 1 && mg3_selected(p);
 }
 
 int launch_cg(const sol_plan* p, cudaStream_t st, int B, int mode, const float* rhs, float* p_out, const float* vy,
               const float* vx, float* vy_out, float* vx_out, int* iters, const CgFuse* fuse) {
     if (p->boundary != SOL_BOUNDARY_OPEN) return fail(SOL_ERR_UNSUPPORTED, "pressure solve requires an OPEN-boundary plan");
+    if (direct_active(p)) return launch_direct(p, st, B, mode, rhs, p_out, vy, vx, vy_out, vx_out, iters, fuse);
     if (p->cg_precond && p->cluster <= 1 && mg_supported(p))
         return launch_cg_mg(p, st, B, mode, rhs, p_out, vy, vx, vy_out, vx_out, iters, fuse);
     if (fuse && (fuse->feat_out || fuse->gfeat_in)) return fail(SOL_ERR_UNSUPPORTED, "cg: fused feature I/O is not available for this solver variant (see cg_fuses)");

@@ -1,0 +1,485 @@
+// Direct pressure projection for OPEN-boundary scenes (reference: the Poisson solve inside
+// IncompressibleFlow.step -> divergence_free, karman-2d/karman_train.py:167-168,185; the NumPy path of the apply
+// scripts solves the same system with a direct sparse solver, karman_apply.py:39).
+//
+// The scene's operator A is fixed for a plan, so the solve is precomputed instead of iterated:
+//   * without the obstacle, A0 is the 5-point Laplacian of a rectangle with p = 0 one cell outside: diagonalised by the
+//     type-I discrete sine transform, A0^-1 D = Sy ((Sy D Sx) / lambda) Sx with the symmetric orthogonal matrices Sy, Sx;
+//   * the obstacle changes only k rows of A (its solid cells and their fluid neighbours, k = 164 at 128x64):
+//     A = A0 + E R^T  ->  A^-1 d = p0 - (W M) (R^T p0),  p0 = A0^-1 d,  W = A0^-1 E (N x k),  M = (I + R^T W)^-1 (k x k)
+//     (capacitance-matrix / Woodbury correction); W M is precomputed on the host in double precision, R^T is sparse.
+// Two launches per projection: k_direct_solve (one CTA per simulation: divergence -> four small dense products in shared
+// memory -> s = R^T p0) and k_direct_apply (all SMs: p = p0 - (W M) s, gradient subtraction, optional feature output).
+// No iteration, no stopping rule: the result is the exact solve up to fp32 round-off (4e-7 relative vs the float64
+// sparse LU of the oracle), where the reference's CG stops at max|r| < 1e-5.
+#include <cooperative_groups.h>
+#include <math.h>
+
+#include <vector>
+
+#include "sol_internal.cuh"
+
+namespace sol {
+
+namespace {
+
+struct DirectArgs {
+    int B;
+    const float* Sy; const float* Sx; const float* ilam;
+    const int* rt_col; const float* rt_val;     // [k][5] sparse rows of R^T (column -1 = unused)
+    const float* Wt;                            // [kp][N]:  Wt[q][c] = (W M)[c][q]
+    int k, kp;
+    const float* my; const float* mx; const unsigned char* active; const float* diag;
+    const float* rhs;                           // MODE 0
+    const float* vy_in; const float* vx_in;     // MODE 1
+    float* p0;                                  // [B][N] scratch
+    float* tvec;                                // [B][kp] scratch
+    float* p_out; float* vy_out; float* vx_out; int* iters;
+    // fused feature I/O (see CgFuse)
+    float* feat_out; const float* re; float isy, isx, isr; const float* gfeat_in; int cfeat;
+};
+
+// acc[rr][cc] += sum_kk At[kk][r0+rr] * Bm[kk][c0+cc]   (At: leading dimension lda, Bm: ldb; TM = 2 or 4 rows per thread)
+template <int TM, int K>
+__device__ __forceinline__ void tile_gemm(const float* __restrict__ At, int lda, const float* __restrict__ Bm, int ldb, int r0, int c0,
+                                          float (&acc)[TM][4]) {
+#pragma unroll 8
+    for (int kk = 0; kk < K; ++kk) {
+        float a[TM];
+        if (TM == 4) {
+            const float4 v = *reinterpret_cast<const float4*>(At + kk * lda + r0);
+            a[0] = v.x; a[1] = v.y; a[2 % TM] = v.z; a[3 % TM] = v.w;
+        } else {
+            const float2 v = *reinterpret_cast<const float2*>(At + kk * lda + r0);
+            a[0] = v.x; a[1] = v.y;
+        }
+        const float4 b = *reinterpret_cast<const float4*>(Bm + kk * ldb + c0);
+#pragma unroll
+        for (int rr = 0; rr < TM; ++rr) {
+            acc[rr][0] = fmaf(a[rr], b.x, acc[rr][0]); acc[rr][1] = fmaf(a[rr], b.y, acc[rr][1]);
+            acc[rr][2] = fmaf(a[rr], b.z, acc[rr][2]); acc[rr][3] = fmaf(a[rr], b.w, acc[rr][3]);
+        }
+    }
+}
+
+template <int TM>
+__device__ __forceinline__ void zero_acc(float (&acc)[TM][4]) {
+#pragma unroll
+    for (int rr = 0; rr < TM; ++rr) acc[rr][0] = acc[rr][1] = acc[rr][2] = acc[rr][3] = 0.0f;
+}
+
+// acc tile -> T[c][r] (transposed, leading dimension ld)
+template <int TM>
+__device__ __forceinline__ void store_transposed(float* __restrict__ T, int ld, int r0, int c0, const float (&acc)[TM][4]) {
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        if (TM == 4) *reinterpret_cast<float4*>(T + (c0 + cc) * ld + r0) = make_float4(acc[0][cc], acc[1][cc], acc[2 % TM][cc], acc[3 % TM][cc]);
+        else *reinterpret_cast<float2*>(T + (c0 + cc) * ld + r0) = make_float2(acc[0][cc], acc[1][cc]);
+    }
+}
+
+// incoming face values (MODE 1), optionally plus the scaled feature gradient of the correction network (fused feat_bwd)
+struct FaceIn {
+    const float* vy; const float* vx; const float* gf; float isy, isx; int cfeat; int Y, X;
+    __device__ __forceinline__ float y(int j, int i) const {
+        float v = vy[j * X + i];
+        if (gf && j < Y) v = fmaf(gf[((size_t)j * X + i) * cfeat], isy, v);
+        return v;
+    }
+    __device__ __forceinline__ float x(int j, int i) const {
+        float v = vx[j * (X + 1) + i];
+        if (gf && i < X) v = fmaf(gf[((size_t)j * X + i) * cfeat + 1], isx, v);
+        return v;
+    }
+};
+
+// A thread-block cluster of CL CTAs per simulation, split along y: p0 = Sy ((Sy D Sx) * ilam) Sx.  Every CTA builds the whole
+// right-hand side D (cheap), then owns YS = Y/CL rows of the three products U = Sy D, V = (U Sx) * ilam, Z = V Sx — no exchange
+// needed, the row split survives right-multiplications — and pushes its rows of Z into every CTA's copy through distributed
+// shared memory for the last product p0 = Sy Z.
+template <int Y, int X, int CL, int TM, int MODE>
+__global__ void __launch_bounds__((Y / CL / TM) * (X / 4), 1) k_direct_solve(const DirectArgs a) {
+    namespace cg = cooperative_groups;
+    constexpr int YS = Y / CL;
+    constexpr int NT = (YS / TM) * (X / 4);
+    constexpr int N = Y * X;
+    extern __shared__ __align__(16) float dsm[];
+    float* sSy = dsm;                  // [Y][YS]: sSy[kk][lr] = Sy[kk][rbase + lr]  (Sy is symmetric)
+    float* sSx = sSy + Y * YS;         // [X][X]
+    float* sD = sSx + X * X;           // [Y][X]  right-hand side
+    float* sZ = sD + N;                // [Y][X]  gathered Z
+    float* t0 = sZ + N;                // [X][YS] transposed slices
+    float* t1 = t0 + X * YS;           // [X][YS]
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    int rank = 0;
+    if (CL > 1) rank = (int)cg::this_cluster().block_rank();
+    const int rbase = rank * YS;
+    // scene constants first: they do not depend on the previous kernel (programmatic dependent launch)
+    for (int k = tid * 4; k < Y * YS; k += NT * 4) {
+        const int kk = k / YS, lr = k - kk * YS;
+        *reinterpret_cast<float4*>(sSy + k) = __ldg(reinterpret_cast<const float4*>(a.Sy + kk * Y + rbase + lr));
+    }
+    for (int k = tid * 4; k < X * X; k += NT * 4) *reinterpret_cast<float4*>(sSx + k) = __ldg(reinterpret_cast<const float4*>(a.Sx + k));
+    pdl_sync();
+    if (CL > 1) cg::this_cluster().sync();      // every CTA of the cluster is running before any remote shared-memory access
+    // ---- right-hand side D[j][i]: every CTA computes its YS rows and pushes them into all copies ----
+    {
+        FaceIn in{a.vy_in + (size_t)b * (Y + 1) * X, a.vx_in + (size_t)b * Y * (X + 1),
+                  a.gfeat_in ? a.gfeat_in + (size_t)b * N * a.cfeat : nullptr, a.isy, a.isx, a.cfeat, Y, X};
+        const float* rhs = (MODE == 0) ? a.rhs + (size_t)b * N : nullptr;
+        float* dst[CL];
+#pragma unroll
+        for (int peer = 0; peer < CL; ++peer) dst[peer] = (CL > 1) ? cg::this_cluster().map_shared_rank(sD, peer) : sD;
+#pragma unroll 4
+        for (int lc = tid; lc < YS * X; lc += NT) {
+            const int c = rbase * X + lc;
+            const int j = c / X, i = c - j * X;
+            float d;
+            if (MODE == 1)
+                d = (a.my[(j + 1) * X + i] * in.y(j + 1, i) - a.my[j * X + i] * in.y(j, i)) +
+                    (a.mx[j * (X + 1) + i + 1] * in.x(j, i + 1) - a.mx[j * (X + 1) + i] * in.x(j, i));
+            else
+                d = rhs[c];
+            d = a.active[c] ? d : 0.0f;
+#pragma unroll
+            for (int peer = 0; peer < CL; ++peer) dst[peer][c] = d;
+        }
+    }
+    if (CL > 1) cg::this_cluster().sync();
+    else __syncthreads();
+    const int tx = tid % (X / 4), ty = tid / (X / 4);
+    const int r0 = ty * TM, c0 = tx * 4;        // r0: row inside this CTA's slice
+    float acc[TM][4];
+    // stage 1: U = Sy D (my rows), transposed into t0
+    zero_acc<TM>(acc);
+    tile_gemm<TM, Y>(sSy, YS, sD, X, r0, c0, acc);
+    store_transposed<TM>(t0, YS, r0, c0, acc);
+    __syncthreads();
+    // stage 2: V = (U Sx) * ilam, transposed into t1
+    zero_acc<TM>(acc);
+    tile_gemm<TM, X>(t0, YS, sSx, X, r0, c0, acc);
+#pragma unroll
+    for (int rr = 0; rr < TM; ++rr) {
+        const float4 l = __ldg(reinterpret_cast<const float4*>(a.ilam + (rbase + r0 + rr) * X + c0));
+        acc[rr][0] *= l.x; acc[rr][1] *= l.y; acc[rr][2] *= l.z; acc[rr][3] *= l.w;
+    }
+    store_transposed<TM>(t1, YS, r0, c0, acc);
+    __syncthreads();
+    // stage 3: Z = V Sx; my rows go into every CTA's sZ
+    zero_acc<TM>(acc);
+    tile_gemm<TM, X>(t1, YS, sSx, X, r0, c0, acc);
+    if (CL > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+#pragma unroll
+        for (int peer = 0; peer < CL; ++peer) {
+            float* rz = cluster.map_shared_rank(sZ, peer);
+#pragma unroll
+            for (int rr = 0; rr < TM; ++rr)
+                *reinterpret_cast<float4*>(rz + (rbase + r0 + rr) * X + c0) = make_float4(acc[rr][0], acc[rr][1], acc[rr][2], acc[rr][3]);
+        }
+        cluster.sync();
+    } else {
+#pragma unroll
+        for (int rr = 0; rr < TM; ++rr) *reinterpret_cast<float4*>(sZ + (r0 + rr) * X + c0) = make_float4(acc[rr][0], acc[rr][1], acc[rr][2], acc[rr][3]);
+        __syncthreads();
+    }
+    // stage 4: p0 = Sy Z (my rows) -> global memory
+    zero_acc<TM>(acc);
+    tile_gemm<TM, Y>(sSy, YS, sZ, X, r0, c0, acc);
+    float* p0g = a.p0 + (size_t)b * N;
+#pragma unroll
+    for (int rr = 0; rr < TM; ++rr)
+        *reinterpret_cast<float4*>(p0g + (rbase + r0 + rr) * X + c0) = make_float4(acc[rr][0], acc[rr][1], acc[rr][2], acc[rr][3]);
+    if (a.iters && tid == 0 && rank == 0) a.iters[b] = 0;      // no iterations: a direct solve
+}
+
+// p = p0 - (W M) s on a tile of R rows (+ the row below it), then the gradient subtraction / optional outputs.  The correction sum
+// over the changed rows is split over QG thread groups (same cells, disjoint q ranges) and reduced through shared memory.
+template <int X, int R, int MODE>
+__global__ void __launch_bounds__(4 * (R + 1) * X) k_direct_apply(const DirectArgs a, int Y) {
+    constexpr int NCELL = (R + 1) * X, QG = 4;
+    __shared__ float sp[QG][NCELL];
+    extern __shared__ __align__(16) float st[];      // [kp]
+    const int N = Y * X;
+    const int b = blockIdx.y;
+    const int j0 = blockIdx.x * R;
+    const int tid = threadIdx.x;
+    pdl_sync();
+    // s = R^T p0: the changed rows of the operator applied to the obstacle-free solution (<= 5 entries per row)
+    for (int q = tid; q < a.kp; q += QG * NCELL) {
+        float sv = 0.0f;
+        if (q < a.k) {
+#pragma unroll
+            for (int e = 0; e < 5; ++e) {
+                const int col = __ldg(a.rt_col + q * 5 + e);
+                if (col >= 0) sv = fmaf(__ldg(a.rt_val + q * 5 + e), a.p0[(size_t)b * N + col], sv);
+            }
+        }
+        st[q] = sv;
+    }
+    __syncthreads();
+    const int g = tid / NCELL, cell = tid - g * NCELL;
+    const int lr = cell / X, i = cell - lr * X;
+    const int j = j0 - 1 + lr;                       // local row 0 is the halo row below the tile
+    {
+        float part = 0.0f;
+        if (j >= 0 && j < Y) {
+            // kp is a multiple of 32 and the rows q >= k of Wt are zero: 8 independent loads in flight per thread
+            const int kq = a.kp / QG;
+            const float* w = a.Wt + (size_t)(g * kq) * N + j * X + i;
+            const float* sq = st + g * kq;
+            float corr[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 1
+            for (int q = 0; q < kq; q += 8) {
+                float wv[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) wv[e] = __ldg(w + (size_t)(q + e) * N);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) corr[e & 3] = fmaf(wv[e], sq[q + e], corr[e & 3]);
+            }
+            part = (corr[0] + corr[1]) + (corr[2] + corr[3]);
+        }
+        sp[g][cell] = part;
+    }
+    __syncthreads();
+    if (g != 0) return;
+    float p = 0.0f;
+    if (j >= 0 && j < Y) {
+        const int c = j * X + i;
+        p = a.p0[(size_t)b * N + c] - ((sp[0][cell] + sp[1][cell]) + (sp[2][cell] + sp[3][cell]));
+        if (!a.active[c]) p = (MODE == 0) ? -a.rhs[(size_t)b * N + c] / a.diag[c] : 0.0f;
+    }
+    sp[0][cell] = p;
+    // only the first NCELL threads (whole warps) are left: a named barrier among them
+    asm volatile("bar.sync 1, %0;" ::"n"(NCELL) : "memory");
+    if (lr == 0 || j >= Y) return;
+    const int c = j * X + i;
+    if (MODE == 0) { a.p_out[(size_t)b * N + c] = p; return; }
+    FaceIn in{a.vy_in + (size_t)b * (Y + 1) * X, a.vx_in + (size_t)b * Y * (X + 1),
+              a.gfeat_in ? a.gfeat_in + (size_t)b * N * a.cfeat : nullptr, a.isy, a.isx, a.cfeat, Y, X};
+    float* vyo = a.vy_out + (size_t)b * (Y + 1) * X;
+    float* vxo = a.vx_out + (size_t)b * Y * (X + 1);
+    const float pdn = sp[0][cell - X];                              // p[j-1][i] (0 below the domain)
+    const float plf = (i > 0) ? sp[0][cell - 1] : 0.0f;             // p[j][i-1] (0 left of the domain)
+    const float oy = a.my[j * X + i] * (in.y(j, i) - (p - pdn));
+    const float ox = a.mx[j * (X + 1) + i] * (in.x(j, i) - (p - plf));
+    vyo[j * X + i] = oy;
+    vxo[j * (X + 1) + i] = ox;
+    if (i == X - 1) vxo[j * (X + 1) + X] = a.mx[j * (X + 1) + X] * (in.x(j, X) + p);
+    if (j == Y - 1) vyo[Y * X + i] = a.my[Y * X + i] * (in.y(Y, i) + p);
+    if (a.p_out) a.p_out[(size_t)b * N + c] = p;
+    if (a.feat_out) {
+        float* f = a.feat_out + ((size_t)b * N + c) * a.cfeat;
+        f[0] = oy * a.isy; f[1] = ox * a.isx; f[2] = a.re[b] * a.isr;
+    }
+}
+
+template <typename T>
+int up(T** dst, const std::vector<T>& src) {
+    SOL_CUDA(cudaMalloc((void**)dst, src.size() * sizeof(T)));
+    SOL_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return SOL_OK;
+}
+
+}  // namespace
+
+bool direct_supported(const sol_plan* p) {
+    return p->boundary == SOL_BOUNDARY_OPEN && ((p->Y == 128 && p->X == 64) || (p->Y == 64 && p->X == 32));
+}
+
+void direct_free(sol_plan* p) {
+    sol_direct& d = p->dir;
+    cudaFree(d.Sy); cudaFree(d.Sx); cudaFree(d.ilam); cudaFree(d.rt_col); cudaFree(d.rt_val); cudaFree(d.Wt);
+    cudaFree(d.p0); cudaFree(d.tvec);
+    d = sol_direct();
+}
+
+// Host precomputation (double precision) of the transform matrices and the capacitance correction.
+int direct_build(sol_plan* p) {
+    sol_direct& d = p->dir;
+    d.tried = true;
+    if (!direct_supported(p)) return SOL_OK;
+    const int Y = p->Y, X = p->X, N = Y * X;
+    const std::vector<unsigned char>& act = p->h_active;
+    const std::vector<float>& dg = p->h_diag;
+    if ((int)act.size() != N || (int)dg.size() != N) return SOL_OK;
+    const double PI = 3.14159265358979323846;
+    std::vector<double> Sy((size_t)Y * Y), Sx((size_t)X * X), il((size_t)N);
+    for (int a = 0; a < Y; ++a)
+        for (int b = 0; b < Y; ++b) Sy[(size_t)a * Y + b] = sqrt(2.0 / (Y + 1)) * sin(PI * (a + 1) * (b + 1) / (Y + 1));
+    for (int a = 0; a < X; ++a)
+        for (int b = 0; b < X; ++b) Sx[(size_t)a * X + b] = sqrt(2.0 / (X + 1)) * sin(PI * (a + 1) * (b + 1) / (X + 1));
+    for (int a = 0; a < Y; ++a)
+        for (int b = 0; b < X; ++b) il[(size_t)a * X + b] = 1.0 / (-4.0 + 2.0 * cos(PI * (a + 1) / (Y + 1)) + 2.0 * cos(PI * (b + 1) / (X + 1)));
+    // rows of A that differ from A0: solid cells and cells with a solid neighbour
+    auto solid = [&](int j, int i) -> bool { return j >= 0 && j < Y && i >= 0 && i < X && !act[(size_t)j * X + i]; };
+    std::vector<int> rows;
+    for (int j = 0; j < Y; ++j)
+        for (int i = 0; i < X; ++i)
+            if (solid(j, i) || solid(j - 1, i) || solid(j + 1, i) || solid(j, i - 1) || solid(j, i + 1)) rows.push_back(j * X + i);
+    const int k = (int)rows.size();
+    const int kp = k == 0 ? 32 : (k + 31) / 32 * 32;
+    std::vector<int> rt_col((size_t)kp * 5, -1);
+    std::vector<float> rt_val((size_t)kp * 5, 0.0f);
+    std::vector<double> rtv((size_t)kp * 5, 0.0);
+    for (int q = 0; q < k; ++q) {
+        const int c = rows[q], j = c / X, i = c - j * X;
+        // A row:  -diag[c] on the diagonal, +1 to active in-domain neighbours (none for a solid cell);  A0 row: -4, +1 to in-domain neighbours
+        rt_col[q * 5] = c; rtv[q * 5] = 4.0 - (double)dg[c];
+        const int nb[4][2] = {{j - 1, i}, {j + 1, i}, {j, i - 1}, {j, i + 1}};
+        for (int e = 0; e < 4; ++e) {
+            const int jj = nb[e][0], ii = nb[e][1];
+            if (jj < 0 || jj >= Y || ii < 0 || ii >= X) continue;
+            const double aval = (act[c] && act[(size_t)jj * X + ii]) ? 1.0 : 0.0;
+            if (aval != 1.0) { rt_col[q * 5 + 1 + e] = jj * X + ii; rtv[q * 5 + 1 + e] = aval - 1.0; }
+        }
+    }
+    for (size_t e = 0; e < rtv.size(); ++e) rt_val[e] = (float)rtv[e];
+    // W[:, q] = A0^-1 e_c = Sy ((Sy[:,j] (x) Sx[:,i]) * ilam) Sx
+    std::vector<double> W((size_t)N * (k > 0 ? k : 1), 0.0), G((size_t)N), T((size_t)N);
+    for (int q = 0; q < k; ++q) {
+        const int c = rows[q], j = c / X, i = c - j * X;
+        for (int a = 0; a < Y; ++a)
+            for (int b = 0; b < X; ++b) G[(size_t)a * X + b] = Sy[(size_t)a * Y + j] * Sx[(size_t)b * X + i] * il[(size_t)a * X + b];
+        // T = G Sx
+        for (int a = 0; a < Y; ++a) {
+            double* tr = &T[(size_t)a * X];
+            for (int b = 0; b < X; ++b) tr[b] = 0.0;
+            for (int m = 0; m < X; ++m) {
+                const double g = G[(size_t)a * X + m];
+                const double* sr = &Sx[(size_t)m * X];
+                for (int b = 0; b < X; ++b) tr[b] += g * sr[b];
+            }
+        }
+        // W[:, q] = Sy T
+        for (int a = 0; a < Y; ++a) {
+            double out[128];
+            for (int b = 0; b < X; ++b) out[b] = 0.0;
+            for (int m = 0; m < Y; ++m) {
+                const double s = Sy[(size_t)a * Y + m];
+                const double* tr = &T[(size_t)m * X];
+                for (int b = 0; b < X; ++b) out[b] += s * tr[b];
+            }
+            for (int b = 0; b < X; ++b) W[((size_t)a * X + b) * k + q] = out[b];
+        }
+    }
+    // M = (I + R^T W)^-1 by Gauss-Jordan with partial pivoting
+    std::vector<double> C((size_t)k * k, 0.0), Inv((size_t)k * k, 0.0);
+    for (int q = 0; q < k; ++q) {
+        Inv[(size_t)q * k + q] = 1.0;
+        for (int e = 0; e < 5; ++e) {
+            const int col = rt_col[q * 5 + e];
+            if (col < 0) continue;
+            const double v = rtv[q * 5 + e];
+            for (int r = 0; r < k; ++r) C[(size_t)q * k + r] += v * W[(size_t)col * k + r];
+        }
+        C[(size_t)q * k + q] += 1.0;
+    }
+    for (int col = 0; col < k; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < k; ++r)
+            if (fabs(C[(size_t)r * k + col]) > fabs(C[(size_t)piv * k + col])) piv = r;
+        if (fabs(C[(size_t)piv * k + col]) < 1e-13) return SOL_OK;      // singular: the direct solver stays disabled
+        if (piv != col)
+            for (int m = 0; m < k; ++m) { std::swap(C[(size_t)piv * k + m], C[(size_t)col * k + m]); std::swap(Inv[(size_t)piv * k + m], Inv[(size_t)col * k + m]); }
+        const double dv = C[(size_t)col * k + col];
+        for (int m = 0; m < k; ++m) { C[(size_t)col * k + m] /= dv; Inv[(size_t)col * k + m] /= dv; }
+        for (int r = 0; r < k; ++r) {
+            if (r == col) continue;
+            const double f = C[(size_t)r * k + col];
+            if (f == 0.0) continue;
+            for (int m = 0; m < k; ++m) { C[(size_t)r * k + m] -= f * C[(size_t)col * k + m]; Inv[(size_t)r * k + m] -= f * Inv[(size_t)col * k + m]; }
+        }
+    }
+    std::vector<float> Syf(Sy.begin(), Sy.end()), Sxf(Sx.begin(), Sx.end()), ilf(il.begin(), il.end());
+    // fold the capacitance matrix into the correction basis: (W M)[c][q] = sum_e W[c][e] M[e][q]
+    std::vector<float> Wt((size_t)kp * N, 0.0f);
+    {
+        std::vector<double> row((size_t)(k > 0 ? k : 1));
+        for (int c = 0; c < N; ++c) {
+            for (int q = 0; q < k; ++q) row[q] = 0.0;
+            for (int e = 0; e < k; ++e) {
+                const double w = W[(size_t)c * k + e];
+                if (w == 0.0) continue;
+                const double* mr = &Inv[(size_t)e * k];
+                for (int q = 0; q < k; ++q) row[q] += w * mr[q];
+            }
+            for (int q = 0; q < k; ++q) Wt[(size_t)q * N + c] = (float)row[q];
+        }
+    }
+    SOL_TRY(up(&d.Sy, Syf)); SOL_TRY(up(&d.Sx, Sxf)); SOL_TRY(up(&d.ilam, ilf));
+    SOL_TRY(up(&d.rt_col, rt_col)); SOL_TRY(up(&d.rt_val, rt_val)); SOL_TRY(up(&d.Wt, Wt));
+    SOL_CUDA(cudaMalloc((void**)&d.p0, (size_t)p->B_max * N * sizeof(float)));
+    SOL_CUDA(cudaMalloc((void**)&d.tvec, (size_t)p->B_max * kp * sizeof(float)));
+    d.k = k; d.kp = kp;
+    d.valid = true;
+    return SOL_OK;
+}
+
+template <int Y, int X, int CL, int TM, int R>
+static int launch_direct_t(const DirectArgs& a, cudaStream_t st, int mode) {
+    constexpr int YS = Y / CL;
+    constexpr int NT = (YS / TM) * (X / 4);
+    const size_t smem = (size_t)(Y * YS + X * X + 2 * Y * X + 2 * X * YS) * sizeof(float);
+    auto k0 = k_direct_solve<Y, X, CL, TM, 0>;
+    auto k1 = k_direct_solve<Y, X, CL, TM, 1>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SOL_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SOL_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+    }
+    if (smem > 200 * 1024) return fail(SOL_ERR_UNSUPPORTED, "direct solve: scene does not fit the shared-memory kernel");
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(CL, a.B); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        int na = 0;
+        if (CL > 1) {
+            attr[na].id = cudaLaunchAttributeClusterDimension;
+            attr[na].val.clusterDim.x = CL; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+            ++na;
+        }
+        if (g_pdl) {
+            attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
+        }
+        cfg.attrs = attr; cfg.numAttrs = na;
+        if (mode == 0) SOL_CUDA(cudaLaunchKernelEx(&cfg, k0, a));
+        else SOL_CUDA(cudaLaunchKernelEx(&cfg, k1, a));
+        SOL_LAUNCHED();
+    }
+    const dim3 grid(cdiv(Y, R), a.B), block(4 * (R + 1) * X);
+    const size_t smem2 = (size_t)a.kp * sizeof(float);
+    if (mode == 0) SOL_CUDA(launch_kernel(k_direct_apply<X, R, 0>, grid, block, smem2, st, a, Y));
+    else SOL_CUDA(launch_kernel(k_direct_apply<X, R, 1>, grid, block, smem2, st, a, Y));
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
+int launch_direct(const sol_plan* p, cudaStream_t st, int B, int mode, const float* rhs, float* p_out, const float* vy, const float* vx,
+                  float* vy_out, float* vx_out, int* iters, const CgFuse* fuse) {
+    const sol_direct& d = p->dir;
+    if (!d.valid) return fail(SOL_ERR_UNSUPPORTED, "direct solve: not available for this plan");
+    DirectArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.Sy = d.Sy; a.Sx = d.Sx; a.ilam = d.ilam; a.rt_col = d.rt_col; a.rt_val = d.rt_val; a.Wt = d.Wt; a.k = d.k; a.kp = d.kp;
+    a.my = p->face_my; a.mx = p->face_mx; a.active = p->active; a.diag = p->diag;
+    a.rhs = rhs; a.vy_in = vy; a.vx_in = vx; a.p0 = d.p0; a.tvec = d.tvec; a.p_out = p_out; a.vy_out = vy_out; a.vx_out = vx_out; a.iters = iters;
+    a.cfeat = 3;
+    if (fuse && (fuse->feat_out || fuse->gfeat_in)) {
+        if (mode != 1) return fail(SOL_ERR_UNSUPPORTED, "direct solve: fused feature I/O needs the projection mode");
+        if (fuse->cfeat < 3 && fuse->feat_out) return fail(SOL_ERR_UNSUPPORTED, "direct solve: fused feature output needs >= 3 feature channels");
+        a.feat_out = fuse->feat_out; a.re = fuse->re; a.isy = fuse->isy; a.isx = fuse->isx; a.isr = fuse->isr;
+        a.gfeat_in = fuse->gfeat_in; a.cfeat = fuse->cfeat;
+    }
+    if (mode == 0 && (!rhs || !p_out)) return fail(SOL_ERR_INVALID, "direct solve: rhs / p_out required");
+    if (mode == 1 && (!vy || !vx || !vy_out || !vx_out)) return fail(SOL_ERR_INVALID, "direct solve: velocity pointers required");
+    if (p->Y == 128 && p->X == 64) return launch_direct_t<128, 64, 4, 2, 3>(a, st, mode);
+    if (p->Y == 64 && p->X == 32) return launch_direct_t<64, 32, 2, 2, 7>(a, st, mode);
+    return fail(SOL_ERR_UNSUPPORTED, "direct solve: unsupported grid");
+}
+
+}  // namespace sol

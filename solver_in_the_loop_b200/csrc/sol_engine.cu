@@ -194,6 +194,7 @@ extern "C" int sol_plan_create(int Y, int X, int B_max, float dx, int boundary, 
         if (rc == SOL_OK && bc_mask_y) rc = upload(&p->bc_mask_y, bc_mask_y, NY);
         if (rc == SOL_OK && bc_val_y) rc = upload(&p->bc_val_y, bc_val_y, NY);
         if (rc == SOL_OK) rc = build_mg(p, act);
+        p->h_active = act; p->h_diag = diag;
         if (rc != SOL_OK) { sol_plan_destroy(p); return rc; }
     }
     *out = p;
@@ -205,6 +206,7 @@ extern "C" int sol_plan_destroy(sol_plan* p) {
     cudaFree(p->active); cudaFree(p->diag); cudaFree(p->face_my); cudaFree(p->face_mx);
     cudaFree(p->inflow); cudaFree(p->bc_mask_y); cudaFree(p->bc_val_y);
     cudaFree(p->mg.dinv); cudaFree(p->mg.diag); cudaFree(p->mg.cinv);
+    direct_free(p);
     delete p;
     return SOL_OK;
 }
@@ -232,6 +234,12 @@ extern "C" int sol_plan_set_option(sol_plan* p, const char* name, int value) {
     if (strcmp(name, "cg_precond") == 0) {
         SOL_CHECK(value == 0 || value == 1, "cg_precond must be 0 or 1");
         p->cg_precond = value;
+        return SOL_OK;
+    }
+    if (strcmp(name, "direct_solve") == 0) {
+        SOL_CHECK(value == 0 || value == 1, "direct_solve must be 0 or 1");
+        p->direct_solve = value;
+        if (value) (void)direct_active(p);      // precompute now (outside any stream capture)
         return SOL_OK;
     }
     return fail(SOL_ERR_INVALID, "sol_plan_set_option: unknown option");
@@ -825,7 +833,8 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
     const size_t in_stride = (m > 1) ? (size_t)(u->stash[1].acts[0] - u->stash[0].acts[0]) : u->nA;
     const int tiles_step = (p->X / 8) * (p->Y / 16) * B;
     const bool burgers = p->boundary == SOL_BOUNDARY_PERIODIC;      // no pressure solve, hence no solve windows
-    const bool overlap = u->deferred_wgrad && sol::g_wgrad_overlap && B + 17 <= p->sm_count && !burgers;
+    // the direct projection takes ~20 us: no window worth filling
+    const bool overlap = u->deferred_wgrad && sol::g_wgrad_overlap && B + 17 <= p->sm_count && !burgers && !direct_active(p);
     const int sm_budget = overlap ? p->sm_count - B - 1 : p->sm_count;        // SMs left beside the solve's B CTAs
     const int nct32 = tiles_step < sm_budget ? tiles_step : sm_budget;          // fixed per sweep: the partial-sum slots must line up
     if (overlap && !u->sstream) {

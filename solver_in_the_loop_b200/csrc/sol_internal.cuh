@@ -93,6 +93,16 @@ struct sol_mg {
     float omega = 0.8f;
 };
 
+// direct pressure solver (sol_direct.cu): transform matrices + capacitance correction, precomputed per plan
+struct sol_direct {
+    bool tried = false, valid = false;
+    int k = 0, kp = 0;                    // rows of A the obstacle changes (padded to a multiple of 32)
+    float *Sy = nullptr, *Sx = nullptr, *ilam = nullptr;
+    int* rt_col = nullptr; float* rt_val = nullptr;
+    float* Wt = nullptr;                  // [kp][N]: the capacitance-corrected basis (W M), transposed
+    float *p0 = nullptr, *tvec = nullptr; // scratch: [B_max][N], [B_max][kp]
+};
+
 struct sol_plan {
     int Y = 0, X = 0, B_max = 0;
     float dx = 1.f;
@@ -114,6 +124,10 @@ struct sol_plan {
     int cg_precond = 1; // 1 = multigrid-preconditioned CG when the grid supports it, 0 = plain CG (reference recurrences)
     sol_mg mg;
     int mg_variant = 0; // 0 auto (compile-time hierarchy when Y == 2X), 2 = generic run-time hierarchy kernel
+    int direct_solve = 1; // 1 = direct projection (fast Poisson + capacitance correction) when the scene supports it
+    sol_direct dir;
+    std::vector<unsigned char> h_active;   // host copies of the masks for the (lazy) direct-solver precomputation
+    std::vector<float> h_diag;
     size_t NY() const { return (size_t)(Y + 1) * X; }
     size_t NX() const { return (size_t)Y * (X + 1); }
     size_t NC() const { return (size_t)Y * X; }
@@ -169,6 +183,14 @@ struct CgFuse {
 bool cg_fuses(const sol_plan* p);
 int launch_cg(const sol_plan* p, cudaStream_t st, int B, int mode, const float* rhs, float* p_out, const float* vy,
               const float* vx, float* vy_out, float* vx_out, int* iters, const CgFuse* fuse = nullptr);
+
+// ---- direct projection (sol_direct.cu) ----
+bool direct_supported(const sol_plan* p);
+int direct_build(sol_plan* p);          // host precomputation + upload (synchronous; never inside a stream capture)
+void direct_free(sol_plan* p);
+bool direct_active(const sol_plan* p);  // option on and precomputation available (builds lazily)
+int launch_direct(const sol_plan* p, cudaStream_t st, int B, int mode, const float* rhs, float* p_out, const float* vy, const float* vx,
+                  float* vy_out, float* vx_out, int* iters, const CgFuse* fuse = nullptr);
 
 // ---- multigrid-preconditioned CG (sol_cg_mg.cu) ----
 bool mg_supported(const sol_plan* p);

@@ -84,11 +84,13 @@ def test_advect(case, cuda_device):
     assert rel(iy, vyt.grad) < 1e-5 and rel(ix, vxt.grad) < 1e-5
 
 
-@pytest.mark.parametrize("cluster,precond", [(1, 1), (1, 2), (1, 0), (2, 0), (4, 0), (8, 0)],
-                         ids=["mgpcg", "mgpcg-generic", "cg", "cg-cluster2", "cg-cluster4", "cg-cluster8"])
+@pytest.mark.parametrize("cluster,precond", [(1, 3), (1, 1), (1, 2), (1, 0), (2, 0), (4, 0), (8, 0)],
+                         ids=["direct", "mgpcg", "mgpcg-generic", "cg", "cg-cluster2", "cg-cluster4", "cg-cluster8"])
 def test_pressure_solve_and_project(case, cuda_device, cluster, precond):
     c = case; plan = c["plan"]; geom = c["geom"]
+    direct = precond == 3       # fast Poisson solve + capacitance correction (no iterations)
     plan.set_cg(tol_abs=1e-7, tol_rel=1e-6, max_it=4000, cluster=cluster)
+    plan.set_option("direct_solve", 1 if direct else 0)
     plan.set_option("mg_variant", 2 if precond == 2 else 0)      # 2: run-time-hierarchy kernel, 0: compile-time hierarchy
     plan.set_option("cg_precond", 1 if precond else 0)
     try:
@@ -100,11 +102,14 @@ def test_pressure_solve_and_project(case, cuda_device, cluster, precond):
         assert rel(d_gpu, rd) < 1e-5
         p, it = plan.pressure_solve(dev(rd, cuda_device))
         print("cluster", cluster, "solve iters", it.tolist(), "p rel", rel(p, rp))
-        assert rel(p, rp) < 2e-4
-        assert int(it.max()) < (40 if precond else 4000) and int(it.min()) >= 5
+        assert rel(p, rp) < (5e-6 if direct else 2e-4)
+        if direct:
+            assert int(it.max()) == 0
+        else:
+            assert int(it.max()) < (40 if precond else 4000) and int(it.min()) >= 5
         oy, ox, op, it2 = plan.project(dev(vy, cuda_device), dev(vx, cuda_device), return_pressure=True)
         print("project rel", rel(oy, ry), rel(ox, rx), rel(op, rp), it2.tolist())
-        assert rel(oy, ry) < 1e-5 and rel(ox, rx) < 1e-4 and rel(op, rp) < 2e-4
+        assert rel(oy, ry) < 1e-5 and rel(ox, rx) < 1e-4 and rel(op, rp) < (5e-6 if direct else 2e-4)
         # divergence-free on fluid cells, obstacle faces exactly zero, idempotent
         d2 = plan.divergence(oy, ox)
         act = torch.tensor(geom.active, device=cuda_device, dtype=torch.float32)
@@ -124,6 +129,7 @@ def test_pressure_solve_and_project(case, cuda_device, cluster, precond):
         plan.set_cg(tol_abs=1e-7, tol_rel=1e-6, max_it=4000, cluster=0)
         plan.set_option("cg_precond", 1)
         plan.set_option("mg_variant", 0)
+        plan.set_option("direct_solve", 1)
 
 
 def test_reference_style_cg_iterations(case, cuda_device):
@@ -131,6 +137,7 @@ def test_reference_style_cg_iterations(case, cuda_device):
     the oracle's restatement of PhiFlow's SparseCG on the same right-hand side."""
     c = case; plan = c["plan"]; geom = c["geom"]
     plan.set_cg(tol_abs=1e-5, tol_rel=0.0, max_it=2000, cluster=0)
+    plan.set_option("direct_solve", 0)
     plan.set_option("cg_precond", 0)     # the reference's unpreconditioned recurrences
     try:
         ry, rx, rp, rd = so.project(c["vy"] * 1.01, c["vx"], geom)
@@ -149,7 +156,13 @@ def test_reference_style_cg_iterations(case, cuda_device):
         p2, it2 = plan.pressure_solve(dev(rd, cuda_device))
         print("mgpcg iters", it2.tolist(), "p vs exact", rel(p2, rp))
         assert int(it2.max()) * 4 < int(it.min()) and rel(p2, rp) < rel(p, rp)
+        # the direct solve has no truncation error at all
+        plan.set_option("direct_solve", 1)
+        p3, it3 = plan.pressure_solve(dev(rd, cuda_device))
+        print("direct p vs exact", rel(p3, rp))
+        assert int(it3.max()) == 0 and rel(p3, rp) < 5e-6 and rel(p3, rp) < rel(p2, rp)
     finally:
+        plan.set_option("direct_solve", 1)
         plan.set_option("cg_precond", 1)
         plan.set_cg(tol_abs=1e-7, tol_rel=1e-6, max_it=4000, cluster=0)
 
