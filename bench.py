@@ -337,9 +337,9 @@ def main():
     # the V(2,2) cycle: 4 fine smoothing sweeps (16 B each) + residual/restrict/prolong (20 B) + coarse levels (1/3 of fine)
     per_iter_bytes = 148.0 if precond else 40.0
     # direct projection: per simulation the compulsory field traffic (20 B/cell) + the precomputed operators it streams
-    # (transform matrices Sy, Sx, 1/lambda; capacitance matrix M; correction basis W: ~164 changed rows x N), all L2-resident
+    # (transform matrices Sy, Sx, 1/lambda; capacitance-corrected basis W M: ~164 changed rows x N), all L2-resident
     KCH = 164 if (Y, X) == (128, 64) else 84
-    direct_bytes_per_sim = 20.0 * Y * X + 4.0 * (Y * Y + X * X + Y * X) + 4.0 * KCH * KCH + 4.0 * KCH * Y * X
+    direct_bytes_per_sim = 20.0 * Y * X + 4.0 * (Y * Y + X * X + Y * X) + 4.0 * KCH * Y * X
     alg_bytes = direct_bytes_per_sim * B if direct else (per_iter_bytes * K + 8.0) * Y * X * B
     peak, peak_src = load_peaks()
     achieved = alg_bytes / t_solve / 1e9

@@ -70,7 +70,11 @@ int sol_plan_set_cg(sol_plan* plan, float tol_abs, float tol_rel, int max_it, in
 /* Tuning knobs that never change results beyond fp32 round-off:
  *   "cg_rows"    rows of the grid each CG thread keeps in registers (0 = auto, 2/4/8/16)
  *   "cg_precond" 1 (default) = multigrid-preconditioned CG where the grid supports it (same stop
- *                rule, ~15x fewer iterations), 0 = the reference's unpreconditioned recurrences */
+ *                rule, ~15x fewer iterations), 0 = the reference's unpreconditioned recurrences
+ *   "direct_solve" 1 (default) = direct projection where the scene supports it (OPEN plans of 128x64 / 64x32 cells, cluster <= 1):
+ *                fast Poisson solve (sine transforms) + capacitance-matrix correction for the obstacle rows, precomputed per plan
+ *                on first use; exact up to fp32 round-off (what the reference's NumPy path does with a sparse direct solver,
+ *                karman_apply.py:39), the CG controls above do not apply and iteration counters read 0.  0 = iterative solvers */
 int sol_plan_set_option(sol_plan* plan, const char* name, int value);
 /* Process-wide knobs:
  *   "conv_path" 0 = auto, 1 = fp32 SIMT kernels, 2 = tcgen05 tensor-core kernels (3xTF32, fp32-accurate)

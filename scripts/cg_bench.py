@@ -13,6 +13,7 @@ torch.cuda.set_device(0)
 for (Y, X) in [(128, 64), (256, 128)]:
     for B in (3, 148):
         plan = engine.Plan.karman(Y, X, B)
+        plan.set_option("direct_solve", 0)      # this script times the iterative solvers (scripts/direct_bench.py: the direct one)
         plan.set_cg(1e-7, 1e-6, 4000, 0)
         re, vy0, vx0, gy, gx, sig = bench.synth_batch(plan, engine, torch, B, 1, 0, 30)
         o = plan.step_fwd(re, vy0, vx0)
