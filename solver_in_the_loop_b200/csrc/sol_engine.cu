@@ -834,7 +834,7 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
     const int tiles_step = (p->X / 8) * (p->Y / 16) * B;
     const bool burgers = p->boundary == SOL_BOUNDARY_PERIODIC;      // no pressure solve, hence no solve windows
     // the direct projection takes ~20 us: no window worth filling
-    const bool overlap = u->deferred_wgrad && sol::g_wgrad_overlap && B + 17 <= p->sm_count && !burgers && !direct_active(p);
+    const bool overlap = u->deferred_wgrad && sol::g_wgrad_overlap && B + 17 <= p->sm_count && !burgers && !direct_for_batch(p, B);
     const int sm_budget = overlap ? p->sm_count - B - 1 : p->sm_count;        // SMs left beside the solve's B CTAs
     const int nct32 = tiles_step < sm_budget ? tiles_step : sm_budget;          // fixed per sweep: the partial-sum slots must line up
     if (overlap && !u->sstream) {

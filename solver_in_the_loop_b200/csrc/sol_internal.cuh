@@ -189,6 +189,7 @@ bool direct_supported(const sol_plan* p);
 int direct_build(sol_plan* p);          // host precomputation + upload (synchronous; never inside a stream capture)
 void direct_free(sol_plan* p);
 bool direct_active(const sol_plan* p);  // option on and precomputation available (builds lazily)
+bool direct_for_batch(const sol_plan* p, int B);   // ... and the batch is small enough for it to be the faster solver
 int launch_direct(const sol_plan* p, cudaStream_t st, int B, int mode, const float* rhs, float* p_out, const float* vy, const float* vx,
                   float* vy_out, float* vx_out, int* iters, const CgFuse* fuse = nullptr);
 
