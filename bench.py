@@ -368,7 +368,8 @@ def main():
         torch.cuda.synchronize()
         t_full = e8.elapsed_time(e9) / 1e3 / nrep
         K_f = float(it_f.float().mean())
-        ach_f = (direct_bytes_per_sim * nsm if direct else (per_iter_bytes * K_f + 8.0) * Y * X * nsm) / t_full / 1e9
+        # (the engine switches to the multigrid CG above 64 simulations per launch: one whole solve per SM is the higher-throughput form)
+        ach_f = (direct_bytes_per_sim * nsm if (direct and K_f == 0.0) else (per_iter_bytes * K_f + 8.0) * Y * X * nsm) / t_full / 1e9
         ach_cg = (40.0 * max(K_f, 0.0) + 8.0) * Y * X * nsm / t_full / 1e9       # the same launch counted with the plain-CG byte model of SURVEY 8d
         full = {"sims": nsm, "us_per_launch": t_full * 1e6, "cg_iters": K_f, "achieved": ach_f, "unit": "GB/s", "frac": ach_f / peak,
                 "achieved_plain_cg_byte_model": ach_cg, "frac_plain_cg_byte_model": ach_cg / peak,
