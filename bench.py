@@ -67,6 +67,8 @@ CONV_TC_DRAM_BYTES = 4.95e6
 CONV_TC_DRAM_SOURCE = ("profiles/r01_b_ncu_top.md: mean of 8 launches, dram read 3.4-6.5 MB + write 0 (the 3.1 MB output tile stays in the "
                        "126 MB L2 under ncu's replay); algorithmic: 3.15 MB in + 3.15 MB out + 0.2 MB weights")
 CG_MG_DRAM_BYTES = 0.42e6   # profiles/r01_b_ncu_top.md: k_cg_mg3 reads 0.42 MB, writes stay in L2 (compulsory: 20 B/cell = 0.49 MB)
+DIRECT_DRAM_BYTES = 7.38e6  # profiles/r01_e_ncu_direct_wgrad.md: k_direct_solve 0.55 MB + k_direct_apply 6.83 MB per launch under ncu's cold
+                            # caches (the 6.3 MB correction basis comes from DRAM once; it is L2-resident in the running iteration)
 
 
 def load_peaks(key="hbm_gbs"):
@@ -441,7 +443,7 @@ def main():
         if direct:
             solver_name = "k_direct_solve + k_direct_apply (direct projection: divergence -> DST fast Poisson solve -> capacitance correction -> gradient subtract)"
         roof_solver = {"kernel": solver_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                       "frac": achieved / peak, "traffic": CG_MG_DRAM_BYTES if (precond and not direct and (Y, X, B) == (128, 64, 3)) else None, "peak_source": peak_src, "cg_iters": K,
+                       "frac": achieved / peak, "traffic": (DIRECT_DRAM_BYTES if direct else CG_MG_DRAM_BYTES if precond else None) if (Y, X, B) == (128, 64, 3) else None, "peak_source": peak_src, "cg_iters": K,
                        "us_per_launch": t_solve_max * 1e6, "algorithmic_bytes_per_launch": alg_bytes,
                        "launches_per_step": 2 * m, "share_of_step": 2 * m * t_solve_max / t_iter, "machine_filling_batch": full,
                        "note": ("direct solve, no iterations: per simulation one CTA does the four small dense transforms (3.1 MFMA, fp32 FMA "
