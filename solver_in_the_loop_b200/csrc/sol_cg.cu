@@ -361,7 +361,12 @@ bool cg_fuses(const sol_plan* p) {
 int launch_cg(const sol_plan* p, cudaStream_t st, int B, int mode, const float* rhs, float* p_out, const float* vy,
               const float* vx, float* vy_out, float* vx_out, int* iters, const CgFuse* fuse) {
     if (p->boundary != SOL_BOUNDARY_OPEN) return fail(SOL_ERR_UNSUPPORTED, "pressure solve requires an OPEN-boundary plan");
-    if (direct_for_batch(p, B)) return launch_direct(p, st, B, mode, rhs, p_out, vy, vx, vy_out, vx_out, iters, fuse);
+    bool may_build = true;
+    if (!p->dir.tried) {      // the precomputation allocates and copies: never inside a stream capture (the iterative path runs instead)
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) may_build = false;
+    }
+    if (may_build && direct_for_batch(p, B)) return launch_direct(p, st, B, mode, rhs, p_out, vy, vx, vy_out, vx_out, iters, fuse);
     if (p->cg_precond && p->cluster <= 1 && mg_supported(p))
         return launch_cg_mg(p, st, B, mode, rhs, p_out, vy, vx, vy_out, vx_out, iters, fuse);
     if (fuse && (fuse->feat_out || fuse->gfeat_in)) return fail(SOL_ERR_UNSUPPORTED, "cg: fused feature I/O is not available for this solver variant (see cg_fuses)");

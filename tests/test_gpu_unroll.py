@@ -111,11 +111,12 @@ def test_graph_replay_matches_eager(cuda_device):
     assert rel(g1, g0) < 1e-5    # thin-layer weight gradients use float atomics (order varies)
 
 
-def test_full_size_properties(cuda_device):
+@pytest.mark.parametrize("direct", [1, 0], ids=["direct", "mgpcg"])
+def test_full_size_properties(cuda_device, direct):
     """BASELINE config sizes (128x64, B=3, msteps=32) through size-independent properties:
     finite decreasing-residual solves, divergence-free predicted states, deterministic c32 grads."""
     Y, X, B, m = 128, 64, 3, 32
-    engine, geom, rho, vy, vx, re, gty, gtx, sig, params, plan, un, w = _setup(Y, X, B, 1, cuda_device, spin=5, direct=0)
+    engine, geom, rho, vy, vx, re, gty, gtx, sig, params, plan, un, w = _setup(Y, X, B, 1, cuda_device, spin=5, direct=direct)
     plan.set_cg(tol_abs=1e-5, tol_rel=0.0, max_it=2000, cluster=0)      # the reference's stop rule (iterative solver)
     un = engine.Unroll(plan, m, B, sig, use_graph=True)
     d = lambda t: dev(t, cuda_device)
@@ -128,8 +129,17 @@ def test_full_size_properties(cuda_device):
     it = un.cg_iters()
     print("loss steps", ls.tolist()[:4], "...", "mean cg iters fwd/bwd", float(it[0].float().mean()), float(it[1].float().mean()))
     assert torch.isfinite(ls).all() and torch.isfinite(g).all()
-    assert int(it.max()) < 2000 and int(it.min()) >= 1
+    if direct:
+        assert int(it.max()) == 0                      # no iterations at all
+    else:
+        assert int(it.max()) < 2000 and int(it.min()) >= 1
     assert float(g.abs().max()) > 0
+    # the corrected states of the forward sweep are divergence-free up to the (not re-projected) correction: the projected
+    # velocity itself must be divergence-free on fluid cells at every size
+    out = plan.step_fwd(d(re), d(vy), d(vx))
+    div = plan.divergence(out["vy"], out["vx"])
+    act = torch.tensor(geom.active, device=cuda_device, dtype=torch.float32)
+    assert float((div * act).abs().max()) < (2e-5 if direct else 2e-4)
 
 
 def test_model_mercury_unrolled_parity(cuda_device):
