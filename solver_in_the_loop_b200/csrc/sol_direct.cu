@@ -17,6 +17,7 @@
 
 #include <vector>
 
+#include "sol_direct_host.h"
 #include "sol_internal.cuh"
 
 namespace sol {
@@ -295,124 +296,20 @@ void direct_free(sol_plan* p) {
     d = sol_direct();
 }
 
-// Host precomputation (double precision) of the transform matrices and the capacitance correction.
+// Host precomputation (sol_direct_host.h, double precision) of the transform matrices and the capacitance correction, then upload.
 int direct_build(sol_plan* p) {
     sol_direct& d = p->dir;
     d.tried = true;
     if (!direct_supported(p)) return SOL_OK;
-    const int Y = p->Y, X = p->X, N = Y * X;
-    const std::vector<unsigned char>& act = p->h_active;
-    const std::vector<float>& dg = p->h_diag;
-    if ((int)act.size() != N || (int)dg.size() != N) return SOL_OK;
-    const double PI = 3.14159265358979323846;
-    std::vector<double> Sy((size_t)Y * Y), Sx((size_t)X * X), il((size_t)N);
-    for (int a = 0; a < Y; ++a)
-        for (int b = 0; b < Y; ++b) Sy[(size_t)a * Y + b] = sqrt(2.0 / (Y + 1)) * sin(PI * (a + 1) * (b + 1) / (Y + 1));
-    for (int a = 0; a < X; ++a)
-        for (int b = 0; b < X; ++b) Sx[(size_t)a * X + b] = sqrt(2.0 / (X + 1)) * sin(PI * (a + 1) * (b + 1) / (X + 1));
-    for (int a = 0; a < Y; ++a)
-        for (int b = 0; b < X; ++b) il[(size_t)a * X + b] = 1.0 / (-4.0 + 2.0 * cos(PI * (a + 1) / (Y + 1)) + 2.0 * cos(PI * (b + 1) / (X + 1)));
-    // rows of A that differ from A0: solid cells and cells with a solid neighbour
-    auto solid = [&](int j, int i) -> bool { return j >= 0 && j < Y && i >= 0 && i < X && !act[(size_t)j * X + i]; };
-    std::vector<int> rows;
-    for (int j = 0; j < Y; ++j)
-        for (int i = 0; i < X; ++i)
-            if (solid(j, i) || solid(j - 1, i) || solid(j + 1, i) || solid(j, i - 1) || solid(j, i + 1)) rows.push_back(j * X + i);
-    const int k = (int)rows.size();
-    const int kp = k == 0 ? 32 : (k + 31) / 32 * 32;
-    std::vector<int> rt_col((size_t)kp * 5, -1);
-    std::vector<float> rt_val((size_t)kp * 5, 0.0f);
-    std::vector<double> rtv((size_t)kp * 5, 0.0);
-    for (int q = 0; q < k; ++q) {
-        const int c = rows[q], j = c / X, i = c - j * X;
-        // A row:  -diag[c] on the diagonal, +1 to active in-domain neighbours (none for a solid cell);  A0 row: -4, +1 to in-domain neighbours
-        rt_col[q * 5] = c; rtv[q * 5] = 4.0 - (double)dg[c];
-        const int nb[4][2] = {{j - 1, i}, {j + 1, i}, {j, i - 1}, {j, i + 1}};
-        for (int e = 0; e < 4; ++e) {
-            const int jj = nb[e][0], ii = nb[e][1];
-            if (jj < 0 || jj >= Y || ii < 0 || ii >= X) continue;
-            const double aval = (act[c] && act[(size_t)jj * X + ii]) ? 1.0 : 0.0;
-            if (aval != 1.0) { rt_col[q * 5 + 1 + e] = jj * X + ii; rtv[q * 5 + 1 + e] = aval - 1.0; }
-        }
-    }
-    for (size_t e = 0; e < rtv.size(); ++e) rt_val[e] = (float)rtv[e];
-    // W[:, q] = A0^-1 e_c = Sy ((Sy[:,j] (x) Sx[:,i]) * ilam) Sx
-    std::vector<double> W((size_t)N * (k > 0 ? k : 1), 0.0), G((size_t)N), T((size_t)N);
-    for (int q = 0; q < k; ++q) {
-        const int c = rows[q], j = c / X, i = c - j * X;
-        for (int a = 0; a < Y; ++a)
-            for (int b = 0; b < X; ++b) G[(size_t)a * X + b] = Sy[(size_t)a * Y + j] * Sx[(size_t)b * X + i] * il[(size_t)a * X + b];
-        // T = G Sx
-        for (int a = 0; a < Y; ++a) {
-            double* tr = &T[(size_t)a * X];
-            for (int b = 0; b < X; ++b) tr[b] = 0.0;
-            for (int m = 0; m < X; ++m) {
-                const double g = G[(size_t)a * X + m];
-                const double* sr = &Sx[(size_t)m * X];
-                for (int b = 0; b < X; ++b) tr[b] += g * sr[b];
-            }
-        }
-        // W[:, q] = Sy T
-        for (int a = 0; a < Y; ++a) {
-            double out[128];
-            for (int b = 0; b < X; ++b) out[b] = 0.0;
-            for (int m = 0; m < Y; ++m) {
-                const double s = Sy[(size_t)a * Y + m];
-                const double* tr = &T[(size_t)m * X];
-                for (int b = 0; b < X; ++b) out[b] += s * tr[b];
-            }
-            for (int b = 0; b < X; ++b) W[((size_t)a * X + b) * k + q] = out[b];
-        }
-    }
-    // M = (I + R^T W)^-1 by Gauss-Jordan with partial pivoting
-    std::vector<double> C((size_t)k * k, 0.0), Inv((size_t)k * k, 0.0);
-    for (int q = 0; q < k; ++q) {
-        Inv[(size_t)q * k + q] = 1.0;
-        for (int e = 0; e < 5; ++e) {
-            const int col = rt_col[q * 5 + e];
-            if (col < 0) continue;
-            const double v = rtv[q * 5 + e];
-            for (int r = 0; r < k; ++r) C[(size_t)q * k + r] += v * W[(size_t)col * k + r];
-        }
-        C[(size_t)q * k + q] += 1.0;
-    }
-    for (int col = 0; col < k; ++col) {
-        int piv = col;
-        for (int r = col + 1; r < k; ++r)
-            if (fabs(C[(size_t)r * k + col]) > fabs(C[(size_t)piv * k + col])) piv = r;
-        if (fabs(C[(size_t)piv * k + col]) < 1e-13) return SOL_OK;      // singular: the direct solver stays disabled
-        if (piv != col)
-            for (int m = 0; m < k; ++m) { std::swap(C[(size_t)piv * k + m], C[(size_t)col * k + m]); std::swap(Inv[(size_t)piv * k + m], Inv[(size_t)col * k + m]); }
-        const double dv = C[(size_t)col * k + col];
-        for (int m = 0; m < k; ++m) { C[(size_t)col * k + m] /= dv; Inv[(size_t)col * k + m] /= dv; }
-        for (int r = 0; r < k; ++r) {
-            if (r == col) continue;
-            const double f = C[(size_t)r * k + col];
-            if (f == 0.0) continue;
-            for (int m = 0; m < k; ++m) { C[(size_t)r * k + m] -= f * C[(size_t)col * k + m]; Inv[(size_t)r * k + m] -= f * Inv[(size_t)col * k + m]; }
-        }
-    }
-    std::vector<float> Syf(Sy.begin(), Sy.end()), Sxf(Sx.begin(), Sx.end()), ilf(il.begin(), il.end());
-    // fold the capacitance matrix into the correction basis: (W M)[c][q] = sum_e W[c][e] M[e][q]
-    std::vector<float> Wt((size_t)kp * N, 0.0f);
-    {
-        std::vector<double> row((size_t)(k > 0 ? k : 1));
-        for (int c = 0; c < N; ++c) {
-            for (int q = 0; q < k; ++q) row[q] = 0.0;
-            for (int e = 0; e < k; ++e) {
-                const double w = W[(size_t)c * k + e];
-                if (w == 0.0) continue;
-                const double* mr = &Inv[(size_t)e * k];
-                for (int q = 0; q < k; ++q) row[q] += w * mr[q];
-            }
-            for (int q = 0; q < k; ++q) Wt[(size_t)q * N + c] = (float)row[q];
-        }
-    }
-    SOL_TRY(up(&d.Sy, Syf)); SOL_TRY(up(&d.Sx, Sxf)); SOL_TRY(up(&d.ilam, ilf));
-    SOL_TRY(up(&d.rt_col, rt_col)); SOL_TRY(up(&d.rt_val, rt_val)); SOL_TRY(up(&d.Wt, Wt));
+    const int N = p->Y * p->X;
+    if ((int)p->h_active.size() != N || (int)p->h_diag.size() != N) return SOL_OK;
+    DirectHost h;
+    if (!direct_precompute(p->Y, p->X, p->h_active.data(), p->h_diag.data(), h)) return SOL_OK;      // singular: stays disabled
+    SOL_TRY(up(&d.Sy, h.Sy)); SOL_TRY(up(&d.Sx, h.Sx)); SOL_TRY(up(&d.ilam, h.ilam));
+    SOL_TRY(up(&d.rt_col, h.rt_col)); SOL_TRY(up(&d.rt_val, h.rt_val)); SOL_TRY(up(&d.Wt, h.Wt));
     SOL_CUDA(cudaMalloc((void**)&d.p0, (size_t)p->B_max * N * sizeof(float)));
-    SOL_CUDA(cudaMalloc((void**)&d.tvec, (size_t)p->B_max * kp * sizeof(float)));
-    d.k = k; d.kp = kp;
+    SOL_CUDA(cudaMalloc((void**)&d.tvec, (size_t)p->B_max * h.kp * sizeof(float)));
+    d.k = h.k; d.kp = h.kp;
     d.valid = true;
     return SOL_OK;
 }

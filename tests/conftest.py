@@ -20,8 +20,8 @@ def emu():
     d = os.path.join(ROOT, "tests", "host_emu")
     so = os.path.join(d, "libsol_emu.so")
     src = os.path.join(d, "emu.cpp")
-    hdr = os.path.join(ROOT, "solver_in_the_loop_b200", "csrc", "sol_cells.cuh")
-    if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(ROOT, "solver_in_the_loop_b200", "csrc", h) for h in ("sol_cells.cuh", "sol_direct_host.h")]
+    if (not os.path.exists(so)) or os.path.getmtime(so) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", "-o", so, src])
     return ctypes.CDLL(so)
 

@@ -104,3 +104,41 @@ void emu_laplace(int B, int Y, int X, const float* p, const unsigned char* activ
 }
 
 }  // extern "C"
+
+// ---- direct pressure projection (sol_direct_host.h + the arithmetic of k_direct_solve / k_direct_apply in fp32) ----
+#include "../../solver_in_the_loop_b200/csrc/sol_direct_host.h"
+
+extern "C" int emu_direct_solve(int Y, int X, int B, const unsigned char* act, const float* diag, const float* rhs, float* p_out) {
+    DirectHost h;
+    if (!direct_precompute(Y, X, act, diag, h)) return -1;
+    const int N = Y * X;
+    std::vector<float> D(N), U(N), V(N), Z(N), P0(N), s(h.kp);
+    for (int b = 0; b < B; ++b) {
+        const float* r = rhs + (size_t)b * N;
+        for (int c = 0; c < N; ++c) D[c] = act[c] ? r[c] : 0.0f;
+        // U = Sy D
+        for (int a = 0; a < Y; ++a)
+            for (int i = 0; i < X; ++i) { float acc = 0.f; for (int m = 0; m < Y; ++m) acc = fmaf(h.Sy[(size_t)m * Y + a], D[(size_t)m * X + i], acc); U[(size_t)a * X + i] = acc; }
+        // V = (U Sx) * ilam
+        for (int a = 0; a < Y; ++a)
+            for (int i = 0; i < X; ++i) { float acc = 0.f; for (int m = 0; m < X; ++m) acc = fmaf(U[(size_t)a * X + m], h.Sx[(size_t)m * X + i], acc); V[(size_t)a * X + i] = acc * h.ilam[(size_t)a * X + i]; }
+        // Z = V Sx
+        for (int a = 0; a < Y; ++a)
+            for (int i = 0; i < X; ++i) { float acc = 0.f; for (int m = 0; m < X; ++m) acc = fmaf(V[(size_t)a * X + m], h.Sx[(size_t)m * X + i], acc); Z[(size_t)a * X + i] = acc; }
+        // p0 = Sy Z
+        for (int a = 0; a < Y; ++a)
+            for (int i = 0; i < X; ++i) { float acc = 0.f; for (int m = 0; m < Y; ++m) acc = fmaf(h.Sy[(size_t)m * Y + a], Z[(size_t)m * X + i], acc); P0[(size_t)a * X + i] = acc; }
+        for (int q = 0; q < h.kp; ++q) {
+            float sv = 0.f;
+            if (q < h.k)
+                for (int e = 0; e < 5; ++e) { const int col = h.rt_col[q * 5 + e]; if (col >= 0) sv = fmaf(h.rt_val[q * 5 + e], P0[col], sv); }
+            s[q] = sv;
+        }
+        for (int c = 0; c < N; ++c) {
+            float corr = 0.f;
+            for (int q = 0; q < h.k; ++q) corr = fmaf(h.Wt[(size_t)q * N + c], s[q], corr);
+            p_out[(size_t)b * N + c] = act[c] ? P0[c] - corr : -r[c] / diag[c];
+        }
+    }
+    return h.k;
+}

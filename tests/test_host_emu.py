@@ -100,3 +100,23 @@ def test_projection_pieces(emu, case):
     emu.emu_gradsub(B, Y, X, _p(vy32), _p(vx32), _p(_f32(pr)), _p(my), _p(mx), _p(oy), _p(ox))
     assert np.abs(oy - vy3.numpy()).max() < 2e-5
     assert np.abs(ox - vx3.numpy()).max() < 2e-5
+
+
+@pytest.mark.parametrize("Y,X", [(64, 32), (128, 64)], ids=["64x32", "128x64"])
+def test_direct_projection_host_logic(emu, Y, X):
+    """The direct pressure solver's host precomputation (sol_direct_host.h: sine-transform matrices, changed rows of the operator,
+    capacitance-corrected basis) + the fp32 arithmetic of its two kernels, against the oracle's float64 sparse LU."""
+    geom = so.KarmanGeom(Y, X)
+    g = torch.Generator().manual_seed(11)
+    vy = torch.randn(2, Y + 1, X, generator=g, dtype=torch.float64); vx = torch.randn(2, Y, X + 1, generator=g, dtype=torch.float64)
+    _, _, pref, d = so.project(vy, vx, geom)
+    act = np.ascontiguousarray(geom.active.astype(np.uint8)); diag = _f32(torch.tensor(geom.diag))
+    d32 = _f32(d); out = np.zeros_like(d32)
+    emu.emu_direct_solve.restype = C.c_int
+    k = emu.emu_direct_solve(Y, X, 2, act.ctypes.data_as(C.c_void_p), _p(diag), _p(d32), _p(out))
+    solid = int((geom.active == 0).sum())
+    assert k > solid and k < 3 * solid                      # solid cells + their fluid neighbours
+    fluid = geom.active > 0
+    err = np.linalg.norm((out - pref.numpy())[:, fluid]) / np.linalg.norm(pref.numpy()[:, fluid])
+    print("direct projection (host emulation) vs sparse LU:", err, "changed rows", k)
+    assert err < 5e-6
