@@ -8,8 +8,6 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import sol_oracle as so
-
 pytestmark = pytest.mark.gpu
 
 
@@ -38,18 +36,17 @@ def test_karman_generate_train_apply(cuda_device, tmp_path):
         assert float((v2 - v).norm() / v.norm()) < 1e-5
 
 
-def test_burgers_train_apply(cuda_device, tmp_path):
+def test_burgers_generate_train_apply(cuda_device, tmp_path):
+    """burgers/Makefile:20-23, 75-77: burgers.py (20 travelling sine forces, random smooth initial state) -> burgers_train.py -> burgers_apply.py."""
     from solver_in_the_loop_b200 import formats
-    from solver_in_the_loop_b200.scripts import burgers_apply, burgers_train
+    from solver_in_the_loop_b200.scripts import burgers, burgers_apply, burgers_train
     data, tf, run = str(tmp_path / "bdata"), str(tmp_path / "btf"), str(tmp_path / "brun")
-    R, frames, dt = 64, 6, 0.1
-    for s in range(2):       # "hi-res" 64x64 trajectories from the oracle, down-sampled 2x by the dataset
-        dx, vy, vx, fy, fx, gy, gx, sv, sf = so.make_burgers_case(R=R, B=1, msteps=frames, L=32.0, dt=dt, seed=s, noise=0.0)
-        vys = [vy] + [g for g in gy]; vxs = [vx] + [g for g in gx]
-        for f in range(frames):
-            sd = formats.sim_dir(data, s)
-            formats.write_zipped_array(os.path.join(sd, "velo_%06d.npz" % f), formats.pack_staggered(vys[f].numpy(), vxs[f].numpy()).astype(np.float32))
-            formats.write_zipped_array(os.path.join(sd, "forc_%06d.npz" % f), formats.pack_staggered(fy[f].numpy(), fx[f].numpy()).astype(np.float32))
+    frames, dt = 6, 0.1
+    for s in range(2):       # "hi-res" 64x64 trajectories, down-sampled 2x by the dataset
+        burgers.main(["-o", data, "-r", "64", "-l", "32", "--dt", str(dt), "--skipsteps", "3", "-t", str(frames), "--seed", str(s), "--sim-index", str(s)])
+    v0 = formats.read_zipped_array(data + "/sim_000000/velo_000000.npz"); f5 = formats.read_zipped_array(data + "/sim_000001/forc_000005.npz")
+    assert v0.shape == (1, 65, 65, 2) and f5.shape == (1, 65, 65, 2) and np.isfinite(v0).all() and 0.05 < np.abs(f5).max() < 3.0
+    assert not np.allclose(formats.read_zipped_array(data + "/sim_000000/forc_000000.npz"), formats.read_zipped_array(data + "/sim_000000/forc_000005.npz"))
     tr = burgers_train.main(["--train", data, "--tf", tf, "-s", "2", "-n", "2", "-b", "2", "-t", str(frames), "-m", "2", "-e", "2", "--dt", str(dt),
                              "-l", "32", "--lr", "1e-4", "--seed", "0"])
     assert tr.t == 2 * (frames - 2) and os.path.isfile(tf + "/model.npz") and os.path.isfile(tf + "/model_epoch0001.pt")
