@@ -34,7 +34,6 @@ struct DirectArgs {
     const float* rhs;                           // MODE 0
     const float* vy_in; const float* vx_in;     // MODE 1
     float* p0;                                  // [B][N] scratch
-    float* tvec;                                // [B][kp] scratch
     float* p_out; float* vy_out; float* vx_out; int* iters;
     // fused feature I/O (see CgFuse)
     float* feat_out; const float* re; float isy, isx, isr; const float* gfeat_in; int cfeat;
@@ -292,7 +291,7 @@ bool direct_supported(const sol_plan* p) {
 void direct_free(sol_plan* p) {
     sol_direct& d = p->dir;
     cudaFree(d.Sy); cudaFree(d.Sx); cudaFree(d.ilam); cudaFree(d.rt_col); cudaFree(d.rt_val); cudaFree(d.Wt);
-    cudaFree(d.p0); cudaFree(d.tvec);
+    cudaFree(d.p0);
     d = sol_direct();
 }
 
@@ -308,7 +307,6 @@ int direct_build(sol_plan* p) {
     SOL_TRY(up(&d.Sy, h.Sy)); SOL_TRY(up(&d.Sx, h.Sx)); SOL_TRY(up(&d.ilam, h.ilam));
     SOL_TRY(up(&d.rt_col, h.rt_col)); SOL_TRY(up(&d.rt_val, h.rt_val)); SOL_TRY(up(&d.Wt, h.Wt));
     SOL_CUDA(cudaMalloc((void**)&d.p0, (size_t)p->B_max * N * sizeof(float)));
-    SOL_CUDA(cudaMalloc((void**)&d.tvec, (size_t)p->B_max * h.kp * sizeof(float)));
     d.k = h.k; d.kp = h.kp;
     d.valid = true;
     return SOL_OK;
@@ -364,7 +362,7 @@ int launch_direct(const sol_plan* p, cudaStream_t st, int B, int mode, const flo
     memset(&a, 0, sizeof(a));
     a.B = B; a.Sy = d.Sy; a.Sx = d.Sx; a.ilam = d.ilam; a.rt_col = d.rt_col; a.rt_val = d.rt_val; a.Wt = d.Wt; a.k = d.k; a.kp = d.kp;
     a.my = p->face_my; a.mx = p->face_mx; a.active = p->active; a.diag = p->diag;
-    a.rhs = rhs; a.vy_in = vy; a.vx_in = vx; a.p0 = d.p0; a.tvec = d.tvec; a.p_out = p_out; a.vy_out = vy_out; a.vx_out = vx_out; a.iters = iters;
+    a.rhs = rhs; a.vy_in = vy; a.vx_in = vx; a.p0 = d.p0; a.p_out = p_out; a.vy_out = vy_out; a.vx_out = vx_out; a.iters = iters;
     a.cfeat = 3;
     if (fuse && (fuse->feat_out || fuse->gfeat_in)) {
         if (mode != 1) return fail(SOL_ERR_UNSUPPORTED, "direct solve: fused feature I/O needs the projection mode");

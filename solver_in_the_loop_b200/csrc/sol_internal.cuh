@@ -100,7 +100,7 @@ struct sol_direct {
     float *Sy = nullptr, *Sx = nullptr, *ilam = nullptr;
     int* rt_col = nullptr; float* rt_val = nullptr;
     float* Wt = nullptr;                  // [kp][N]: the capacitance-corrected basis (W M), transposed
-    float *p0 = nullptr, *tvec = nullptr; // scratch: [B_max][N], [B_max][kp]
+    float* p0 = nullptr;                  // scratch: [B_max][N] obstacle-free solution
 };
 
 struct sol_plan {
