@@ -223,7 +223,11 @@ class KarmanFlow(IncompressibleFlow):
         Y, X = smoke.domain.resolution
         B = smoke._batch_size
         dev = smoke.velocity._vy.device
-        key = (Y, X, B, str(dev), id(velBCy), id(velBCyMask))
+        def digest(a_):      # content, not identity: callers often rebuild (np.copy) the BC arrays every step
+            a_ = a_.detach().cpu().numpy() if isinstance(a_, torch.Tensor) else np.asarray(a_)
+            return hash(np.ascontiguousarray(a_, dtype=np.float32).tobytes())
+
+        key = (Y, X, B, str(dev), digest(velBCy), digest(velBCyMask))
         if key in self._plans:
             return self._plans[key]
         dxy = smoke.domain.dx
