@@ -344,6 +344,14 @@ class CorrectionModel:
 
     @classmethod
     def load(cls, path, **kw):
+        if str(path).endswith(".h5"):
+            # the reference Makefiles name Keras checkpoints (model.h5); this package's train scripts write model.npz beside them
+            import os
+            alt = str(path)[:-3] + ".npz"
+            if not os.path.exists(alt):
+                raise SolError("%s is a Keras HDF5 checkpoint: convert it with `python -m solver_in_the_loop_b200.scripts.keras_h5_to_npz "
+                               "model.h5 model.npz` (needs h5py) or pass the model.npz written by this package's train scripts" % path)
+            path = alt
         z = np.load(path)
         ws = [z["arr_%d" % i] for i in range(len(z.files))]
         kw.setdefault("cin0", int(ws[0].shape[2]))                        # 3 karman, 4 / 2 burgers

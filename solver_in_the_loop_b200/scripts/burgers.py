@@ -13,6 +13,7 @@ import os
 import numpy as np
 import torch
 
+from . import device_index
 from .. import formats
 from ..phi_compat import PERIODIC, BurgersTest, BurgersVelocitySMAC, Domain, StaggeredGrid, box
 
@@ -77,7 +78,7 @@ class SinForces:
 def main(argv=None):
     p = vars(parse(argv))
     logging.basicConfig(level=logging.INFO)
-    torch.cuda.set_device(int(p["gpu"].split(",")[0]) if p["gpu"] not in ("-1", "") else 0)
+    torch.cuda.set_device(device_index(p["gpu"]))
     dev = torch.device("cuda", torch.cuda.current_device())
     np.random.seed(p["seed"])
     res, dx = p["res"], p["len"] / p["res"]

@@ -9,6 +9,7 @@ import pickle
 import numpy as np
 import torch
 
+from . import device_index
 from .. import formats
 from ..phi_compat import (PERIODIC, BurgersTest, BurgersVelocitySMAC, CorrectionModel, Domain, StaggeredGrid, box, burgers_to_feature,
                           to_feature_noforce, to_staggered)
@@ -32,7 +33,7 @@ def parse(argv=None):
 def main(argv=None):
     p = vars(parse(argv))
     logging.basicConfig(level=logging.INFO)
-    torch.cuda.set_device(int(p["gpu"].split(",")[0]))
+    torch.cuda.set_device(device_index(p["gpu"]))
     dev = torch.device("cuda", torch.cuda.current_device())
     res = p["res"]
     dm = Domain(resolution=[res, res], box=box([p["len"]] * 2), boundaries=PERIODIC)

@@ -10,6 +10,7 @@ import random
 import numpy as np
 import torch
 
+from . import device_index
 from .. import dist as sdist
 from .. import engine
 from ..dataset import BurgersPhifDataset
@@ -40,7 +41,7 @@ def main(argv=None):
     logging.basicConfig(level=logging.INFO)
     rank, local, world = sdist.init_from_env("nccl")
     if world == 1:
-        torch.cuda.set_device(int(p["gpu"].split(",")[0]))
+        torch.cuda.set_device(device_index(p["gpu"]))
     if p["nsims"] % p["sbatch"]:
         p["nsims"] = (p["nsims"] // p["sbatch"]) * p["sbatch"]
     seed = 0 if p["seed"] is None else p["seed"]

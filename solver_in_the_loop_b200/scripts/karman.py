@@ -8,6 +8,7 @@ import os
 import numpy as np
 import torch
 
+from . import device_index
 from .. import formats
 from ..phi_compat import OPEN, Domain, Fluid, KarmanFlow, StaggeredGrid, box, unstack_staggered_tensor
 
@@ -35,7 +36,7 @@ def parse(argv=None):
 def main(argv=None):
     p = vars(parse(argv))
     logging.basicConfig(level=logging.INFO)
-    torch.cuda.set_device(int(p["gpu"].split(",")[0]))
+    torch.cuda.set_device(device_index(p["gpu"]))
     np.random.seed(p["seed"])
     res, L = p["res"], p["len"]
     st = Fluid(Domain(resolution=[res * 2, res], box=box[0:L * 2, 0:L], boundaries=OPEN), buoyancy_factor=0)
