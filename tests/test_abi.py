@@ -40,3 +40,21 @@ def test_engine_refuses_cpu_tensors():
     from solver_in_the_loop_b200 import engine
     with pytest.raises(engine.SolError):
         engine._ptr(torch.zeros(4))
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/sol_b200.h is the drop-in boundary: it must compile as C99 (no C++ / CUDA / torch types in the signatures) and a C
+    translation unit that references every declared entry point must link against the shared library."""
+    import subprocess
+    from solver_in_the_loop_b200 import _lib
+    names = _declared()
+    src = tmp_path / "abi_check.c"
+    body = "\n".join("    p[%d] = (fn)%s;" % (i, n) for i, n in enumerate(names))
+    src.write_text('#include "sol_b200.h"\n#include <stdio.h>\ntypedef void (*fn)(void);\nint main(void) {\n    fn p[%d];\n%s\n    printf("%%d %%d\\n", sol_abi_version(), p[0] != 0);\n    return 0;\n}\n'
+                   % (len(names), body))
+    exe = tmp_path / "abi_check"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-l:libsol_b200.so", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split()[0] == "1", out.stderr
