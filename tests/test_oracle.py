@@ -164,3 +164,23 @@ def test_burgers_step_properties():
     fy = torch.ones_like(vy); fx = torch.zeros_like(vx)
     a = so.burgers_step(vy, vx, 0.1, 1.0); b = so.burgers_step(vy, vx, 0.1, 1.0, fy=fy, fx=fx)
     assert torch.allclose(b[0] - a[0], 0.1 * fy) and torch.allclose(b[1], a[1])
+
+
+def test_projection_against_an_independent_solver():
+    """The oracle's sparse-LU pressure solve vs an independent route to the same answer: sine-transform fast Poisson solve of the
+    obstacle-free rectangle + capacitance-matrix correction of the rows the obstacle changes (float64, scripts/probes/direct_model.py)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("direct_model", os.path.join(root, "scripts", "probes", "direct_model.py"))
+    dm = importlib.util.module_from_spec(spec); spec.loader.exec_module(dm)
+    geom = so.KarmanGeom(64, 32)
+    g = torch.Generator().manual_seed(21)
+    vy = torch.randn(1, 65, 32, generator=g, dtype=torch.float64); vx = torch.randn(1, 64, 33, generator=g, dtype=torch.float64)
+    _, _, pref, d = so.project(vy, vx, geom)
+    S = dm.build(geom, np.float64)
+    p = dm.solve(S, d[0].numpy())
+    fluid = geom.active > 0
+    err = np.linalg.norm((p - pref[0].numpy())[fluid]) / np.linalg.norm(pref[0].numpy()[fluid])
+    assert err < 1e-10, err
+    assert S["k"] > int((geom.active == 0).sum())
