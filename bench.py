@@ -43,14 +43,13 @@ def parse():
     ap.add_argument("--spin", type=int, default=200, help="spin-up solver steps for the synthetic wake")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cluster", type=int, default=0)
-    ap.add_argument("--conv-chain", type=int, default=0, help="1 = consecutive tensor-core conv layers chained by tile flags")
-    ap.add_argument("--conv-stack", type=int, default=0, help="1 = the ten 32->32 layers of a sweep in one persistent launch")
+    ap.add_argument("--conv-variant", type=int, default=0, help="accumulator layout of the 3xFP16 conv kernel (tuning)")
     ap.add_argument("--wgrad-overlap", type=int, default=1, help="1 = deferred weight-gradient GEMMs run beside the adjoint solves")
     ap.add_argument("--wgrad-window-us", type=int, default=-1, help="tuning: time budget of one adjoint-solve window (us at 128x64)")
     ap.add_argument("--fuse-small", type=int, default=0, help="1 = corr_bwd folded into the diffusion adjoint")
     ap.add_argument("--fuse-solver-io", type=int, default=1, help="1 = to_feature / feat_bwd folded into the projection kernel")
     ap.add_argument("--pdl", type=int, default=1, help="1 = programmatic dependent launch of every kernel, 0 = plain stream order")
-    ap.add_argument("--conv-path", type=int, default=0, help="0 auto, 1 fp32 SIMT, 2 tcgen05 3xTF32")
+    ap.add_argument("--conv-path", type=int, default=0, help="0 auto, 1 fp32 SIMT, 2 tcgen05 3xFP16, 3 tcgen05 3xTF32")
     ap.add_argument("--wgrad-path", type=int, default=0, help="0 auto, 1 per-step SIMT, 2 deferred tcgen05")
     ap.add_argument("--cg-rows", type=int, default=0)
     ap.add_argument("--mg-variant", type=int, default=0, help="0 = compile-time-hierarchy multigrid kernel, 2 = run-time-hierarchy kernel")
@@ -253,8 +252,7 @@ def main():
 
     engine.set_option("conv_path", args.conv_path)
     engine.set_option("pdl", args.pdl)
-    engine.set_option("conv_chain", args.conv_chain)
-    engine.set_option("conv_stack", args.conv_stack)
+    engine.set_option("conv_variant", args.conv_variant)
     engine.set_option("wgrad_overlap", args.wgrad_overlap)
     engine.set_option("fuse_small", args.fuse_small)
     engine.set_option("fuse_solver_io", args.fuse_solver_io)
@@ -430,7 +428,7 @@ def main():
                               "max|r|<1e-5 per sim, <=2000 it (reference stop rule)"), "mean_cg_iters": [k_fwd, k_bwd],
                        "l2": "working set (activation stash %.2f GB/iter) exceeds the 126 MB L2; no explicit flush"
                              % (trainer.unroll.workspace.numel() / 1e9),
-                       "cuda_graph": not args.no_graph, "conv_path": args.conv_path, "wgrad_path": args.wgrad_path, "cg_precond": args.cg_precond, "direct_solve": args.direct_solve, "pdl": args.pdl, "conv_chain": args.conv_chain, "conv_stack": args.conv_stack, "wgrad_overlap": args.wgrad_overlap, "fuse_small": args.fuse_small, "fuse_solver_io": args.fuse_solver_io, "loss": float(loss_host)},
+                       "cuda_graph": not args.no_graph, "conv_path": args.conv_path, "wgrad_path": args.wgrad_path, "cg_precond": args.cg_precond, "direct_solve": args.direct_solve, "pdl": args.pdl, "conv_variant": args.conv_variant, "wgrad_overlap": args.wgrad_overlap, "fuse_small": args.fuse_small, "fuse_solver_io": args.fuse_solver_io, "loss": float(loss_host)},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": trainer.h2d_bytes_per_step(), "d2h_bytes_per_step": 4,
                     "ms_per_step": t_e2e / args.steps * 1e3, "wall_ms_per_step": t_e2e_wall / args.steps * 1e3},
             "gpu_launches": int(launches),

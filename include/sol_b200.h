@@ -77,19 +77,17 @@ int sol_plan_set_cg(sol_plan* plan, float tol_abs, float tol_rel, int max_it, in
  *                karman_apply.py:39), the CG controls above do not apply and iteration counters read 0.  0 = iterative solvers */
 int sol_plan_set_option(sol_plan* plan, const char* name, int value);
 /* Process-wide knobs:
- *   "conv_path" 0 = auto, 1 = fp32 SIMT kernels, 2 = tcgen05 tensor-core kernels (3xTF32, fp32-accurate)
+ *   "conv_path" 0 = auto (= 2), 1 = fp32 SIMT kernels, 2 = tcgen05 tensor-core kernels with block-scaled 3xFP16 operand
+ *         splitting (fp32-accurate), 3 = tcgen05 with 3xTF32 splitting (the round-1 kernel, twice the operand traffic)
+ *   "conv_variant" (tuning) accumulator layout of the 3xFP16 kernel: 0 = two alternating sets, 1 = one set, 2 = two merged sets
  *   "wgrad_path" 0 = auto, 1 = per-step fp32 SIMT weight gradients, 2 = deferred tcgen05 weight-gradient GEMM
  *   "fuse_small" 1 = the correction-gradient scaling (adjoint of "velocity + correction") is folded into the
  *         diffusion adjoint of the following step, 0 (default: measured faster) = separate kernel
  *   "fuse_solver_io" 1 (default) = to_feature and its adjoint are folded into the projection kernel (2 launches fewer per
  *         step) where the solver variant supports it, 0 = separate kernels
- *   "conv_stack" 1 = the ten consecutive 32->32 layers of a sweep run as ONE persistent tensor-core launch with per-tile
- *         flags between layers (when all its CTAs are co-resident; measured slower), 0 (default) = one launch per layer
  *   "wgrad_overlap" 1 (default) = the deferred weight-gradient GEMMs of already finished steps run on a side stream
  *         while an adjoint pressure solve keeps only B SMs busy, 0 = all of them after the adjoint sweep
  *   "wgrad_window_us" (tuning) time budget of one such window at 128x64, default 110
- *   "conv_chain" 1 = consecutive tensor-core conv layers of the unrolled sweep are chained by per-tile
- *         completion flags (a tile starts when the tiles under its halo are stored), 0 (default) = whole-kernel dependencies
  *   "pdl" 1 (default) = kernels are launched with programmatic stream serialization (the prologue of a kernel
  *         overlaps the tail of its predecessor on the stream), 0 = plain stream order
  *   "tc_base_offset_mode" (debug) how the UMMA shared-memory descriptors encode unaligned starts */

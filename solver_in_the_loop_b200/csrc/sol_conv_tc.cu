@@ -51,8 +51,6 @@ struct TcArgs {
     int B, Y, X;
     int act;
     float slope;
-    const int* dep_flags;   // tile-completion flags of the producer launch of `in` (nullptr: whole-grid dependency)
-    int* out_flags;         // this launch's tile-completion flags (nullptr: none)
     int weights_ready;      // 1: the split weights were complete before the previous kernel of the stream started
     long long* trace;       // diagnostics: 16 slots per CTA of clock64 phase stamps (null in production), already offset
                             // to this launch's block of gridsize x 16 slots
@@ -134,24 +132,7 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
                 tma_load_2d(s_b + 2 * n * TC_B_BYTES, &map_w, bar_bfull + 8 * n, 0, tap * 64);
             }
         }
-        if (a.dep_flags) {
-            // tile-level dependency: the halo covers this tile and its (up to 8) neighbours in the producer launch
-            if (lane < 9) {
-                const int nx = (int)blockIdx.x + lane % 3 - 1, ny = (int)blockIdx.y + lane / 3 - 1;
-                if (nx >= 0 && nx < (int)gridDim.x && ny >= 0 && ny < (int)gridDim.y) {
-                    const int* f = a.dep_flags + nx + (int)gridDim.x * (ny + (int)gridDim.y * (int)blockIdx.z);
-                    int v;
-                    do {
-                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-                        if (!v) __nanosleep(100);
-                    } while (!v);
-                }
-            }
-            __syncwarp();
-            asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy stores of the producer tiles -> TMA reads
-        } else {
-            pdl_wait();
-        }
+        pdl_wait();
         if (leader && a.trace) {
             const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
             unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -161,7 +142,7 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
             mbar_arrive_expect_tx(bar_afull, TC_A_BYTES);
             tma_load_4d(s_ahi, &map_in, bar_afull, 0, x0 - 2, y0 - 2, b);
         }
-    } else if (!a.dep_flags) {
+    } else {
         pdl_wait();
     }
 
@@ -329,16 +310,7 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
         if (t == 0) {
             tma_store_4d(&map_out, s_alo, 0, x0, y0, b);
             tma_store_commit();
-            if (a.out_flags) {
-                // publish the tile for the chained consumer launch: the bulk store is complete, then the flag is released
-                tma_store_wait_all();
-                asm volatile("fence.proxy.async;" ::: "memory");
-                __threadfence();
-                int* f = a.out_flags + blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(1) : "memory");
-            } else {
-                tma_store_wait_read();       // shared memory must stay valid until the bulk store has read it
-            }
+            tma_store_wait_read();       // shared memory must stay valid until the bulk store has read it
         }
     }
 
@@ -348,282 +320,6 @@ k_conv5x5_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_consta
         a.trace[cta * 16 + 12] = (long long)gt;
         tc_stamp(a.trace, 10);
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 1) {
-        __syncwarp();
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)TC_TMEM_COLS) : "memory");
-    }
-}
-
-// =================================================================================================
-// Persistent conv STACK: up to STK_MAX consecutive 32->32 layers in ONE launch.  Every CTA keeps its 8x16 tile for all
-// layers; between layers a tile waits only for the (up to 9) tiles of the previous layer under its halo (per-tile
-// completion flags, acquire/release + proxy fences — the protocol of the tile-flag chaining above), so there is no
-// kernel hand-over, no barrier/TMEM set-up and no weight-ring refill between layers.  All CTAs of the grid must be
-// co-resident (checked on the host); the flag polls are bounded (trap instead of a hang).
-// =================================================================================================
-namespace {
-constexpr int STK_MAX = 10;
-struct StackLayer {
-    const float* bias;
-    const float* addend;    // may have been written by an earlier layer of the SAME launch: read with ld.global.cg
-    const float* ref;       // constant during the launch
-    int act;
-    int wrow;               // first row of this layer's [25 taps][hi|lo][32] block in the weight map
-};
-struct StackArgs {
-    CUtensorMap map_in[STK_MAX];
-    CUtensorMap map_out[STK_MAX];
-    StackLayer L[STK_MAX];
-    int nlayers, B, Y, X;
-    float slope;
-    int* flags;             // [nlayers][tiles], zero before the launch
-};
-}  // namespace
-
-// launch bounds of 256 threads x 2 CTAs cap the kernel at 128 registers: registers are allocated for warps in groups of four
-// (6 warps count as 8), so two CTAs per SM need 8 x 32 x regs x 2 <= 65,536
-__global__ void __launch_bounds__(256, 2)
-k_conv5x5_c32_tc_stack(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ StackArgs a) {
-    extern __shared__ uint8_t tc_smem_raw[];
-    const uint32_t raw = smem_u32(tc_smem_raw);
-    const uint32_t base = (raw + 1023u) & ~1023u;
-    uint8_t* gbase = tc_smem_raw + (base - raw);
-    const uint32_t s_ahi = base + TC_OFF_AHI, s_alo = base + TC_OFF_ALO, s_b = base + TC_OFF_B;
-    const uint32_t s_bar = base + TC_OFF_BAR;
-    const uint32_t bar_afull = s_bar + 0, bar_asplit = s_bar + 8, bar_acc = s_bar + 16;
-    const uint32_t bar_bfull = s_bar + 32, bar_bempty = s_bar + 32 + 8 * TC_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + TC_OFF_BAR + 32 + 16 * TC_STAGES);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x0 = blockIdx.x * TC_TX, y0 = blockIdx.y * TC_TY, b = blockIdx.z;
-    const int tile = (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
-    const int ntiles = (int)(gridDim.x * gridDim.y * gridDim.z);
-    const int tap0 = (int)((unsigned)tile * 7u % 25u);      // per-CTA rotated tap order (see k_conv5x5_c32_tc)
-    const int NL = a.nlayers;
-
-    if (warp == 0 && lane == 0) {
-        mbar_init(bar_afull, 1);
-        mbar_init(bar_asplit, TC_THREADS);
-        mbar_init(bar_acc, 1);
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TC_TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_acc = *tmem_slot;
-
-    // weight producer state (warp 0): global tap counter over all layers; slot = g % STAGES, phase = (g / STAGES) & 1
-    int gp = 0;
-    auto produce = [&](bool leader, int upto) {      // issue the weight loads of global taps [gp, upto)
-#pragma unroll 1
-        for (; gp < upto; ++gp) {
-            const int s = gp % TC_STAGES;
-            const uint32_t ph = (uint32_t)(gp / TC_STAGES) & 1u;
-            const int l = gp / 25, n = gp - l * 25;
-            int tap = tap0 + n; if (tap >= 25) tap -= 25;
-            mbar_wait(bar_bempty + 8 * s, ph ^ 1u);
-            if (leader) {
-                mbar_arrive_expect_tx(bar_bfull + 8 * s, 2 * TC_B_BYTES);
-                tma_load_2d(s_b + 2 * s * TC_B_BYTES, &map_w, bar_bfull + 8 * s, 0, a.L[l].wrow + tap * 64);
-            }
-        }
-    };
-    if (warp == 0) {
-        const bool leader = elect_one();
-        produce(leader, TC_STAGES);      // the split weights were settled long before this launch: independent of the predecessor
-    }
-    pdl_wait();
-
-    int gc = 0;      // consumer (MMA warp) global tap counter
-#pragma unroll 1
-    for (int L = 0; L < NL; ++L) {
-        const uint32_t lph = (uint32_t)L & 1u;
-        const StackLayer ly = a.L[L];
-        if (warp == 0) {
-            const bool leader = elect_one();
-            if (L > 0) {
-                // the halo covers this tile and its (up to 8) neighbours of the previous layer
-                const int* fl = a.flags + (size_t)(L - 1) * ntiles;
-                if (lane < 9) {
-                    const int nx = (int)blockIdx.x + lane % 3 - 1, ny = (int)blockIdx.y + lane / 3 - 1;
-                    if (nx >= 0 && nx < (int)gridDim.x && ny >= 0 && ny < (int)gridDim.y) {
-                        const int* f = fl + nx + (int)gridDim.x * (ny + (int)gridDim.y * (int)blockIdx.z);
-                        int v, spins = 0;
-                        do {
-                            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-                            if (!v) {
-                                __nanosleep(64);
-                                if (++spins > (1 << 22)) asm volatile("trap;");     // a lost producer tile: fail loudly, never hang
-                            }
-                        } while (!v);
-                    }
-                }
-                __syncwarp();
-                asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy view of the producers' stores -> TMA reads
-            }
-            if (leader) {
-                mbar_arrive_expect_tx(bar_afull, TC_A_BYTES);
-                tma_load_4d(s_ahi, &a.map_in[L], bar_afull, 0, x0 - 2, y0 - 2, b);
-            }
-        }
-
-        // ---- operand split by all warps ----
-        mbar_wait(bar_afull, lph);
-        {
-            float4* hi4 = reinterpret_cast<float4*>(gbase + TC_OFF_AHI);
-            float4* lo4 = reinterpret_cast<float4*>(gbase + TC_OFF_ALO);
-#pragma unroll 5
-            for (int it = 0; it < TC_A_BYTES / 16 / TC_THREADS; ++it) {
-                const int i = (int)threadIdx.x + it * TC_THREADS;
-                const float4 v = hi4[i];
-                float4 h, l;
-                h.x = tf32_rn(v.x); l.x = tf32_rn(v.x - h.x);
-                h.y = tf32_rn(v.y); l.y = tf32_rn(v.y - h.y);
-                h.z = tf32_rn(v.z); l.z = tf32_rn(v.z - h.z);
-                h.w = tf32_rn(v.w); l.w = tf32_rn(v.w - h.w);
-                hi4[i] = h;
-                lo4[i] = l;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");      // this thread's TMEM reads of the previous layer are done
-            mbar_arrive(bar_asplit);
-        }
-
-        if (warp == 0) {
-            const bool leader = elect_one();
-            produce(leader, (L + 1) * 25);                                   // rest of this layer's taps
-            if (L + 1 < NL) produce(leader, (L + 1) * 25 + TC_STAGES);       // and the head of the next layer's, as slots drain
-        } else if (warp == 1) {
-            const bool leader = elect_one();
-            const uint64_t dA_hi = make_desc(s_ahi, TC_HW * 128, 0);
-            const uint64_t dA_lo = make_desc(s_alo, TC_HW * 128, 0);
-            const uint64_t dB = make_desc(s_b, 1024, 0);
-            mbar_wait(bar_asplit, lph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-            for (int n = 0; n < 25; ++n, ++gc) {
-                const int s = gc % TC_STAGES;
-                const uint32_t ph = (uint32_t)(gc / TC_STAGES) & 1u;
-                int tap = tap0 + n; if (tap >= 25) tap -= 25;
-                mbar_wait(bar_bfull + 8 * s, ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (leader) {
-                    const int dy = tap / 5, dx = tap - dy * 5;
-                    const uint64_t a_off = (uint64_t)((dy * TC_HW + dx) * 8);
-                    const uint64_t b_off = (uint64_t)(s * (2 * TC_B_BYTES / 16));
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint32_t set = (uint32_t)(ks & 1);
-                        const uint32_t acc1 = tmem_acc + set * 96u, acc2 = acc1 + 64u;
-                        const uint32_t first = (n == 0 && ks < 2) ? 0u : 1u;
-                        umma_tf32(acc1, dA_hi + a_off + 2 * ks, dB + b_off + 2 * ks, TC_IDESC64, first);
-                        umma_tf32(acc2, dA_lo + a_off + 2 * ks, dB + b_off + 2 * ks, TC_IDESC32, first);
-                    }
-                    umma_commit(bar_bempty + 8 * s);
-                }
-                __syncwarp();
-            }
-            if (leader) umma_commit(bar_acc);
-            __syncwarp();
-        } else {
-            // ---- epilogue (warps 2..5) ----
-            const int t = threadIdx.x - 64;
-            const int q = warp & 3;
-            const int r = q * 32 + lane;
-            const int gy = y0 + (r >> 3), gx = x0 + (r & 7);
-            const bool inside = gy < a.Y && gx < a.X;
-            const size_t o = (((size_t)b * a.Y + gy) * a.X + gx) * 32;
-            float4 ad[8], rf[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) { ad[c] = make_float4(0.f, 0.f, 0.f, 0.f); rf[c] = make_float4(1.f, 1.f, 1.f, 1.f); }
-            if (inside) {
-                if (ly.addend) {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) ad[c] = __ldcg(reinterpret_cast<const float4*>(ly.addend + o) + c);
-                }
-                if (ly.act == SOL_ACT_DLRELU) {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) rf[c] = __ldg(reinterpret_cast<const float4*>(ly.ref + o) + c);
-                }
-            }
-            if (ly.bias) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float4 bv = __ldg(reinterpret_cast<const float4*>(ly.bias) + c);
-                    ad[c].x += bv.x; ad[c].y += bv.y; ad[c].z += bv.z; ad[c].w += bv.w;
-                }
-            }
-            mbar_wait(bar_acc, lph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float acc[32];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) { acc[4 * c] = ad[c].x; acc[4 * c + 1] = ad[c].y; acc[4 * c + 2] = ad[c].z; acc[4 * c + 3] = ad[c].w; }
-#pragma unroll 1
-            for (int j = 0; j < 3 * TC_NSET; j += 2) {
-                uint32_t v0[32], v1[32];
-                const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + 32u * (uint32_t)j;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v0[0]), "=r"(v0[1]), "=r"(v0[2]), "=r"(v0[3]), "=r"(v0[4]), "=r"(v0[5]), "=r"(v0[6]), "=r"(v0[7]),
-                      "=r"(v0[8]), "=r"(v0[9]), "=r"(v0[10]), "=r"(v0[11]), "=r"(v0[12]), "=r"(v0[13]), "=r"(v0[14]), "=r"(v0[15]),
-                      "=r"(v0[16]), "=r"(v0[17]), "=r"(v0[18]), "=r"(v0[19]), "=r"(v0[20]), "=r"(v0[21]), "=r"(v0[22]), "=r"(v0[23]),
-                      "=r"(v0[24]), "=r"(v0[25]), "=r"(v0[26]), "=r"(v0[27]), "=r"(v0[28]), "=r"(v0[29]), "=r"(v0[30]), "=r"(v0[31])
-                    : "r"(taddr));
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v1[0]), "=r"(v1[1]), "=r"(v1[2]), "=r"(v1[3]), "=r"(v1[4]), "=r"(v1[5]), "=r"(v1[6]), "=r"(v1[7]),
-                      "=r"(v1[8]), "=r"(v1[9]), "=r"(v1[10]), "=r"(v1[11]), "=r"(v1[12]), "=r"(v1[13]), "=r"(v1[14]), "=r"(v1[15]),
-                      "=r"(v1[16]), "=r"(v1[17]), "=r"(v1[18]), "=r"(v1[19]), "=r"(v1[20]), "=r"(v1[21]), "=r"(v1[22]), "=r"(v1[23]),
-                      "=r"(v1[24]), "=r"(v1[25]), "=r"(v1[26]), "=r"(v1[27]), "=r"(v1[28]), "=r"(v1[29]), "=r"(v1[30]), "=r"(v1[31])
-                    : "r"(taddr + 32u));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int c = 0; c < 32; ++c) acc[c] += __uint_as_float(v0[c]) + __uint_as_float(v1[c]);
-            }
-            {
-                uint8_t* stage = gbase + TC_OFF_ALO + r * 128;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float4 f = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
-                    if (ly.act == SOL_ACT_LRELU) {
-                        f.x = f.x > 0.f ? f.x : a.slope * f.x; f.y = f.y > 0.f ? f.y : a.slope * f.y;
-                        f.z = f.z > 0.f ? f.z : a.slope * f.z; f.w = f.w > 0.f ? f.w : a.slope * f.w;
-                    } else if (ly.act == SOL_ACT_DLRELU) {
-                        f.x = rf[c].x > 0.f ? f.x : a.slope * f.x; f.y = rf[c].y > 0.f ? f.y : a.slope * f.y;
-                        f.z = rf[c].z > 0.f ? f.z : a.slope * f.z; f.w = rf[c].w > 0.f ? f.w : a.slope * f.w;
-                    }
-                    *reinterpret_cast<float4*>(stage + ((c ^ (r & 7)) << 4)) = f;
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (t == 0) {
-                tma_store_4d(&a.map_out[L], s_alo, 0, x0, y0, b);
-                tma_store_commit();
-                // the tile must be complete in global memory before its flag is released; the staging buffer (the A_lo
-                // region) is reused by the next layer's split only after this CTA has seen its own flag
-                tma_store_wait_all();
-                asm volatile("fence.proxy.async;" ::: "memory");
-                __threadfence();
-                int* f = a.flags + (size_t)L * ntiles + tile;
-                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(1) : "memory");
-            }
-        }
-    }
-
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
@@ -662,14 +358,13 @@ EncodeTiledFn get_encode_tiled() {
 
 static long long* g_tc_trace = nullptr;
 static int g_tc_trace_cap = 0, g_tc_trace_seq = 0;     // capacity in launches, launches traced so far
-int g_conv_chain = 0;   // measured slower than whole-kernel PDL edges at 192 tiles (late CTA residency); kept as an option
 int g_tc_base_offset_mode = 0;   // measured on B200: the swizzle phase comes from the absolute address bits; base_offset stays 0
-int g_conv_path = 2;    // default: tcgen05 convolutions (1 = fp32 SIMT validation kernels)
+int g_conv_path = 2;    // default: tcgen05 3xFP16 convolutions (1 = fp32 SIMT validation kernels, 3 = tcgen05 3xTF32)
 int g_wgrad_path = 2;   // default: deferred tcgen05 weight-gradient GEMM (1 = per-step fp32 SIMT)
 
 int tc_tiles_per_launch(int B, int Y, int X) { return cdiv(X, TC_TX) * cdiv(Y, TC_TY) * B; }
 
-size_t tc_weights_floats() { return (size_t)2 * 25 * 32 * 32; }
+size_t tc_weights_floats() { return (size_t)2 * 25 * 32 * 32; }      // the larger of the two split layouts (3xTF32); 256-byte multiple
 
 int launch_prep_tc_weights(cudaStream_t st, const float* w, float* wprep) {
     SOL_CUDA(launch_kernel(k_prep_tc_weights, dim3(cdiv(25 * 32 * 32, 256)), dim3(256), 0, st, w, wprep));
@@ -678,8 +373,7 @@ int launch_prep_tc_weights(cudaStream_t st, const float* w, float* wprep) {
 }
 
 int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, const float* wprep, const float* bias,
-                      const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready,
-                      const int* dep_flags, int* out_flags) {
+                      const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready) {
     tc::EncodeTiledFn enc = tc::get_encode_tiled();
     if (!enc) return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     if (((uintptr_t)in & 15) || ((uintptr_t)wprep & 15)) return fail(SOL_ERR_INVALID, "conv tc: operands must be 16-byte aligned");
@@ -715,7 +409,6 @@ int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, con
         ++g_tc_trace_seq;
     }
     a.weights_ready = weights_ready ? 1 : 0;
-    a.dep_flags = dep_flags; a.out_flags = out_flags;
     a.bias = bias; a.addend = addend; a.ref = ref; a.out = out; a.B = B; a.Y = Y; a.X = X; a.act = act; a.slope = slope;
     static bool attr_done = false;
     if (!attr_done) {
@@ -728,95 +421,33 @@ int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, con
     return SOL_OK;
 }
 
-// Consecutive 32->32 layers of the engine's sweeps in one persistent launch (when the grid is co-resident).  Correct, but measured
-// SLOWER on B200 at the bench shape (22.0 vs 20.5 ms per iteration): the per-layer critical path (neighbour tiles complete in global
-// memory -> flag -> halo load -> split -> 200 MMAs -> epilogue -> bulk store) is the same serial chain as with one launch per layer,
-// and "bulk store complete + release flag + acquire poll" costs about 2 us more than the programmatic kernel hand-over.  Default off.
-int g_conv_stack = 0;
+// ---- path dispatch for the 32->32 layers: 1 = fp32 SIMT, 2 = tcgen05 3xFP16 (sol_conv_h.cu, default), 3 = tcgen05 3xTF32 ----
+bool conv_path_is_tc() { return g_conv_path == 2 || g_conv_path == 3; }
 
-// true when every CTA of a (B, Y, X) stack launch can be resident at the same time (the per-tile flag waits need it)
-int g_conv_stack_cap = -1;      // CTAs of the stack kernel that can be resident at once (-1 = not computed yet)
-int g_conv_stack_err = 0;       // diagnostics: which step of the capacity computation failed
-// cudaOccupancyMaxActiveBlocksPerMultiprocessor reports 1 for every kernel that allocates tensor memory (measured on B200, also
-// for k_conv5x5_c32_tc, whose CTAs demonstrably run two per SM: scripts/tc_trace.py), so the capacity is computed from the
-// resources themselves: registers, shared memory (with the full carve-out) and the 512 tensor-memory columns of an SM.
-bool conv_stack_fits(int B, int Y, int X) {
-    if (g_conv_stack_cap < 0) {
-        g_conv_stack_cap = 0;
-        int dev = 0;
-        cudaDeviceProp pr;
-        cudaFuncAttributes fa;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&pr, dev) != cudaSuccess) { g_conv_stack_err = 1; cudaGetLastError(); return false; }
-        if (cudaFuncSetAttribute(k_conv5x5_c32_tc_stack, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM) != cudaSuccess) { g_conv_stack_err = 2; cudaGetLastError(); return false; }
-        if (cudaFuncSetAttribute(k_conv5x5_c32_tc_stack, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) { g_conv_stack_err = 4; cudaGetLastError(); return false; }
-        if (cudaFuncGetAttributes(&fa, k_conv5x5_c32_tc_stack) != cudaSuccess) { g_conv_stack_err = 3; cudaGetLastError(); return false; }
-        const int regs_per_warp = ((fa.numRegs + 7) / 8 * 8) * 32;
-        const int warps = (TC_THREADS + 31) / 32;
-        int per_sm = pr.regsPerMultiprocessor / (regs_per_warp * ((warps + 3) / 4 * 4));      // warp allocation granularity 4
-        const int by_smem = (int)(pr.sharedMemPerMultiprocessor / ((size_t)TC_SMEM + fa.sharedSizeBytes + pr.reservedSharedMemPerBlock));
-        if (by_smem < per_sm) per_sm = by_smem;
-        if (per_sm > 512 / TC_TMEM_COLS) per_sm = 512 / TC_TMEM_COLS;
-        g_conv_stack_cap = per_sm * pr.multiProcessorCount;
-    }
-    return tc_tiles_per_launch(B, Y, X) <= g_conv_stack_cap;
+int launch_split_weights(cudaStream_t st, const float* w, float* wsplit) {
+    if (g_conv_path == 3) return launch_prep_tc_weights(st, w, wsplit);
+    return launch_prep_h_weights(st, w, wsplit);
 }
 
-int launch_conv_stack(cudaStream_t st, int B, int Y, int X, int nlayers, const ConvStackLayer* layers, const float* wprep_all,
-                      int wprep_layers, float slope, int* flags) {
-    tc::EncodeTiledFn enc = tc::get_encode_tiled();
-    if (!enc) return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    if (nlayers < 1 || nlayers > STK_MAX) return fail(SOL_ERR_INVALID, "conv stack: 1..10 layers");
-    if (!conv_stack_fits(B, Y, X)) return fail(SOL_ERR_UNSUPPORTED, "conv stack: the grid is not co-resident");
-    alignas(64) CUtensorMap map_w;
-    StackArgs a;
-    memset(&a, 0, sizeof(a));
-    cuuint64_t dims[4] = {32, (cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)B};
-    cuuint64_t strides[3] = {128, (cuuint64_t)X * 128, (cuuint64_t)Y * X * 128};
-    cuuint32_t box[4] = {32, TC_HW, TC_HH, 1};
-    cuuint32_t obox[4] = {32, TC_TX, TC_TY, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    for (int l = 0; l < nlayers; ++l) {
-        const ConvStackLayer& h = layers[l];
-        if (((uintptr_t)h.in & 15) || ((uintptr_t)h.out & 15)) return fail(SOL_ERR_INVALID, "conv stack: operands must be 16-byte aligned");
-        if (h.act == SOL_ACT_DLRELU && !h.ref) return fail(SOL_ERR_INVALID, "conv stack: SOL_ACT_DLRELU needs ref");
-        if (h.weight_index < 0 || h.weight_index >= wprep_layers) return fail(SOL_ERR_INVALID, "conv stack: weight index out of range");
-        CUresult r = enc(&a.map_in[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)h.in, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled(stack input) failed");
-        r = enc(&a.map_out[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)h.out, dims, strides, obox, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled(stack output) failed");
-        a.L[l].bias = h.bias; a.L[l].addend = h.addend; a.L[l].ref = h.ref; a.L[l].act = h.act; a.L[l].wrow = h.weight_index * 1600;
-    }
-    {
-        cuuint64_t wd[2] = {32, (cuuint64_t)1600 * wprep_layers};
-        cuuint64_t ws[1] = {128};
-        cuuint32_t wb[2] = {32, 64};
-        cuuint32_t we[2] = {1, 1};
-        CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)wprep_all, wd, ws, wb, we, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled(stack weights) failed");
-    }
-    a.nlayers = nlayers; a.B = B; a.Y = Y; a.X = X; a.slope = slope; a.flags = flags;
-    dim3 grid(cdiv(X, TC_TX), cdiv(Y, TC_TY), B);
-    SOL_CUDA(launch_kernel(k_conv5x5_c32_tc_stack, grid, dim3(TC_THREADS), TC_SMEM, st, map_w, a));
-    SOL_LAUNCHED();
-    return SOL_OK;
+int launch_conv5x5_c32_presplit(cudaStream_t st, int B, int Y, int X, const float* in, const float* wsplit, const float* bias,
+                                const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready) {
+    if (act == SOL_ACT_DLRELU && !ref) return fail(SOL_ERR_INVALID, "conv5x5: SOL_ACT_DLRELU needs ref");
+    if (g_conv_path == 3) return launch_conv5x5_tc(st, B, Y, X, in, wsplit, bias, addend, ref, act, slope, out, weights_ready);
+    return launch_conv5x5_h(st, B, Y, X, in, wsplit, bias, addend, ref, act, slope, out, weights_ready);
 }
 
 int launch_conv5x5_c32_auto(cudaStream_t st, int B, int Y, int X, const float* in, const float* w, const float* wprep,
                             const float* bias, const float* addend, const float* ref, int act, float slope, float* out) {
-    if (g_conv_path != 2) return launch_conv5x5(st, B, Y, X, 32, 32, in, w, bias, addend, ref, act, slope, out);
-    if (act == SOL_ACT_DLRELU && !ref) return fail(SOL_ERR_INVALID, "conv5x5: SOL_ACT_DLRELU needs ref");
+    if (!conv_path_is_tc()) return launch_conv5x5(st, B, Y, X, 32, 32, in, w, bias, addend, ref, act, slope, out);
     const bool engine_weights = wprep != nullptr;   // the unrolled sweep splits all weights before its first step
     if (!wprep) {
         // stand-alone call: split the weights into a process-wide scratch buffer (stream-ordered reuse)
         static float* scratch = nullptr;
         if (!scratch) SOL_CUDA(cudaMalloc((void**)&scratch, tc_weights_floats() * sizeof(float)));
-        SOL_TRY(launch_prep_tc_weights(st, w, scratch));
+        SOL_TRY(launch_split_weights(st, w, scratch));
         wprep = scratch;
     }
-    return launch_conv5x5_tc(st, B, Y, X, in, wprep, bias, addend, ref, act, slope, out, engine_weights);
+    return launch_conv5x5_c32_presplit(st, B, Y, X, in, wprep, bias, addend, ref, act, slope, out, engine_weights);
 }
 
 }  // namespace sol
@@ -824,11 +455,6 @@ int launch_conv5x5_c32_auto(cudaStream_t st, int B, int Y, int X, const float* i
 // Diagnostics hook (not part of the public ABI): device buffer of `launches` x gridsize x 16 int64 that the next
 // `launches` tensor-core convolution launches (also when captured into a CUDA graph) fill with clock64 /
 // globaltimer phase stamps; pass null to switch tracing off.
-extern "C" int sol_debug_conv_stack_capacity(int B, int Y, int X) {
-    const bool fits = sol::conv_stack_fits(B, Y, X);
-    return fits ? sol::g_conv_stack_cap : -(sol::g_conv_stack_err * 1000 + sol::g_conv_stack_cap);
-}
-
 extern "C" void sol_debug_conv_trace(long long* buf, int launches) {
     sol::g_tc_trace = buf; sol::g_tc_trace_cap = launches; sol::g_tc_trace_seq = 0;
 }

@@ -248,7 +248,7 @@ extern "C" int sol_plan_set_option(sol_plan* p, const char* name, int value) {
 extern "C" int sol_set_option(const char* name, int value) {
     SOL_CHECK(name != nullptr, "sol_set_option: NULL name");
     if (strcmp(name, "conv_path") == 0) {
-        SOL_CHECK(value >= 0 && value <= 2, "conv_path must be 0,1,2");
+        SOL_CHECK(value >= 0 && value <= 3, "conv_path must be 0,1,2,3");
         sol::g_conv_path = value == 0 ? 2 : value;
         return SOL_OK;
     }
@@ -274,12 +274,9 @@ extern "C" int sol_set_option(const char* name, int value) {
         sol::g_wgrad_overlap = value ? 1 : 0;
         return SOL_OK;
     }
-    if (strcmp(name, "conv_chain") == 0) {
-        sol::g_conv_chain = value ? 1 : 0;
-        return SOL_OK;
-    }
-    if (strcmp(name, "conv_stack") == 0) {
-        sol::g_conv_stack = value ? 1 : 0;
+    if (strcmp(name, "conv_variant") == 0) {
+        SOL_CHECK(value >= 0 && value <= 2, "conv_variant must be 0,1,2");
+        sol::g_conv_variant = value;
         return SOL_OK;
     }
     if (strcmp(name, "pdl") == 0) {
@@ -412,14 +409,15 @@ extern "C" size_t sol_conv5x5_split_floats(void) { return tc_weights_floats(); }
 
 extern "C" int sol_conv5x5_split_weights(void* stream, const float* w, float* wsplit) {
     SOL_CHECK(w && wsplit, "sol_conv5x5_split_weights: NULL pointer");
-    return launch_prep_tc_weights((cudaStream_t)stream, w, wsplit);
+    return launch_split_weights((cudaStream_t)stream, w, wsplit);
 }
 
 extern "C" int sol_conv5x5_c32_presplit(void* stream, int B, int Y, int X, const float* in, const float* wsplit, const float* bias,
                                         const float* addend, const float* ref, int act, float slope, float* out, int weights_settled) {
     SOL_CHECK(in && wsplit && out && B >= 1 && Y >= 1 && X >= 1, "sol_conv5x5_c32_presplit: bad arguments");
     SOL_CHECK(!(act == SOL_ACT_DLRELU && !ref), "sol_conv5x5_c32_presplit: SOL_ACT_DLRELU needs ref");
-    return launch_conv5x5_tc((cudaStream_t)stream, B, Y, X, in, wsplit, bias, addend, ref, act, slope, out, weights_settled != 0);
+    SOL_CHECK(conv_path_is_tc(), "sol_conv5x5_c32_presplit: option conv_path selects the SIMT kernels");
+    return launch_conv5x5_c32_presplit((cudaStream_t)stream, B, Y, X, in, wsplit, bias, addend, ref, act, slope, out, weights_settled != 0);
 }
 
 extern "C" int sol_conv5x5_flip_weights(void* stream, int Cin, int Cout, const float* w, float* wT) {
@@ -485,10 +483,6 @@ struct sol_unroll {
     float *g_corr, *g_feat, *gbuf[3];
     float* wT;
     float *wprep_fwd, *wprep_bwd;   // [10 layers][2*25*32*32] pre-split tensor-core weights
-    int* tc_flags;     // tile-completion flags of the tensor-core conv launches of one sweep: [10*msteps][tiles]
-    int tc_tiles = 0;  // tiles per launch
-    int tc_seq = 0;    // next flag block (host-side cursor, reset at the start of each sweep)
-    const int* tc_prev = nullptr;   // flags of the conv launch directly preceding on the stream (nullptr: something else ran)
     float* gst;        // deferred weight gradient: [10 layers][msteps][B,Y,X,32] output-gradient stash
     float* g0_st;      // [msteps][B,Y,X,32] output gradient of layer 0
     bool deferred_wgrad = false;   // decided per backward sweep: option wgrad_path == 2 and the grid tiles evenly (Y%16, X%8)
@@ -565,14 +559,12 @@ int carve(sol_unroll* u, void* ws, size_t* total) {
     u->nA = nA;
     if (mercury) {      // per-step SIMT weight gradients, no tensor-core operand buffers, no deferred-gradient stash
         u->gbuf[0] = cv.take<float>(NC * 64); u->gbuf[1] = cv.take<float>(nA); u->gbuf[2] = nullptr;
-        u->wprep_fwd = u->wprep_bwd = nullptr; u->tc_flags = nullptr; u->tc_tiles = 0;
+        u->wprep_fwd = u->wprep_bwd = nullptr;
         u->gst = u->g0_st = u->gcorr_st = u->partials = nullptr; u->partial_stride = 0;
     } else {
         for (int k = 0; k < 3; ++k) u->gbuf[k] = cv.take<float>(nA);
         u->wprep_fwd = cv.take<float>(tc_weights_floats() * 10);
         u->wprep_bwd = cv.take<float>(tc_weights_floats() * 10);
-        u->tc_tiles = tc_tiles_per_launch(u->cfg.B, u->plan->Y, u->plan->X);
-        u->tc_flags = cv.take<int>((size_t)10 * u->cfg.msteps * u->tc_tiles);
         u->gst = cv.take<float>(nA * 10 * c.msteps);
         u->g0_st = cv.take<float>(nA * c.msteps);
         u->gcorr_st = cv.take<float>(NC * 2 * c.msteps);
@@ -597,24 +589,11 @@ int check_cfg(const sol_plan* p, const sol_unroll_cfg* c) {
     return SOL_OK;
 }
 
-// A 32->32 layer of the sweep.  Directly consecutive tensor-core launches are chained by per-tile completion
-// flags instead of the whole-grid dependency: a tile of layer n+1 starts as soon as the (up to 9) tiles of
-// layer n under its halo are stored.  Output buffers of chained launches never alias what a live
-// predecessor reads (the forward stash and the deferred-gradient stash are write-once per sweep).
-int chained_conv(sol_unroll* u, cudaStream_t st, const float* in, const float* w, const float* wprep, const float* bias, const float* addend,
-                 const float* ref, int act, float slope, float* out) {
+// A 32->32 layer of the sweep (tensor-core path with the weights split at the start of the sweep, else SIMT)
+int layer_conv(sol_unroll* u, cudaStream_t st, const float* in, const float* w, const float* wprep, const float* bias, const float* addend,
+               const float* ref, int act, float slope, float* out) {
     const sol_plan* p = u->plan;
-    const int B = u->cfg.B, Y = p->Y, X = p->X;
-    const bool chain = sol::g_conv_path == 2 && sol::g_pdl && sol::g_conv_chain && wprep && u->tc_seq < 10 * u->cfg.msteps;
-    if (!chain) {
-        u->tc_prev = nullptr;
-        return launch_conv5x5_c32_auto(st, B, Y, X, in, w, wprep, bias, addend, ref, act, slope, out);
-    }
-    int* mine = u->tc_flags + (size_t)u->tc_seq * u->tc_tiles;
-    ++u->tc_seq;
-    const int* dep = u->tc_prev;
-    u->tc_prev = mine;
-    return launch_conv5x5_tc(st, B, Y, X, in, wprep, bias, addend, ref, act, slope, out, true, dep, mine);
+    return launch_conv5x5_c32_auto(st, u->cfg.B, p->Y, p->X, in, w, wprep, bias, addend, ref, act, slope, out);
 }
 
 // ---- CNN forward / backward over the stash of one step (model_mars_moon, karman_train.py:101-138)
@@ -628,21 +607,8 @@ int cnn_forward(sol_unroll* u, cudaStream_t st, const float* w, const StepStash&
         SOL_TRY(launch_conv5x5(st, B, Y, X, 32, 64, s.acts[0], w + L[1].w_off, w + L[1].b_off, nullptr, nullptr, SOL_ACT_LRELU, 0.0f, s.acts[1]));
         return launch_conv5x5(st, B, Y, X, 64, 2, s.acts[1], w + L[2].w_off, w + L[2].b_off, nullptr, nullptr, SOL_ACT_NONE, 0.0f, corr);
     }
-    const bool tc = sol::g_conv_path == 2;
+    const bool tc = conv_path_is_tc();
     SOL_TRY(launch_conv5x5(st, B, Y, X, L[0].cin, 32, s.feat, w + L[0].w_off, w + L[0].b_off, nullptr, nullptr, SOL_ACT_LRELU, a, s.acts[0]));
-    u->tc_prev = nullptr;
-    if (tc && sol::g_conv_stack && u->tc_seq + 10 <= 10 * u->cfg.msteps && conv_stack_fits(B, Y, X)) {
-        // the ten 32->32 layers in ONE persistent launch (per-tile flags between layers)
-        ConvStackLayer ls[10];
-        for (int k = 1; k <= 5; ++k) {
-            ls[2 * k - 2] = ConvStackLayer{s.acts[2 * k - 2], s.acts[2 * k - 1], w + L[2 * k - 1].b_off, nullptr, nullptr, SOL_ACT_LRELU, 2 * k - 2};
-            ls[2 * k - 1] = ConvStackLayer{s.acts[2 * k - 1], s.acts[2 * k], w + L[2 * k].b_off, s.acts[2 * k - 2], nullptr, SOL_ACT_LRELU, 2 * k - 1};
-        }
-        int* flags = u->tc_flags + (size_t)u->tc_seq * u->tc_tiles;
-        u->tc_seq += 10;
-        SOL_TRY(launch_conv_stack(st, B, Y, X, 10, ls, u->wprep_fwd, 10, a, flags));
-        return launch_conv5x5(st, B, Y, X, 32, 2, s.acts[10], w + L[11].w_off, w + L[11].b_off, nullptr, nullptr, SOL_ACT_NONE, a, corr);
-    }
     for (int k = 1; k <= 5; ++k) {
         const LayerDesc& l1 = L[2 * k - 1];
         const LayerDesc& l2 = L[2 * k];
@@ -651,10 +617,9 @@ int cnn_forward(sol_unroll* u, cudaStream_t st, const float* w, const StepStash&
         float* a_k = s.acts[2 * k];
         const float* p1 = tc ? u->wprep_fwd + tc_weights_floats() * (2 * k - 2) : nullptr;
         const float* p2 = tc ? u->wprep_fwd + tc_weights_floats() * (2 * k - 1) : nullptr;
-        SOL_TRY(chained_conv(u, st, a_prev, w + l1.w_off, p1, w + l1.b_off, nullptr, nullptr, SOL_ACT_LRELU, a, t_k));
-        SOL_TRY(chained_conv(u, st, t_k, w + l2.w_off, p2, w + l2.b_off, a_prev, nullptr, SOL_ACT_LRELU, a, a_k));
+        SOL_TRY(layer_conv(u, st, a_prev, w + l1.w_off, p1, w + l1.b_off, nullptr, nullptr, SOL_ACT_LRELU, a, t_k));
+        SOL_TRY(layer_conv(u, st, t_k, w + l2.w_off, p2, w + l2.b_off, a_prev, nullptr, SOL_ACT_LRELU, a, a_k));
     }
-    u->tc_prev = nullptr;
     return launch_conv5x5(st, B, Y, X, 32, 2, s.acts[10], w + L[11].w_off, w + L[11].b_off, nullptr, nullptr, SOL_ACT_NONE, a, corr);
 }
 
@@ -675,7 +640,7 @@ int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, cons
         SOL_TRY(launch_wgrad(st, B, Y, X, L[0].cin, 32, s.feat, g32, gw + L[0].w_off, gw + L[0].b_off, 1, nullptr, false));
         return launch_conv5x5(st, B, Y, X, 32, L[0].cin, g32, wT + L[0].w_off, nullptr, nullptr, nullptr, SOL_ACT_NONE, 0.0f, g_feat);
     }
-    const bool tc = sol::g_conv_path == 2;
+    const bool tc = conv_path_is_tc();
     const bool deferred = u->deferred_wgrad;        // weight gradients in one GEMM per layer after the sweep
     // output-gradient tensor of layer l (1..10) for this step
     auto gout = [&](int l, float* fallback) -> float* {
@@ -687,23 +652,6 @@ int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, cons
     if (!deferred)
         SOL_TRY(launch_wgrad(st, B, Y, X, 32, 2, s.acts[10], g_corr, gw + L[11].w_off, gw + L[11].b_off, 1, nullptr, false));
     SOL_TRY(launch_conv5x5(st, B, Y, X, 2, 32, g_corr, wT + L[11].w_off, nullptr, nullptr, s.acts[10], SOL_ACT_DLRELU, a, gS));
-    u->tc_prev = nullptr;
-    if (tc && deferred && sol::g_conv_stack && u->tc_seq + 10 <= 10 * u->cfg.msteps && conv_stack_fits(B, Y, X)) {
-        // the ten data-gradient layers in ONE persistent launch; every output gradient goes to its write-once stash slot
-        ConvStackLayer ls[10];
-        int n = 0;
-        for (int k = 5; k >= 1; --k) {
-            float* gT = gout(2 * k - 1, nullptr);
-            float* gN = (k >= 2) ? gout(2 * k - 2, nullptr) : u->g0_st + (size_t)step * u->nA;
-            ls[n++] = ConvStackLayer{gS, gT, nullptr, nullptr, s.acts[2 * k - 1], SOL_ACT_DLRELU, 2 * k - 1};
-            ls[n++] = ConvStackLayer{gT, gN, nullptr, gS, s.acts[2 * k - 2], SOL_ACT_DLRELU, 2 * k - 2};
-            gS = gN;
-        }
-        int* flags = u->tc_flags + (size_t)u->tc_seq * u->tc_tiles;
-        u->tc_seq += 10;
-        SOL_TRY(launch_conv_stack(st, B, Y, X, 10, ls, u->wprep_bwd, 10, a, flags));
-        return launch_conv5x5(st, B, Y, X, 32, L[0].cin, gS, wT + L[0].w_off, nullptr, nullptr, nullptr, SOL_ACT_NONE, a, g_feat);
-    }
     for (int k = 5; k >= 1; --k) {
         const LayerDesc& l1 = L[2 * k - 1];
         const LayerDesc& l2 = L[2 * k];
@@ -717,19 +665,16 @@ int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, cons
         // gS = d/d(a_{k-1} + conv_{2k}(t_k) + b)
         if (!deferred) {
             SOL_TRY(launch_wgrad(st, B, Y, X, 32, 32, t_k, gS, nullptr, nullptr, !first, u->partials + u->partial_stride * (2 * k - 1), false));
-            u->tc_prev = nullptr;
-        }
+                }
         const float* p2 = tc ? u->wprep_bwd + tc_weights_floats() * (2 * k - 1) : nullptr;
         const float* p1 = tc ? u->wprep_bwd + tc_weights_floats() * (2 * k - 2) : nullptr;
-        SOL_TRY(chained_conv(u, st, gS, wT + l2.w_off, p2, nullptr, nullptr, t_k, SOL_ACT_DLRELU, a, gT));
+        SOL_TRY(layer_conv(u, st, gS, wT + l2.w_off, p2, nullptr, nullptr, t_k, SOL_ACT_DLRELU, a, gT));
         if (!deferred) {
             SOL_TRY(launch_wgrad(st, B, Y, X, 32, 32, a_prev, gT, nullptr, nullptr, !first, u->partials + u->partial_stride * (2 * k - 2), false));
-            u->tc_prev = nullptr;
-        }
-        SOL_TRY(chained_conv(u, st, gT, wT + l1.w_off, p1, nullptr, gS, a_prev, SOL_ACT_DLRELU, a, gN));
+                }
+        SOL_TRY(layer_conv(u, st, gT, wT + l1.w_off, p1, nullptr, gS, a_prev, SOL_ACT_DLRELU, a, gN));
         gS = gN;
     }
-    u->tc_prev = nullptr;
     // input layer (cin0 -> 32): gS is the gradient w.r.t. its pre-activation
     if (!deferred)
         SOL_TRY(launch_wgrad(st, B, Y, X, L[0].cin, 32, s.feat, gS, gw + L[0].w_off, gw + L[0].b_off, 1, nullptr, false));
@@ -757,13 +702,10 @@ int do_forward(sol_unroll* u, cudaStream_t st, const float* weights, const float
     }
     if (gt_vy) SOL_CUDA(cudaMemsetAsync(loss_steps, 0, sizeof(float) * m, st));
     const bool mars = c.model == SOL_MODEL_MARS_MOON;
-    if (sol::g_conv_path == 2 && mars) {
+    if (conv_path_is_tc() && mars) {
         for (int l = 1; l <= 10; ++l)
-            SOL_TRY(launch_prep_tc_weights(st, weights + u->L[l].w_off, u->wprep_fwd + tc_weights_floats() * (l - 1)));
-        SOL_CUDA(cudaMemsetAsync(u->tc_flags, 0, sizeof(int) * (size_t)10 * c.msteps * u->tc_tiles, st));
+            SOL_TRY(launch_split_weights(st, weights + u->L[l].w_off, u->wprep_fwd + tc_weights_floats() * (l - 1)));
     }
-    u->tc_seq = ring ? 10 * c.msteps : 0;      // a rollout never chains conv launches by tile flags (the flag blocks are per unrolled step)
-    u->tc_prev = nullptr;
     const float* cvy = vy0; const float* cvx = vx0; const float* crho = dens ? rho0 : nullptr;
     const bool fuse_io = sol::g_fuse_solver_io && cg_fuses(p);
     for (int i = 0; i < m; ++i) {
@@ -819,12 +761,10 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
     u->deferred_wgrad = mars && (sol::g_wgrad_path == 2) && (p->Y % 16 == 0) && (p->X % 8 == 0);
     for (size_t l = 0; l < u->L.size(); ++l)
         SOL_TRY(launch_flip_weights(st, u->L[l].cin, u->L[l].cout, weights + u->L[l].w_off, u->wT + u->L[l].w_off));
-    if (sol::g_conv_path == 2 && mars) {
+    if (conv_path_is_tc() && mars) {
         for (int l = 1; l <= 10; ++l)
-            SOL_TRY(launch_prep_tc_weights(st, u->wT + u->L[l].w_off, u->wprep_bwd + tc_weights_floats() * (l - 1)));
-        SOL_CUDA(cudaMemsetAsync(u->tc_flags, 0, sizeof(int) * (size_t)10 * m * u->tc_tiles, st));
+            SOL_TRY(launch_split_weights(st, u->wT + u->L[l].w_off, u->wprep_bwd + tc_weights_floats() * (l - 1)));
     }
-    u->tc_seq = 0; u->tc_prev = nullptr;
     // ---- deferred weight gradients: work items (layer, step range) over the stashed activations / output gradients.
     // While an adjoint pressure solve occupies B SMs for ~100 us, the other SMs are idle: items whose steps are already
     // complete run there on a side stream (option "wgrad_overlap"), the remainder after the sweep.

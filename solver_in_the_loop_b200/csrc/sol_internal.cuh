@@ -217,28 +217,23 @@ int launch_wgrad_c32_tc(cudaStream_t st, int sm_count, int steps, int B, int Y, 
                         const float* g, size_t g_step_stride, float* part, int* nctas_out, int accumulate = 0);
 int launch_colsum32(cudaStream_t st, const float* g, size_t npix, float* db);
 
-// ---- tensor-core convolution (sol_conv_tc.cu) ----
-extern int g_conv_path;             // 1 SIMT fp32, 2 tcgen05 3xTF32 (default; option value 0 = auto = 2)
+// ---- tensor-core convolutions (sol_conv_h.cu: 3xFP16, default; sol_conv_tc.cu: 3xTF32) ----
+extern int g_conv_path;             // 1 SIMT fp32, 2 tcgen05 3xFP16 (default; option value 0 = auto = 2), 3 tcgen05 3xTF32
+extern int g_conv_variant;          // accumulator layout of the 3xFP16 kernel (tuning)
 extern int g_tc_base_offset_mode;
-size_t tc_weights_floats();
+bool conv_path_is_tc();
+size_t tc_weights_floats();         // floats of one layer's pre-split weights (either layout fits)
+size_t h_weights_floats();
 int launch_prep_tc_weights(cudaStream_t st, const float* w, float* wprep);
+int launch_prep_h_weights(cudaStream_t st, const float* w, float* wsplit);
+int launch_split_weights(cudaStream_t st, const float* w, float* wsplit);      // layout of the selected path
 int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, const float* wprep, const float* bias,
-                      const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready,
-                      const int* dep_flags = nullptr, int* out_flags = nullptr);
+                      const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready);
+int launch_conv5x5_h(cudaStream_t st, int B, int Y, int X, const float* in, const float* wsplit, const float* bias,
+                     const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready);
+int launch_conv5x5_c32_presplit(cudaStream_t st, int B, int Y, int X, const float* in, const float* wsplit, const float* bias,
+                                const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready);
 int tc_tiles_per_launch(int B, int Y, int X);
-// persistent stack of consecutive 32->32 layers (one launch, per-tile flags between layers)
-struct ConvStackLayer {
-    const float* in; float* out;
-    const float* bias; const float* addend; const float* ref;
-    int act;
-    int weight_index;       // which [25][hi|lo][32][32] block of the pre-split weight array
-};
-extern int g_conv_stack;
-bool conv_stack_fits(int B, int Y, int X);
-// flags: int[nlayers * tc_tiles_per_launch(B,Y,X)], zero before the launch; wprep_all: wprep_layers consecutive pre-split weight blocks
-int launch_conv_stack(cudaStream_t st, int B, int Y, int X, int nlayers, const ConvStackLayer* layers, const float* wprep_all,
-                      int wprep_layers, float slope, int* flags);
-extern int g_conv_chain;
 extern int g_fuse_small;
 extern int g_fuse_solver_io;
 extern int g_wgrad_overlap;

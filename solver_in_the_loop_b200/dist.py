@@ -46,3 +46,45 @@ def allreduce_bucket(bucket: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=group)
     return bucket
+
+
+class DataParallelStep:
+    """The rank-independent half of one optimiser step (karman_train.py:449-457): the flat bucket
+    [gradients | per-step losses] of this rank's simulations -> ONE all-reduce(SUM) -> optional per-variable
+    clip_by_norm -> the identical TF1-Adam update on every rank.  `SolTrainer` fills the bucket with the CUDA engine
+    and updates with the `sol_adam_tf1` kernel; the world-size-2 gloo test fills it on CPU and drives this same code.
+
+    Subclasses provide `_adam(lr)` (update self.weights from self.grad) and `layer_shapes` ((Cin, Cout) per Conv2D).
+    """
+
+    def _init_bucket(self, n_params: int, msteps: int, device, process_group=None):
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (dist.is_available() and dist.is_initialized()):
+            self.world = dist.get_world_size(process_group)
+        self.n_params, self.msteps = int(n_params), int(msteps)
+        self.bucket = make_bucket(n_params, msteps, device)
+        self.grad = self.bucket[:n_params]
+        self.loss_steps = self.bucket[n_params:]
+        self.t = 0
+
+    def _clip_by_norm(self, clip: float):
+        """tf.clip_by_norm(grad, 1e-3) per variable (karman_train.py:452-454)."""
+        o = 0
+        for ci, co in self.layer_shapes:
+            for n in (25 * ci * co, co):
+                g = self.grad[o:o + n]
+                nrm = g.norm()
+                g.mul_(torch.clamp(clip / (nrm + 1e-30), max=1.0))
+                o += n
+
+    def reduce_and_update(self, lr: float, clip_grad: bool = False) -> torch.Tensor:
+        """All-reduce the bucket, clip, Adam.  Returns the global total loss (0-d tensor): sum_i loss_i / msteps
+        over all simulations of all ranks (karman_train.py:436)."""
+        if self.world > 1:
+            allreduce_bucket(self.bucket, self.pg)
+        if clip_grad:
+            self._clip_by_norm(1e-3)
+        self.t += 1
+        self._adam(lr)
+        return self.loss_steps.sum() / self.msteps

@@ -15,6 +15,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib, engine
+from .dist import DataParallelStep
 
 
 def model_layers(model: str = "mars_moon", cin0: int = 3):
@@ -49,16 +50,12 @@ def lr_schedule(epoch: int, current_lr: float) -> float:
     return current_lr
 
 
-class SolTrainer:
+class SolTrainer(DataParallelStep):
     def __init__(self, plan: engine.Plan, msteps: int, batch: int, sig: Sequence[float], lr: float = 1e-4,
                  weights: Optional[torch.Tensor] = None, seed: int = 0, dt: float = 1.0, use_graph: bool = True,
                  clip_grad: bool = False, process_group=None, with_density: bool = False, cin0: int = 3, model: str = "mars_moon"):
         self.plan, self.msteps, self.batch = plan, int(msteps), int(batch)
         self.lr, self.clip_grad = float(lr), bool(clip_grad)
-        self.pg = process_group
-        self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            self.world = torch.distributed.get_world_size(process_group)
         self.model = model
         model_id = {"mars_moon": _lib.SOL_MODEL_MARS_MOON, "mercury": _lib.SOL_MODEL_MERCURY}[model]      # --model (karman_train.py:33)
         self.unroll = engine.Unroll(plan, msteps, batch, sig, dt=dt, model=model_id, cin0=cin0, with_density=with_density,
@@ -67,13 +64,12 @@ class SolTrainer:
         dev = plan.device
         w0 = glorot_uniform_params(model, cin0=cin0, seed=seed) if weights is None else weights
         self.weights = w0.to(device=dev, dtype=torch.float32).contiguous().clone()
-        # flat all-reduce bucket: [gradients | per-step losses]
-        self.bucket = torch.zeros(n + self.msteps, device=dev)
-        self.grad = self.bucket[:n]
-        self.unroll.loss_steps = self.bucket[n:]
+        # flat all-reduce bucket: [gradients | per-step losses] (dist.DataParallelStep)
+        self._init_bucket(n, self.msteps, dev, process_group)
+        self.layer_shapes = model_layers(model, cin0)
+        self.unroll.loss_steps = self.loss_steps
         self.adam_m = torch.zeros(n, device=dev)
         self.adam_v = torch.zeros(n, device=dev)
-        self.t = 0
         # pinned staging for the host-facing call
         self._pin = None
         self._dev_in = None
@@ -83,23 +79,10 @@ class SolTrainer:
         """One optimiser step on device tensors.  Returns the (global) total loss as a 0-d device
         tensor: sum_i loss_i / msteps summed over all simulations of all ranks (karman_train.py:436)."""
         self.unroll.train_iter(self.weights, re, vy0, vx0, gt_vy, gt_vx, self.grad, rho0=rho0)
-        if self.world > 1:
-            torch.distributed.all_reduce(self.bucket, op=torch.distributed.ReduceOp.SUM, group=self.pg)
-        if self.clip_grad:
-            self._clip_by_norm(1e-3)
-        self.t += 1
-        engine.adam_tf1(self.weights, self.grad, self.adam_m, self.adam_v, self.t, self.lr if lr is None else lr)
-        return self.unroll.loss_steps.sum() / self.msteps
+        return self.reduce_and_update(self.lr if lr is None else lr, self.clip_grad)
 
-    def _clip_by_norm(self, clip: float):
-        """tf.clip_by_norm(grad, 1e-3) per variable (karman_train.py:452-454)."""
-        o = 0
-        for ci, co in model_layers(self.model, self.unroll.cfg.cin0):
-            for n in (25 * ci * co, co):
-                g = self.grad[o:o + n]
-                nrm = g.norm()
-                g.mul_(torch.clamp(clip / (nrm + 1e-30), max=1.0))
-                o += n
+    def _adam(self, lr: float):
+        engine.adam_tf1(self.weights, self.grad, self.adam_m, self.adam_v, self.t, lr)
 
     # ---- host-facing call (what karman_train.py's feed_dict does) --------------------------------
     def train_step_host(self, re, vy0, vx0, gt_vy, gt_vx, lr: Optional[float] = None) -> float:

@@ -33,27 +33,25 @@ def _setup(Y, X, B, m, device, use_graph=False, spin=25, direct=1):
 
 
 _PATHS = {
-    # id: (conv_path, wgrad_path, pdl, conv_chain, wgrad_overlap, fuse_small, fuse_solver_io, conv_stack)
-    "simt": (1, 1, 1, 0, 1, 1, 0, 0),
-    "tcgen05-conv": (2, 1, 1, 0, 1, 1, 0, 0),
-    "tcgen05-conv-stack-fwd-only": (2, 1, 1, 0, 1, 1, 0, 1),
-    "tcgen05-conv+wgrad": (2, 2, 1, 0, 1, 1, 0, 0),
-    "tcgen05-conv+wgrad-tilechain-solverio": (2, 2, 1, 1, 1, 1, 1, 0),
-    "tcgen05-conv+wgrad-serial-unfused": (2, 2, 1, 0, 0, 0, 0, 0),
-    "tcgen05-conv+wgrad-nopdl": (2, 2, 0, 0, 1, 1, 0, 0),
-    "defaults(perlayer,solverio,unfused-small)": (2, 2, 1, 0, 1, 0, 1, 0),
-    "stack-solverio-unfused-small": (2, 2, 1, 0, 1, 0, 1, 1),
-    "stack-nopdl-serial": (2, 2, 0, 0, 0, 0, 1, 1),
+    # id: (conv_path, wgrad_path, pdl, wgrad_overlap, fuse_small, fuse_solver_io, conv_variant)
+    "simt": (1, 1, 1, 1, 1, 0, 0),
+    "fp16x3-conv": (2, 1, 1, 1, 1, 0, 0),
+    "fp16x3-conv+wgrad": (2, 2, 1, 1, 1, 0, 0),
+    "fp16x3-conv+wgrad-serial-unfused": (2, 2, 1, 0, 0, 0, 0),
+    "fp16x3-conv+wgrad-nopdl": (2, 2, 0, 1, 1, 0, 0),
+    "defaults(fp16x3,solverio,unfused-small)": (2, 2, 1, 1, 0, 1, 0),
+    "fp16x3-one-accumulator-set": (2, 2, 1, 1, 0, 1, 1),
+    "fp16x3-merged-accumulators": (2, 2, 1, 1, 0, 1, 2),
+    "tf32x3-conv+wgrad": (3, 2, 1, 1, 0, 1, 0),
 }
-_NAMES = ("conv_path", "wgrad_path", "pdl", "conv_chain", "wgrad_overlap", "fuse_small", "fuse_solver_io", "conv_stack")
-_DEFAULTS = (0, 0, 1, 0, 1, 0, 1, 0)
+_NAMES = ("conv_path", "wgrad_path", "pdl", "wgrad_overlap", "fuse_small", "fuse_solver_io", "conv_variant")
+_DEFAULTS = (0, 0, 1, 1, 0, 1, 0)
 
 
 @pytest.fixture(params=list(_PATHS.values()), ids=list(_PATHS.keys()))
 def conv_path(request):
-    """Kernel families (SIMT / tcgen05), plain vs programmatic-dependent stream order, whole-kernel vs tile-flag
-    dependencies between consecutive conv layers, one launch per layer vs the persistent ten-layer stack, weight
-    gradients beside the adjoint solves vs after the sweep."""
+    """Kernel families (SIMT / tcgen05 3xFP16 / tcgen05 3xTF32), plain vs programmatic-dependent stream order, accumulator
+    layouts of the 3xFP16 kernel, weight gradients beside the adjoint solves vs after the sweep."""
     from solver_in_the_loop_b200 import engine
     for n, v in zip(_NAMES, request.param):
         engine.set_option(n, v)
