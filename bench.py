@@ -50,24 +50,42 @@ def parse():
     ap.add_argument("--fuse-solver-io", type=int, default=1, help="1 = to_feature / feat_bwd folded into the projection kernel")
     ap.add_argument("--pdl", type=int, default=1, help="1 = programmatic dependent launch of every kernel, 0 = plain stream order")
     ap.add_argument("--conv-path", type=int, default=0, help="0 auto, 1 fp32 SIMT, 2 tcgen05 3xFP16, 3 tcgen05 3xTF32")
-    ap.add_argument("--wgrad-path", type=int, default=0, help="0 auto, 1 per-step SIMT, 2 deferred tcgen05")
+    ap.add_argument("--wgrad-path", type=int, default=0, help="0 auto, 1 per-step SIMT, 2 deferred tcgen05 3xFP16, 3 deferred tcgen05 3xTF32")
     ap.add_argument("--cg-rows", type=int, default=0)
     ap.add_argument("--mg-variant", type=int, default=0, help="0 = compile-time-hierarchy multigrid kernel, 2 = run-time-hierarchy kernel")
     ap.add_argument("--cg-precond", type=int, default=1, help="1 = multigrid-preconditioned CG, 0 = the reference's plain CG")
     ap.add_argument("--direct-solve", type=int, default=1, help="1 = direct projection (fast Poisson + capacitance correction) where supported")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-msteps", type=int, default=4, help="unroll length of the bounded CPU sample")
+    ap.add_argument("--cpu-msteps", type=int, default=0, help="unroll length of the CPU arm (0 = the workload's own msteps)")
+    ap.add_argument("--config", default="sol32", choices=["sol32", "c2", "c4"],
+                    help="sol32: 128x64, 3 sims/GPU, msteps 32 (the metric's configuration); c2: 128x64, 4 sims, msteps 4; "
+                         "c4: 256x128, 4 sims/GPU, msteps 16 (BASELINE config 4's per-GPU shard)")
     return ap.parse_args()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_conv5x5_c32_tc launch at the bench shape, from the committed
-# `ncu --set full` capture (None until a capture of the current kernel is committed under profiles/)
-CONV_TC_DRAM_BYTES = 4.95e6
-CONV_TC_DRAM_SOURCE = ("profiles/r01_b_ncu_top.md: mean of 8 launches, dram read 3.4-6.5 MB + write 0 (the 3.1 MB output tile stays in the "
-                       "126 MB L2 under ncu's replay); algorithmic: 3.15 MB in + 3.15 MB out + 0.2 MB weights")
-CG_MG_DRAM_BYTES = 0.42e6   # profiles/r01_b_ncu_top.md: k_cg_mg3 reads 0.42 MB, writes stay in L2 (compulsory: 20 B/cell = 0.49 MB)
-DIRECT_DRAM_BYTES = 7.38e6  # profiles/r01_e_ncu_direct_wgrad.md: k_direct_solve 0.55 MB + k_direct_apply 6.83 MB per launch under ncu's cold
-                            # caches (the 6.3 MB correction basis comes from DRAM once; it is L2-resident in the running iteration)
+def csrc_sha256():
+    """Content hash of the kernel sources (works on the GPU box, where there is no .git): the ncu summaries under
+    profiles/ carry the hash of the build they were captured from, and `traffic` is only reported when it matches."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "solver_in_the_loop_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    h.update(open(os.path.join(ROOT, "include", "sol_b200.h"), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def profile_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` summary
+    profiles/ncu_<kernel>.json (written by scripts/gpu_round.sh); (None, reason) when there is no capture of THIS build."""
+    p = os.path.join(ROOT, "profiles", "ncu_%s.json" % kernel)
+    if not os.path.exists(p):
+        return None, "no ncu capture committed for %s" % kernel
+    d = json.load(open(p))
+    if d.get("csrc_sha256") != csrc_sha256():
+        return None, "profiles/ncu_%s.json was captured from another build (csrc hash %s, this build %s)" % (kernel, d.get("csrc_sha256"), csrc_sha256())
+    return float(d["dram_bytes_per_launch"]), "profiles/ncu_%s.json: %s" % (kernel, d.get("how", "ncu --set full"))
 
 
 def load_peaks(key="hbm_gbs"):
@@ -129,7 +147,15 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle timed on the host cores
 # --------------------------------------------------------------------------------------------------
-def cpu_reference(Y, X, B, msteps, steps, warmup, spin=20):
+def apply_config(args):
+    """--config presets (explicit --Y/--X/--batch/--msteps still win when they differ from the defaults)."""
+    preset = {"sol32": (128, 64, 3, 32), "c2": (128, 64, 4, 4), "c4": (256, 128, 4, 16)}[args.config]
+    dflt = (128, 64, 3, 32)
+    cur = (args.Y, args.X, args.batch, args.msteps)
+    args.Y, args.X, args.batch, args.msteps = [c if c != d else p for c, d, p in zip(cur, dflt, preset)]
+
+
+def cpu_reference(Y, X, B, msteps, steps, warmup, spin=200):
     """One training iteration of the CPU restatement (fp32, reference-style CG with the reference's
     stop rule, torch-CPU conv2d, torch autograd adjoint, TF1 Adam), timed on all host cores."""
     import torch
@@ -174,22 +200,23 @@ def cpu_reference(Y, X, B, msteps, steps, warmup, spin=20):
     kf = float(torch.cat([x.float() for x in stats.get("fwd_iters", [torch.zeros(1)])]).mean())
     kb = float(torch.cat([x.float() for x in stats.get("bwd_iters", [torch.zeros(1)])]).mean())
     return dict(value=msteps * B * Y * X / t, sec_per_iter=t, cores=ncores_used, host_cores=ncores, k_fwd=kf, k_bwd=kb,
-                sample="%d iterations of karman-2d %dx%d batch %d msteps=%d (bounded sample of the msteps=32 workload; "
-                       "throughput per step-cell is unroll-length invariant)" % (steps, Y, X, B, msteps))
+                sample="%d timed iterations (+%d warm-up) of karman-2d %dx%d batch %d msteps=%d, synthetic wake after %d spin-up steps"
+                       % (steps, warmup, Y, X, B, msteps, spin))
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 5))
+    apply_config(args)
+    steps = max(3, min(args.steps, 5))      # >= 3 timed iterations of the real workload (~4 s each at SOL-32)
     warm = 1 if args.warmup > 0 else 0
-    r = cpu_reference(args.Y, args.X, args.batch, args.cpu_msteps, steps, warm)
+    r = cpu_reference(args.Y, args.X, args.batch, args.msteps if args.cpu_msteps <= 0 else args.cpu_msteps, steps, warm, spin=args.spin)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": r["sec_per_iter"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "karman-2d %dx%d SOL-32 (batch %d sims, msteps %d)" % (args.Y, args.X, args.batch, args.msteps),
+        "config": {"workload": "karman-2d %dx%d %s: msteps=%d, %d sims/GPU, Re in reference Makefile set" % (args.Y, args.X, args.config.upper(), args.msteps, args.batch),
                    "sample": r["sample"], "cg": "reference SparseCG recurrences, max|r|<1e-5, <=2000 it",
                    "mean_cg_iters": [r["k_fwd"], r["k_bwd"]]},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
@@ -237,6 +264,7 @@ def main():
     from solver_in_the_loop_b200 import engine
     from solver_in_the_loop_b200.trainer import SolTrainer
 
+    apply_config(args)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -315,89 +343,61 @@ def main():
     t_e2e = max(e2.elapsed_time(e3) / 1e3, 0.0)
     t_e2e_wall = time.perf_counter() - tw0
 
-    # ------------------------------------------------------------------ pressure-solve kernel roofline (live, CUDA events)
+    # ------------------------------------------------------------------ pressure-projection kernels (live, CUDA events, graph replay)
+    def time_graph(fn, n, reps=5):
+        """us per call of fn() inside a CUDA graph of n dependent calls (the engine replays graphs too: no host launch cost)."""
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        st = torch.cuda.Stream()
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            fn()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                for _ in range(n):
+                    fn()
+            g.replay()
+            st.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(st)
+            for _ in range(reps):
+                g.replay()
+            a1.record(st)
+            st.synchronize()
+        return a0.elapsed_time(a1) * 1e3 / (n * reps)
+
     plan.set_cg(tol_abs=1e-5, tol_rel=0.0, max_it=2000, cluster=args.cluster)
     o = plan.step_fwd(re, vy0, vx0)
     adv_y, adv_x = plan.advect(o["vy1"], o["vx1"])
-    for _ in range(3):
-        plan.project(adv_y, adv_x)
-    nrep = 20
-    torch.cuda.synchronize()
-    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e4.record()
-    for _ in range(nrep):
-        py, px, it_k = plan.project(adv_y, adv_x)
-    e5.record()
-    torch.cuda.synchronize()
-    t_solve = e4.elapsed_time(e5) / 1e3 / nrep
+    proj_out = plan.faces(B)
+    it_k = torch.zeros(B, dtype=torch.int32, device=dev)
+
+    def proj():
+        engine.check(plan.lib.sol_project(plan.handle, torch.cuda.current_stream().cuda_stream, B, adv_y.data_ptr(), adv_x.data_ptr(),
+                                          proj_out[0].data_ptr(), proj_out[1].data_ptr(), None, it_k.data_ptr()))
+    t_solve = time_graph(proj, 20) * 1e-6
     K = float(it_k.float().mean())
     precond = bool(args.cg_precond) and args.cluster <= 1
-    direct = bool(args.direct_solve) and args.cluster <= 1 and (Y, X) in ((128, 64), (64, 32)) and K == 0.0
-    # algorithmic bytes per cell per solve: plain CG 40K+8; multigrid-preconditioned CG adds
-    # the V(2,2) cycle: 4 fine smoothing sweeps (16 B each) + residual/restrict/prolong (20 B) + coarse levels (1/3 of fine)
-    per_iter_bytes = 148.0 if precond else 40.0
-    # direct projection: per simulation the compulsory field traffic (20 B/cell) + the precomputed operators it streams
-    # (transform matrices Sy, Sx, 1/lambda; capacitance-corrected basis W M: ~164 changed rows x N), all L2-resident
-    KCH = 164 if (Y, X) == (128, 64) else 84
-    direct_bytes_per_sim = 20.0 * Y * X + 4.0 * (Y * Y + X * X + Y * X) + 4.0 * KCH * Y * X
-    alg_bytes = direct_bytes_per_sim * B if direct else (per_iter_bytes * K + 8.0) * Y * X * B
+    direct = bool(args.direct_solve) and K == 0.0
     peak, peak_src = load_peaks()
-    achieved = alg_bytes / t_solve / 1e9
-
-    # the same kernel with one simulation per SM (machine-filling batch): the per-launch time is unchanged, so the
-    # algorithmic bandwidth scales with the number of busy SMs
-    full = None
-    if rank == 0 and world == 1:
-        nsm = torch.cuda.get_device_properties(dev).multi_processor_count
-        plan_f = engine.Plan.karman(Y, X, nsm)
-        plan_f.set_option("cg_rows", args.cg_rows)
-        plan_f.set_option("cg_precond", args.cg_precond)
-        plan_f.set_option("mg_variant", args.mg_variant)
-        plan_f.set_option("direct_solve", args.direct_solve)
-        plan_f.set_cg(tol_abs=1e-5, tol_rel=0.0, max_it=2000, cluster=args.cluster)
-        rep = (nsm + B - 1) // B
-        fy = adv_y.repeat(rep, 1, 1)[:nsm].contiguous(); fx = adv_x.repeat(rep, 1, 1)[:nsm].contiguous()
-        for _ in range(3):
-            plan_f.project(fy, fx)
-        torch.cuda.synchronize()
-        e8, e9 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e8.record()
-        for _ in range(nrep):
-            _, _, it_f = plan_f.project(fy, fx)
-        e9.record()
-        torch.cuda.synchronize()
-        t_full = e8.elapsed_time(e9) / 1e3 / nrep
-        K_f = float(it_f.float().mean())
-        # (the engine switches to the multigrid CG above 64 simulations per launch: one whole solve per SM is the higher-throughput form)
-        ach_f = (direct_bytes_per_sim * nsm if (direct and K_f == 0.0) else (per_iter_bytes * K_f + 8.0) * Y * X * nsm) / t_full / 1e9
-        ach_cg = (40.0 * max(K_f, 0.0) + 8.0) * Y * X * nsm / t_full / 1e9       # the same launch counted with the plain-CG byte model of SURVEY 8d
-        full = {"sims": nsm, "us_per_launch": t_full * 1e6, "cg_iters": K_f, "achieved": ach_f, "unit": "GB/s", "frac": ach_f / peak,
-                "achieved_plain_cg_byte_model": ach_cg, "frac_plain_cg_byte_model": ach_cg / peak,
-                "note": "one simulation per SM: same kernel, same per-launch latency, every SM busy"}
-        plan_f.close()
+    nsm = torch.cuda.get_device_properties(dev).multi_processor_count
+    N = Y * X
 
     # ------------------------------------------------------------------ 32->32 convolution kernel roofline (live, CUDA events)
     t_conv = None
     if args.conv_path != 1:
-        wl = torch.randn(5, 5, 32, 32, device=dev) * 0.03
+        wl = torch.randn(5, 5, 32, 32, device=dev) * 0.01
         bl = torch.randn(32, device=dev) * 0.1
         ws = engine.conv5x5_split_weights(wl)
         torch.cuda.synchronize()            # the split weights are settled before the chain starts
         act_a = torch.randn(B, Y, X, 32, device=dev)
         act_b = torch.empty_like(act_a)
-        for _ in range(4):
+
+        def conv_pair():     # dependent chain, ping-pong buffers, exactly like consecutive layers
             engine.conv5x5_c32_presplit(act_a, ws, bl, act=1, out=act_b, weights_settled=True)
             engine.conv5x5_c32_presplit(act_b, ws, bl, act=1, out=act_a, weights_settled=True)
-        nconv = 100
-        torch.cuda.synchronize()
-        e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e6.record()
-        for _ in range(nconv // 2):      # dependent chain, ping-pong buffers, exactly like consecutive layers
-            engine.conv5x5_c32_presplit(act_a, ws, bl, act=1, out=act_b, weights_settled=True)
-            engine.conv5x5_c32_presplit(act_b, ws, bl, act=1, out=act_a, weights_settled=True)
-        e7.record()
-        torch.cuda.synchronize()
-        t_conv = e6.elapsed_time(e7) / 1e3 / nconv
+        t_conv = time_graph(conv_pair, 50) * 1e-6 / 2
     conv_flops = 2.0 * 25 * 32 * 32 * B * Y * X           # algorithmic (fp32-equivalent) flops of one launch
     tpeak, tpeak_src = load_peaks("bf16_tflops")
 
@@ -413,22 +413,25 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference(Y, X, B, args.cpu_msteps, 2, 1)
+        r = cpu_reference(Y, X, B, m if args.cpu_msteps <= 0 else args.cpu_msteps, 2, 1, spin=args.spin)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
                "mean_cg_iters": [r["k_fwd"], r["k_bwd"]]}
 
     if rank == 0:
+        conv_kernel = {0: "k_conv5x5_c32_h", 2: "k_conv5x5_c32_h", 3: "k_conv5x5_c32_tc"}.get(args.conv_path, "k_conv5x5_c32")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "karman-2d %dx%d SOL-32: msteps=%d, %d sims/GPU, Re in reference Makefile set" % (Y, X, m, B),
+            "config": {"workload": "karman-2d %dx%d %s: msteps=%d, %d sims/GPU, Re in reference Makefile set" % (Y, X, args.config.upper(), m, B),
                        "global_batch": B * world, "parallelism": "dp%d over simulations, 1 all-reduce/step" % world,
                        "cg": ("direct projection (exact solve, no iterations)" if (k_fwd == 0.0 and args.direct_solve) else
                               "max|r|<1e-5 per sim, <=2000 it (reference stop rule)"), "mean_cg_iters": [k_fwd, k_bwd],
                        "l2": "working set (activation stash %.2f GB/iter) exceeds the 126 MB L2; no explicit flush"
                              % (trainer.unroll.workspace.numel() / 1e9),
-                       "cuda_graph": not args.no_graph, "conv_path": args.conv_path, "wgrad_path": args.wgrad_path, "cg_precond": args.cg_precond, "direct_solve": args.direct_solve, "pdl": args.pdl, "conv_variant": args.conv_variant, "wgrad_overlap": args.wgrad_overlap, "fuse_small": args.fuse_small, "fuse_solver_io": args.fuse_solver_io, "loss": float(loss_host)},
+                       "cuda_graph": not args.no_graph, "conv_path": args.conv_path, "conv_variant": args.conv_variant, "wgrad_path": args.wgrad_path,
+                       "cg_precond": args.cg_precond, "direct_solve": args.direct_solve, "pdl": args.pdl, "wgrad_overlap": args.wgrad_overlap,
+                       "fuse_small": args.fuse_small, "fuse_solver_io": args.fuse_solver_io, "csrc_sha256": csrc_sha256(), "loss": float(loss_host)},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": trainer.h2d_bytes_per_step(), "d2h_bytes_per_step": 4,
                     "ms_per_step": t_e2e / args.steps * 1e3, "wall_ms_per_step": t_e2e_wall / args.steps * 1e3},
             "gpu_launches": int(launches),
@@ -436,33 +439,51 @@ def main():
             "roofline": None,
         }
         t_iter = t_dev / args.steps
-        solver_name = ("k_cg_mg3 (fused projection: divergence + multigrid-preconditioned CG + gradient subtract)" if precond
-                       else "k_cg (fused projection: divergence + CG + gradient subtract)")
+        # ---- projection: two honest yardsticks.  (1) DRAM: the compulsory field traffic of one projection, 20 B per
+        # cell (read vy, vx; write vy, vx, + features), against the measured HBM peak: tiny by construction, the solver state and
+        # the precomputed operators are on-chip / L2-resident.  (2) FP32 FMA issue: the direct solve is four small dense products
+        # per simulation (2*Y*X*(Y+X) MAC) + the capacitance correction (kp*Y*X MAC); peak = 128 FMA/clk/SM at the max SM clock.
+        comp_bytes = 20.0 * N * B
+        ach_dram = comp_bytes / t_solve_max / 1e9
+        traffic_s, traffic_s_src = profile_traffic("k_direct_solve+k_direct_apply" if direct else ("k_cg_mg3" if precond else "k_cg"))
         if direct:
-            solver_name = "k_direct_solve + k_direct_apply (direct projection: divergence -> DST fast Poisson solve -> capacitance correction -> gradient subtract)"
-        roof_solver = {"kernel": solver_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                       "frac": achieved / peak, "traffic": (DIRECT_DRAM_BYTES if direct else CG_MG_DRAM_BYTES if precond else None) if (Y, X, B) == (128, 64, 3) else None, "peak_source": peak_src, "cg_iters": K,
-                       "us_per_launch": t_solve_max * 1e6, "algorithmic_bytes_per_launch": alg_bytes,
-                       "launches_per_step": 2 * m, "share_of_step": 2 * m * t_solve_max / t_iter, "machine_filling_batch": full,
-                       "note": ("direct solve, no iterations: per simulation one CTA does the four small dense transforms (3.1 MFMA, fp32 FMA "
-                                "issue-bound on one SM) and the whole machine applies the capacitance correction; achieved = field + "
-                                "operator bytes streamed (L2-resident) / CUDA-event time of the two launches") if direct else
-                               ("solver state is register/SMEM-resident (DRAM traffic ~20 B/cell regardless of K); achieved = "
-                                "(%gK+8) B/cell algorithmic bytes / CUDA-event launch time; one CTA per simulation, so at "
-                                "B=%d sims only %d of 148 SMs are busy (latency-bound; scripts/cg_bench.py reports B=148)" % (per_iter_bytes, B, B))}
+            kp = plan.direct_rows()
+            fma = (2.0 * N * (Y + X) + float(kp) * N) * B
+            fma_peak_gpu = nsm * 128.0 * 1.965e9
+            solver_name = "k_direct_solve + k_direct_apply (divergence -> DST fast Poisson solve -> capacitance correction -> gradient subtract)"
+            extra = {"fp32_fma_per_launch": fma, "fp32_fma_frac_of_gpu_peak": fma / t_solve_max / fma_peak_gpu,
+                     "note": "direct solve, no iterations: latency-bound at %d simulations (a cluster of CTAs per simulation); the HBM "
+                             "fraction is the compulsory 20 B/cell over the launch time, the FMA fraction counts the transform and "
+                             "correction MACs against 128 FMA/clk/SM x %d SMs" % (B, nsm)}
+        else:
+            solver_name = ("k_cg_mg3 (fused projection: divergence + multigrid-preconditioned CG + gradient subtract)" if precond
+                           else "k_cg (fused projection: divergence + CG + gradient subtract)")
+            extra = {"streaming_cg_model_gbs": (40.0 * K + 8.0) * N * B / t_solve_max / 1e9,
+                     "note": "solver state is register/SMEM-resident: DRAM traffic is the compulsory 20 B/cell whatever K; "
+                             "streaming_cg_model_gbs = what SURVEY 8d's (40K+8) B/cell streaming formulation would have to move in the "
+                             "same time (context, not a roofline fraction); one CTA per simulation: latency-bound at %d simulations" % B}
+        roof_solver = {"kernel": solver_name, "bound": "hbm", "achieved": ach_dram, "peak": peak, "unit": "GB/s", "frac": ach_dram / peak,
+                       "traffic": traffic_s, "traffic_source": traffic_s_src, "peak_source": peak_src, "cg_iters": K,
+                       "us_per_launch": t_solve_max * 1e6, "algorithmic_bytes_per_launch": comp_bytes,
+                       "launches_per_step": 2 * m, "share_of_step": 2 * m * t_solve_max / t_iter}
+        roof_solver.update(extra)
         if t_conv is not None:
             tf = conv_flops / t_conv_max / 1e12
-            roof_conv = {"kernel": "k_conv5x5_c32_tc (tcgen05 3xTF32 implicit-GEMM 5x5 conv 32->32, fwd layers and data gradients)",
+            traffic_c, traffic_c_src = profile_traffic(conv_kernel)
+            split = 3.0
+            ceiling = tpeak / (6.0 if args.conv_path == 3 else 3.0)
+            roof_conv = {"kernel": "%s (tcgen05 %s implicit-GEMM 5x5 conv 32->32, forward layers and data gradients)"
+                                   % (conv_kernel, "3xTF32" if args.conv_path == 3 else "block-scaled 3xFP16"),
                          "bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
-                         "traffic": CONV_TC_DRAM_BYTES if (Y, X, B) == (128, 64, 3) else None, "traffic_source": CONV_TC_DRAM_SOURCE,
-                         "peak_source": tpeak_src + ", dense bf16 (tf32 issues at half that rate)", "us_per_launch": t_conv_max * 1e6,
-                         "algorithmic_flops_per_launch": conv_flops, "executed_tensor_tflops": 3.0 * tf,
+                         "traffic": traffic_c if (Y, X, B) == (128, 64, 3) else None, "traffic_source": traffic_c_src,
+                         "peak_source": tpeak_src + ", dense bf16", "us_per_launch": t_conv_max * 1e6,
+                         "algorithmic_flops_per_launch": conv_flops, "executed_tensor_tflops": split * tf,
                          "launches_per_step": 20 * m, "share_of_step": 20 * m * t_conv_max / t_iter,
-                         "frac_of_formulation_ceiling": tf / (tpeak / 6.0),
-                         "note": "achieved = 2*25*32*32 flop/pixel x B*Y*X pixels / CUDA-event launch time of a dependent "
-                                 "ping-pong chain; fp32-accurate 3xTF32 executes 3 tf32 MMAs per algorithmic product, so the "
-                                 "tensor pipe runs 3x the algorithmic rate at half the bf16 peak (ceiling = peak/6); "
-                                 "%d pixels = %d CTA tiles on 148 SMs: latency- not throughput-bound" % (B * Y * X, B * Y * X // 128)}
+                         "frac_of_formulation_ceiling": tf / ceiling,
+                         "note": "achieved = 2*25*32*32 flop/pixel x B*Y*X pixels / CUDA-event time per launch of a graph-replayed dependent "
+                                 "ping-pong chain; the fp32-accurate operand split executes 3 MMAs per algorithmic product (ceiling = "
+                                 "peak/%d); N<=64 UMMAs are bound by the 128 B/clk shared-memory operand read, and %d pixels = %d CTA tiles "
+                                 "on 148 SMs leave the layer latency-bound" % (6 if args.conv_path == 3 else 3, B * Y * X, B * Y * X // 128)}
         else:
             roof_conv = None
         if roof_conv is not None and roof_conv["share_of_step"] >= roof_solver["share_of_step"]:

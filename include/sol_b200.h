@@ -76,11 +76,16 @@ int sol_plan_set_cg(sol_plan* plan, float tol_abs, float tol_rel, int max_it, in
  *                on first use; exact up to fp32 round-off (what the reference's NumPy path does with a sparse direct solver,
  *                karman_apply.py:39), the CG controls above do not apply and iteration counters read 0.  0 = iterative solvers */
 int sol_plan_set_option(sol_plan* plan, const char* name, int value);
+/* Read-only plan facts for measurement scripts: "direct_active" (1 when the direct projection is what sol_project runs for
+ * batch 1), "direct_rows" (rows of the pressure operator the obstacle changes, padded to 32: the k of the capacitance matrix),
+ * "sm_count". */
+int sol_plan_query(sol_plan* plan, const char* name, int* value);
 /* Process-wide knobs:
  *   "conv_path" 0 = auto (= 2), 1 = fp32 SIMT kernels, 2 = tcgen05 tensor-core kernels with block-scaled 3xFP16 operand
  *         splitting (fp32-accurate), 3 = tcgen05 with 3xTF32 splitting (the round-1 kernel, twice the operand traffic)
- *   "conv_variant" (tuning) accumulator layout of the 3xFP16 kernel: 0 = two alternating sets, 1 = one set, 2 = two merged sets
- *   "wgrad_path" 0 = auto, 1 = per-step fp32 SIMT weight gradients, 2 = deferred tcgen05 weight-gradient GEMM
+ *   "conv_variant" (tuning) accumulator layout of the 3xFP16 kernel: 0 = two merged sets (default), 1 = two sets, 2 = one set
+ *   "wgrad_path" 0 = auto (= 2), 1 = per-step fp32 SIMT weight gradients, 2 = deferred tcgen05 weight-gradient GEMM with
+ *         block-scaled 3xFP16 operands, 3 = deferred tcgen05 GEMM with 3xTF32 operands (the round-1 kernel)
  *   "fuse_small" 1 = the correction-gradient scaling (adjoint of "velocity + correction") is folded into the
  *         diffusion adjoint of the following step, 0 (default: measured faster) = separate kernel
  *   "fuse_solver_io" 1 (default) = to_feature and its adjoint are folded into the projection kernel (2 launches fewer per

@@ -18,7 +18,7 @@ w64 = torch.randn(5, 5, 32, 32, generator=g, dtype=torch.float64) * 0.03
 b64 = torch.randn(32, generator=g, dtype=torch.float64) * 0.1
 ref = torch.nn.functional.conv2d(x64.permute(0, 3, 1, 2), w64.permute(3, 2, 0, 1), b64, padding=2).permute(0, 2, 3, 1)
 x = x64.float().to(dev); w = w64.float().to(dev); b = b64.float().to(dev)
-for name, path, variant in (("fp16x3 two sets", 2, 0), ("fp16x3 one set", 2, 1), ("fp16x3 merged sets", 2, 2), ("tf32x3 (round 1)", 3, 0)):
+for name, path, variant in (("fp16x3 merged sets", 2, 0), ("fp16x3 two sets", 2, 1), ("fp16x3 one set", 2, 2), ("tf32x3 (round 1)", 3, 0)):
     engine.set_option("conv_path", path); engine.set_option("conv_variant", variant)
     ws = engine.conv5x5_split_weights(w)
     torch.cuda.synchronize()

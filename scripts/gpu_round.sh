@@ -1,27 +1,32 @@
 #!/bin/bash
-# One-call GPU bundle: parity tests, smoke, both bench arms, ncu launch list (+ optional full-set capture of the top kernels).
-set -u
-mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.log 2>&1
-timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1
-echo "pytest exit $?" | tee -a gpurun_out/pytest_gpu.log
-tail -4 gpurun_out/pytest_gpu.log; grep -E "^FAILED|^ERROR" gpurun_out/pytest_gpu.log | head -20
-timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1
-echo "smoke exit $?" | tee -a gpurun_out/smoke.log; tail -2 gpurun_out/smoke.log
-timeout 600 python bench.py ${BENCH_ARGS:-} > gpurun_out/bench.log 2>&1
-echo "bench exit $?" | tee -a gpurun_out/bench.log; tail -2 gpurun_out/bench.log
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>&1
-echo "bench ref exit $?" | tee -a gpurun_out/bench_ref.log; tail -2 gpurun_out/bench_ref.log
-timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
-    --log-file gpurun_out/launches.csv python scripts/profile_iter.py --msteps 32 > gpurun_out/prof_launches.log 2>&1
-echo "launch-list exit $?"; tail -2 gpurun_out/prof_launches.log
-if [ "${FULL:-0}" = "1" ]; then
-timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on \
-    -k regex:'k_cg_mg3|k_conv5x5_c32_tc|k_wgrad_c32_tc' -c 9 -o gpurun_out/prof_top -f python scripts/profile_iter.py --msteps 2 > gpurun_out/prof_full.log 2>&1
-echo "full exit $?"; tail -2 gpurun_out/prof_full.log
+# Evidence bundle for the CURRENT build, run on the GPU box:   gpurun --timeout 2400 -- 'bash scripts/gpu_round.sh r02_x'
+#   gpurun_out/<tag>/pytest_gpu.log         the -m gpu suite
+#   gpurun_out/<tag>/bench_n1.json, bench_reference_n1.json   both bench arms (CUDA-event timing, never under a profiler)
+#   gpurun_out/<tag>/launches.csv           every launch of one SOL-32 iteration (ncu gpu__time_duration.sum)
+#   gpurun_out/<tag>/ncu_<kernel>.json      `ncu --set full`, warm caches, per kernel: DRAM bytes, duration, tensor-pipe %, SASS histogram,
+#                                           stamped with the source hash of this build (bench.py reads `traffic` from profiles/ncu_*.json)
+# Copy what is to be judged into profiles/ (tracked); gpurun_out/ is scratch.
+TAG=${1:-round}
+WHAT=${2:-all}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > $OUT/smi.txt 2>&1
+if [[ $WHAT == all || $WHAT == *tests* ]]; then
+  timeout 2400 python -m pytest tests -q -m gpu > $OUT/pytest_gpu.log 2>&1; tail -3 $OUT/pytest_gpu.log
 fi
-if [ -n "${EXTRA:-}" ]; then
-timeout ${EXTRA_TIMEOUT:-600} bash -c "$EXTRA" > gpurun_out/extra.log 2>&1
-echo "extra exit $?" | tee -a gpurun_out/extra.log; tail -40 gpurun_out/extra.log
+if [[ $WHAT == all || $WHAT == *bench* ]]; then
+  python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference_n1.json 2> $OUT/bench_reference_n1.err
+  python bench.py --steps 20 --warmup 5 > $OUT/bench_n1.json 2> $OUT/bench_n1.err
+  python -c "import json;d=json.load(open('$OUT/bench_n1.json'));print('ms_per_step %.3f value %.3e e2e %.3e roofline frac %.4f (%s, %.2f us)'%(d['ms_per_step'],d['value'],d['e2e']['value'],d['roofline']['frac'],d['roofline']['kernel'][:20],d['roofline']['us_per_launch']))"
 fi
-ls -la gpurun_out
+if [[ $WHAT == all || $WHAT == *ncu* ]]; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $OUT/launches.csv \
+      python scripts/profile_iter.py --msteps 32 --graph > $OUT/launches.log 2>&1
+  python scripts/launch_summary.py $OUT/launches.csv > $OUT/launches.md 2>/dev/null; head -30 $OUT/launches.md
+  timeout 1500 ncu --set full --clock-control none --cache-control none --import-source on --profile-from-start off -f -o $OUT/prof \
+      python scripts/profile_iter.py --msteps 2 > $OUT/prof.log 2>&1
+  python scripts/ncu_to_json.py $OUT/prof.ncu-rep $OUT "ncu --set full --clock-control none --cache-control none (warm caches), scripts/profile_iter.py --msteps 2, mean over the captured launches" > $OUT/ncu_kernels.md
+  cat $OUT/ncu_kernels.md
+  # the report itself is large: keep only the top kernel's for the source page
+  ls -la $OUT/prof.ncu-rep
+fi

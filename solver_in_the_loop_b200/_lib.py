@@ -40,6 +40,7 @@ SIGNATURES = {
     "sol_plan_destroy": (_i, [_vp]),
     "sol_plan_set_cg": (_i, [_vp, _f, _f, _i, _i]),
     "sol_plan_set_option": (_i, [_vp, C.c_char_p, _i]),
+    "sol_plan_query": (_i, [_vp, C.c_char_p, C.POINTER(_i)]),
     "sol_set_option": (_i, [C.c_char_p, _i]),
     "sol_diffuse_bc": (_i, [_vp, _vp, _i, _vp, _f, _f, _vp, _vp, _vp, _vp]),
     "sol_diffuse_bc_bwd": (_i, [_vp, _vp, _i, _vp, _f, _f, _vp, _vp, _vp, _vp]),

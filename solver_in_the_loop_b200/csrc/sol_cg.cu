@@ -351,11 +351,14 @@ bool direct_active(const sol_plan* p) {
 
 // One cluster per simulation is latency-optimal for a handful of simulations; with one simulation per SM (B = 148) the multigrid
 // CG kernel, which keeps a whole solve inside one CTA, has the higher throughput (measured 114 vs 180 us per launch).
-bool direct_for_batch(const sol_plan* p, int B) { return B <= 64 && direct_active(p); }
+// (grids the multigrid kernel does not cover keep the direct solver at every batch size)
+bool direct_for_batch(const sol_plan* p, int B) { return (B <= 64 || !mg_supported(p)) && direct_active(p); }
 
-bool cg_fuses(const sol_plan* p) {
-    if (direct_active(p)) return true;
-    return p->boundary == SOL_BOUNDARY_OPEN && p->cg_precond && p->cluster <= 1 && mg3_selected(p);
+// the solver launch_cg() picks for this batch takes the fused feature I/O: the direct projection, or the compile-time-hierarchy
+// multigrid kernel (the same predicate order as launch_cg)
+bool cg_fuses(const sol_plan* p, int B) {
+    if (direct_for_batch(p, B)) return true;
+    return p->boundary == SOL_BOUNDARY_OPEN && p->cg_precond && p->cluster <= 1 && mg_supported(p) && mg3_selected(p);
 }
 
 int launch_cg(const sol_plan* p, cudaStream_t st, int B, int mode, const float* rhs, float* p_out, const float* vy,

@@ -27,6 +27,7 @@ struct ConvArgs {
     int B, Y, X;
     int act;
     float slope;
+    unsigned int* amax_out;     // optional: running max|out| (bit pattern) of the output tensor, for the fp16 weight-gradient GEMM
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope, float ref) {
@@ -181,25 +182,34 @@ __global__ void __launch_bounds__(128) k_conv5x5_expand(const ConvArgs a) {
         }
     }
     const int gy = y0 + ty, gx = x0 + tx;
-    if (gy >= a.Y || gx >= a.X) return;
-    const size_t o4 = (((size_t)b * a.Y + gy) * a.X + gx) * 8;
-    float4* out4 = reinterpret_cast<float4*>(a.out) + o4;
+    const bool inside = gy < a.Y && gx < a.X;
+    unsigned int amax = 0u;
+    if (inside) {
+        const size_t o4 = (((size_t)b * a.Y + gy) * a.X + gx) * 8;
+        float4* out4 = reinterpret_cast<float4*>(a.out) + o4;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        float4 f = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-        if (a.bias) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias) + q);
-            f.x += bv.x; f.y += bv.y; f.z += bv.z; f.w += bv.w;
+        for (int q = 0; q < 8; ++q) {
+            float4 f = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+            if (a.bias) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias) + q);
+                f.x += bv.x; f.y += bv.y; f.z += bv.z; f.w += bv.w;
+            }
+            if (a.addend) {
+                const float4 ad = __ldg(reinterpret_cast<const float4*>(a.addend) + o4 + q);
+                f.x += ad.x; f.y += ad.y; f.z += ad.z; f.w += ad.w;
+            }
+            float4 rf = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.act == SOL_ACT_DLRELU) rf = __ldg(reinterpret_cast<const float4*>(a.ref) + o4 + q);
+            f.x = apply_act(f.x, a.act, a.slope, rf.x); f.y = apply_act(f.y, a.act, a.slope, rf.y);
+            f.z = apply_act(f.z, a.act, a.slope, rf.z); f.w = apply_act(f.w, a.act, a.slope, rf.w);
+            out4[q] = f;
+            amax = max(amax, max(max(__float_as_uint(f.x) & 0x7fffffffu, __float_as_uint(f.y) & 0x7fffffffu),
+                                 max(__float_as_uint(f.z) & 0x7fffffffu, __float_as_uint(f.w) & 0x7fffffffu)));
         }
-        if (a.addend) {
-            const float4 ad = __ldg(reinterpret_cast<const float4*>(a.addend) + o4 + q);
-            f.x += ad.x; f.y += ad.y; f.z += ad.z; f.w += ad.w;
-        }
-        float4 rf = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.act == SOL_ACT_DLRELU) rf = __ldg(reinterpret_cast<const float4*>(a.ref) + o4 + q);
-        f.x = apply_act(f.x, a.act, a.slope, rf.x); f.y = apply_act(f.y, a.act, a.slope, rf.y);
-        f.z = apply_act(f.z, a.act, a.slope, rf.z); f.w = apply_act(f.w, a.act, a.slope, rf.w);
-        out4[q] = f;
+    }
+    if (a.amax_out) {       // one atomic per warp (warp-uniform branch: every lane reaches the reduction)
+        amax = __reduce_max_sync(0xffffffffu, amax);
+        if ((tid & 31) == 0 && amax) atomicMax(a.amax_out, amax);
     }
 }
 
@@ -440,10 +450,11 @@ __global__ void __launch_bounds__(256) k_wgrad_generic(const float* __restrict__
 }
 
 int launch_conv5x5(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const float* in, const float* w, const float* bias,
-                   const float* addend, const float* ref, int act, float slope, float* out) {
+                   const float* addend, const float* ref, int act, float slope, float* out, unsigned int* amax_out) {
     ConvArgs a;
     a.in = in; a.w = w; a.bias = bias; a.addend = addend; a.ref = ref; a.out = out;
-    a.B = B; a.Y = Y; a.X = X; a.act = act; a.slope = slope;
+    a.B = B; a.Y = Y; a.X = X; a.act = act; a.slope = slope; a.amax_out = amax_out;
+    if (amax_out && !(Cout == 32 && Cin >= 2 && Cin <= 4)) return fail(SOL_ERR_UNSUPPORTED, "conv5x5: only the Cin <= 4 -> 32 kernels track max|out|");
     if (act == SOL_ACT_DLRELU && !ref) return fail(SOL_ERR_INVALID, "conv5x5: SOL_ACT_DLRELU needs ref");
     if (Cin == 32 && Cout == 32) {
         // pick the tile height that gives at least ~one CTA per SM

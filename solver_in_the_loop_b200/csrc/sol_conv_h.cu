@@ -36,12 +36,10 @@ namespace {
 constexpr int H_TX = 8, H_TY = 16, H_HW = 12, H_HH = 20;
 constexpr int H_A_BYTES = H_HH * H_HW * 128;          // 30720: fp32 halo tile, converted in place to packed fp16 hi|lo
 constexpr int H_STAGE_BYTES = 8192;                   // one tap pair: 64 rows x 128 B
-constexpr int H_STAGES = 5;                           // 10 taps of weights in flight
 constexpr int H_NPAIR = 13;
 constexpr int H_THREADS = 192;
 constexpr int H_OFF_B = H_A_BYTES;                    // 1024-aligned (30 x 1024)
-constexpr int H_OFF_BAR = H_OFF_B + H_STAGES * H_STAGE_BYTES;
-constexpr int H_SMEM = H_OFF_BAR + 256 + 1024;        // + barriers / scratch + alignment slack
+constexpr int h_smem_bytes(int stages) { return H_OFF_B + stages * H_STAGE_BYTES + 256 + 1024; }     // + barriers / scratch + alignment slack
 constexpr int H_WPAIR_FLOATS = H_NPAIR * 64 * 32;     // split weights of one layer, in floats (two halves each)
 
 struct HArgs {
@@ -53,6 +51,7 @@ struct HArgs {
     int act;
     float slope;
     int weights_ready;          // 1: the split weights were complete before the previous kernel of the stream started
+    unsigned int* amax_out;     // optional: running max|out| (bit pattern) of the output tensor, for the fp16 weight-gradient GEMM
     long long* trace;           // diagnostics: 16 slots per CTA of phase stamps (null in production)
 };
 
@@ -115,13 +114,15 @@ __device__ __forceinline__ void split8(const float4& a, const float4& b, float s
 // NSET: independent accumulator sets used alternately (chained UMMAs into one TMEM tile serialise on the MMA latency and
 //       accumulate with truncation; the sets are summed with RN fp32 adds in the epilogue).
 // MERGE: the A_lo x B_hi product accumulates into the columns of A_hi x B_lo (64 instead of 96 columns per set).
-template <int NSET, bool MERGE>
-__global__ void __launch_bounds__(H_THREADS, 2)
+// H_STAGES: weight ring depth in tap pairs.  MINB: CTAs per SM the register allocation must allow.
+template <int NSET, bool MERGE, int H_STAGES, int MINB>
+__global__ void __launch_bounds__(H_THREADS, MINB)
 k_conv5x5_c32_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_out, const HArgs a) {
     constexpr int SETW = MERGE ? 64 : 96;                   // TMEM columns per accumulator set
     constexpr int NBLK = NSET * SETW / 32;                  // 32-column blocks the epilogue sums
     constexpr uint32_t TMEM_COLS = NSET * SETW <= 64 ? 64u : (NSET * SETW <= 128 ? 128u : 256u);
+    constexpr int H_OFF_BAR = H_OFF_B + H_STAGES * H_STAGE_BYTES;
     extern __shared__ uint8_t h_smem_raw[];
     const uint32_t raw = smem_u32(h_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -347,6 +348,7 @@ k_conv5x5_c32_h(const __grid_constant__ CUtensorMap map_in, const __grid_constan
         }
         // Output tile -> shared memory (the operand tile is free once the accumulators are complete) in the 128B-swizzled
         // layout of the output tensor map, then ONE bulk tensor store per CTA (clipped at the image border by the TMA unit).
+        uint32_t omax = 0u;
         {
             uint8_t* stage = gbase + r * 128;
 #pragma unroll
@@ -361,6 +363,7 @@ k_conv5x5_c32_h(const __grid_constant__ CUtensorMap map_in, const __grid_constan
                     f.z = (pos >> (4 * c + 2)) & 1u ? f.z : a.slope * f.z; f.w = (pos >> (4 * c + 3)) & 1u ? f.w : a.slope * f.w;
                 }
                 *reinterpret_cast<float4*>(stage + ((c ^ (r & 7)) << 4)) = f;
+                omax = max(omax, max(max(absbits(f.x), absbits(f.y)), max(absbits(f.z), absbits(f.w))));
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> bulk store reads
@@ -368,8 +371,12 @@ k_conv5x5_c32_h(const __grid_constant__ CUtensorMap map_in, const __grid_constan
         if (t == 0) {
             tma_store_4d(&map_out, s_a, 0, x0, y0, b);
             tma_store_commit();
-            tma_store_wait_read();       // shared memory must stay valid until the bulk store has read it
         }
+        if (a.amax_out) {                // rows outside the image hold garbage the bulk store clips: they do not count
+            omax = __reduce_max_sync(0xffffffffu, inside ? omax : 0u);
+            if (lane == 0 && omax) atomicMax(a.amax_out, omax);
+        }
+        if (t == 0) tma_store_wait_read();       // shared memory must stay valid until the bulk store has read it
     }
 
     if (threadIdx.x == 64 && a.trace) {              // the thread that issued the bulk store: end of this CTA's useful work
@@ -414,7 +421,7 @@ __global__ void __launch_bounds__(256) k_prep_h_weights(const float* __restrict_
     if (pair == 0 && threadIdx.x == 0) *inv_scale = invT;
 }
 
-int g_conv_variant = 0;     // accumulator layout of k_conv5x5_c32_h: 0 = two sets of 96 columns, 1 = one set, 2 = two merged sets of 64
+int g_conv_variant = 0;     // accumulator layout of k_conv5x5_c32_h: 0 = two merged sets of 64 columns (default), 1 = two sets of 96, 2 = one set of 96
 
 size_t h_weights_floats() { return (size_t)H_WPAIR_FLOATS + 64; }      // 13 pairs + the scale slot, 256-byte multiple
 
@@ -428,7 +435,7 @@ static long long* g_h_trace = nullptr;
 static int g_h_trace_cap = 0, g_h_trace_seq = 0;     // capacity in launches, launches traced so far
 
 int launch_conv5x5_h(cudaStream_t st, int B, int Y, int X, const float* in, const float* wsplit, const float* bias,
-                     const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready) {
+                     const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready, unsigned int* amax_out) {
     tc::EncodeTiledFn enc = tc::get_encode_tiled();
     if (!enc) return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     if (((uintptr_t)in & 15) || ((uintptr_t)wsplit & 15) || ((uintptr_t)out & 15)) return fail(SOL_ERR_INVALID, "conv h: operands must be 16-byte aligned");
@@ -465,22 +472,24 @@ int launch_conv5x5_h(cudaStream_t st, int B, int Y, int X, const float* in, cons
         ++g_h_trace_seq;
     }
     a.weights_ready = weights_ready ? 1 : 0;
+    a.amax_out = amax_out;
     a.w_inv_scale = wsplit + H_WPAIR_FLOATS;
     a.bias = bias; a.addend = addend; a.ref = ref; a.B = B; a.Y = Y; a.X = X; a.act = act; a.slope = slope;
-    static bool attr_done = false;
-    if (!attr_done) {
-        SOL_CUDA(cudaFuncSetAttribute(k_conv5x5_c32_h<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
-        SOL_CUDA(cudaFuncSetAttribute(k_conv5x5_c32_h<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
-        SOL_CUDA(cudaFuncSetAttribute(k_conv5x5_c32_h<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
-        attr_done = true;
-    }
     dim3 grid(cdiv(X, H_TX), cdiv(Y, H_TY), B);
-    if (g_conv_variant == 1)
-        SOL_CUDA(launch_kernel(k_conv5x5_c32_h<1, false>, grid, dim3(H_THREADS), H_SMEM, st, map_in, map_w, map_out, a));
-    else if (g_conv_variant == 2)
-        SOL_CUDA(launch_kernel(k_conv5x5_c32_h<2, true>, grid, dim3(H_THREADS), H_SMEM, st, map_in, map_w, map_out, a));
-    else
-        SOL_CUDA(launch_kernel(k_conv5x5_c32_h<2, false>, grid, dim3(H_THREADS), H_SMEM, st, map_in, map_w, map_out, a));
+    auto go = [&](auto kern, int stages) -> cudaError_t {
+        const int smem = h_smem_bytes(stages);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);      // cheap; also safe per device
+        if (e != cudaSuccess) return e;
+        return launch_kernel(kern, grid, dim3(H_THREADS), (size_t)smem, st, map_in, map_w, map_out, a);
+    };
+    // measured on B200 at the bench shape (profiles/r02/r02_c_conv_variants.txt): the three accumulator layouts are within 1 %
+    // (9.7-9.8 us per layer); deeper rings do not help; 3-4 CTAs per SM are SLOWER (12-14 us: programmatic dependent launch
+    // packs the early CTAs of the next layer three deep on the same SMs, which then share one shared-memory port)
+    switch (g_conv_variant) {
+        case 1: SOL_CUDA(go(k_conv5x5_c32_h<2, false, 5, 2>, 5)); break;
+        case 2: SOL_CUDA(go(k_conv5x5_c32_h<1, false, 5, 2>, 5)); break;
+        default: SOL_CUDA(go(k_conv5x5_c32_h<2, true, 5, 2>, 5)); break;
+    }
     SOL_LAUNCHED();
     return SOL_OK;
 }

@@ -360,7 +360,7 @@ static long long* g_tc_trace = nullptr;
 static int g_tc_trace_cap = 0, g_tc_trace_seq = 0;     // capacity in launches, launches traced so far
 int g_tc_base_offset_mode = 0;   // measured on B200: the swizzle phase comes from the absolute address bits; base_offset stays 0
 int g_conv_path = 2;    // default: tcgen05 3xFP16 convolutions (1 = fp32 SIMT validation kernels, 3 = tcgen05 3xTF32)
-int g_wgrad_path = 2;   // default: deferred tcgen05 weight-gradient GEMM (1 = per-step fp32 SIMT)
+int g_wgrad_path = 2;   // default: deferred tcgen05 3xFP16 weight-gradient GEMM (1 = per-step fp32 SIMT, 3 = deferred tcgen05 3xTF32)
 
 int tc_tiles_per_launch(int B, int Y, int X) { return cdiv(X, TC_TX) * cdiv(Y, TC_TY) * B; }
 
@@ -430,15 +430,23 @@ int launch_split_weights(cudaStream_t st, const float* w, float* wsplit) {
 }
 
 int launch_conv5x5_c32_presplit(cudaStream_t st, int B, int Y, int X, const float* in, const float* wsplit, const float* bias,
-                                const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready) {
+                                const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready,
+                                unsigned int* amax_out) {
     if (act == SOL_ACT_DLRELU && !ref) return fail(SOL_ERR_INVALID, "conv5x5: SOL_ACT_DLRELU needs ref");
-    if (g_conv_path == 3) return launch_conv5x5_tc(st, B, Y, X, in, wsplit, bias, addend, ref, act, slope, out, weights_ready);
-    return launch_conv5x5_h(st, B, Y, X, in, wsplit, bias, addend, ref, act, slope, out, weights_ready);
+    if (g_conv_path == 3) {
+        if (amax_out) return fail(SOL_ERR_UNSUPPORTED, "conv5x5: the 3xTF32 kernel does not track max|out|");
+        return launch_conv5x5_tc(st, B, Y, X, in, wsplit, bias, addend, ref, act, slope, out, weights_ready);
+    }
+    return launch_conv5x5_h(st, B, Y, X, in, wsplit, bias, addend, ref, act, slope, out, weights_ready, amax_out);
 }
 
 int launch_conv5x5_c32_auto(cudaStream_t st, int B, int Y, int X, const float* in, const float* w, const float* wprep,
-                            const float* bias, const float* addend, const float* ref, int act, float slope, float* out) {
-    if (!conv_path_is_tc()) return launch_conv5x5(st, B, Y, X, 32, 32, in, w, bias, addend, ref, act, slope, out);
+                            const float* bias, const float* addend, const float* ref, int act, float slope, float* out,
+                            unsigned int* amax_out) {
+    if (!conv_path_is_tc()) {
+        if (amax_out) return fail(SOL_ERR_UNSUPPORTED, "conv5x5: the SIMT 32->32 kernel does not track max|out|");
+        return launch_conv5x5(st, B, Y, X, 32, 32, in, w, bias, addend, ref, act, slope, out);
+    }
     const bool engine_weights = wprep != nullptr;   // the unrolled sweep splits all weights before its first step
     if (!wprep) {
         // stand-alone call: split the weights into a process-wide scratch buffer (stream-ordered reuse)
@@ -447,7 +455,7 @@ int launch_conv5x5_c32_auto(cudaStream_t st, int B, int Y, int X, const float* i
         SOL_TRY(launch_split_weights(st, w, scratch));
         wprep = scratch;
     }
-    return launch_conv5x5_c32_presplit(st, B, Y, X, in, wprep, bias, addend, ref, act, slope, out, engine_weights);
+    return launch_conv5x5_c32_presplit(st, B, Y, X, in, wprep, bias, addend, ref, act, slope, out, engine_weights, amax_out);
 }
 
 }  // namespace sol

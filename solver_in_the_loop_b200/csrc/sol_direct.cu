@@ -34,6 +34,7 @@ struct DirectArgs {
     const float* rhs;                           // MODE 0
     const float* vy_in; const float* vx_in;     // MODE 1
     float* p0;                                  // [B][N] scratch
+    float* zbuf;                                // [B][N] scratch of the streamed kernel (large grids)
     float* p_out; float* vy_out; float* vx_out; int* iters;
     // fused feature I/O (see CgFuse)
     float* feat_out; const float* re; float isy, isx, isr; const float* gfeat_in; int cfeat;
@@ -194,6 +195,113 @@ __global__ void __launch_bounds__((Y / CL / TM) * (X / 4), 1) k_direct_solve(con
     if (a.iters && tid == 0 && rank == 0) a.iters[b] = 0;      // no iterations: a direct solve
 }
 
+// Larger grids (256x128): the two operands every CTA needs COMPLETELY — D for U = Sy D and Z for p0 = Sy Z, 128 KB each — do not fit
+// next to the transform matrices.  Same four products and the same row split over the cluster, but D and Z live in global
+// memory (L2-resident scratch: every CTA writes its rows, cluster barrier) and are streamed through a double-buffered
+// shared-memory chunk of KC rows (next chunk in registers while the current one feeds the FMAs: one barrier per chunk).
+template <int Y, int X, int CL, int TM, int KC, int MODE>
+__global__ void __launch_bounds__((Y / CL / TM) * (X / 4), 1) k_direct_solve_big(const DirectArgs a) {
+    namespace cg = cooperative_groups;
+    constexpr int YS = Y / CL;
+    constexpr int NT = (YS / TM) * (X / 4);
+    constexpr int N = Y * X;
+    constexpr int CH4 = KC * X / 4 / NT;            // float4 per thread and chunk
+    static_assert(KC * X / 4 % NT == 0 && Y % KC == 0, "chunk geometry");
+    extern __shared__ __align__(16) float dsm[];
+    float* sSy = dsm;                  // [Y][YS]: sSy[kk][lr] = Sy[kk][rbase + lr]  (Sy is symmetric)
+    float* sSx = sSy + Y * YS;         // [X][X]
+    float* t0 = sSx + X * X;           // [X][YS] transposed slices
+    float* t1 = t0 + X * YS;           // [X][YS]
+    float* ch = t1 + X * YS;           // [2][KC][X] streamed operand rows
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int rbase = rank * YS;
+    for (int k = tid * 4; k < Y * YS; k += NT * 4) {
+        const int kk = k / YS, lr = k - kk * YS;
+        *reinterpret_cast<float4*>(sSy + k) = __ldg(reinterpret_cast<const float4*>(a.Sy + kk * Y + rbase + lr));
+    }
+    for (int k = tid * 4; k < X * X; k += NT * 4) *reinterpret_cast<float4*>(sSx + k) = __ldg(reinterpret_cast<const float4*>(a.Sx + k));
+    pdl_sync();
+    float* Dg = a.p0 + (size_t)b * N;       // the obstacle-free solution's buffer doubles as the scratch of D (dead before p0 is written)
+    float* Zg = a.zbuf + (size_t)b * N;
+    // ---- right-hand side: my YS rows -> global scratch ----
+    {
+        FaceIn in{a.vy_in + (size_t)b * (Y + 1) * X, a.vx_in + (size_t)b * Y * (X + 1),
+                  a.gfeat_in ? a.gfeat_in + (size_t)b * N * a.cfeat : nullptr, a.isy, a.isx, a.cfeat, Y, X};
+        const float* rhs = (MODE == 0) ? a.rhs + (size_t)b * N : nullptr;
+#pragma unroll 4
+        for (int lc = tid; lc < YS * X; lc += NT) {
+            const int c = rbase * X + lc;
+            const int j = c / X, i = c - j * X;
+            float d;
+            if (MODE == 1)
+                d = (a.my[(j + 1) * X + i] * in.y(j + 1, i) - a.my[j * X + i] * in.y(j, i)) +
+                    (a.mx[j * (X + 1) + i + 1] * in.x(j, i + 1) - a.mx[j * (X + 1) + i] * in.x(j, i));
+            else
+                d = rhs[c];
+            Dg[c] = a.active[c] ? d : 0.0f;
+        }
+    }
+    cluster.sync();       // release / acquire at cluster scope: the peers' rows of D are visible
+    const int tx = tid % (X / 4), ty = tid / (X / 4);
+    const int r0 = ty * TM, c0 = tx * 4;
+    float acc[TM][4];
+    // acc (+)= Sy[my rows, :] * G for a [Y][X] operand G streamed from global memory
+    auto stream_gemm = [&](const float* __restrict__ G) {
+        float4 nx[CH4];
+#pragma unroll
+        for (int e = 0; e < CH4; ++e) nx[e] = __ldcg(reinterpret_cast<const float4*>(G) + tid + e * NT);
+#pragma unroll
+        for (int e = 0; e < CH4; ++e) reinterpret_cast<float4*>(ch)[tid + e * NT] = nx[e];
+        __syncthreads();
+#pragma unroll 1
+        for (int c = 0; c < Y / KC; ++c) {
+            if (c + 1 < Y / KC) {
+#pragma unroll
+                for (int e = 0; e < CH4; ++e) nx[e] = __ldcg(reinterpret_cast<const float4*>(G + (size_t)(c + 1) * KC * X) + tid + e * NT);
+            }
+            tile_gemm<TM, KC>(sSy + c * KC * YS, YS, ch + (c & 1) * KC * X, X, r0, c0, acc);
+            if (c + 1 < Y / KC) {
+#pragma unroll
+                for (int e = 0; e < CH4; ++e) reinterpret_cast<float4*>(ch + ((c + 1) & 1) * KC * X)[tid + e * NT] = nx[e];
+            }
+            __syncthreads();
+        }
+    };
+    // stage 1: U = Sy D (my rows), transposed into t0
+    zero_acc<TM>(acc);
+    stream_gemm(Dg);
+    store_transposed<TM>(t0, YS, r0, c0, acc);
+    __syncthreads();
+    // stage 2: V = (U Sx) * ilam, transposed into t1
+    zero_acc<TM>(acc);
+    tile_gemm<TM, X>(t0, YS, sSx, X, r0, c0, acc);
+#pragma unroll
+    for (int rr = 0; rr < TM; ++rr) {
+        const float4 l = __ldg(reinterpret_cast<const float4*>(a.ilam + (rbase + r0 + rr) * X + c0));
+        acc[rr][0] *= l.x; acc[rr][1] *= l.y; acc[rr][2] *= l.z; acc[rr][3] *= l.w;
+    }
+    store_transposed<TM>(t1, YS, r0, c0, acc);
+    __syncthreads();
+    // stage 3: Z = V Sx; my rows -> global scratch
+    zero_acc<TM>(acc);
+    tile_gemm<TM, X>(t1, YS, sSx, X, r0, c0, acc);
+#pragma unroll
+    for (int rr = 0; rr < TM; ++rr)
+        *reinterpret_cast<float4*>(Zg + (rbase + r0 + rr) * X + c0) = make_float4(acc[rr][0], acc[rr][1], acc[rr][2], acc[rr][3]);
+    cluster.sync();       // every CTA is done reading D (p0 may be overwritten) and all of Z is visible
+    // stage 4: p0 = Sy Z (my rows) -> global memory
+    zero_acc<TM>(acc);
+    stream_gemm(Zg);
+    float* p0g = a.p0 + (size_t)b * N;
+#pragma unroll
+    for (int rr = 0; rr < TM; ++rr)
+        *reinterpret_cast<float4*>(p0g + (rbase + r0 + rr) * X + c0) = make_float4(acc[rr][0], acc[rr][1], acc[rr][2], acc[rr][3]);
+    if (a.iters && tid == 0 && rank == 0) a.iters[b] = 0;      // no iterations: a direct solve
+}
+
 // p = p0 - (W M) s on a tile of R rows (+ the row below it), then the gradient subtraction / optional outputs.  The correction sum
 // over the changed rows is split over QG thread groups (same cells, disjoint q ranges) and reduced through shared memory.
 template <int X, int R, int MODE>
@@ -285,13 +393,13 @@ int up(T** dst, const std::vector<T>& src) {
 }  // namespace
 
 bool direct_supported(const sol_plan* p) {
-    return p->boundary == SOL_BOUNDARY_OPEN && ((p->Y == 128 && p->X == 64) || (p->Y == 64 && p->X == 32));
+    return p->boundary == SOL_BOUNDARY_OPEN && ((p->Y == 128 && p->X == 64) || (p->Y == 64 && p->X == 32) || (p->Y == 256 && p->X == 128));
 }
 
 void direct_free(sol_plan* p) {
     sol_direct& d = p->dir;
     cudaFree(d.Sy); cudaFree(d.Sx); cudaFree(d.ilam); cudaFree(d.rt_col); cudaFree(d.rt_val); cudaFree(d.Wt);
-    cudaFree(d.p0);
+    cudaFree(d.p0); cudaFree(d.zbuf);
     d = sol_direct();
 }
 
@@ -307,6 +415,7 @@ int direct_build(sol_plan* p) {
     SOL_TRY(up(&d.Sy, h.Sy)); SOL_TRY(up(&d.Sx, h.Sx)); SOL_TRY(up(&d.ilam, h.ilam));
     SOL_TRY(up(&d.rt_col, h.rt_col)); SOL_TRY(up(&d.rt_val, h.rt_val)); SOL_TRY(up(&d.Wt, h.Wt));
     SOL_CUDA(cudaMalloc((void**)&d.p0, (size_t)p->B_max * N * sizeof(float)));
+    if (p->Y * p->X > 128 * 64) SOL_CUDA(cudaMalloc((void**)&d.zbuf, (size_t)p->B_max * N * sizeof(float)));
     d.k = h.k; d.kp = h.kp;
     d.valid = true;
     return SOL_OK;
@@ -354,6 +463,41 @@ static int launch_direct_t(const DirectArgs& a, cudaStream_t st, int mode) {
     return SOL_OK;
 }
 
+template <int Y, int X, int CL, int TM, int KC, int R>
+static int launch_direct_big_t(const DirectArgs& a, cudaStream_t st, int mode) {
+    constexpr int YS = Y / CL;
+    constexpr int NT = (YS / TM) * (X / 4);
+    const size_t smem = (size_t)(Y * YS + X * X + 2 * X * YS + 2 * KC * X) * sizeof(float);
+    auto k0 = k_direct_solve_big<Y, X, CL, TM, KC, 0>;
+    auto k1 = k_direct_solve_big<Y, X, CL, TM, KC, 1>;
+    SOL_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SOL_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(CL, a.B); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        int na = 0;
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = CL; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+        if (g_pdl) {
+            attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
+        }
+        cfg.attrs = attr; cfg.numAttrs = na;
+        if (mode == 0) SOL_CUDA(cudaLaunchKernelEx(&cfg, k0, a));
+        else SOL_CUDA(cudaLaunchKernelEx(&cfg, k1, a));
+        SOL_LAUNCHED();
+    }
+    const dim3 grid(cdiv(Y, R), a.B), block(4 * (R + 1) * X);
+    const size_t smem2 = (size_t)a.kp * sizeof(float);
+    if (mode == 0) SOL_CUDA(launch_kernel(k_direct_apply<X, R, 0>, grid, block, smem2, st, a, Y));
+    else SOL_CUDA(launch_kernel(k_direct_apply<X, R, 1>, grid, block, smem2, st, a, Y));
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
 int launch_direct(const sol_plan* p, cudaStream_t st, int B, int mode, const float* rhs, float* p_out, const float* vy, const float* vx,
                   float* vy_out, float* vx_out, int* iters, const CgFuse* fuse) {
     const sol_direct& d = p->dir;
@@ -362,7 +506,7 @@ int launch_direct(const sol_plan* p, cudaStream_t st, int B, int mode, const flo
     memset(&a, 0, sizeof(a));
     a.B = B; a.Sy = d.Sy; a.Sx = d.Sx; a.ilam = d.ilam; a.rt_col = d.rt_col; a.rt_val = d.rt_val; a.Wt = d.Wt; a.k = d.k; a.kp = d.kp;
     a.my = p->face_my; a.mx = p->face_mx; a.active = p->active; a.diag = p->diag;
-    a.rhs = rhs; a.vy_in = vy; a.vx_in = vx; a.p0 = d.p0; a.p_out = p_out; a.vy_out = vy_out; a.vx_out = vx_out; a.iters = iters;
+    a.rhs = rhs; a.vy_in = vy; a.vx_in = vx; a.p0 = d.p0; a.zbuf = d.zbuf; a.p_out = p_out; a.vy_out = vy_out; a.vx_out = vx_out; a.iters = iters;
     a.cfeat = 3;
     if (fuse && (fuse->feat_out || fuse->gfeat_in)) {
         if (mode != 1) return fail(SOL_ERR_UNSUPPORTED, "direct solve: fused feature I/O needs the projection mode");
@@ -374,6 +518,7 @@ int launch_direct(const sol_plan* p, cudaStream_t st, int B, int mode, const flo
     if (mode == 1 && (!vy || !vx || !vy_out || !vx_out)) return fail(SOL_ERR_INVALID, "direct solve: velocity pointers required");
     if (p->Y == 128 && p->X == 64) return launch_direct_t<128, 64, 4, 2, 3>(a, st, mode);
     if (p->Y == 64 && p->X == 32) return launch_direct_t<64, 32, 2, 2, 7>(a, st, mode);
+    if (p->Y == 256 && p->X == 128) return launch_direct_big_t<256, 128, 8, 2, 32, 1>(a, st, mode);
     return fail(SOL_ERR_UNSUPPORTED, "direct solve: unsupported grid");
 }
 

@@ -245,6 +245,14 @@ extern "C" int sol_plan_set_option(sol_plan* p, const char* name, int value) {
     return fail(SOL_ERR_INVALID, "sol_plan_set_option: unknown option");
 }
 
+extern "C" int sol_plan_query(sol_plan* p, const char* name, int* value) {
+    SOL_CHECK(p != nullptr && name != nullptr && value != nullptr, "sol_plan_query: NULL pointer");
+    if (strcmp(name, "direct_active") == 0) { *value = direct_for_batch(p, 1) ? 1 : 0; return SOL_OK; }
+    if (strcmp(name, "direct_rows") == 0) { *value = direct_active(p) ? p->dir.kp : 0; return SOL_OK; }
+    if (strcmp(name, "sm_count") == 0) { *value = p->sm_count; return SOL_OK; }
+    return fail(SOL_ERR_INVALID, "sol_plan_query: unknown name");
+}
+
 extern "C" int sol_set_option(const char* name, int value) {
     SOL_CHECK(name != nullptr, "sol_set_option: NULL name");
     if (strcmp(name, "conv_path") == 0) {
@@ -253,7 +261,7 @@ extern "C" int sol_set_option(const char* name, int value) {
         return SOL_OK;
     }
     if (strcmp(name, "wgrad_path") == 0) {
-        SOL_CHECK(value >= 0 && value <= 2, "wgrad_path must be 0,1,2");
+        SOL_CHECK(value >= 0 && value <= 3, "wgrad_path must be 0,1,2,3");
         sol::g_wgrad_path = value == 0 ? 2 : value;
         return SOL_OK;
     }
@@ -430,7 +438,7 @@ extern "C" size_t sol_conv5x5_wgrad_workspace(int Cin, int Cout) { return wgrad_
 extern "C" int sol_conv5x5_wgrad(void* stream, int B, int Y, int X, int Cin, int Cout, const float* in, const float* g_out, float* dW,
                                  float* db, int accumulate, float* partials) {
     SOL_CHECK(in && g_out && dW && db, "sol_conv5x5_wgrad: NULL pointer");
-    if (Cin == 32 && Cout == 32 && sol::g_wgrad_path == 2 && Y % 16 == 0 && X % 8 == 0) {
+    if (Cin == 32 && Cout == 32 && sol::g_wgrad_path >= 2 && Y % 16 == 0 && X % 8 == 0) {
         // tensor-core GEMM over the pixels of this one batch (the engine defers it over all unrolled steps)
         SOL_CHECK(partials != nullptr, "sol_conv5x5_wgrad: partials workspace required");
         cudaStream_t st = (cudaStream_t)stream;
@@ -438,7 +446,17 @@ extern "C" int sol_conv5x5_wgrad(void* stream, int B, int Y, int X, int Cin, int
         SOL_CUDA(cudaGetDevice(&dev));
         SOL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const size_t stride = (size_t)B * Y * X * 32;
-        SOL_TRY(launch_wgrad_c32_tc(st, sms, 1, B, Y, X, in, stride, g_out, stride, partials, &nctas));
+        if (sol::g_wgrad_path == 3) {
+            SOL_TRY(launch_wgrad_c32_tc(st, sms, 1, B, Y, X, in, stride, g_out, stride, partials, &nctas));
+        } else {
+            // stand-alone call: nobody tracked the operand maxima, measure them (stream-ordered scratch slots)
+            static unsigned int* slots = nullptr;
+            if (!slots) SOL_CUDA(cudaMalloc((void**)&slots, 2 * sizeof(unsigned int)));
+            SOL_CUDA(cudaMemsetAsync(slots, 0, 2 * sizeof(unsigned int), st));
+            SOL_TRY(launch_amax(st, in, stride, slots));
+            SOL_TRY(launch_amax(st, g_out, stride, slots + 1));
+            SOL_TRY(launch_wgrad_c32_h(st, sms, 1, B, Y, X, in, stride, g_out, stride, slots, slots + 1, partials, &nctas));
+        }
         return launch_wgrad_finalize_n(st, nctas, partials, dW, db, accumulate);
     }
     return launch_wgrad((cudaStream_t)stream, B, Y, X, Cin, Cout, in, g_out, dW, db, accumulate, partials, true);
@@ -485,7 +503,9 @@ struct sol_unroll {
     float *wprep_fwd, *wprep_bwd;   // [10 layers][2*25*32*32] pre-split tensor-core weights
     float* gst;        // deferred weight gradient: [10 layers][msteps][B,Y,X,32] output-gradient stash
     float* g0_st;      // [msteps][B,Y,X,32] output gradient of layer 0
-    bool deferred_wgrad = false;   // decided per backward sweep: option wgrad_path == 2 and the grid tiles evenly (Y%16, X%8)
+    bool deferred_wgrad = false;   // decided per backward sweep: option wgrad_path >= 2 and the grid tiles evenly (Y%16, X%8)
+    unsigned int* amax = nullptr;  // [24] running max|x| (bit patterns): [l] input activations of layer l, [12 + l] its output gradients (l = 1..10)
+    bool track_amax = false;       // the 3xFP16 conv kernels of this sweep keep them up to date (else the weight-gradient launches measure them)
     float* gcorr_st;   // [msteps][B,Y,X,2]  output gradient of layer 11
     size_t nA = 0;
     float* partials;   // [n_c32][WG_MAX_CTAS][25632]
@@ -571,6 +591,7 @@ int carve(sol_unroll* u, void* ws, size_t* total) {
         u->partial_stride = wgrad_workspace_floats(32, 32);
         u->partials = cv.take<float>(u->partial_stride * 10);
     }
+    u->amax = cv.take<unsigned int>(24);
     u->iters = cv.take<int>((size_t)2 * c.msteps * c.B);
     u->re_buf = cv.take<float>(c.B);
     *total = align_up(cv.off, 256);
@@ -591,9 +612,9 @@ int check_cfg(const sol_plan* p, const sol_unroll_cfg* c) {
 
 // A 32->32 layer of the sweep (tensor-core path with the weights split at the start of the sweep, else SIMT)
 int layer_conv(sol_unroll* u, cudaStream_t st, const float* in, const float* w, const float* wprep, const float* bias, const float* addend,
-               const float* ref, int act, float slope, float* out) {
+               const float* ref, int act, float slope, float* out, unsigned int* amax_out = nullptr) {
     const sol_plan* p = u->plan;
-    return launch_conv5x5_c32_auto(st, u->cfg.B, p->Y, p->X, in, w, wprep, bias, addend, ref, act, slope, out);
+    return launch_conv5x5_c32_auto(st, u->cfg.B, p->Y, p->X, in, w, wprep, bias, addend, ref, act, slope, out, amax_out);
 }
 
 // ---- CNN forward / backward over the stash of one step (model_mars_moon, karman_train.py:101-138)
@@ -608,7 +629,9 @@ int cnn_forward(sol_unroll* u, cudaStream_t st, const float* w, const StepStash&
         return launch_conv5x5(st, B, Y, X, 64, 2, s.acts[1], w + L[2].w_off, w + L[2].b_off, nullptr, nullptr, SOL_ACT_NONE, 0.0f, corr);
     }
     const bool tc = conv_path_is_tc();
-    SOL_TRY(launch_conv5x5(st, B, Y, X, L[0].cin, 32, s.feat, w + L[0].w_off, w + L[0].b_off, nullptr, nullptr, SOL_ACT_LRELU, a, s.acts[0]));
+    unsigned int* am = u->track_amax ? u->amax : nullptr;       // am[l]: max|input of layer l| over the sweep
+    SOL_TRY(launch_conv5x5(st, B, Y, X, L[0].cin, 32, s.feat, w + L[0].w_off, w + L[0].b_off, nullptr, nullptr, SOL_ACT_LRELU, a, s.acts[0],
+                           am ? am + 1 : nullptr));
     for (int k = 1; k <= 5; ++k) {
         const LayerDesc& l1 = L[2 * k - 1];
         const LayerDesc& l2 = L[2 * k];
@@ -617,8 +640,9 @@ int cnn_forward(sol_unroll* u, cudaStream_t st, const float* w, const StepStash&
         float* a_k = s.acts[2 * k];
         const float* p1 = tc ? u->wprep_fwd + tc_weights_floats() * (2 * k - 2) : nullptr;
         const float* p2 = tc ? u->wprep_fwd + tc_weights_floats() * (2 * k - 1) : nullptr;
-        SOL_TRY(layer_conv(u, st, a_prev, w + l1.w_off, p1, w + l1.b_off, nullptr, nullptr, SOL_ACT_LRELU, a, t_k));
-        SOL_TRY(layer_conv(u, st, t_k, w + l2.w_off, p2, w + l2.b_off, a_prev, nullptr, SOL_ACT_LRELU, a, a_k));
+        SOL_TRY(layer_conv(u, st, a_prev, w + l1.w_off, p1, w + l1.b_off, nullptr, nullptr, SOL_ACT_LRELU, a, t_k, am ? am + 2 * k : nullptr));
+        SOL_TRY(layer_conv(u, st, t_k, w + l2.w_off, p2, w + l2.b_off, a_prev, nullptr, SOL_ACT_LRELU, a, a_k,
+                           (am && k < 5) ? am + 2 * k + 1 : nullptr));
     }
     return launch_conv5x5(st, B, Y, X, 32, 2, s.acts[10], w + L[11].w_off, w + L[11].b_off, nullptr, nullptr, SOL_ACT_NONE, a, corr);
 }
@@ -651,7 +675,8 @@ int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, cons
     // output layer (32 -> 2)
     if (!deferred)
         SOL_TRY(launch_wgrad(st, B, Y, X, 32, 2, s.acts[10], g_corr, gw + L[11].w_off, gw + L[11].b_off, 1, nullptr, false));
-    SOL_TRY(launch_conv5x5(st, B, Y, X, 2, 32, g_corr, wT + L[11].w_off, nullptr, nullptr, s.acts[10], SOL_ACT_DLRELU, a, gS));
+    unsigned int* gm = (u->track_amax && deferred) ? u->amax + 12 : nullptr;       // gm[l]: max|output gradient of layer l| over the sweep
+    SOL_TRY(launch_conv5x5(st, B, Y, X, 2, 32, g_corr, wT + L[11].w_off, nullptr, nullptr, s.acts[10], SOL_ACT_DLRELU, a, gS, gm ? gm + 10 : nullptr));
     for (int k = 5; k >= 1; --k) {
         const LayerDesc& l1 = L[2 * k - 1];
         const LayerDesc& l2 = L[2 * k];
@@ -668,11 +693,11 @@ int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, cons
                 }
         const float* p2 = tc ? u->wprep_bwd + tc_weights_floats() * (2 * k - 1) : nullptr;
         const float* p1 = tc ? u->wprep_bwd + tc_weights_floats() * (2 * k - 2) : nullptr;
-        SOL_TRY(layer_conv(u, st, gS, wT + l2.w_off, p2, nullptr, nullptr, t_k, SOL_ACT_DLRELU, a, gT));
+        SOL_TRY(layer_conv(u, st, gS, wT + l2.w_off, p2, nullptr, nullptr, t_k, SOL_ACT_DLRELU, a, gT, gm ? gm + 2 * k - 1 : nullptr));
         if (!deferred) {
             SOL_TRY(launch_wgrad(st, B, Y, X, 32, 32, a_prev, gT, nullptr, nullptr, !first, u->partials + u->partial_stride * (2 * k - 2), false));
                 }
-        SOL_TRY(layer_conv(u, st, gT, wT + l1.w_off, p1, nullptr, gS, a_prev, SOL_ACT_DLRELU, a, gN));
+        SOL_TRY(layer_conv(u, st, gT, wT + l1.w_off, p1, nullptr, gS, a_prev, SOL_ACT_DLRELU, a, gN, (gm && k >= 2) ? gm + 2 * k - 2 : nullptr));
         gS = gN;
     }
     // input layer (cin0 -> 32): gS is the gradient w.r.t. its pre-activation
@@ -706,8 +731,11 @@ int do_forward(sol_unroll* u, cudaStream_t st, const float* weights, const float
         for (int l = 1; l <= 10; ++l)
             SOL_TRY(launch_split_weights(st, weights + u->L[l].w_off, u->wprep_fwd + tc_weights_floats() * (l - 1)));
     }
+    // operand maxima for the 3xFP16 weight-gradient GEMM: tracked by the 3xFP16 conv kernels as they produce the tensors
+    u->track_amax = mars && sol::g_conv_path == 2 && sol::g_wgrad_path == 2 && (p->Y % 16 == 0) && (p->X % 8 == 0);
+    SOL_CUDA(cudaMemsetAsync(u->amax, 0, 24 * sizeof(unsigned int), st));
     const float* cvy = vy0; const float* cvx = vx0; const float* crho = dens ? rho0 : nullptr;
-    const bool fuse_io = sol::g_fuse_solver_io && cg_fuses(p);
+    const bool fuse_io = sol::g_fuse_solver_io && cg_fuses(p, B);
     for (int i = 0; i < m; ++i) {
         StepStash& s = u->stash[ring ? 0 : i];
         int* it_slot = u->iters + (size_t)(ring ? 0 : i) * B;
@@ -758,7 +786,7 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
     const int B = c.B, m = c.msteps;
     SOL_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * u->nparams, st));
     const bool mars = c.model == SOL_MODEL_MARS_MOON;
-    u->deferred_wgrad = mars && (sol::g_wgrad_path == 2) && (p->Y % 16 == 0) && (p->X % 8 == 0);
+    u->deferred_wgrad = mars && (sol::g_wgrad_path >= 2) && (p->Y % 16 == 0) && (p->X % 8 == 0);
     for (size_t l = 0; l < u->L.size(); ++l)
         SOL_TRY(launch_flip_weights(st, u->L[l].cin, u->L[l].cout, weights + u->L[l].w_off, u->wT + u->L[l].w_off));
     if (conv_path_is_tc() && mars) {
@@ -792,9 +820,21 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
             return launch_wgrad_thin_multi(s, it.nsteps, B, p->Y, p->X, u->L[0].cin, 32, u->stash[it.step0].feat, in_stride,
                                            u->g0_st + (size_t)it.step0 * u->nA, u->nA, gw + u->L[0].w_off, gw + u->L[0].b_off, 2 * sm_budget);
         int nctas = 0;
-        SOL_TRY(launch_wgrad_c32_tc(s, nct32, it.nsteps, B, p->Y, p->X, u->stash[it.step0].acts[l - 1], in_stride,
-                                    u->gst + ((size_t)(l - 1) * m + it.step0) * u->nA, u->nA, u->partials + u->partial_stride * (l - 1), &nctas,
-                                    started[l] ? 1 : 0));
+        const float* act_in = u->stash[it.step0].acts[l - 1];
+        const float* g_out = u->gst + ((size_t)(l - 1) * m + it.step0) * u->nA;
+        if (sol::g_wgrad_path == 3) {
+            SOL_TRY(launch_wgrad_c32_tc(s, nct32, it.nsteps, B, p->Y, p->X, act_in, in_stride, g_out, u->nA, u->partials + u->partial_stride * (l - 1),
+                                        &nctas, started[l] ? 1 : 0));
+        } else {
+            if (!u->track_amax) {       // the tensors were produced by kernels that do not track their maxima: measure them now
+                for (int k = 0; k < it.nsteps; ++k) {
+                    SOL_TRY(launch_amax(s, act_in + (size_t)k * in_stride, u->nA, u->amax + l));
+                    SOL_TRY(launch_amax(s, g_out + (size_t)k * u->nA, u->nA, u->amax + 12 + l));
+                }
+            }
+            SOL_TRY(launch_wgrad_c32_h(s, nct32, it.nsteps, B, p->Y, p->X, act_in, in_stride, g_out, u->nA, u->amax + l, u->amax + 12 + l,
+                                       u->partials + u->partial_stride * (l - 1), &nctas, started[l] ? 1 : 0));
+        }
         started[l] = true;
         return nctas == nct32 ? SOL_OK : fail(SOL_ERR_CUDA, "deferred wgrad: CTA count changed between chunks");
     };
@@ -838,7 +878,7 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
 
     const float* Gy = u->stash[m - 1].gl_vy;
     const float* Gx = u->stash[m - 1].gl_vx;
-    const bool fuse_io = sol::g_fuse_solver_io && !burgers && cg_fuses(p);
+    const bool fuse_io = sol::g_fuse_solver_io && !burgers && cg_fuses(p, B);
     bool corr_ready = false;
     for (int i = m - 1; i >= 0; --i) {
         StepStash& s = u->stash[i];

@@ -101,6 +101,7 @@ struct sol_direct {
     int* rt_col = nullptr; float* rt_val = nullptr;
     float* Wt = nullptr;                  // [kp][N]: the capacitance-corrected basis (W M), transposed
     float* p0 = nullptr;                  // scratch: [B_max][N] obstacle-free solution
+    float* zbuf = nullptr;                // scratch: [B_max][N] (streamed kernel of the large grids)
 };
 
 struct sol_plan {
@@ -180,7 +181,7 @@ struct CgFuse {
     const float* gfeat_in = nullptr;    // [B,Y,X,cfeat]: vy_in[j,i] += gfeat[...,0]*isy (j < Y), vx_in[j,i] += gfeat[...,1]*isx (i < X)
     int cfeat = 3;
 };
-bool cg_fuses(const sol_plan* p);
+bool cg_fuses(const sol_plan* p, int B);     // true when launch_cg(p, .., B, ..) accepts a CgFuse
 int launch_cg(const sol_plan* p, cudaStream_t st, int B, int mode, const float* rhs, float* p_out, const float* vy,
               const float* vx, float* vy_out, float* vx_out, int* iters, const CgFuse* fuse = nullptr);
 
@@ -201,7 +202,7 @@ bool mg3_selected(const sol_plan* p);
 
 // ---- convolutions (sol_conv.cu) ----
 int launch_conv5x5(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const float* in, const float* w, const float* bias,
-                   const float* addend, const float* ref, int act, float slope, float* out);
+                   const float* addend, const float* ref, int act, float slope, float* out, unsigned int* amax_out = nullptr);
 int launch_flip_weights(cudaStream_t st, int Cin, int Cout, const float* w, float* wT);
 size_t wgrad_workspace_floats(int Cin, int Cout);
 int launch_wgrad(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const float* in, const float* g_out, float* dW, float* db,
@@ -212,10 +213,15 @@ int launch_wgrad_thin_multi(cudaStream_t st, int steps, int B, int Y, int X, int
 int launch_wgrad_finalize_n(cudaStream_t st, int nctas, const float* partials, float* dW, float* db, int accumulate);
 
 // ---- deferred tensor-core weight gradient (sol_wgrad_tc.cu) ----
-extern int g_wgrad_path;            // 1 SIMT per step, 2 tcgen05 deferred over the whole sweep (default; 0 = auto = 2)
+extern int g_wgrad_path;            // 1 SIMT per step, 2 tcgen05 3xFP16 deferred over the whole sweep (default; 0 = auto = 2), 3 tcgen05 3xTF32 deferred
 int launch_wgrad_c32_tc(cudaStream_t st, int sm_count, int steps, int B, int Y, int X, const float* in, size_t in_step_stride,
                         const float* g, size_t g_step_stride, float* part, int* nctas_out, int accumulate = 0);
 int launch_colsum32(cudaStream_t st, const float* g, size_t npix, float* db);
+// 3xFP16 form (sol_wgrad_h.cu): needs max|in|, max|g| of the tensors (device slots, bit patterns) for its power-of-two scales
+int launch_wgrad_c32_h(cudaStream_t st, int sm_count, int steps, int B, int Y, int X, const float* in, size_t in_step_stride,
+                       const float* g, size_t g_step_stride, const unsigned int* amax_in, const unsigned int* amax_g, float* part,
+                       int* nctas_out, int accumulate = 0);
+int launch_amax(cudaStream_t st, const float* x, size_t n, unsigned int* slot);      // slot = max(slot, max|x|)
 
 // ---- tensor-core convolutions (sol_conv_h.cu: 3xFP16, default; sol_conv_tc.cu: 3xTF32) ----
 extern int g_conv_path;             // 1 SIMT fp32, 2 tcgen05 3xFP16 (default; option value 0 = auto = 2), 3 tcgen05 3xTF32
@@ -230,9 +236,10 @@ int launch_split_weights(cudaStream_t st, const float* w, float* wsplit);      /
 int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, const float* wprep, const float* bias,
                       const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready);
 int launch_conv5x5_h(cudaStream_t st, int B, int Y, int X, const float* in, const float* wsplit, const float* bias,
-                     const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready);
+                     const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready, unsigned int* amax_out = nullptr);
 int launch_conv5x5_c32_presplit(cudaStream_t st, int B, int Y, int X, const float* in, const float* wsplit, const float* bias,
-                                const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready);
+                                const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready,
+                                unsigned int* amax_out = nullptr);
 int tc_tiles_per_launch(int B, int Y, int X);
 extern int g_fuse_small;
 extern int g_fuse_solver_io;
@@ -240,6 +247,7 @@ extern int g_wgrad_overlap;
 extern int g_wgrad_window_us;
 // 32->32 layers: tensor-core path when enabled (wprep = pre-split weights or NULL for internal scratch), else SIMT
 int launch_conv5x5_c32_auto(cudaStream_t st, int B, int Y, int X, const float* in, const float* w, const float* wprep,
-                            const float* bias, const float* addend, const float* ref, int act, float slope, float* out);
+                            const float* bias, const float* addend, const float* ref, int act, float slope, float* out,
+                            unsigned int* amax_out = nullptr);
 
 }  // namespace sol

@@ -90,6 +90,15 @@ class Plan:
     def set_option(self, name: str, value: int):
         check(self.lib.sol_plan_set_option(self.handle, name.encode(), int(value)))
 
+    def query(self, name: str) -> int:
+        v = C.c_int()
+        check(self.lib.sol_plan_query(self.handle, name.encode(), C.byref(v)))
+        return v.value
+
+    def direct_rows(self) -> int:
+        """k of the capacitance matrix of the direct projection (0 when the iterative solvers are in use)."""
+        return self.query("direct_rows")
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.sol_plan_destroy(self.handle)

@@ -227,7 +227,7 @@ def test_conv5x5(eng, cuda_device, cin, cout, shape):
     assert rel(o, expect) < 2e-6
 
 
-_TC_KERNELS = {"fp16x3": (2, 0), "fp16x3-one-set": (2, 1), "fp16x3-merged": (2, 2), "tf32x3": (3, 0)}
+_TC_KERNELS = {"fp16x3": (2, 0), "fp16x3-two-sets": (2, 1), "fp16x3-one-set": (2, 2), "tf32x3": (3, 0)}
 
 
 @pytest.mark.parametrize("kern", list(_TC_KERNELS.values()), ids=list(_TC_KERNELS.keys()))

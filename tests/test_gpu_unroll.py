@@ -40,9 +40,11 @@ _PATHS = {
     "fp16x3-conv+wgrad-serial-unfused": (2, 2, 1, 0, 0, 0, 0),
     "fp16x3-conv+wgrad-nopdl": (2, 2, 0, 1, 1, 0, 0),
     "defaults(fp16x3,solverio,unfused-small)": (2, 2, 1, 1, 0, 1, 0),
-    "fp16x3-one-accumulator-set": (2, 2, 1, 1, 0, 1, 1),
-    "fp16x3-merged-accumulators": (2, 2, 1, 1, 0, 1, 2),
-    "tf32x3-conv+wgrad": (3, 2, 1, 1, 0, 1, 0),
+    "fp16x3-two-accumulator-sets": (2, 2, 1, 1, 0, 1, 1),
+    "fp16x3-one-accumulator-set": (2, 2, 1, 1, 0, 1, 2),
+    "tf32x3-conv+fp16x3-wgrad(measured-maxima)": (3, 2, 1, 1, 0, 1, 0),
+    "tf32x3-conv+wgrad": (3, 3, 1, 1, 0, 1, 0),
+    "simt-conv+fp16x3-wgrad(measured-maxima)": (1, 2, 1, 1, 0, 1, 0),
 }
 _NAMES = ("conv_path", "wgrad_path", "pdl", "wgrad_overlap", "fuse_small", "fuse_solver_io", "conv_variant")
 _DEFAULTS = (0, 0, 1, 1, 0, 1, 0)

@@ -102,7 +102,7 @@ def test_projection_pieces(emu, case):
     assert np.abs(ox - vx3.numpy()).max() < 2e-5
 
 
-@pytest.mark.parametrize("Y,X", [(64, 32), (128, 64)], ids=["64x32", "128x64"])
+@pytest.mark.parametrize("Y,X", [(64, 32), (128, 64), (256, 128)], ids=["64x32", "128x64", "256x128"])
 def test_direct_projection_host_logic(emu, Y, X):
     """The direct pressure solver's host precomputation (sol_direct_host.h: sine-transform matrices, changed rows of the operator,
     capacitance-corrected basis) + the fp32 arithmetic of its two kernels, against the oracle's float64 sparse LU."""
@@ -114,9 +114,12 @@ def test_direct_projection_host_logic(emu, Y, X):
     d32 = _f32(d); out = np.zeros_like(d32)
     emu.emu_direct_solve.restype = C.c_int
     k = emu.emu_direct_solve(Y, X, 2, act.ctypes.data_as(C.c_void_p), _p(diag), _p(d32), _p(out))
-    solid = int((geom.active == 0).sum())
-    assert k > solid and k < 3 * solid                      # solid cells + their fluid neighbours
+    a = geom.active > 0
+    surf = np.zeros_like(a)
+    surf[1:, :] |= a[1:, :] != a[:-1, :]; surf[:-1, :] |= a[1:, :] != a[:-1, :]
+    surf[:, 1:] |= a[:, 1:] != a[:, :-1]; surf[:, :-1] |= a[:, 1:] != a[:, :-1]
+    assert k == int(surf.sum())                             # only the cells on either side of the obstacle surface
     fluid = geom.active > 0
     err = np.linalg.norm((out - pref.numpy())[:, fluid]) / np.linalg.norm(pref.numpy()[:, fluid])
     print("direct projection (host emulation) vs sparse LU:", err, "changed rows", k)
-    assert err < 5e-6
+    assert err < (5e-6 if Y <= 128 else 1e-5)               # fp32 transforms: the round-off grows with the grid
