@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--conv-variant", type=int, default=0, help="accumulator layout of the 3xFP16 conv kernel (tuning)")
     ap.add_argument("--wgrad-overlap", type=int, default=1, help="1 = deferred weight-gradient GEMMs run beside the adjoint solves")
+    ap.add_argument("--wgrad-bg-ctas", type=int, default=-1, help="tuning: CTAs of the background weight-gradient launches beside the adjoint conv chain (0 = off)")
+    ap.add_argument("--wgrad-bg-chunk", type=int, default=-1, help="tuning: unrolled steps per background weight-gradient launch")
     ap.add_argument("--wgrad-window-us", type=int, default=-1, help="tuning: time budget of one adjoint-solve window (us at 128x64)")
     ap.add_argument("--fuse-small", type=int, default=0, help="1 = corr_bwd folded into the diffusion adjoint")
     ap.add_argument("--fuse-solver-io", type=int, default=1, help="1 = to_feature / feat_bwd folded into the projection kernel")
@@ -286,6 +288,10 @@ def main():
     engine.set_option("fuse_solver_io", args.fuse_solver_io)
     if args.wgrad_window_us >= 0:
         engine.set_option("wgrad_window_us", args.wgrad_window_us)
+    if args.wgrad_bg_ctas >= 0:
+        engine.set_option("wgrad_bg_ctas", args.wgrad_bg_ctas)
+    if args.wgrad_bg_chunk >= 1:
+        engine.set_option("wgrad_bg_chunk", args.wgrad_bg_chunk)
     engine.set_option("wgrad_path", args.wgrad_path)
     plan = engine.Plan.karman(Y, X, B)
     plan.set_option("cg_rows", args.cg_rows)

@@ -23,10 +23,10 @@ if [[ $WHAT == all || $WHAT == *ncu* ]]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $OUT/launches.csv \
       python scripts/profile_iter.py --msteps 32 --graph > $OUT/launches.log 2>&1
   python scripts/launch_summary.py $OUT/launches.csv > $OUT/launches.md 2>/dev/null; head -30 $OUT/launches.md
-  timeout 1500 ncu --set full --clock-control none --cache-control none --import-source on --profile-from-start off -f -o $OUT/prof \
+  timeout 1500 ncu --set full --clock-control none --cache-control none --profile-from-start off -f -o $OUT/prof \
       python scripts/profile_iter.py --msteps 2 > $OUT/prof.log 2>&1
   python scripts/ncu_to_json.py $OUT/prof.ncu-rep $OUT "ncu --set full --clock-control none --cache-control none (warm caches), scripts/profile_iter.py --msteps 2, mean over the captured launches" > $OUT/ncu_kernels.md
   cat $OUT/ncu_kernels.md
-  # the report itself is large: keep only the top kernel's for the source page
-  ls -la $OUT/prof.ncu-rep
+  # gpurun merges at most 64 MiB back: keep the per-kernel JSON summaries, drop the report itself
+  ls -la $OUT/prof.ncu-rep; rm -f $OUT/prof.ncu-rep
 fi

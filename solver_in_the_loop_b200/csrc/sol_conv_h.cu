@@ -397,26 +397,32 @@ k_conv5x5_c32_h(const __grid_constant__ CUtensorMap map_in, const __grid_constan
 // wsplit[pair][row][64 halves]: row < 32: hi of Bt[n = row], row >= 32: lo of Bt[n = row - 32];  halves 0..31 = cin of tap
 // 2*pair, 32..63 = cin of tap 2*pair+1 (zero for the missing 26th tap);  Bt[tap][n][k] = w[tap][k][n] * T  (w: Keras
 // [5,5,K=Cin,N=Cout]).  T = 2^j puts max|w| into [2^14, 2^15); 1/T goes to the float slot behind the 13 pairs.
-__global__ void __launch_bounds__(256) k_prep_h_weights(const float* __restrict__ w, __half* __restrict__ wsplit, float* __restrict__ inv_scale) {
+// One launch splits `gridDim.y` layers: layer l reads w + l*w_stride and writes wsplit + l*split_stride (floats).
+__global__ void __launch_bounds__(1024) k_prep_h_weights(const float* __restrict__ w_base, size_t w_stride, float* __restrict__ split_base,
+                                                         size_t split_stride) {
     pdl_sync();
-    __shared__ uint32_t red[8];
+    const float* w = w_base + (size_t)blockIdx.y * w_stride;
+    __half* wsplit = reinterpret_cast<__half*>(split_base + (size_t)blockIdx.y * split_stride);
+    float* inv_scale = split_base + (size_t)blockIdx.y * split_stride + H_WPAIR_FLOATS;
+    __shared__ uint32_t red[32];
     uint32_t amax = 0u;
-    for (int i = threadIdx.x; i < 25 * 32 * 32; i += 256) amax = max(amax, __float_as_uint(w[i]) & 0x7fffffffu);
+    for (int i = threadIdx.x; i < 25 * 32 * 32; i += 1024) amax = max(amax, __float_as_uint(__ldg(w + i)) & 0x7fffffffu);
     amax = __reduce_max_sync(0xffffffffu, amax);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
     __syncthreads();
     uint32_t m = red[0];
 #pragma unroll
-    for (int k = 1; k < 8; ++k) m = max(m, red[k]);
+    for (int k = 1; k < 32; ++k) m = max(m, red[k]);
     float T, invT;
     pow2_scale(m, T, invT);
     const int pair = blockIdx.x;
-    for (int idx = threadIdx.x; idx < 64 * 64; idx += 256) {
-        const int row = idx >> 6, col = idx & 63;
-        const int tap = 2 * pair + (col >> 5), k = col & 31, n = row & 31;
-        const float v = tap < 25 ? w[(tap * 32 + k) * 32 + n] * T : 0.0f;
+    for (int idx = threadIdx.x; idx < 64 * 64; idx += 1024) {
+        // consecutive threads read consecutive n (the contiguous index of w) and write 128-byte-strided halves: the reads coalesce
+        const int n = idx & 31, lo = (idx >> 5) & 1, col = idx >> 6;
+        const int tap = 2 * pair + (col >> 5), k = col & 31, row = lo * 32 + n;
+        const float v = tap < 25 ? __ldg(w + (tap * 32 + k) * 32 + n) * T : 0.0f;
         const __half h = __float2half_rn(v);
-        wsplit[((size_t)pair * 64 + row) * 64 + col] = row < 32 ? h : __float2half_rn(v - __half2float(h));
+        wsplit[((size_t)pair * 64 + row) * 64 + col] = lo ? __float2half_rn(v - __half2float(h)) : h;
     }
     if (pair == 0 && threadIdx.x == 0) *inv_scale = invT;
 }
@@ -425,8 +431,8 @@ int g_conv_variant = 0;     // accumulator layout of k_conv5x5_c32_h: 0 = two me
 
 size_t h_weights_floats() { return (size_t)H_WPAIR_FLOATS + 64; }      // 13 pairs + the scale slot, 256-byte multiple
 
-int launch_prep_h_weights(cudaStream_t st, const float* w, float* wsplit) {
-    SOL_CUDA(launch_kernel(k_prep_h_weights, dim3(H_NPAIR), dim3(256), 0, st, w, reinterpret_cast<__half*>(wsplit), wsplit + H_WPAIR_FLOATS));
+int launch_prep_h_weights(cudaStream_t st, const float* w, float* wsplit, int nlayers, size_t w_stride, size_t split_stride) {
+    SOL_CUDA(launch_kernel(k_prep_h_weights, dim3(H_NPAIR, nlayers), dim3(1024), 0, st, w, w_stride, wsplit, split_stride));
     SOL_LAUNCHED();
     return SOL_OK;
 }

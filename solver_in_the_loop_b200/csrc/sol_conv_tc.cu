@@ -429,6 +429,14 @@ int launch_split_weights(cudaStream_t st, const float* w, float* wsplit) {
     return launch_prep_h_weights(st, w, wsplit);
 }
 
+int launch_split_weights_multi(cudaStream_t st, const float* w, size_t w_stride, float* wsplit, int nlayers) {
+    if (g_conv_path == 3) {
+        for (int l = 0; l < nlayers; ++l) SOL_TRY(launch_prep_tc_weights(st, w + (size_t)l * w_stride, wsplit + (size_t)l * tc_weights_floats()));
+        return SOL_OK;
+    }
+    return launch_prep_h_weights(st, w, wsplit, nlayers, w_stride, tc_weights_floats());
+}
+
 int launch_conv5x5_c32_presplit(cudaStream_t st, int B, int Y, int X, const float* in, const float* wsplit, const float* bias,
                                 const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready,
                                 unsigned int* amax_out) {

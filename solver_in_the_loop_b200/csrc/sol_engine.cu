@@ -278,6 +278,16 @@ extern "C" int sol_set_option(const char* name, int value) {
         sol::g_wgrad_window_us = value;
         return SOL_OK;
     }
+    if (strcmp(name, "wgrad_bg_ctas") == 0) {
+        SOL_CHECK(value >= 0 && value <= 148, "wgrad_bg_ctas out of range");
+        sol::g_wgrad_bg_ctas = value;
+        return SOL_OK;
+    }
+    if (strcmp(name, "wgrad_bg_chunk") == 0) {
+        SOL_CHECK(value >= 1 && value <= 64, "wgrad_bg_chunk out of range");
+        sol::g_wgrad_bg_chunk = value;
+        return SOL_OK;
+    }
     if (strcmp(name, "wgrad_overlap") == 0) {
         sol::g_wgrad_overlap = value ? 1 : 0;
         return SOL_OK;
@@ -728,8 +738,7 @@ int do_forward(sol_unroll* u, cudaStream_t st, const float* weights, const float
     if (gt_vy) SOL_CUDA(cudaMemsetAsync(loss_steps, 0, sizeof(float) * m, st));
     const bool mars = c.model == SOL_MODEL_MARS_MOON;
     if (conv_path_is_tc() && mars) {
-        for (int l = 1; l <= 10; ++l)
-            SOL_TRY(launch_split_weights(st, weights + u->L[l].w_off, u->wprep_fwd + tc_weights_floats() * (l - 1)));
+        SOL_TRY(launch_split_weights_multi(st, weights + u->L[1].w_off, u->L[2].w_off - u->L[1].w_off, u->wprep_fwd, 10));
     }
     // operand maxima for the 3xFP16 weight-gradient GEMM: tracked by the 3xFP16 conv kernels as they produce the tensors
     u->track_amax = mars && sol::g_conv_path == 2 && sol::g_wgrad_path == 2 && (p->Y % 16 == 0) && (p->X % 8 == 0);
@@ -790,41 +799,45 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
     for (size_t l = 0; l < u->L.size(); ++l)
         SOL_TRY(launch_flip_weights(st, u->L[l].cin, u->L[l].cout, weights + u->L[l].w_off, u->wT + u->L[l].w_off));
     if (conv_path_is_tc() && mars) {
-        for (int l = 1; l <= 10; ++l)
-            SOL_TRY(launch_split_weights(st, u->wT + u->L[l].w_off, u->wprep_bwd + tc_weights_floats() * (l - 1)));
+        SOL_TRY(launch_split_weights_multi(st, u->wT + u->L[1].w_off, u->L[2].w_off - u->L[1].w_off, u->wprep_bwd, 10));
     }
     // ---- deferred weight gradients: work items (layer, step range) over the stashed activations / output gradients.
     // While an adjoint pressure solve occupies B SMs for ~100 us, the other SMs are idle: items whose steps are already
     // complete run there on a side stream (option "wgrad_overlap"), the remainder after the sweep.
     struct WgItem { int layer, step0, nsteps; };
-    bool started[12] = {false};
+    int slots[12] = {0};      // per layer: CTA partial-sum slots that already hold data (launches may use different CTA counts)
     const size_t in_stride = (m > 1) ? (size_t)(u->stash[1].acts[0] - u->stash[0].acts[0]) : u->nA;
     const int tiles_step = (p->X / 8) * (p->Y / 16) * B;
     const bool burgers = p->boundary == SOL_BOUNDARY_PERIODIC;      // no pressure solve, hence no solve windows
-    // the direct projection takes ~20 us: no window worth filling
+    // (a) iterative solvers: the adjoint solve of a step keeps only B SMs busy for ~100 us: weight-gradient items fill that window.
+    // (b) direct projection (no window worth filling): the adjoint conv chain needs at most 2 CTAs on tiles/2 SMs, so a persistent
+    //     background launch on the SMs beyond that runs beside it without lengthening its critical path.
     const bool overlap = u->deferred_wgrad && sol::g_wgrad_overlap && B + 17 <= p->sm_count && !burgers && !direct_for_batch(p, B);
+    const int bg_free = p->sm_count - (tiles_step + 1) / 2;      // SMs the two-per-SM conv tiles leave alone
+    const int bg_ctas = std::min(sol::g_wgrad_bg_ctas, bg_free);
+    const bool background = u->deferred_wgrad && sol::g_wgrad_overlap && !overlap && !burgers && bg_ctas >= 16 && m >= 2 * sol::g_wgrad_bg_chunk;
     const int sm_budget = overlap ? p->sm_count - B - 1 : p->sm_count;        // SMs left beside the solve's B CTAs
-    const int nct32 = tiles_step < sm_budget ? tiles_step : sm_budget;          // fixed per sweep: the partial-sum slots must line up
-    if (overlap && !u->sstream) {
+    const int nct32 = tiles_step < sm_budget ? tiles_step : sm_budget;
+    if ((overlap || background) && !u->sstream) {
         SOL_CUDA(cudaStreamCreateWithFlags(&u->sstream, cudaStreamNonBlocking));
         SOL_CUDA(cudaEventCreateWithFlags(&u->ev_wfork, cudaEventDisableTiming));
         SOL_CUDA(cudaEventCreateWithFlags(&u->ev_wjoin, cudaEventDisableTiming));
     }
-    auto launch_item = [&](cudaStream_t s, const WgItem& it) -> int {
+    auto launch_item = [&](cudaStream_t s, const WgItem& it, int ctas) -> int {
         const int l = it.layer;
         if (l == 11)
             return launch_wgrad_thin_multi(s, it.nsteps, B, p->Y, p->X, 32, 2, u->stash[it.step0].acts[10], in_stride,
                                            u->gcorr_st + (size_t)it.step0 * p->NC() * B * 2, (size_t)p->NC() * B * 2, gw + u->L[11].w_off,
-                                           gw + u->L[11].b_off, 2 * sm_budget);
+                                           gw + u->L[11].b_off, 2 * ctas);
         if (l == 0)
             return launch_wgrad_thin_multi(s, it.nsteps, B, p->Y, p->X, u->L[0].cin, 32, u->stash[it.step0].feat, in_stride,
-                                           u->g0_st + (size_t)it.step0 * u->nA, u->nA, gw + u->L[0].w_off, gw + u->L[0].b_off, 2 * sm_budget);
+                                           u->g0_st + (size_t)it.step0 * u->nA, u->nA, gw + u->L[0].w_off, gw + u->L[0].b_off, 2 * ctas);
         int nctas = 0;
         const float* act_in = u->stash[it.step0].acts[l - 1];
         const float* g_out = u->gst + ((size_t)(l - 1) * m + it.step0) * u->nA;
         if (sol::g_wgrad_path == 3) {
-            SOL_TRY(launch_wgrad_c32_tc(s, nct32, it.nsteps, B, p->Y, p->X, act_in, in_stride, g_out, u->nA, u->partials + u->partial_stride * (l - 1),
-                                        &nctas, started[l] ? 1 : 0));
+            SOL_TRY(launch_wgrad_c32_tc(s, ctas, it.nsteps, B, p->Y, p->X, act_in, in_stride, g_out, u->nA, u->partials + u->partial_stride * (l - 1),
+                                        &nctas, slots[l]));
         } else {
             if (!u->track_amax) {       // the tensors were produced by kernels that do not track their maxima: measure them now
                 for (int k = 0; k < it.nsteps; ++k) {
@@ -832,11 +845,11 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
                     SOL_TRY(launch_amax(s, g_out + (size_t)k * u->nA, u->nA, u->amax + 12 + l));
                 }
             }
-            SOL_TRY(launch_wgrad_c32_h(s, nct32, it.nsteps, B, p->Y, p->X, act_in, in_stride, g_out, u->nA, u->amax + l, u->amax + 12 + l,
-                                       u->partials + u->partial_stride * (l - 1), &nctas, started[l] ? 1 : 0));
+            SOL_TRY(launch_wgrad_c32_h(s, ctas, it.nsteps, B, p->Y, p->X, act_in, in_stride, g_out, u->nA, u->amax + l, u->amax + 12 + l,
+                                       u->partials + u->partial_stride * (l - 1), &nctas, slots[l]));
         }
-        started[l] = true;
-        return nctas == nct32 ? SOL_OK : fail(SOL_ERR_CUDA, "deferred wgrad: CTA count changed between chunks");
+        if (nctas > slots[l]) slots[l] = nctas;
+        return SOL_OK;
     };
     // Greedy schedule: done[l] = steps >= done[l] of layer l are already issued.  In the window of step i the steps
     // >= i are complete; the layer with the largest backlog gets an item as long as its estimated time fits what is
@@ -867,7 +880,7 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
                 if (any) break;
                 n = 1;                                  // always make progress: one step of the fullest layer
             }
-            SOL_TRY(launch_item(s, WgItem{best, done[best] - n, n}));
+            SOL_TRY(launch_item(s, WgItem{best, done[best] - n, n}, nct32));
             done[best] -= n;
             left -= item_cost(best, n);
             any = true;
@@ -876,6 +889,7 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
         return SOL_OK;
     };
 
+    bool bg_pending = false;
     const float* Gy = u->stash[m - 1].gl_vy;
     const float* Gx = u->stash[m - 1].gl_vx;
     const bool fuse_io = sol::g_fuse_solver_io && !burgers && cg_fuses(p, B);
@@ -885,6 +899,16 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
         float* g_corr = u->deferred_wgrad ? u->gcorr_st + (size_t)i * p->NC() * B * 2 : u->g_corr;
         if (!corr_ready) SOL_TRY(launch_corr_bwd(p, st, B, Gy, Gx, c.sig_vy, c.sig_vx, g_corr));   // else: written by diffuse_bc_bwd of step i+1
         SOL_TRY(cnn_backward(u, st, weights, gw, s, g_corr, u->g_feat, i == m - 1, i));
+        if (background && i >= sol::g_wgrad_bg_chunk && done[1] - i >= sol::g_wgrad_bg_chunk) {
+            // the output gradients of steps [i, done) are complete: their weight-gradient items run on the side stream from here on
+            SOL_CUDA(cudaEventRecord(u->ev_wfork, st));
+            SOL_CUDA(cudaStreamWaitEvent(u->sstream, u->ev_wfork, 0));
+            for (int l = 0; l <= 11; ++l) {
+                SOL_TRY(launch_item(u->sstream, WgItem{l, i, done[l] - i}, bg_ctas));
+                done[l] = i;
+            }
+            bg_pending = true;
+        }
         if (!fuse_io) SOL_TRY(launch_feat_bwd(p, st, B, Gy, Gx, u->g_feat, c.cin0, c.sig_vy, c.sig_vx, u->H_vy, u->H_vx));
         if (burgers) {
             // adjoint of advect -> diffuse (+ dt*f: no state dependence); the periodic diffusion operator is symmetric
@@ -934,10 +958,14 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
     if (u->deferred_wgrad) {
         // what the solve windows did not absorb: ONE launch per layer over its remaining steps [0, done[l]), then the
         // per-layer reduction of the CTA partial sums
+        if (bg_pending) {
+            SOL_CUDA(cudaEventRecord(u->ev_wjoin, u->sstream));
+            SOL_CUDA(cudaStreamWaitEvent(st, u->ev_wjoin, 0));
+        }
         for (int l = 0; l <= 11; ++l)
-            if (done[l] > 0) { SOL_TRY(launch_item(st, WgItem{l, 0, done[l]})); done[l] = 0; }
+            if (done[l] > 0) { SOL_TRY(launch_item(st, WgItem{l, 0, done[l]}, nct32)); done[l] = 0; }
         for (int l = 1; l <= 10; ++l)
-            SOL_TRY(launch_wgrad_finalize_n(st, nct32, u->partials + u->partial_stride * (l - 1), gw + u->L[l].w_off, gw + u->L[l].b_off, 0));
+            SOL_TRY(launch_wgrad_finalize_n(st, slots[l], u->partials + u->partial_stride * (l - 1), gw + u->L[l].w_off, gw + u->L[l].b_off, 0));
         return SOL_OK;
     }
     if (!mars) return SOL_OK;      // model_mercury accumulated into gw step by step

@@ -231,8 +231,10 @@ bool conv_path_is_tc();
 size_t tc_weights_floats();         // floats of one layer's pre-split weights (either layout fits)
 size_t h_weights_floats();
 int launch_prep_tc_weights(cudaStream_t st, const float* w, float* wprep);
-int launch_prep_h_weights(cudaStream_t st, const float* w, float* wsplit);
+int launch_prep_h_weights(cudaStream_t st, const float* w, float* wsplit, int nlayers = 1, size_t w_stride = 0, size_t split_stride = 0);
 int launch_split_weights(cudaStream_t st, const float* w, float* wsplit);      // layout of the selected path
+// `nlayers` equally spaced 32->32 weight tensors (w + l*w_stride) -> wsplit + l*tc_weights_floats(): one launch on the 3xFP16 path
+int launch_split_weights_multi(cudaStream_t st, const float* w, size_t w_stride, float* wsplit, int nlayers);
 int launch_conv5x5_tc(cudaStream_t st, int B, int Y, int X, const float* in, const float* wprep, const float* bias,
                       const float* addend, const float* ref, int act, float slope, float* out, bool weights_ready);
 int launch_conv5x5_h(cudaStream_t st, int B, int Y, int X, const float* in, const float* wsplit, const float* bias,
@@ -245,6 +247,8 @@ extern int g_fuse_small;
 extern int g_fuse_solver_io;
 extern int g_wgrad_overlap;
 extern int g_wgrad_window_us;
+extern int g_wgrad_bg_ctas;          // CTAs of the background weight-gradient launches beside the adjoint conv chain (0 = off)
+extern int g_wgrad_bg_chunk;         // unrolled steps per background launch
 // 32->32 layers: tensor-core path when enabled (wprep = pre-split weights or NULL for internal scratch), else SIMT
 int launch_conv5x5_c32_auto(cudaStream_t st, int B, int Y, int X, const float* in, const float* w, const float* wprep,
                             const float* bias, const float* addend, const float* ref, int act, float slope, float* out,

@@ -61,7 +61,7 @@ struct WgHArgs {
     const uint32_t* amax_g;         // same for the output gradients
     int tiles_x, tiles_y, images;   // tiles per image row / column, number of images (steps*B)
     int B;                          // images per step (the 5th tensor dimension is the step)
-    int accumulate;
+    int accumulate;                 // CTAs with blockIdx.x < accumulate add to their partial slot, the others overwrite it
 };
 
 __device__ __forceinline__ void umma_f16_mn(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -278,7 +278,7 @@ k_wgrad_c32_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant_
             // ---- drain: accumulator (group, M-block q), lane m -> tap, cin = lane, 32 columns = cout; RN fp32 adds into the partial slot
             mbar_wait(bar_acc, (uint32_t)seg & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const bool add = a.accumulate || seg > 0;
+            const bool add = ((int)blockIdx.x < a.accumulate) || seg > 0;
 #pragma unroll 1
             for (int grp = 0; grp < WGH_NGROUP; ++grp) {
                 int dy, dx;
@@ -314,7 +314,7 @@ k_wgrad_c32_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant_
 #pragma unroll
             for (int c = 0; c < 8; ++c) atomicAdd(bsm + oct * 8 + c, bsum[c]);
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (tt < 32) part[25 * 32 * 32 + tt] = a.accumulate ? part[25 * 32 * 32 + tt] + bsm[tt] : bsm[tt];
+            if (tt < 32) part[25 * 32 * 32 + tt] = ((int)blockIdx.x < a.accumulate) ? part[25 * 32 * 32 + tt] + bsm[tt] : bsm[tt];
         }
     }
 
@@ -339,6 +339,9 @@ __global__ void __launch_bounds__(256) k_amax(const float4* __restrict__ x, size
     m = __reduce_max_sync(0xffffffffu, m);
     if ((threadIdx.x & 31) == 0 && m) atomicMax(slot, m);
 }
+
+int g_wgrad_bg_ctas = 48;
+int g_wgrad_bg_chunk = 4;
 
 int launch_amax(cudaStream_t st, const float* x, size_t n, uint32_t* slot) {
     if (n % 4 || ((uintptr_t)x & 15)) return fail(SOL_ERR_INVALID, "amax: needs a 16-byte aligned tensor of 4k floats");

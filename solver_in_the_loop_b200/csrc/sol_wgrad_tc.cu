@@ -49,7 +49,7 @@ struct WgTcArgs {
     float* part;        // [gridDim.x][25*32*32 + 32]
     int tiles_x, tiles_y, images;   // tiles per image row / column, number of images (msteps*B)
     int B;              // images per step (the 5th tensor dimension is the step)
-    int accumulate;
+    int accumulate;                 // CTAs with blockIdx.x < accumulate add to their partial slot, the others overwrite it
 };
 
 }  // namespace
@@ -205,7 +205,7 @@ k_wgrad_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant
             atomicAdd(bsm + ch + 0, bsum.x); atomicAdd(bsm + ch + 1, bsum.y);
             atomicAdd(bsm + ch + 2, bsum.z); atomicAdd(bsm + ch + 3, bsum.w);
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (tt < 32) part[25 * 32 * 32 + tt] = a.accumulate ? part[25 * 32 * 32 + tt] + bsm[tt] : bsm[tt];
+            if (tt < 32) part[25 * 32 * 32 + tt] = ((int)blockIdx.x < a.accumulate) ? part[25 * 32 * 32 + tt] + bsm[tt] : bsm[tt];
         }
 #pragma unroll 1
         for (int grp = 0; grp < WG_NGROUP; ++grp) {
@@ -226,7 +226,7 @@ k_wgrad_c32_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                                            __uint_as_float(v0[4 * c + 1]) + __uint_as_float(v1[4 * c + 1]),
                                            __uint_as_float(v0[4 * c + 2]) + __uint_as_float(v1[4 * c + 2]),
                                            __uint_as_float(v0[4 * c + 3]) + __uint_as_float(v1[4 * c + 3]));
-                    if (a.accumulate) { const float4 o = dst[c]; f.x += o.x; f.y += o.y; f.z += o.z; f.w += o.w; }
+                    if ((int)blockIdx.x < a.accumulate) { const float4 o = dst[c]; f.x += o.x; f.y += o.y; f.z += o.z; f.w += o.w; }
                     dst[c] = f;
                 }
             }

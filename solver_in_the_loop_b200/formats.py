@@ -35,7 +35,10 @@ def write_zipped_array(filename: str, array: np.ndarray) -> None:
     if array.shape[-1] != 1:
         array = array[..., ::-1]
     os.makedirs(os.path.dirname(os.path.abspath(filename)), exist_ok=True)
-    np.savez_compressed(filename, array)
+    # write-then-rename: a concurrent reader (another rank preloading the dataset) never sees a half-written zip
+    tmp = "%s.tmp%d.npz" % (filename, os.getpid())
+    np.savez_compressed(tmp, array)
+    os.replace(tmp, filename if str(filename).endswith(".npz") else str(filename) + ".npz")
 
 
 def frame_paths(sim_dir: str, step: int, names=("dens", "velo")):

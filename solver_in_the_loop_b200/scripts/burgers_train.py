@@ -10,7 +10,7 @@ import random
 import numpy as np
 import torch
 
-from . import device_index
+from . import device_index, load_init_weights, rank0_preprocess_then_barrier, reject_unimplemented
 from .. import dist as sdist
 from .. import engine
 from ..dataset import BurgersPhifDataset
@@ -24,11 +24,11 @@ def parse(argv=None):
     ap.add_argument("--gpu", default="0"); ap.add_argument("--cuda", action="store_true")
     ap.add_argument("--train", default=None); ap.add_argument("--skip-ds", action="store_true"); ap.add_argument("--only-ds", action="store_true")
     ap.add_argument("--log", default=None)
-    ap.add_argument("-s", "--scale", default=4, type=int); ap.add_argument("-n", "--nsims", default=1, type=int)
-    ap.add_argument("-b", "--sbatch", default=1, type=int); ap.add_argument("-t", "--simsteps", default=200, type=int)
+    ap.add_argument("-s", "--scale", default=4, type=int); ap.add_argument("-n", "--nsims", default=10, type=int)
+    ap.add_argument("-b", "--sbatch", default=2, type=int); ap.add_argument("-t", "--simsteps", default=200, type=int)
     ap.add_argument("-m", "--msteps", default=2, type=int); ap.add_argument("-e", "--epochs", default=10, type=int)
     ap.add_argument("--dt", default=1.0, type=float); ap.add_argument("--noforce", action="store_true")
-    ap.add_argument("--seed", default=None, type=int); ap.add_argument("-l", "--len", default=96, type=int)
+    ap.add_argument("--seed", default=0, type=int); ap.add_argument("-l", "--len", default=32, type=int)
     ap.add_argument("--model", default="mars_moon")
     ap.add_argument("--lr", default=1e-3, type=float); ap.add_argument("--adplr", action="store_true")
     ap.add_argument("--resume", default=-1, type=int); ap.add_argument("--inittf", default=None); ap.add_argument("--pretf", default=None)
@@ -38,7 +38,8 @@ def parse(argv=None):
 
 def main(argv=None):
     p = vars(parse(argv))
-    logging.basicConfig(level=logging.INFO)
+    logging.basicConfig(level=logging.INFO, **({"handlers": [logging.StreamHandler(), logging.FileHandler(p["log"])]} if p["log"] else {}))
+    reject_unimplemented(p, ("pretf",))                     # burgers_train.py:43: supervised-baseline weights
     rank, local, world = sdist.init_from_env("nccl")
     if world == 1:
         torch.cuda.set_device(device_index(p["gpu"]))
@@ -46,8 +47,9 @@ def main(argv=None):
         p["nsims"] = (p["nsims"] // p["sbatch"]) * p["sbatch"]
     seed = 0 if p["seed"] is None else p["seed"]
     random.seed(seed); np.random.seed(seed)
-    ds = BurgersPhifDataset(p["train"], p["simsteps"], num_sims=p["nsims"], batch_size=p["sbatch"], print_fn=log.info,
-                            skip_preprocessing=p["skip_ds"], scale=p["scale"])
+    ds = rank0_preprocess_then_barrier(
+        lambda skip: BurgersPhifDataset(p["train"], p["simsteps"], num_sims=p["nsims"], batch_size=p["sbatch"], print_fn=log.info,
+                                        skip_preprocessing=skip, scale=p["scale"]), p["skip_ds"], rank, world)
     if p["only_ds"]:
         return
     if p["resume"] > 0:
@@ -63,7 +65,7 @@ def main(argv=None):
     trainer = BurgersTrainer(plan, p["msteps"], hi - lo, sv, sf, dt=p["dt"], noforce=p["noforce"], lr=p["lr"], seed=seed, model=p["model"])
     os.makedirs(p["tf"], exist_ok=True)
     if p["inittf"]:
-        trainer.weights.copy_(torch.from_numpy(np.concatenate([a.reshape(-1) for a in np.load(p["inittf"]).values()])))
+        load_init_weights(trainer, p["inittf"], 2 if p["noforce"] else 4, p["model"])
     if p["resume"] < 1:
         if rank == 0:
             with open(p["tf"] + "/dataStats.pickle", "wb") as f:

@@ -26,8 +26,8 @@ def parse(argv=None):
     ap.add_argument("--re", default=1e6, type=float, help="Reynolds number")
     ap.add_argument("--initdH", default=None); ap.add_argument("--initvH", default=None)
     ap.add_argument("-t", "--simsteps", default=1500, type=int)
-    ap.add_argument("--skipsteps", default=999, type=int)
-    ap.add_argument("-s", "--scale", default=4, type=int)
+    ap.add_argument("-s", "--skipsteps", default=999, type=int, help="skip first steps (vortices may not form)")
+    ap.add_argument("-d", "--scale", default=4, type=int, help="down-sampling scale of hires (only with --initdH / --initvH)")
     ap.add_argument("--seed", default=0, type=int)
     ap.add_argument("--sim-index", default=None, type=int, help="index of the sim_%%06d folder (default: next free)")
     return ap.parse_args(argv)
@@ -40,10 +40,16 @@ def main(argv=None):
     np.random.seed(p["seed"])
     res, L = p["res"], p["len"]
     st = Fluid(Domain(resolution=[res * 2, res], box=box[0:L * 2, 0:L], boundaries=OPEN), buoyancy_factor=0)
-    vn = st.velocity.staggered_tensor()
-    vn[..., 0] = 1.0
-    vn[..., vn.shape[1] // 2 + 10:vn.shape[1] // 2 + 20, vn.shape[2] // 2 - 2:vn.shape[2] // 2 + 2, 1] = 1.0
-    st = st.copied_with(velocity=StaggeredGrid(unstack_staggered_tensor(vn), st.velocity.box))
+    if p["initvH"]:      # karman.py:100-104: down-sampled hi-res frame (read_zipped_array reverts the channel order)
+        vn = torch.from_numpy(formats.downsample(formats.read_zipped_array(p["initvH"]), p["scale"], True).astype(np.float32)).cuda()
+    else:
+        vn = st.velocity.staggered_tensor()
+        vn[..., 0] = 1.0
+        vn[..., vn.shape[1] // 2 + 10:vn.shape[1] // 2 + 20, vn.shape[2] // 2 - 2:vn.shape[2] // 2 + 2, 1] = 1.0
+    d0 = None
+    if p["initdH"]:
+        d0 = torch.from_numpy(formats.downsample(formats.read_zipped_array(p["initdH"]), p["scale"], False).astype(np.float32)).cuda()
+    st = st.copied_with(velocity=StaggeredGrid(unstack_staggered_tensor(vn), st.velocity.box), **({"density": d0} if d0 is not None else {}))
     bc = np.zeros(tuple(st.velocity.data[0].data.shape))
     bc[..., 0:2, 0:bc.shape[2] - 1, 0] = 1.0
     bc[..., 0:bc.shape[1], 0:1, 0] = 1.0

@@ -18,12 +18,12 @@ log = logging.getLogger("karman_apply")
 def parse(argv=None):
     ap = argparse.ArgumentParser(description="Parameter Parser", formatter_class=argparse.ArgumentDefaultsHelpFormatter)
     ap.add_argument("--gpu", default="0"); ap.add_argument("--cuda", action="store_true")
-    ap.add_argument("-o", "--output", default=None); ap.add_argument("-r", "--res", default=32, type=int)
+    ap.add_argument("-o", "--output", default="/tmp/phiflow/run"); ap.add_argument("-r", "--res", default=32, type=int)
     ap.add_argument("-l", "--len", default=100, type=int); ap.add_argument("--re", default=1e6, type=float)
     ap.add_argument("--initdH", default=None); ap.add_argument("--initvH", default=None)
     ap.add_argument("-t", "--simsteps", default=500, type=int); ap.add_argument("-s", "--scale", default=4, type=int)
-    ap.add_argument("--stats", default=None, help="dataStats.pickle of the training run")
-    ap.add_argument("--model", default=None, help="model.npz (Keras-ordered weights)")
+    ap.add_argument("--stats", default="/tmp/phiflow/data/dataStats.pickle", help="dataStats.pickle of the training run")
+    ap.add_argument("--model", default="/tmp/phiflow/tf/model.h5", help="Keras-ordered weights: model.npz, or model.h5 with the .npz beside it")
     ap.add_argument("--fused", action="store_true", help="run all frames in ONE library call (sol_unroll_rollout) instead of the eager loop")
     return ap.parse_args(argv)
 
@@ -61,7 +61,10 @@ def main(argv=None):
     def write(i):
         if sim_path is None:
             return
-        for name, arr in (("denTf", st.density.data), ("velTf", st.velocity.staggered_tensor()), ("corTf", cv.staggered_tensor())):
+        frames = [("denTf", st.density.data), ("velTf", st.velocity.staggered_tensor())]
+        if not p["fused"] or i == 0:       # the fused rollout applies the correction in-kernel and never materialises it
+            frames.append(("corTf", cv.staggered_tensor()))
+        for name, arr in frames:
             formats.write_zipped_array(os.path.join(sim_path, "%s_%06d.npz" % (name, i)), arr.cpu().numpy())
 
     write(0)

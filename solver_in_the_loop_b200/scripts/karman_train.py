@@ -10,7 +10,7 @@ import random
 import numpy as np
 import torch
 
-from . import device_index
+from . import device_index, load_init_weights, rank0_preprocess_then_barrier, reject_unimplemented
 from .. import dist as sdist
 from .. import engine
 from ..dataset import PhifDataset
@@ -38,7 +38,8 @@ def parse(argv=None):
 
 def main(argv=None):
     p = vars(parse(argv))
-    logging.basicConfig(level=logging.INFO)
+    logging.basicConfig(level=logging.INFO, **({"handlers": [logging.StreamHandler(), logging.FileHandler(p["log"])]} if p["log"] else {}))
+    reject_unimplemented(p, ("pretf", "reg_loss"))          # karman_train.py:352-356,441-445: supervised-baseline weights / L2 regulariser
     rank, local, world = sdist.init_from_env("nccl")
     if world == 1:
         torch.cuda.set_device(device_index(p["gpu"]))
@@ -46,8 +47,9 @@ def main(argv=None):
         p["nsims"] = (p["nsims"] // p["sbatch"]) * p["sbatch"]
     seed = 0 if p["seed"] is None else p["seed"]
     random.seed(seed); np.random.seed(seed)
-    ds = PhifDataset(p["train"], p["simsteps"], num_sims=p["nsims"], batch_size=p["sbatch"], print_fn=log.info,
-                     skip_preprocessing=p["skip_ds"], scale=p["scale"])
+    ds = rank0_preprocess_then_barrier(
+        lambda skip: PhifDataset(p["train"], p["simsteps"], num_sims=p["nsims"], batch_size=p["sbatch"], print_fn=log.info,
+                                 skip_preprocessing=skip, scale=p["scale"]), p["skip_ds"], rank, world)
     if p["only_ds"]:
         return
     if p["resume"] > 0:
@@ -62,7 +64,7 @@ def main(argv=None):
     trainer = SolTrainer(plan, p["msteps"], hi - lo, sig, lr=p["lr"], seed=seed, clip_grad=p["clip_grad"], model=p["model"])
     os.makedirs(p["tf"], exist_ok=True)
     if p["inittf"]:
-        trainer.weights.copy_(torch.from_numpy(np.concatenate([a.reshape(-1) for a in np.load(p["inittf"]).values()])))
+        load_init_weights(trainer, p["inittf"], 3, p["model"])
     if p["resume"] < 1:
         if rank == 0:
             with open(p["tf"] + "/dataStats.pickle", "wb") as f:
