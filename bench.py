@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--wgrad-bg-ctas", type=int, default=-1, help="tuning: CTAs of the background weight-gradient launches beside the adjoint conv chain (0 = off)")
     ap.add_argument("--wgrad-bg-chunk", type=int, default=-1, help="tuning: unrolled steps per background weight-gradient launch")
     ap.add_argument("--wgrad-window-us", type=int, default=-1, help="tuning: time budget of one adjoint-solve window (us at 128x64)")
+    ap.add_argument("--fuse-stencil", type=int, default=1, help="1 = diffuse+BC and the advections in one shared-memory-staged launch")
     ap.add_argument("--fuse-small", type=int, default=0, help="1 = corr_bwd folded into the diffusion adjoint")
     ap.add_argument("--fuse-solver-io", type=int, default=1, help="1 = to_feature / feat_bwd folded into the projection kernel")
     ap.add_argument("--pdl", type=int, default=1, help="1 = programmatic dependent launch of every kernel, 0 = plain stream order")
@@ -285,6 +286,7 @@ def main():
     engine.set_option("conv_variant", args.conv_variant)
     engine.set_option("wgrad_overlap", args.wgrad_overlap)
     engine.set_option("fuse_small", args.fuse_small)
+    engine.set_option("fuse_stencil", args.fuse_stencil)
     engine.set_option("fuse_solver_io", args.fuse_solver_io)
     if args.wgrad_window_us >= 0:
         engine.set_option("wgrad_window_us", args.wgrad_window_us)
@@ -437,7 +439,7 @@ def main():
                              % (trainer.unroll.workspace.numel() / 1e9),
                        "cuda_graph": not args.no_graph, "conv_path": args.conv_path, "conv_variant": args.conv_variant, "wgrad_path": args.wgrad_path,
                        "cg_precond": args.cg_precond, "direct_solve": args.direct_solve, "pdl": args.pdl, "wgrad_overlap": args.wgrad_overlap,
-                       "fuse_small": args.fuse_small, "fuse_solver_io": args.fuse_solver_io, "csrc_sha256": csrc_sha256(), "loss": float(loss_host)},
+                       "fuse_small": args.fuse_small, "fuse_stencil": args.fuse_stencil, "fuse_solver_io": args.fuse_solver_io, "csrc_sha256": csrc_sha256(), "loss": float(loss_host)},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": trainer.h2d_bytes_per_step(), "d2h_bytes_per_step": 4,
                     "ms_per_step": t_e2e / args.steps * 1e3, "wall_ms_per_step": t_e2e_wall / args.steps * 1e3},
             "gpu_launches": int(launches),

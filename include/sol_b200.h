@@ -95,6 +95,12 @@ int sol_plan_query(sol_plan* plan, const char* name, int* value);
  *   "wgrad_window_us" (tuning) time budget of one such window at 128x64, default 110
  *   "pdl" 1 (default) = kernels are launched with programmatic stream serialization (the prologue of a kernel
  *         overlaps the tail of its predecessor on the stream), 0 = plain stream order
+ *   "wgrad_bg_ctas" / "wgrad_bg_chunk" (tuning) with the direct projection there is no solve window: the weight-gradient items of
+ *         finished steps then run as persistent background launches of at most this many CTAs (default 48, 0 = off; one launch
+ *         per layer per chunk of steps, default 4) on the SMs the adjoint conv chain does not need
+ *   "fuse_stencil" 1 (default) = viscosity + BC and the three advections of a step are ONE launch with the stencil halo staged in
+ *         shared memory (OPEN plans), 0 = one kernel per stage (global gathers)
+ *   "nvtx" 1 = NVTX ranges around the stages of the unrolled sweeps (for nsys / ncu --nvtx; host-side, default 0)
  *   "tc_base_offset_mode" (debug) how the UMMA shared-memory descriptors encode unaligned starts */
 int sol_set_option(const char* name, int value);
 
@@ -106,6 +112,11 @@ int sol_diffuse_bc(sol_plan* plan, void* stream, int B, const float* re, float d
 /* adjoint of sol_diffuse_bc w.r.t. (vy, vx) */
 int sol_diffuse_bc_bwd(sol_plan* plan, void* stream, int B, const float* re, float dt, float res,
                        const float* g_vy_out, const float* g_vx_out, float* g_vy, float* g_vx);
+
+/* sol_diffuse_bc followed by sol_advect in ONE launch (OPEN plans): the viscosity + BC result (vy1, vx1: also the stash of the
+ * advection adjoint) is staged in shared memory with its halo and advected from there; identical results. rho/rho_out may be NULL. */
+int sol_diffuse_advect(sol_plan* plan, void* stream, int B, const float* re, float dt, float res, const float* vy, const float* vx,
+                       const float* rho, float* vy1, float* vx1, float* vy2, float* vx2, float* rho_out);
 
 /* advect.semi_lagrangian(density|velocity, velocity, dt) + Inflow effect
  * (IncompressibleFlow.step via karman_train.py:185).  rho/rho_out may be NULL. */

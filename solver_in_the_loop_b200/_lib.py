@@ -44,6 +44,7 @@ SIGNATURES = {
     "sol_set_option": (_i, [C.c_char_p, _i]),
     "sol_diffuse_bc": (_i, [_vp, _vp, _i, _vp, _f, _f, _vp, _vp, _vp, _vp]),
     "sol_diffuse_bc_bwd": (_i, [_vp, _vp, _i, _vp, _f, _f, _vp, _vp, _vp, _vp]),
+    "sol_diffuse_advect": (_i, [_vp, _vp, _i, _vp, _f, _f] + [_vp] * 8),
     "sol_advect": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sol_advect_bwd": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sol_pressure_solve": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),

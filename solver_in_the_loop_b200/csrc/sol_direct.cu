@@ -35,6 +35,7 @@ struct DirectArgs {
     const float* vy_in; const float* vx_in;     // MODE 1
     float* p0;                                  // [B][N] scratch
     float* zbuf;                                // [B][N] scratch of the streamed kernel (large grids)
+    long long* trace;                           // diagnostics: 16 clock64 stamps per CTA of k_direct_solve (null in production)
     float* p_out; float* vy_out; float* vx_out; int* iters;
     // fused feature I/O (see CgFuse)
     float* feat_out; const float* re; float isy, isx, isr; const float* gfeat_in; int cfeat;
@@ -79,6 +80,55 @@ __device__ __forceinline__ void store_transposed(float* __restrict__ T, int ld, 
     }
 }
 
+// ---- even / odd symmetry of the sine transform ----
+// S[a][n-1-b] = (-1)^a S[a][b] (0-based): an output of even index only sees the mirror SUMS of the contracted vector, one of odd index
+// only the mirror DIFFERENCES, so every product needs half the multiplications once the operand has been folded:
+//   fold_rows(M): rows kk < K/2 <- M[kk] + M[K-1-kk],  rows K-1-kk <- M[kk] - M[K-1-kk]     (in place)
+// Left transform  (Sy M, rows r0 even / r0+1 odd):  acc[0] += At[kk][r0] * M[kk],  acc[1] += At[kk][r0+1] * M[K-1-kk],  kk < K/2
+// Right transform (M Sx, columns c0.. even/odd/even/odd): acc[.][0,2] += sums[m] * Sx[m][c],  acc[.][1,3] += diffs[m] * Sx[m][c],  m < K/2
+template <int NT>
+__device__ __forceinline__ void fold_rows(float* __restrict__ M, int K, int ld, int tid) {
+    const int ld4 = ld / 4;
+    for (int e = tid; e < (K / 2) * ld4; e += NT) {
+        const int kk = e / ld4, c4 = e - kk * ld4;
+        float4* pa = reinterpret_cast<float4*>(M + kk * ld) + c4;
+        float4* pb = reinterpret_cast<float4*>(M + (K - 1 - kk) * ld) + c4;
+        const float4 u = *pa, v = *pb;
+        *pa = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+        *pb = make_float4(u.x - v.x, u.y - v.y, u.z - v.z, u.w - v.w);
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void tile_gemm_sym_left(const float* __restrict__ At, int lda, const float* __restrict__ Mf, int ldb, int r0, int c0,
+                                                   float (&acc)[2][4]) {
+#pragma unroll 8
+    for (int kk = 0; kk < K / 2; ++kk) {
+        const float2 a = *reinterpret_cast<const float2*>(At + kk * lda + r0);
+        const float4 bs = *reinterpret_cast<const float4*>(Mf + kk * ldb + c0);
+        const float4 bd = *reinterpret_cast<const float4*>(Mf + (K - 1 - kk) * ldb + c0);
+        acc[0][0] = fmaf(a.x, bs.x, acc[0][0]); acc[0][1] = fmaf(a.x, bs.y, acc[0][1]);
+        acc[0][2] = fmaf(a.x, bs.z, acc[0][2]); acc[0][3] = fmaf(a.x, bs.w, acc[0][3]);
+        acc[1][0] = fmaf(a.y, bd.x, acc[1][0]); acc[1][1] = fmaf(a.y, bd.y, acc[1][1]);
+        acc[1][2] = fmaf(a.y, bd.z, acc[1][2]); acc[1][3] = fmaf(a.y, bd.w, acc[1][3]);
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void tile_gemm_sym_right(const float* __restrict__ Atf, int lda, const float* __restrict__ Bm, int ldb, int r0, int c0,
+                                                    float (&acc)[2][4]) {
+#pragma unroll 8
+    for (int m = 0; m < K / 2; ++m) {
+        const float2 as = *reinterpret_cast<const float2*>(Atf + m * lda + r0);
+        const float2 ad = *reinterpret_cast<const float2*>(Atf + (K - 1 - m) * lda + r0);
+        const float4 b = *reinterpret_cast<const float4*>(Bm + m * ldb + c0);
+        acc[0][0] = fmaf(as.x, b.x, acc[0][0]); acc[0][1] = fmaf(ad.x, b.y, acc[0][1]);
+        acc[0][2] = fmaf(as.x, b.z, acc[0][2]); acc[0][3] = fmaf(ad.x, b.w, acc[0][3]);
+        acc[1][0] = fmaf(as.y, b.x, acc[1][0]); acc[1][1] = fmaf(ad.y, b.y, acc[1][1]);
+        acc[1][2] = fmaf(as.y, b.z, acc[1][2]); acc[1][3] = fmaf(ad.y, b.w, acc[1][3]);
+    }
+}
+
 // incoming face values (MODE 1), optionally plus the scaled feature gradient of the correction network (fused feat_bwd)
 struct FaceIn {
     const float* vy; const float* vx; const float* gf; float isy, isx; int cfeat; int Y, X;
@@ -98,9 +148,12 @@ struct FaceIn {
 // right-hand side D (cheap), then owns YS = Y/CL rows of the three products U = Sy D, V = (U Sx) * ilam, Z = V Sx — no exchange
 // needed, the row split survives right-multiplications — and pushes its rows of Z into every CTA's copy through distributed
 // shared memory for the last product p0 = Sy Z.
+#define DSTAMP(slot) do { if (a.trace && threadIdx.x == 0) a.trace[(blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = clock64(); } while (0)
+
 template <int Y, int X, int CL, int TM, int MODE>
 __global__ void __launch_bounds__((Y / CL / TM) * (X / 4), 1) k_direct_solve(const DirectArgs a) {
     namespace cg = cooperative_groups;
+    DSTAMP(0);
     constexpr int YS = Y / CL;
     constexpr int NT = (YS / TM) * (X / 4);
     constexpr int N = Y * X;
@@ -122,8 +175,11 @@ __global__ void __launch_bounds__((Y / CL / TM) * (X / 4), 1) k_direct_solve(con
         *reinterpret_cast<float4*>(sSy + k) = __ldg(reinterpret_cast<const float4*>(a.Sy + kk * Y + rbase + lr));
     }
     for (int k = tid * 4; k < X * X; k += NT * 4) *reinterpret_cast<float4*>(sSx + k) = __ldg(reinterpret_cast<const float4*>(a.Sx + k));
+    DSTAMP(1);
     pdl_sync();
+    DSTAMP(2);
     if (CL > 1) cg::this_cluster().sync();      // every CTA of the cluster is running before any remote shared-memory access
+    DSTAMP(3);
     // ---- right-hand side D[j][i]: every CTA computes its YS rows and pushes them into all copies ----
     {
         FaceIn in{a.vy_in + (size_t)b * (Y + 1) * X, a.vx_in + (size_t)b * Y * (X + 1),
@@ -147,19 +203,27 @@ __global__ void __launch_bounds__((Y / CL / TM) * (X / 4), 1) k_direct_solve(con
             for (int peer = 0; peer < CL; ++peer) dst[peer][c] = d;
         }
     }
+    DSTAMP(4);
     if (CL > 1) cg::this_cluster().sync();
     else __syncthreads();
+    DSTAMP(5);
+    static_assert(TM == 2 && (Y / CL) % 2 == 0 && X % 8 == 0, "the folded products pair an even with an odd row / column");
     const int tx = tid % (X / 4), ty = tid / (X / 4);
-    const int r0 = ty * TM, c0 = tx * 4;        // r0: row inside this CTA's slice
+    const int r0 = ty * TM, c0 = tx * 4;        // r0: row inside this CTA's slice (even); rbase is even too
     float acc[TM][4];
-    // stage 1: U = Sy D (my rows), transposed into t0
+    // stage 1: U = Sy D (my rows) on the folded D, transposed into t0
+    fold_rows<NT>(sD, Y, X, tid);
+    __syncthreads();
     zero_acc<TM>(acc);
-    tile_gemm<TM, Y>(sSy, YS, sD, X, r0, c0, acc);
+    tile_gemm_sym_left<Y>(sSy, YS, sD, X, r0, c0, acc);
     store_transposed<TM>(t0, YS, r0, c0, acc);
     __syncthreads();
+    fold_rows<NT>(t0, X, YS, tid);
+    __syncthreads();
+    DSTAMP(6);
     // stage 2: V = (U Sx) * ilam, transposed into t1
     zero_acc<TM>(acc);
-    tile_gemm<TM, X>(t0, YS, sSx, X, r0, c0, acc);
+    tile_gemm_sym_right<X>(t0, YS, sSx, X, r0, c0, acc);
 #pragma unroll
     for (int rr = 0; rr < TM; ++rr) {
         const float4 l = __ldg(reinterpret_cast<const float4*>(a.ilam + (rbase + r0 + rr) * X + c0));
@@ -167,9 +231,13 @@ __global__ void __launch_bounds__((Y / CL / TM) * (X / 4), 1) k_direct_solve(con
     }
     store_transposed<TM>(t1, YS, r0, c0, acc);
     __syncthreads();
+    fold_rows<NT>(t1, X, YS, tid);
+    __syncthreads();
+    DSTAMP(7);
     // stage 3: Z = V Sx; my rows go into every CTA's sZ
     zero_acc<TM>(acc);
-    tile_gemm<TM, X>(t1, YS, sSx, X, r0, c0, acc);
+    tile_gemm_sym_right<X>(t1, YS, sSx, X, r0, c0, acc);
+    DSTAMP(8);
     if (CL > 1) {
         cg::cluster_group cluster = cg::this_cluster();
 #pragma unroll
@@ -185,14 +253,18 @@ __global__ void __launch_bounds__((Y / CL / TM) * (X / 4), 1) k_direct_solve(con
         for (int rr = 0; rr < TM; ++rr) *reinterpret_cast<float4*>(sZ + (r0 + rr) * X + c0) = make_float4(acc[rr][0], acc[rr][1], acc[rr][2], acc[rr][3]);
         __syncthreads();
     }
-    // stage 4: p0 = Sy Z (my rows) -> global memory
+    DSTAMP(9);
+    // stage 4: p0 = Sy Z (my rows) on the folded Z -> global memory
+    fold_rows<NT>(sZ, Y, X, tid);
+    __syncthreads();
     zero_acc<TM>(acc);
-    tile_gemm<TM, Y>(sSy, YS, sZ, X, r0, c0, acc);
+    tile_gemm_sym_left<Y>(sSy, YS, sZ, X, r0, c0, acc);
     float* p0g = a.p0 + (size_t)b * N;
 #pragma unroll
     for (int rr = 0; rr < TM; ++rr)
         *reinterpret_cast<float4*>(p0g + (rbase + r0 + rr) * X + c0) = make_float4(acc[rr][0], acc[rr][1], acc[rr][2], acc[rr][3]);
     if (a.iters && tid == 0 && rank == 0) a.iters[b] = 0;      // no iterations: a direct solve
+    DSTAMP(10);
 }
 
 // Larger grids (256x128): the two operands every CTA needs COMPLETELY — D for U = Sy D and Z for p0 = Sy Z, 128 KB each — do not fit
@@ -206,13 +278,13 @@ __global__ void __launch_bounds__((Y / CL / TM) * (X / 4), 1) k_direct_solve_big
     constexpr int NT = (YS / TM) * (X / 4);
     constexpr int N = Y * X;
     constexpr int CH4 = KC * X / 4 / NT;            // float4 per thread and chunk
-    static_assert(KC * X / 4 % NT == 0 && Y % KC == 0, "chunk geometry");
+    static_assert(KC * X / 4 % NT == 0 && (Y / 2) % KC == 0, "chunk geometry");
     extern __shared__ __align__(16) float dsm[];
     float* sSy = dsm;                  // [Y][YS]: sSy[kk][lr] = Sy[kk][rbase + lr]  (Sy is symmetric)
     float* sSx = sSy + Y * YS;         // [X][X]
     float* t0 = sSx + X * X;           // [X][YS] transposed slices
     float* t1 = t0 + X * YS;           // [X][YS]
-    float* ch = t1 + X * YS;           // [2][KC][X] streamed operand rows
+    float* ch = t1 + X * YS;           // [2 buffers][sums | differences][KC][X] streamed, folded operand rows
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
     cg::cluster_group cluster = cg::this_cluster();
@@ -248,25 +320,48 @@ __global__ void __launch_bounds__((Y / CL / TM) * (X / 4), 1) k_direct_solve_big
     const int tx = tid % (X / 4), ty = tid / (X / 4);
     const int r0 = ty * TM, c0 = tx * 4;
     float acc[TM][4];
-    // acc (+)= Sy[my rows, :] * G for a [Y][X] operand G streamed from global memory
+    static_assert(TM == 2 && (Y / CL) % 2 == 0 && X % 8 == 0, "the folded products pair an even with an odd row / column");
+    // acc (+)= Sy[my rows, :] * G for a [Y][X] operand G streamed from global memory, with the even / odd fold of the sine transform
+    // (see fold_rows): chunk c brings rows kk in [c*KC, (c+1)*KC) AND their mirrors Y-1-kk, folded on the fly into sums / differences
     auto stream_gemm = [&](const float* __restrict__ G) {
-        float4 nx[CH4];
+        float4 ns[CH4], nd[CH4];
+        auto fetch = [&](int c) {
 #pragma unroll
-        for (int e = 0; e < CH4; ++e) nx[e] = __ldcg(reinterpret_cast<const float4*>(G) + tid + e * NT);
+            for (int e = 0; e < CH4; ++e) {
+                const int idx = tid + e * NT, l = idx / (X / 4), c4 = idx - l * (X / 4);
+                const float4 u = __ldcg(reinterpret_cast<const float4*>(G + (size_t)(c * KC + l) * X) + c4);
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(G + (size_t)(Y - 1 - c * KC - l) * X) + c4);
+                ns[e] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+                nd[e] = make_float4(u.x - v.x, u.y - v.y, u.z - v.z, u.w - v.w);
+            }
+        };
+        auto stash = [&](int buf) {
 #pragma unroll
-        for (int e = 0; e < CH4; ++e) reinterpret_cast<float4*>(ch)[tid + e * NT] = nx[e];
+            for (int e = 0; e < CH4; ++e) {
+                reinterpret_cast<float4*>(ch + buf * 2 * KC * X)[tid + e * NT] = ns[e];
+                reinterpret_cast<float4*>(ch + buf * 2 * KC * X + KC * X)[tid + e * NT] = nd[e];
+            }
+        };
+        fetch(0);
+        stash(0);
         __syncthreads();
 #pragma unroll 1
-        for (int c = 0; c < Y / KC; ++c) {
-            if (c + 1 < Y / KC) {
-#pragma unroll
-                for (int e = 0; e < CH4; ++e) nx[e] = __ldcg(reinterpret_cast<const float4*>(G + (size_t)(c + 1) * KC * X) + tid + e * NT);
+        for (int c = 0; c < Y / 2 / KC; ++c) {
+            if (c + 1 < Y / 2 / KC) fetch(c + 1);
+            const float* At = sSy + c * KC * YS;
+            const float* Ms = ch + (c & 1) * 2 * KC * X;
+            const float* Md = Ms + KC * X;
+#pragma unroll 8
+            for (int l = 0; l < KC; ++l) {
+                const float2 av = *reinterpret_cast<const float2*>(At + l * YS + r0);
+                const float4 bs = *reinterpret_cast<const float4*>(Ms + l * X + c0);
+                const float4 bd = *reinterpret_cast<const float4*>(Md + l * X + c0);
+                acc[0][0] = fmaf(av.x, bs.x, acc[0][0]); acc[0][1] = fmaf(av.x, bs.y, acc[0][1]);
+                acc[0][2] = fmaf(av.x, bs.z, acc[0][2]); acc[0][3] = fmaf(av.x, bs.w, acc[0][3]);
+                acc[1][0] = fmaf(av.y, bd.x, acc[1][0]); acc[1][1] = fmaf(av.y, bd.y, acc[1][1]);
+                acc[1][2] = fmaf(av.y, bd.z, acc[1][2]); acc[1][3] = fmaf(av.y, bd.w, acc[1][3]);
             }
-            tile_gemm<TM, KC>(sSy + c * KC * YS, YS, ch + (c & 1) * KC * X, X, r0, c0, acc);
-            if (c + 1 < Y / KC) {
-#pragma unroll
-                for (int e = 0; e < CH4; ++e) reinterpret_cast<float4*>(ch + ((c + 1) & 1) * KC * X)[tid + e * NT] = nx[e];
-            }
+            if (c + 1 < Y / 2 / KC) stash((c + 1) & 1);
             __syncthreads();
         }
     };
@@ -275,9 +370,11 @@ __global__ void __launch_bounds__((Y / CL / TM) * (X / 4), 1) k_direct_solve_big
     stream_gemm(Dg);
     store_transposed<TM>(t0, YS, r0, c0, acc);
     __syncthreads();
+    fold_rows<NT>(t0, X, YS, tid);
+    __syncthreads();
     // stage 2: V = (U Sx) * ilam, transposed into t1
     zero_acc<TM>(acc);
-    tile_gemm<TM, X>(t0, YS, sSx, X, r0, c0, acc);
+    tile_gemm_sym_right<X>(t0, YS, sSx, X, r0, c0, acc);
 #pragma unroll
     for (int rr = 0; rr < TM; ++rr) {
         const float4 l = __ldg(reinterpret_cast<const float4*>(a.ilam + (rbase + r0 + rr) * X + c0));
@@ -285,9 +382,11 @@ __global__ void __launch_bounds__((Y / CL / TM) * (X / 4), 1) k_direct_solve_big
     }
     store_transposed<TM>(t1, YS, r0, c0, acc);
     __syncthreads();
+    fold_rows<NT>(t1, X, YS, tid);
+    __syncthreads();
     // stage 3: Z = V Sx; my rows -> global scratch
     zero_acc<TM>(acc);
-    tile_gemm<TM, X>(t1, YS, sSx, X, r0, c0, acc);
+    tile_gemm_sym_right<X>(t1, YS, sSx, X, r0, c0, acc);
 #pragma unroll
     for (int rr = 0; rr < TM; ++rr)
         *reinterpret_cast<float4*>(Zg + (rbase + r0 + rr) * X + c0) = make_float4(acc[rr][0], acc[rr][1], acc[rr][2], acc[rr][3]);
@@ -392,6 +491,8 @@ int up(T** dst, const std::vector<T>& src) {
 
 }  // namespace
 
+long long* g_direct_trace = nullptr;      // diagnostics (sol_debug_direct_trace)
+
 bool direct_supported(const sol_plan* p) {
     return p->boundary == SOL_BOUNDARY_OPEN && ((p->Y == 128 && p->X == 64) || (p->Y == 64 && p->X == 32) || (p->Y == 256 && p->X == 128));
 }
@@ -467,7 +568,7 @@ template <int Y, int X, int CL, int TM, int KC, int R>
 static int launch_direct_big_t(const DirectArgs& a, cudaStream_t st, int mode) {
     constexpr int YS = Y / CL;
     constexpr int NT = (YS / TM) * (X / 4);
-    const size_t smem = (size_t)(Y * YS + X * X + 2 * X * YS + 2 * KC * X) * sizeof(float);
+    const size_t smem = (size_t)(Y * YS + X * X + 2 * X * YS + 4 * KC * X) * sizeof(float);
     auto k0 = k_direct_solve_big<Y, X, CL, TM, KC, 0>;
     auto k1 = k_direct_solve_big<Y, X, CL, TM, KC, 1>;
     SOL_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -514,12 +615,16 @@ int launch_direct(const sol_plan* p, cudaStream_t st, int B, int mode, const flo
         a.feat_out = fuse->feat_out; a.re = fuse->re; a.isy = fuse->isy; a.isx = fuse->isx; a.isr = fuse->isr;
         a.gfeat_in = fuse->gfeat_in; a.cfeat = fuse->cfeat;
     }
+    a.trace = g_direct_trace;
     if (mode == 0 && (!rhs || !p_out)) return fail(SOL_ERR_INVALID, "direct solve: rhs / p_out required");
     if (mode == 1 && (!vy || !vx || !vy_out || !vx_out)) return fail(SOL_ERR_INVALID, "direct solve: velocity pointers required");
     if (p->Y == 128 && p->X == 64) return launch_direct_t<128, 64, 4, 2, 3>(a, st, mode);
     if (p->Y == 64 && p->X == 32) return launch_direct_t<64, 32, 2, 2, 7>(a, st, mode);
-    if (p->Y == 256 && p->X == 128) return launch_direct_big_t<256, 128, 8, 2, 32, 1>(a, st, mode);
+    if (p->Y == 256 && p->X == 128) return launch_direct_big_t<256, 128, 8, 2, 16, 1>(a, st, mode);
     return fail(SOL_ERR_UNSUPPORTED, "direct solve: unsupported grid");
 }
 
 }  // namespace sol
+
+// Diagnostics hook (not part of the public ABI): 16 clock64 stamps per CTA of the next k_direct_solve launches; null = off.
+extern "C" void sol_debug_direct_trace(long long* buf) { sol::g_direct_trace = buf; }

@@ -9,9 +9,25 @@
 #include <algorithm>
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "sol_internal.cuh"
 
 using namespace sol;
+
+namespace sol {
+int g_nvtx = 0;      // option "nvtx": NVTX ranges around the stages of the unrolled sweeps (host side; eager launches or graph capture)
+}
+namespace {
+// RAII range: "fwd step 3 / cnn" etc. show up in nsys / `ncu --nvtx`; a no-op unless the option is on
+struct NvtxRange {
+    bool on;
+    explicit NvtxRange(const char* fmt, int a = 0, int b = 0) : on(sol::g_nvtx != 0) {
+        if (on) { char buf[96]; snprintf(buf, sizeof(buf), fmt, a, b); nvtxRangePushA(buf); }
+    }
+    ~NvtxRange() { if (on) nvtxRangePop(); }
+};
+}  // namespace
 
 namespace {
 
@@ -301,6 +317,14 @@ extern "C" int sol_set_option(const char* name, int value) {
         sol::g_pdl = value ? 1 : 0;
         return SOL_OK;
     }
+    if (strcmp(name, "fuse_stencil") == 0) {
+        sol::g_fuse_stencil = value ? 1 : 0;
+        return SOL_OK;
+    }
+    if (strcmp(name, "nvtx") == 0) {
+        sol::g_nvtx = value ? 1 : 0;
+        return SOL_OK;
+    }
     if (strcmp(name, "tc_base_offset_mode") == 0) {
         sol::g_tc_base_offset_mode = value ? 1 : 0;
         return SOL_OK;
@@ -327,6 +351,14 @@ extern "C" int sol_diffuse_bc_bwd(sol_plan* p, void* stream, int B, const float*
     SOL_PLAN_B(p, B);
     SOL_CHECK(re && gy && gx && gy_in && gx_in, "sol_diffuse_bc_bwd: NULL pointer");
     return launch_diffuse_bc_bwd(p, (cudaStream_t)stream, B, re, dt, res, gy, gx, gy_in, gx_in, nullptr, nullptr);
+}
+
+extern "C" int sol_diffuse_advect(sol_plan* p, void* stream, int B, const float* re, float dt, float res, const float* vy, const float* vx,
+                                  const float* rho, float* vy1, float* vx1, float* vy2, float* vx2, float* rho_out) {
+    SOL_PLAN_B(p, B);
+    SOL_CHECK(re && vy && vx && vy1 && vx1 && vy2 && vx2, "sol_diffuse_advect: NULL pointer");
+    SOL_CHECK((rho == nullptr) == (rho_out == nullptr), "sol_diffuse_advect: rho and rho_out go together");
+    return launch_diffuse_advect(p, (cudaStream_t)stream, B, re, dt, res, vy, vx, rho, vy1, vx1, vy2, vx2, rho_out);
 }
 
 extern "C" int sol_advect(sol_plan* p, void* stream, int B, float dt, const float* vy, const float* vx, const float* rho, float* vy_out,
@@ -374,8 +406,12 @@ extern "C" int sol_step_fwd(sol_plan* p, void* stream, int B, const float* re, f
     cudaStream_t st = (cudaStream_t)stream;
     float* d_vy = vy1 ? vy1 : vy_out;
     float* d_vx = vx1 ? vx1 : vx_out;
-    SOL_TRY(launch_diffuse_bc(p, st, B, re, dt, res, vy_in, vx_in, d_vy, d_vx));
-    SOL_TRY(launch_advect(p, st, B, dt, d_vy, d_vx, rho_in, scratch_vy, scratch_vx, rho_out));
+    if (sol::g_fuse_stencil && p->boundary == SOL_BOUNDARY_OPEN && d_vy != vy_in && d_vx != vx_in) {
+        SOL_TRY(launch_diffuse_advect(p, st, B, re, dt, res, vy_in, vx_in, rho_in, d_vy, d_vx, scratch_vy, scratch_vx, rho_out));
+    } else {
+        SOL_TRY(launch_diffuse_bc(p, st, B, re, dt, res, vy_in, vx_in, d_vy, d_vx));
+        SOL_TRY(launch_advect(p, st, B, dt, d_vy, d_vx, rho_in, scratch_vy, scratch_vx, rho_out));
+    }
     return launch_cg(p, st, B, 1, nullptr, p_out, scratch_vy, scratch_vx, vy_out, vx_out, iters);
 }
 
@@ -768,8 +804,17 @@ int do_forward(sol_unroll* u, cudaStream_t st, const float* weights, const float
             cvy = nvy; cvx = nvx;
             continue;
         }
-        SOL_TRY(launch_diffuse_bc(p, st, B, re, c.dt, c.res, cvy, cvx, s.vy1, s.vx1));
-        SOL_TRY(launch_advect(p, st, B, c.dt, s.vy1, s.vx1, crho, u->vy2, u->vx2, nrho));
+        NvtxRange r_step("fwd step %d", i);
+        {
+            NvtxRange r("diffuse+bc, advect");
+            if (sol::g_fuse_stencil) {
+                SOL_TRY(launch_diffuse_advect(p, st, B, re, c.dt, c.res, cvy, cvx, crho, s.vy1, s.vx1, u->vy2, u->vx2, nrho));
+            } else {
+                SOL_TRY(launch_diffuse_bc(p, st, B, re, c.dt, c.res, cvy, cvx, s.vy1, s.vx1));
+                SOL_TRY(launch_advect(p, st, B, c.dt, s.vy1, s.vx1, crho, u->vy2, u->vx2, nrho));
+            }
+        }
+        NvtxRange r_proj("pressure projection (+features)");
         if (fuse_io && c.cin0 == 3) {      // the projection kernel also writes the CNN features of the projected velocity
             CgFuse f; f.feat_out = s.feat; f.re = re; f.isy = 1.0f / c.sig_vy; f.isx = 1.0f / c.sig_vx; f.isr = 1.0f / c.sig_ext; f.cfeat = 3;
             SOL_TRY(launch_cg(p, st, B, 1, nullptr, nullptr, u->vy2, u->vx2, u->vy3, u->vx3, it_slot, &f));
@@ -777,7 +822,12 @@ int do_forward(sol_unroll* u, cudaStream_t st, const float* weights, const float
             SOL_TRY(launch_cg(p, st, B, 1, nullptr, nullptr, u->vy2, u->vx2, u->vy3, u->vx3, it_slot));
             SOL_TRY(launch_to_feature(p, st, B, u->vy3, u->vx3, re, c.sig_vy, c.sig_vx, c.sig_ext, s.feat));
         }
-        SOL_TRY(cnn_forward(u, st, weights, s, u->corr));
+        r_proj.~NvtxRange(); r_proj.on = false;
+        {
+            NvtxRange r("correction cnn");
+            SOL_TRY(cnn_forward(u, st, weights, s, u->corr));
+        }
+        NvtxRange r_loss("correct + loss");
         SOL_TRY(launch_correct_loss(p, st, B, u->vy3, u->vx3, u->corr, c.sig_vy, c.sig_vx, gt_vy ? gt_vy + (size_t)i * NY : nullptr,
                                     gt_vx ? gt_vx + (size_t)i * NX : nullptr, 1.0f / (float)m, nvy, nvx, s.gl_vy, s.gl_vx,
                                     gt_vy ? loss_steps + i : nullptr));
@@ -897,8 +947,12 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
     for (int i = m - 1; i >= 0; --i) {
         StepStash& s = u->stash[i];
         float* g_corr = u->deferred_wgrad ? u->gcorr_st + (size_t)i * p->NC() * B * 2 : u->g_corr;
+        NvtxRange r_step("bwd step %d", i);
         if (!corr_ready) SOL_TRY(launch_corr_bwd(p, st, B, Gy, Gx, c.sig_vy, c.sig_vx, g_corr));   // else: written by diffuse_bc_bwd of step i+1
-        SOL_TRY(cnn_backward(u, st, weights, gw, s, g_corr, u->g_feat, i == m - 1, i));
+        {
+            NvtxRange r("correction cnn adjoint");
+            SOL_TRY(cnn_backward(u, st, weights, gw, s, g_corr, u->g_feat, i == m - 1, i));
+        }
         if (background && i >= sol::g_wgrad_bg_chunk && done[1] - i >= sol::g_wgrad_bg_chunk) {
             // the output gradients of steps [i, done) are complete: their weight-gradient items run on the side stream from here on
             SOL_CUDA(cudaEventRecord(u->ev_wfork, st));
@@ -958,6 +1012,7 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
     if (u->deferred_wgrad) {
         // what the solve windows did not absorb: ONE launch per layer over its remaining steps [0, done[l]), then the
         // per-layer reduction of the CTA partial sums
+        NvtxRange r_w("deferred weight gradients (tail + finalize)");
         if (bg_pending) {
             SOL_CUDA(cudaEventRecord(u->ev_wjoin, u->sstream));
             SOL_CUDA(cudaStreamWaitEvent(st, u->ev_wjoin, 0));

@@ -146,6 +146,10 @@ int launch_advect(const sol_plan* p, cudaStream_t st, int B, float dt, const flo
                   float* vy_out, float* vx_out, float* rho_out);
 int launch_advect_bwd(const sol_plan* p, cudaStream_t st, int B, float dt, const float* vy, const float* vx,
                       const float* gy_out, const float* gx_out, float* gy, float* gx);
+// fused diffuse+BC -> advection with the stencil halo staged in shared memory (sol_stencil_fused.cu; OPEN plans)
+extern int g_fuse_stencil;
+int launch_diffuse_advect(const sol_plan* p, cudaStream_t st, int B, const float* re, float dt, float res, const float* vy, const float* vx,
+                          const float* rho, float* vy1, float* vx1, float* vy2, float* vx2, float* rho_out);
 int launch_divergence(const sol_plan* p, cudaStream_t st, int B, const float* vy, const float* vx, float* div);
 int launch_to_feature(const sol_plan* p, cudaStream_t st, int B, const float* vy, const float* vx, const float* re,
                       float sy, float sx, float sr, float* feat);

@@ -340,7 +340,10 @@ __global__ void __launch_bounds__(256) k_amax(const float4* __restrict__ x, size
     if ((threadIdx.x & 31) == 0 && m) atomicMax(slot, m);
 }
 
-int g_wgrad_bg_ctas = 48;
+// measured on B200 at the bench shape (profiles/r02/r02_g_wgrad_background.txt): every (CTAs, chunk) setting is SLOWER than no
+// background launches (12.80 ms): with 48 SMs taken the conv chain fills every remaining SM two CTAs deep, the early CTAs of the
+// next layer find no free slot (no prologue overlap), and the side stream's tail delays the end of the sweep.  Default off.
+int g_wgrad_bg_ctas = 0;
 int g_wgrad_bg_chunk = 4;
 
 int launch_amax(cudaStream_t st, const float* x, size_t n, uint32_t* slot) {

@@ -133,6 +133,15 @@ class Plan:
                                           _ptr(gy), _ptr(gx), _ptr(oy), _ptr(ox)))
         return oy, ox
 
+    def diffuse_advect(self, re, vy, vx, rho=None, dt=1.0, res=None):
+        """diffuse_bc + advect in one launch (shared-memory staged halo): returns (vy1, vx1, vy2, vx2[, rho_out])."""
+        B = vy.shape[0]
+        y1, x1 = self.faces(B); y2, x2 = self.faces(B)
+        orho = self.cells(B) if rho is not None else None
+        check(self.lib.sol_diffuse_advect(self.handle, _stream(), B, _ptr(re), dt, float(self.X if res is None else res), _ptr(vy), _ptr(vx),
+                                          _ptr(rho), _ptr(y1), _ptr(x1), _ptr(y2), _ptr(x2), _ptr(orho)))
+        return (y1, x1, y2, x2, orho) if rho is not None else (y1, x1, y2, x2)
+
     def advect(self, vy, vx, rho=None, dt=1.0):
         B = vy.shape[0]
         oy, ox = self.faces(B)

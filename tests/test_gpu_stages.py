@@ -331,3 +331,30 @@ def test_adam_tf1(eng, cuda_device):
         th, m, v = so.adam_tf1_step(th, gr, m, v, t, 1e-3)
         eng.adam_tf1(d_th, dev(gr, cuda_device), d_m, d_v, t, 1e-3)
     assert rel(d_th, th) < 1e-6 and rel(d_m, m) < 1e-6 and rel(d_v, v) < 5e-5   # fp32 (1-beta2)
+
+
+@pytest.mark.parametrize("Y,X,B", [(128, 64, 3), (64, 32, 2), (40, 24, 2), (256, 128, 2), (20, 70, 1)], ids=["128x64", "64x32", "40x24", "256x128", "20x70"])
+@pytest.mark.parametrize("vscale", [1.0, 12.0], ids=["cfl<1", "cfl>halo"])
+def test_fused_diffuse_advect_equals_stage_kernels(eng, cuda_device, Y, X, B, vscale):
+    """The shared-memory-staged fused kernel (diffuse + BC -> advection of vy, vx, rho + inflow) returns exactly what the two stage
+    kernels return — on full and ragged tiles, and when back-traces leave the staged halo (exact slow path) — and matches the oracle."""
+    geom = so.KarmanGeom(Y, X)
+    g = torch.Generator().manual_seed(5)
+    vy = (1.0 + 0.5 * torch.randn(B, Y + 1, X, generator=g, dtype=torch.float64)) * vscale
+    vx = 0.5 * torch.randn(B, Y, X + 1, generator=g, dtype=torch.float64) * vscale
+    rho = torch.rand(B, Y, X, generator=g, dtype=torch.float64)
+    re = torch.tensor([so.REYNOLDS_TRAIN[b % 6] for b in range(B)], dtype=torch.float64)
+    plan = eng.Plan.karman(Y, X, B)
+    d = lambda t: dev(t, cuda_device)
+    y1, x1 = plan.diffuse_bc(d(re), d(vy), d(vx))
+    y2, x2, r2 = plan.advect(y1, x1, rho=d(rho))
+    f1, g1, f2, g2, fr = plan.diffuse_advect(d(re), d(vy), d(vx), rho=d(rho))
+    torch.cuda.synchronize()
+    for a, b_ in ((f1, y1), (g1, x1), (f2, y2), (g2, x2), (fr, r2)):
+        assert torch.equal(a, b_)
+    # and against the float64 oracle (the fp32 back-trace of a large velocity loses absolute precision: relative to the field norm)
+    alpha = (1.0 * X * X / re).view(B, 1, 1)
+    oy1, ox1 = so.diffuse_bc(vy, vx, alpha, torch.tensor(geom.bc_mask_y), torch.tensor(geom.bc_val_y))
+    oy2, ox2 = so.advect_velocity(oy1, ox1, 1.0 / geom.dx)
+    assert rel(f1, oy1) < 1e-6 and rel(g1, ox1) < 1e-6
+    assert rel(f2, oy2) < (2e-6 if vscale == 1.0 else 5e-5) and rel(g2, ox2) < (2e-6 if vscale == 1.0 else 5e-5)
