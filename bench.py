@@ -275,6 +275,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("SOL_NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert world == args.gpus or world == 1, "launch with torch.distributed.run --nproc-per-node N for --gpus N"
     dev = torch.device("cuda", local)
@@ -292,6 +293,8 @@ def main():
         engine.set_option("wgrad_window_us", args.wgrad_window_us)
     if args.wgrad_bg_ctas >= 0:
         engine.set_option("wgrad_bg_ctas", args.wgrad_bg_ctas)
+    if os.environ.get("SOL_WGRAD_ISSUERS"):
+        engine.set_option("wgrad_issuers", int(os.environ["SOL_WGRAD_ISSUERS"]))
     if args.wgrad_bg_chunk >= 1:
         engine.set_option("wgrad_bg_chunk", args.wgrad_bg_chunk)
     engine.set_option("wgrad_path", args.wgrad_path)

@@ -99,33 +99,52 @@ __device__ __forceinline__ void fold_rows(float* __restrict__ M, int K, int ld, 
     }
 }
 
-template <int K>
+template <int TM, int K>
 __device__ __forceinline__ void tile_gemm_sym_left(const float* __restrict__ At, int lda, const float* __restrict__ Mf, int ldb, int r0, int c0,
-                                                   float (&acc)[2][4]) {
+                                                   float (&acc)[TM][4]) {
 #pragma unroll 8
     for (int kk = 0; kk < K / 2; ++kk) {
-        const float2 a = *reinterpret_cast<const float2*>(At + kk * lda + r0);
+        float a[TM];
+        if (TM == 4) {
+            const float4 v = *reinterpret_cast<const float4*>(At + kk * lda + r0);
+            a[0] = v.x; a[1] = v.y; a[2 % TM] = v.z; a[3 % TM] = v.w;
+        } else {
+            const float2 v = *reinterpret_cast<const float2*>(At + kk * lda + r0);
+            a[0] = v.x; a[1] = v.y;
+        }
         const float4 bs = *reinterpret_cast<const float4*>(Mf + kk * ldb + c0);
         const float4 bd = *reinterpret_cast<const float4*>(Mf + (K - 1 - kk) * ldb + c0);
-        acc[0][0] = fmaf(a.x, bs.x, acc[0][0]); acc[0][1] = fmaf(a.x, bs.y, acc[0][1]);
-        acc[0][2] = fmaf(a.x, bs.z, acc[0][2]); acc[0][3] = fmaf(a.x, bs.w, acc[0][3]);
-        acc[1][0] = fmaf(a.y, bd.x, acc[1][0]); acc[1][1] = fmaf(a.y, bd.y, acc[1][1]);
-        acc[1][2] = fmaf(a.y, bd.z, acc[1][2]); acc[1][3] = fmaf(a.y, bd.w, acc[1][3]);
+#pragma unroll
+        for (int rr = 0; rr < TM; ++rr) {
+            const float4 bm = (rr & 1) ? bd : bs;        // even rows see the mirror sums, odd rows the differences
+            acc[rr][0] = fmaf(a[rr], bm.x, acc[rr][0]); acc[rr][1] = fmaf(a[rr], bm.y, acc[rr][1]);
+            acc[rr][2] = fmaf(a[rr], bm.z, acc[rr][2]); acc[rr][3] = fmaf(a[rr], bm.w, acc[rr][3]);
+        }
     }
 }
 
-template <int K>
+template <int TM, int K>
 __device__ __forceinline__ void tile_gemm_sym_right(const float* __restrict__ Atf, int lda, const float* __restrict__ Bm, int ldb, int r0, int c0,
-                                                    float (&acc)[2][4]) {
+                                                    float (&acc)[TM][4]) {
 #pragma unroll 8
     for (int m = 0; m < K / 2; ++m) {
-        const float2 as = *reinterpret_cast<const float2*>(Atf + m * lda + r0);
-        const float2 ad = *reinterpret_cast<const float2*>(Atf + (K - 1 - m) * lda + r0);
+        float as[TM], ad[TM];
+        if (TM == 4) {
+            const float4 u = *reinterpret_cast<const float4*>(Atf + m * lda + r0);
+            const float4 v = *reinterpret_cast<const float4*>(Atf + (K - 1 - m) * lda + r0);
+            as[0] = u.x; as[1] = u.y; as[2 % TM] = u.z; as[3 % TM] = u.w;
+            ad[0] = v.x; ad[1] = v.y; ad[2 % TM] = v.z; ad[3 % TM] = v.w;
+        } else {
+            const float2 u = *reinterpret_cast<const float2*>(Atf + m * lda + r0);
+            const float2 v = *reinterpret_cast<const float2*>(Atf + (K - 1 - m) * lda + r0);
+            as[0] = u.x; as[1] = u.y; ad[0] = v.x; ad[1] = v.y;
+        }
         const float4 b = *reinterpret_cast<const float4*>(Bm + m * ldb + c0);
-        acc[0][0] = fmaf(as.x, b.x, acc[0][0]); acc[0][1] = fmaf(ad.x, b.y, acc[0][1]);
-        acc[0][2] = fmaf(as.x, b.z, acc[0][2]); acc[0][3] = fmaf(ad.x, b.w, acc[0][3]);
-        acc[1][0] = fmaf(as.y, b.x, acc[1][0]); acc[1][1] = fmaf(ad.y, b.y, acc[1][1]);
-        acc[1][2] = fmaf(as.y, b.z, acc[1][2]); acc[1][3] = fmaf(ad.y, b.w, acc[1][3]);
+#pragma unroll
+        for (int rr = 0; rr < TM; ++rr) {              // even columns see the mirror sums, odd columns the differences
+            acc[rr][0] = fmaf(as[rr], b.x, acc[rr][0]); acc[rr][1] = fmaf(ad[rr], b.y, acc[rr][1]);
+            acc[rr][2] = fmaf(as[rr], b.z, acc[rr][2]); acc[rr][3] = fmaf(ad[rr], b.w, acc[rr][3]);
+        }
     }
 }
 
@@ -143,6 +162,36 @@ struct FaceIn {
         return v;
     }
 };
+
+// masked divergence of four consecutive cells (j, i..i+3), i % 4 == 0: 128-bit loads of the y-face rows and their masks, the five
+// x-faces as scalars (row pitch X+1); same arithmetic per cell as divergence_cell (sol_cells.cuh) on FaceIn values
+template <int X>
+__device__ __forceinline__ void divergence4(const FaceIn& in, const float* __restrict__ my, const float* __restrict__ mx,
+                                            const unsigned char* __restrict__ active, int j, int i, float (&d)[4]) {
+    const float4 yl4 = *reinterpret_cast<const float4*>(in.vy + j * X + i), yh4 = *reinterpret_cast<const float4*>(in.vy + (j + 1) * X + i);
+    const float4 ml4 = __ldg(reinterpret_cast<const float4*>(my + j * X + i)), mh4 = __ldg(reinterpret_cast<const float4*>(my + (j + 1) * X + i));
+    float yl[4] = {yl4.x, yl4.y, yl4.z, yl4.w}, yh[4] = {yh4.x, yh4.y, yh4.z, yh4.w};
+    const float ml[4] = {ml4.x, ml4.y, ml4.z, ml4.w}, mh[4] = {mh4.x, mh4.y, mh4.z, mh4.w};
+    float xv[5], mv[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) { xv[c] = in.vx[j * (X + 1) + i + c]; mv[c] = __ldg(mx + j * (X + 1) + i + c); }
+    if (in.gf) {      // fused feat_bwd: the incoming gradient plus the scaled feature gradient (FaceIn::y / ::x)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            yl[c] = fmaf(in.gf[((size_t)j * X + i + c) * in.cfeat], in.isy, yl[c]);
+            if (j + 1 < in.Y) yh[c] = fmaf(in.gf[((size_t)(j + 1) * X + i + c) * in.cfeat], in.isy, yh[c]);
+            xv[c] = fmaf(in.gf[((size_t)j * X + i + c) * in.cfeat + 1], in.isx, xv[c]);
+        }
+        if (i + 4 < X) xv[4] = fmaf(in.gf[((size_t)j * X + i + 4) * in.cfeat + 1], in.isx, xv[4]);
+    }
+    const uchar4 ac = *reinterpret_cast<const uchar4*>(active + j * X + i);
+    const unsigned char av[4] = {ac.x, ac.y, ac.z, ac.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float v = (mh[c] * yh[c] - ml[c] * yl[c]) + (mv[c + 1] * xv[c + 1] - mv[c] * xv[c]);
+        d[c] = av[c] ? v : 0.0f;
+    }
+}
 
 // A thread-block cluster of CL CTAs per simulation, split along y: p0 = Sy ((Sy D Sx) * ilam) Sx.  Every CTA builds the whole
 // right-hand side D (cheap), then owns YS = Y/CL rows of the three products U = Sy D, V = (U Sx) * ilam, Z = V Sx — no exchange
@@ -188,26 +237,27 @@ __global__ void __launch_bounds__((Y / CL / TM) * (X / 4), 1) k_direct_solve(con
         float* dst[CL];
 #pragma unroll
         for (int peer = 0; peer < CL; ++peer) dst[peer] = (CL > 1) ? cg::this_cluster().map_shared_rank(sD, peer) : sD;
-#pragma unroll 4
-        for (int lc = tid; lc < YS * X; lc += NT) {
+#pragma unroll 2
+        for (int lc = tid * 4; lc < YS * X; lc += NT * 4) {
             const int c = rbase * X + lc;
             const int j = c / X, i = c - j * X;
-            float d;
-            if (MODE == 1)
-                d = (a.my[(j + 1) * X + i] * in.y(j + 1, i) - a.my[j * X + i] * in.y(j, i)) +
-                    (a.mx[j * (X + 1) + i + 1] * in.x(j, i + 1) - a.mx[j * (X + 1) + i] * in.x(j, i));
-            else
-                d = rhs[c];
-            d = a.active[c] ? d : 0.0f;
+            float d[4];
+            if (MODE == 1) {
+                divergence4<X>(in, a.my, a.mx, a.active, j, i, d);
+            } else {
+                const float4 r4 = *reinterpret_cast<const float4*>(rhs + c);
+                const uchar4 ac = *reinterpret_cast<const uchar4*>(a.active + c);
+                d[0] = ac.x ? r4.x : 0.0f; d[1] = ac.y ? r4.y : 0.0f; d[2] = ac.z ? r4.z : 0.0f; d[3] = ac.w ? r4.w : 0.0f;
+            }
 #pragma unroll
-            for (int peer = 0; peer < CL; ++peer) dst[peer][c] = d;
+            for (int peer = 0; peer < CL; ++peer) *reinterpret_cast<float4*>(dst[peer] + c) = make_float4(d[0], d[1], d[2], d[3]);
         }
     }
     DSTAMP(4);
     if (CL > 1) cg::this_cluster().sync();
     else __syncthreads();
     DSTAMP(5);
-    static_assert(TM == 2 && (Y / CL) % 2 == 0 && X % 8 == 0, "the folded products pair an even with an odd row / column");
+    static_assert(TM % 2 == 0 && (Y / CL) % TM == 0 && X % 8 == 0, "the folded products pair even with odd rows / columns");
     const int tx = tid % (X / 4), ty = tid / (X / 4);
     const int r0 = ty * TM, c0 = tx * 4;        // r0: row inside this CTA's slice (even); rbase is even too
     float acc[TM][4];
@@ -215,7 +265,7 @@ __global__ void __launch_bounds__((Y / CL / TM) * (X / 4), 1) k_direct_solve(con
     fold_rows<NT>(sD, Y, X, tid);
     __syncthreads();
     zero_acc<TM>(acc);
-    tile_gemm_sym_left<Y>(sSy, YS, sD, X, r0, c0, acc);
+    tile_gemm_sym_left<TM, Y>(sSy, YS, sD, X, r0, c0, acc);
     store_transposed<TM>(t0, YS, r0, c0, acc);
     __syncthreads();
     fold_rows<NT>(t0, X, YS, tid);
@@ -223,7 +273,7 @@ __global__ void __launch_bounds__((Y / CL / TM) * (X / 4), 1) k_direct_solve(con
     DSTAMP(6);
     // stage 2: V = (U Sx) * ilam, transposed into t1
     zero_acc<TM>(acc);
-    tile_gemm_sym_right<X>(t0, YS, sSx, X, r0, c0, acc);
+    tile_gemm_sym_right<TM, X>(t0, YS, sSx, X, r0, c0, acc);
 #pragma unroll
     for (int rr = 0; rr < TM; ++rr) {
         const float4 l = __ldg(reinterpret_cast<const float4*>(a.ilam + (rbase + r0 + rr) * X + c0));
@@ -236,7 +286,7 @@ __global__ void __launch_bounds__((Y / CL / TM) * (X / 4), 1) k_direct_solve(con
     DSTAMP(7);
     // stage 3: Z = V Sx; my rows go into every CTA's sZ
     zero_acc<TM>(acc);
-    tile_gemm_sym_right<X>(t1, YS, sSx, X, r0, c0, acc);
+    tile_gemm_sym_right<TM, X>(t1, YS, sSx, X, r0, c0, acc);
     DSTAMP(8);
     if (CL > 1) {
         cg::cluster_group cluster = cg::this_cluster();
@@ -258,7 +308,7 @@ __global__ void __launch_bounds__((Y / CL / TM) * (X / 4), 1) k_direct_solve(con
     fold_rows<NT>(sZ, Y, X, tid);
     __syncthreads();
     zero_acc<TM>(acc);
-    tile_gemm_sym_left<Y>(sSy, YS, sZ, X, r0, c0, acc);
+    tile_gemm_sym_left<TM, Y>(sSy, YS, sZ, X, r0, c0, acc);
     float* p0g = a.p0 + (size_t)b * N;
 #pragma unroll
     for (int rr = 0; rr < TM; ++rr)
@@ -303,24 +353,27 @@ __global__ void __launch_bounds__((Y / CL / TM) * (X / 4), 1) k_direct_solve_big
         FaceIn in{a.vy_in + (size_t)b * (Y + 1) * X, a.vx_in + (size_t)b * Y * (X + 1),
                   a.gfeat_in ? a.gfeat_in + (size_t)b * N * a.cfeat : nullptr, a.isy, a.isx, a.cfeat, Y, X};
         const float* rhs = (MODE == 0) ? a.rhs + (size_t)b * N : nullptr;
-#pragma unroll 4
-        for (int lc = tid; lc < YS * X; lc += NT) {
+#pragma unroll 2
+        for (int lc = tid * 4; lc < YS * X; lc += NT * 4) {
             const int c = rbase * X + lc;
             const int j = c / X, i = c - j * X;
-            float d;
-            if (MODE == 1)
-                d = (a.my[(j + 1) * X + i] * in.y(j + 1, i) - a.my[j * X + i] * in.y(j, i)) +
-                    (a.mx[j * (X + 1) + i + 1] * in.x(j, i + 1) - a.mx[j * (X + 1) + i] * in.x(j, i));
-            else
-                d = rhs[c];
-            Dg[c] = a.active[c] ? d : 0.0f;
+            float d[4];
+            if (MODE == 1) {
+                divergence4<X>(in, a.my, a.mx, a.active, j, i, d);
+            } else {
+                const float4 r4 = *reinterpret_cast<const float4*>(rhs + c);
+                const uchar4 ac = *reinterpret_cast<const uchar4*>(a.active + c);
+                d[0] = ac.x ? r4.x : 0.0f; d[1] = ac.y ? r4.y : 0.0f; d[2] = ac.z ? r4.z : 0.0f; d[3] = ac.w ? r4.w : 0.0f;
+            }
+            *reinterpret_cast<float4*>(Dg + c) = make_float4(d[0], d[1], d[2], d[3]);
         }
     }
     cluster.sync();       // release / acquire at cluster scope: the peers' rows of D are visible
     const int tx = tid % (X / 4), ty = tid / (X / 4);
     const int r0 = ty * TM, c0 = tx * 4;
     float acc[TM][4];
-    static_assert(TM == 2 && (Y / CL) % 2 == 0 && X % 8 == 0, "the folded products pair an even with an odd row / column");
+    static_assert(TM % 2 == 0 && (Y / CL) % TM == 0 && X % 8 == 0, "the folded products pair even with odd rows / columns");
+    static_assert(TM == 2, "the streamed product is written for row pairs");
     // acc (+)= Sy[my rows, :] * G for a [Y][X] operand G streamed from global memory, with the even / odd fold of the sine transform
     // (see fold_rows): chunk c brings rows kk in [c*KC, (c+1)*KC) AND their mirrors Y-1-kk, folded on the fly into sums / differences
     auto stream_gemm = [&](const float* __restrict__ G) {
@@ -374,7 +427,7 @@ __global__ void __launch_bounds__((Y / CL / TM) * (X / 4), 1) k_direct_solve_big
     __syncthreads();
     // stage 2: V = (U Sx) * ilam, transposed into t1
     zero_acc<TM>(acc);
-    tile_gemm_sym_right<X>(t0, YS, sSx, X, r0, c0, acc);
+    tile_gemm_sym_right<TM, X>(t0, YS, sSx, X, r0, c0, acc);
 #pragma unroll
     for (int rr = 0; rr < TM; ++rr) {
         const float4 l = __ldg(reinterpret_cast<const float4*>(a.ilam + (rbase + r0 + rr) * X + c0));
@@ -386,7 +439,7 @@ __global__ void __launch_bounds__((Y / CL / TM) * (X / 4), 1) k_direct_solve_big
     __syncthreads();
     // stage 3: Z = V Sx; my rows -> global scratch
     zero_acc<TM>(acc);
-    tile_gemm_sym_right<X>(t1, YS, sSx, X, r0, c0, acc);
+    tile_gemm_sym_right<TM, X>(t1, YS, sSx, X, r0, c0, acc);
 #pragma unroll
     for (int rr = 0; rr < TM; ++rr)
         *reinterpret_cast<float4*>(Zg + (rbase + r0 + rr) * X + c0) = make_float4(acc[rr][0], acc[rr][1], acc[rr][2], acc[rr][3]);
@@ -618,7 +671,7 @@ int launch_direct(const sol_plan* p, cudaStream_t st, int B, int mode, const flo
     a.trace = g_direct_trace;
     if (mode == 0 && (!rhs || !p_out)) return fail(SOL_ERR_INVALID, "direct solve: rhs / p_out required");
     if (mode == 1 && (!vy || !vx || !vy_out || !vx_out)) return fail(SOL_ERR_INVALID, "direct solve: velocity pointers required");
-    if (p->Y == 128 && p->X == 64) return launch_direct_t<128, 64, 4, 2, 3>(a, st, mode);
+    if (p->Y == 128 && p->X == 64) return launch_direct_t<128, 64, 4, 4, 3>(a, st, mode);      // 4x4 register tiles: the folded left products are shared-memory-bandwidth bound
     if (p->Y == 64 && p->X == 32) return launch_direct_t<64, 32, 2, 2, 7>(a, st, mode);
     if (p->Y == 256 && p->X == 128) return launch_direct_big_t<256, 128, 8, 2, 16, 1>(a, st, mode);
     return fail(SOL_ERR_UNSUPPORTED, "direct solve: unsupported grid");

@@ -304,6 +304,11 @@ extern "C" int sol_set_option(const char* name, int value) {
         sol::g_wgrad_bg_chunk = value;
         return SOL_OK;
     }
+    if (strcmp(name, "wgrad_issuers") == 0) {
+        SOL_CHECK(value == 1 || value == 2, "wgrad_issuers must be 1 or 2");
+        sol::g_wgrad_issuers = value;
+        return SOL_OK;
+    }
     if (strcmp(name, "wgrad_overlap") == 0) {
         sol::g_wgrad_overlap = value ? 1 : 0;
         return SOL_OK;
@@ -543,7 +548,7 @@ struct sol_unroll {
     float *sA_vy, *sA_vx, *sB_vy, *sB_vx, *rhoA, *rhoB;
     float *vy2, *vx2, *vy3, *vx3;
     float* corr;
-    float *G_vy[2], *G_vx[2], *H_vy, *H_vx, *K_vy, *K_vx;
+    float *G_vy[2], *G_vx[2], *H_vy, *H_vx, *H2_vy, *H2_vx, *K_vy, *K_vx;
     float *g_corr, *g_feat, *gbuf[3];
     float* wT;
     float *wprep_fwd, *wprep_bwd;   // [10 layers][2*25*32*32] pre-split tensor-core weights
@@ -618,6 +623,7 @@ int carve(sol_unroll* u, void* ws, size_t* total) {
     u->corr = cv.take<float>(NC * 2);
     for (int k = 0; k < 2; ++k) { u->G_vy[k] = cv.take<float>(NY); u->G_vx[k] = cv.take<float>(NX); }
     u->H_vy = cv.take<float>(NY); u->H_vx = cv.take<float>(NX);
+    u->H2_vy = cv.take<float>(NY); u->H2_vx = cv.take<float>(NX);
     u->K_vy = cv.take<float>(NY); u->K_vx = cv.take<float>(NX);
     u->g_corr = cv.take<float>(NC * 2);
     u->g_feat = cv.take<float>(NC * c.cin0);
@@ -944,6 +950,11 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
     const float* Gx = u->stash[m - 1].gl_vx;
     const bool fuse_io = sol::g_fuse_solver_io && !burgers && cg_fuses(p, B);
     bool corr_ready = false;
+    if (fuse_io) {      // the first scatter targets; every later pair is zeroed by the preceding diffusion adjoint
+        float* Hy0 = ((m - 1) & 1) ? u->H2_vy : u->H_vy; float* Hx0 = ((m - 1) & 1) ? u->H2_vx : u->H_vx;
+        SOL_CUDA(cudaMemsetAsync(Hy0, 0, sizeof(float) * p->NY() * B, st));
+        SOL_CUDA(cudaMemsetAsync(Hx0, 0, sizeof(float) * p->NX() * B, st));
+    }
     for (int i = m - 1; i >= 0; --i) {
         StepStash& s = u->stash[i];
         float* g_corr = u->deferred_wgrad ? u->gcorr_st + (size_t)i * p->NC() * B * 2 : u->g_corr;
@@ -989,24 +1000,30 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
             SOL_CUDA(cudaEventRecord(u->ev_wjoin, u->sstream));
             joined = false;
         }
+        // scatter targets of the advection adjoint: with the fused solver I/O nothing else uses H, so two buffer pairs alternate and
+        // the diffusion adjoint of a step zeroes the pair of the NEXT one (no memset nodes inside the sweep)
+        float* Hy = (fuse_io && (i & 1)) ? u->H2_vy : u->H_vy;
+        float* Hx = (fuse_io && (i & 1)) ? u->H2_vx : u->H_vx;
+        float* Zy = fuse_io ? ((i & 1) ? u->H_vy : u->H2_vy) : nullptr;
+        float* Zx = fuse_io ? ((i & 1) ? u->H_vx : u->H2_vx) : nullptr;
         if (fuse_io) {      // the adjoint projection adds the feature gradient to the incoming velocity gradient itself
             CgFuse f; f.gfeat_in = u->g_feat; f.isy = 1.0f / c.sig_vy; f.isx = 1.0f / c.sig_vx; f.cfeat = c.cin0;
             SOL_TRY(launch_cg(p, st, B, 1, nullptr, nullptr, Gy, Gx, u->K_vy, u->K_vx, u->iters + (size_t)(m + i) * B, &f));
         } else {
             SOL_TRY(launch_cg(p, st, B, 1, nullptr, nullptr, u->H_vy, u->H_vx, u->K_vy, u->K_vx, u->iters + (size_t)(m + i) * B));
         }
-        SOL_TRY(launch_advect_bwd(p, st, B, c.dt, s.vy1, s.vx1, u->K_vy, u->K_vx, u->H_vy, u->H_vx));
+        SOL_TRY(launch_advect_bwd(p, st, B, c.dt, s.vy1, s.vx1, u->K_vy, u->K_vx, Hy, Hx, fuse_io));
         if (!joined) SOL_CUDA(cudaStreamWaitEvent(st, u->ev_wjoin, 0));
         if (i > 0) {
             float* ny = u->G_vy[i & 1]; float* nx = u->G_vx[i & 1];
             float* gc_next = nullptr;       // fused corr_bwd of step i-1
             if (sol::g_fuse_small) gc_next = u->deferred_wgrad ? u->gcorr_st + (size_t)(i - 1) * p->NC() * B * 2 : u->g_corr;
-            SOL_TRY(launch_diffuse_bc_bwd(p, st, B, re, c.dt, c.res, u->H_vy, u->H_vx, ny, nx, u->stash[i - 1].gl_vy, u->stash[i - 1].gl_vx,
-                                          gc_next, c.sig_vy, c.sig_vx));
+            SOL_TRY(launch_diffuse_bc_bwd(p, st, B, re, c.dt, c.res, Hy, Hx, ny, nx, u->stash[i - 1].gl_vy, u->stash[i - 1].gl_vx,
+                                          gc_next, c.sig_vy, c.sig_vx, Zy, Zx));
             corr_ready = gc_next != nullptr;
             Gy = ny; Gx = nx;
         } else if (g_vy0 && g_vx0) {
-            SOL_TRY(launch_diffuse_bc_bwd(p, st, B, re, c.dt, c.res, u->H_vy, u->H_vx, g_vy0, g_vx0, nullptr, nullptr));
+            SOL_TRY(launch_diffuse_bc_bwd(p, st, B, re, c.dt, c.res, Hy, Hx, g_vy0, g_vx0, nullptr, nullptr));
         }
     }
     if (u->deferred_wgrad) {

@@ -141,11 +141,12 @@ int launch_diffuse_bc(const sol_plan* p, cudaStream_t st, int B, const float* re
                       const float* vy, const float* vx, float* vy_out, float* vx_out);
 int launch_diffuse_bc_bwd(const sol_plan* p, cudaStream_t st, int B, const float* re, float dt, float res,
                           const float* gy, const float* gx, float* gy_in, float* gx_in, const float* add_y, const float* add_x,
-                          float* g_corr = nullptr, float sy = 1.0f, float sx = 1.0f);
+                          float* g_corr = nullptr, float sy = 1.0f, float sx = 1.0f, float* zero_y = nullptr, float* zero_x = nullptr);
 int launch_advect(const sol_plan* p, cudaStream_t st, int B, float dt, const float* vy, const float* vx, const float* rho,
                   float* vy_out, float* vx_out, float* rho_out);
+// gy / gx are scatter targets: zeroed here by two memsets unless the caller guarantees they already are (targets_are_zero)
 int launch_advect_bwd(const sol_plan* p, cudaStream_t st, int B, float dt, const float* vy, const float* vx,
-                      const float* gy_out, const float* gx_out, float* gy, float* gx);
+                      const float* gy_out, const float* gx_out, float* gy, float* gx, bool targets_are_zero = false);
 // fused diffuse+BC -> advection with the stencil halo staged in shared memory (sol_stencil_fused.cu; OPEN plans)
 extern int g_fuse_stencil;
 int launch_diffuse_advect(const sol_plan* p, cudaStream_t st, int B, const float* re, float dt, float res, const float* vy, const float* vx,
@@ -252,7 +253,8 @@ extern int g_fuse_solver_io;
 extern int g_wgrad_overlap;
 extern int g_wgrad_window_us;
 extern int g_wgrad_bg_ctas;          // CTAs of the background weight-gradient launches beside the adjoint conv chain (0 = off)
-extern int g_wgrad_bg_chunk;         // unrolled steps per background launch
+extern int g_wgrad_bg_chunk;
+extern int g_wgrad_issuers;          // MMA-issuing warps of the 3xFP16 weight-gradient kernel (1 or 2)         // unrolled steps per background launch
 // 32->32 layers: tensor-core path when enabled (wprep = pre-split weights or NULL for internal scratch), else SIMT
 int launch_conv5x5_c32_auto(cudaStream_t st, int B, int Y, int X, const float* in, const float* w, const float* wprep,
                             const float* bias, const float* addend, const float* ref, int act, float slope, float* out,

@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(256) k_diffuse_bc_bwd(int B, int Y, int X, con
                                                         const float* __restrict__ bcm,
                                                         const float* __restrict__ add_y, const float* __restrict__ add_x,
                                                         float* __restrict__ gy_in, float* __restrict__ gx_in,
-                                                        float* __restrict__ g_corr, float sy, float sx) {
+                                                        float* __restrict__ g_corr, float sy, float sx,
+                                                        float* __restrict__ zero_y, float* __restrict__ zero_x) {
     pdl_sync();
     const int NY = (Y + 1) * X, NX = Y * (X + 1), NF = NY + NX;
     const size_t total = (size_t)B * NF;
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(256) k_diffuse_bc_bwd(int B, int Y, int X, con
             float v = diffuse_bc_bwd_cell(gy + (size_t)b * NY, Y + 1, X, f.j, f.i, alpha, bcm);
             if (add_y) v += add_y[o];
             gy_in[o] = v;
+            if (zero_y) zero_y[o] = 0.0f;          // scatter target of the NEXT advection adjoint (no memset nodes in the sweep)
             // fused corr_bwd of the step that consumes this gradient: g_corr[b,j,i,0] = sigma_y * G_y[b,j,i]
             if (g_corr && f.j < Y) g_corr[((size_t)b * Y * X + f.j * X + f.i) * 2 + 0] = sy * v;
         } else {
@@ -82,6 +84,7 @@ __global__ void __launch_bounds__(256) k_diffuse_bc_bwd(int B, int Y, int X, con
             float v = diffuse_bc_bwd_cell(gx + (size_t)b * NX, Y, X + 1, f.j, f.i, alpha, nullptr);
             if (add_x) v += add_x[o];
             gx_in[o] = v;
+            if (zero_x) zero_x[o] = 0.0f;
             if (g_corr && f.i < X) g_corr[((size_t)b * Y * X + f.j * X + f.i) * 2 + 1] = sx * v;
         }
     }
@@ -98,10 +101,10 @@ int launch_diffuse_bc(const sol_plan* p, cudaStream_t st, int B, const float* re
 
 int launch_diffuse_bc_bwd(const sol_plan* p, cudaStream_t st, int B, const float* re, float dt, float res,
                           const float* gy, const float* gx, float* gy_in, float* gx_in, const float* add_y, const float* add_x,
-                          float* g_corr, float sy, float sx) {
+                          float* g_corr, float sy, float sx, float* zero_y, float* zero_x) {
     const size_t total = (size_t)B * (p->NY() + p->NX());
     SOL_CUDA(launch_kernel(k_diffuse_bc_bwd, dim3(grid_for(total, 256, p->sm_count)), dim3(256), 0, st, B, p->Y, p->X, re, dt * res * res, gy, gx, p->bc_mask_y,
-                                                                        add_y, add_x, gy_in, gx_in, g_corr, sy, sx));
+                                                                        add_y, add_x, gy_in, gx_in, g_corr, sy, sx, zero_y, zero_x));
     SOL_LAUNCHED();
     return SOL_OK;
 }
@@ -175,9 +178,11 @@ int launch_advect(const sol_plan* p, cudaStream_t st, int B, float dt, const flo
 }
 
 int launch_advect_bwd(const sol_plan* p, cudaStream_t st, int B, float dt, const float* vy, const float* vx,
-                      const float* gy_out, const float* gx_out, float* gy, float* gx) {
-    SOL_CUDA(cudaMemsetAsync(gy, 0, (size_t)B * p->NY() * sizeof(float), st));
-    SOL_CUDA(cudaMemsetAsync(gx, 0, (size_t)B * p->NX() * sizeof(float), st));
+                      const float* gy_out, const float* gx_out, float* gy, float* gx, bool targets_are_zero) {
+    if (!targets_are_zero) {
+        SOL_CUDA(cudaMemsetAsync(gy, 0, (size_t)B * p->NY() * sizeof(float), st));
+        SOL_CUDA(cudaMemsetAsync(gx, 0, (size_t)B * p->NX() * sizeof(float), st));
+    }
     const size_t total = (size_t)B * (p->NY() + p->NX());
     const float s = dt / p->dx;
     const int g = grid_for(total, 256, p->sm_count);

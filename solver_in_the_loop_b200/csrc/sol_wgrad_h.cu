@@ -45,7 +45,7 @@ constexpr int WGH_STAGE_BYTES = WGH_OFF_GL + WGH_G_BYTES;   // 94208 = 92 x 1024
 constexpr int WGH_NSTAGE = 2;
 constexpr int WGH_OFF_BAR = WGH_NSTAGE * WGH_STAGE_BYTES;
 constexpr int WGH_SMEM = WGH_OFF_BAR + 256 + 1024;
-constexpr int WGH_THREADS = 192;
+constexpr int WGH_THREADS = 224;                        // warp 0 TMA, warps 1 and 6 MMA issuers, warps 2..5 splitters / drain
 constexpr int WGH_TMEM_COLS = 512;                      // 7 tap groups x 64 columns used
 constexpr int WGH_NGROUP = 7;
 constexpr int WGH_DRAIN = 16;                           // tiles between two accumulator drains
@@ -56,6 +56,7 @@ constexpr uint32_t WGH_IDESC32 = (1u << 4) | (1u << 15) | (1u << 16) | ((32u >> 
 constexpr uint32_t WGH_IDESC64 = (1u << 4) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
 struct WgHArgs {
+    int issuers;                    // 1: warp 1 issues every MMA; 2: the tap groups are split between warps 1 and 6 (two instruction streams)
     float* part;                    // [gridDim.x][25*32*32 + 32]
     const uint32_t* amax_in;        // running max|activation| of the tensor (bit pattern), complete for the steps of this launch
     const uint32_t* amax_g;         // same for the output gradients
@@ -138,9 +139,9 @@ k_wgrad_c32_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant_
         for (int s = 0; s < WGH_NSTAGE; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_split + 8 * s, 128);
-            mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, (uint32_t)a.issuers);
         }
-        mbar_init(bar_acc, 1);
+        mbar_init(bar_acc, (uint32_t)a.issuers);
         mbar_init(bar_drained, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -172,8 +173,13 @@ k_wgrad_c32_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant_
                 tma_load_5d(st + WGH_OFF_GF, &map_g, bar_full + 8 * s, 0, txi * WGH_TX, tyi * WGH_TY, bb, step);
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
+    } else if (warp == 1 || warp == 6) {
+        // ================= MMA issuer(s) =================
+        // One UMMA of this shape costs ~35 clk of serialised issue / dependency overhead on top of its operand fetch when a single
+        // thread issues them back to back; two independent instruction streams (disjoint accumulator groups) overlap that overhead.
+        if (warp == 6 && a.issuers < 2) goto done;
+        const int g_lo = (a.issuers == 2 && warp == 6) ? 4 : 0;
+        const int g_hi = (a.issuers == 2 && warp == 1) ? 4 : WGH_NGROUP;
         const bool leader = elect_one();
         int n = 0;
         for (int seg = 0; seg < nseg; ++seg) {
@@ -208,6 +214,7 @@ k_wgrad_c32_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant_
                             const uint32_t acc_flag = (j == 0) ? accum : 1u;
 #pragma unroll
                             for (int grp = 0; grp < WGH_NGROUP; ++grp) {
+                                if (grp < g_lo || grp >= g_hi) continue;
                                 // groups 0..4: taps (dy=grp, dx=0..3); group 5: taps (dy=0..3, dx=4); group 6: tap (4,4) (+3 unused)
                                 const int dy0 = (grp < 5) ? grp : (grp == 5 ? 0 : 4);
                                 const int dx0 = (grp < 5) ? 0 : 4;
@@ -318,6 +325,7 @@ k_wgrad_c32_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant_
         }
     }
 
+done:
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
@@ -345,6 +353,7 @@ __global__ void __launch_bounds__(256) k_amax(const float4* __restrict__ x, size
 // next layer find no free slot (no prologue overlap), and the side stream's tail delays the end of the sweep.  Default off.
 int g_wgrad_bg_ctas = 0;
 int g_wgrad_bg_chunk = 4;
+int g_wgrad_issuers = 2;     // MMA-issuing warps of k_wgrad_c32_h (tuning)
 
 int launch_amax(cudaStream_t st, const float* x, size_t n, uint32_t* slot) {
     if (n % 4 || ((uintptr_t)x & 15)) return fail(SOL_ERR_INVALID, "amax: needs a 16-byte aligned tensor of 4k floats");
@@ -385,6 +394,7 @@ int launch_wgrad_c32_h(cudaStream_t st, int sm_count, int steps, int B, int Y, i
             return fail(SOL_ERR_CUDA, "cuTensorMapEncodeTiled(wgrad gradients) failed");
     }
     WgHArgs a;
+    a.issuers = g_wgrad_issuers == 1 ? 1 : 2;
     a.part = part; a.amax_in = amax_in; a.amax_g = amax_g;
     a.tiles_x = X / WGH_TX; a.tiles_y = Y / WGH_TY; a.images = steps * B; a.B = B; a.accumulate = accumulate;
     const int ntiles = a.tiles_x * a.tiles_y * a.images;
