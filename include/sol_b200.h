@@ -98,6 +98,10 @@ int sol_plan_query(sol_plan* plan, const char* name, int* value);
  *   "wgrad_bg_ctas" / "wgrad_bg_chunk" (tuning) with the direct projection there is no solve window: the weight-gradient items of
  *         finished steps then run as persistent background launches of at most this many CTAs (default 48, 0 = off; one launch
  *         per layer per chunk of steps, default 4) on the SMs the adjoint conv chain does not need
+ *   "deterministic" 1 = the reductions the engine has a choice about are ordered instead of atomic: the weight gradients of the
+ *         first / last layer go through private CTA slots, the per-step losses through per-CTA partials, both summed in CTA
+ *         order; bit-identical from run to run EXCEPT for the scatter-add of the advection adjoint, whose floating-point
+ *         atomics (sol_advect_bwd) remain order-dependent at round-off level.  0 (default) = atomics
  *   "fuse_stencil" 1 (default) = viscosity + BC and the three advections of a step are ONE launch with the stencil halo staged in
  *         shared memory (OPEN plans), 0 = one kernel per stage (global gathers)
  *   "nvtx" 1 = NVTX ranges around the stages of the unrolled sweeps (for nsys / ncu --nvtx; host-side, default 0)

@@ -17,6 +17,8 @@
 
 namespace sol {
 
+constexpr int THIN_SLOT = 25 * 4 * 32 + 32;      // floats of one CTA's partial slot in the deterministic thin weight-gradient mode
+
 struct ConvArgs {
     const float* in;
     const float* w;
@@ -620,7 +622,8 @@ __global__ void __launch_bounds__(256) k_wgrad_finalize(int nctas, const float* 
 // ------------------------------------------------------------------------------------------------
 template <int CIN>
 __global__ void __launch_bounds__(256, 2) k_wgrad_expand(const float* __restrict__ in, const float* __restrict__ g, float* dW, float* db,
-                                                         int steps, int B, int Y, int X, size_t in_step_stride, size_t g_step_stride) {
+                                                         int steps, int B, int Y, int X, size_t in_step_stride, size_t g_step_stride,
+                                                         float* part) {
     pdl_sync();
     constexpr int COUT = 32;
     constexpr int NOWN = 5 * CIN * 4;              // owner = (dy, ci, cout octet)
@@ -739,18 +742,26 @@ __global__ void __launch_bounds__(256, 2) k_wgrad_expand(const float* __restrict
                 float s = acc[d][j];
 #pragma unroll
                 for (int q = 0; q < P - 1; ++q) s += red[(q * 40 + d * 8 + j) * NOWN + own];
-                atomicAdd(dW + ((dy * 5 + d) * CIN + ci) * COUT + cq * 8 + j, s);
+                const int e = ((dy * 5 + d) * CIN + ci) * COUT + cq * 8 + j;
+                // deterministic mode: a private slot per CTA, summed in CTA order by k_thin_finalize; else one atomic per value
+                if (part) part[(size_t)blockIdx.x * THIN_SLOT + e] = s; else atomicAdd(dW + e, s);
             }
     } else if (!worker) {
-        atomicAdd(db + 2 * (tid - 240), dbacc0);
-        atomicAdd(db + 2 * (tid - 240) + 1, dbacc1);
+        if (part) {
+            part[(size_t)blockIdx.x * THIN_SLOT + 25 * CIN * COUT + 2 * (tid - 240)] = dbacc0;
+            part[(size_t)blockIdx.x * THIN_SLOT + 25 * CIN * COUT + 2 * (tid - 240) + 1] = dbacc1;
+        } else {
+            atomicAdd(db + 2 * (tid - 240), dbacc0);
+            atomicAdd(db + 2 * (tid - 240) + 1, dbacc1);
+        }
     }
 }
 
 // 32 -> COUT <= 2: owner = (dy, cin quad), 40 accumulators = 5 dx x 4 cin x COUT
 template <int COUT>
 __global__ void __launch_bounds__(256, 2) k_wgrad_reduce(const float* __restrict__ in, const float* __restrict__ g, float* dW, float* db,
-                                                         int steps, int B, int Y, int X, size_t in_step_stride, size_t g_step_stride) {
+                                                         int steps, int B, int Y, int X, size_t in_step_stride, size_t g_step_stride,
+                                                         float* part) {
     pdl_sync();
     static_assert(COUT == 2, "accumulator tile is written for two output channels");
     constexpr int CIN = 32, NOWN = 40, P = 6, TR = 2 * P, TW = 32, PR = TR + 4, PW = TW + 4, PS = 36;   // PS: padded pixel stride
@@ -861,16 +872,29 @@ __global__ void __launch_bounds__(256, 2) k_wgrad_reduce(const float* __restrict
                     float s = acc[d][k][co];
 #pragma unroll
                     for (int q = 0; q < P - 1; ++q) s += red[(q * 40 + (d * 4 + k) * COUT + co) * NOWN + own];
-                    atomicAdd(dW + ((dy * 5 + d) * CIN + c4 * 4 + k) * COUT + co, s);
+                    const int e = ((dy * 5 + d) * CIN + c4 * 4 + k) * COUT + co;
+                    if (part) part[(size_t)blockIdx.x * THIN_SLOT + e] = s; else atomicAdd(dW + e, s);
                 }
     } else if (!worker && tid < 240 + COUT) {
-        atomicAdd(db + (tid - 240), dbacc);
+        if (part) part[(size_t)blockIdx.x * THIN_SLOT + 25 * CIN * COUT + (tid - 240)] = dbacc; else atomicAdd(db + (tid - 240), dbacc);
     }
+}
+
+// deterministic mode of the thin-layer weight gradients: dW / db += sum over the CTA slots, in CTA order
+__global__ void __launch_bounds__(256) k_thin_finalize(int nctas, const float* __restrict__ part, int nW, int nb, float* __restrict__ dW,
+                                                       float* __restrict__ db) {
+    pdl_sync();
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nW + nb) return;
+    float s = 0.0f;
+    for (int c = 0; c < nctas; ++c) s += part[(size_t)c * THIN_SLOT + e];
+    float* dst = e < nW ? dW + e : db + (e - nW);
+    *dst += s;
 }
 
 template <int CIN>
 static int launch_wgrad_expand(cudaStream_t st, int steps, int B, int Y, int X, const float* in, size_t in_step_stride, const float* g,
-                               size_t g_step_stride, float* dW, float* db, int max_ctas) {
+                               size_t g_step_stride, float* dW, float* db, int max_ctas, float* part) {
     constexpr int P = 240 / (20 * CIN), TR = 2 * P;
     const size_t smem = (size_t)(TR * 32 * 32 + CIN * (TR + 4) * 36) * sizeof(float);
     auto kern = k_wgrad_expand<CIN>;
@@ -882,13 +906,17 @@ static int launch_wgrad_expand(cudaStream_t st, int steps, int B, int Y, int X, 
     const int ntiles = cdiv(X, 32) * cdiv(Y, TR) * B * steps;
     const int cap = max_ctas > 0 ? max_ctas : 2 * 148;
     const int grid = ntiles < cap ? ntiles : cap;
-    SOL_CUDA(launch_kernel(kern, dim3(grid), dim3(256), smem, st, in, g, dW, db, steps, B, Y, X, in_step_stride, g_step_stride));
+    SOL_CUDA(launch_kernel(kern, dim3(grid), dim3(256), smem, st, in, g, dW, db, steps, B, Y, X, in_step_stride, g_step_stride, part));
     SOL_LAUNCHED();
+    if (part) {
+        SOL_CUDA(launch_kernel(k_thin_finalize, dim3(cdiv(25 * CIN * 32 + 32, 256)), dim3(256), 0, st, grid, (const float*)part, 25 * CIN * 32, 32, dW, db));
+        SOL_LAUNCHED();
+    }
     return SOL_OK;
 }
 
 static int launch_wgrad_reduce2(cudaStream_t st, int steps, int B, int Y, int X, const float* in, size_t in_step_stride, const float* g,
-                                size_t g_step_stride, float* dW, float* db, int max_ctas) {
+                                size_t g_step_stride, float* dW, float* db, int max_ctas, float* part) {
     const size_t smem = (size_t)(16 * 36 * 36 + 12 * 32 * 2) * sizeof(float);
     auto kern = k_wgrad_reduce<2>;
     static bool attr_done = false;
@@ -899,20 +927,28 @@ static int launch_wgrad_reduce2(cudaStream_t st, int steps, int B, int Y, int X,
     const int ntiles = cdiv(X, 32) * cdiv(Y, 12) * B * steps;
     const int cap = max_ctas > 0 ? max_ctas : 2 * 148;
     const int grid = ntiles < cap ? ntiles : cap;
-    SOL_CUDA(launch_kernel(kern, dim3(grid), dim3(256), smem, st, in, g, dW, db, steps, B, Y, X, in_step_stride, g_step_stride));
+    SOL_CUDA(launch_kernel(kern, dim3(grid), dim3(256), smem, st, in, g, dW, db, steps, B, Y, X, in_step_stride, g_step_stride, part));
     SOL_LAUNCHED();
+    if (part) {
+        SOL_CUDA(launch_kernel(k_thin_finalize, dim3(cdiv(25 * 32 * 2 + 2, 256)), dim3(256), 0, st, grid, (const float*)part, 25 * 32 * 2, 2, dW, db));
+        SOL_LAUNCHED();
+    }
     return SOL_OK;
 }
 
-// thin-layer weight gradient accumulated INTO dW/db (atomics) over `steps` unrolled steps
+size_t wgrad_thin_part_floats() { return (size_t)2 * 148 * THIN_SLOT; }
+
+// thin-layer weight gradient accumulated INTO dW/db over `steps` unrolled steps: one atomic per value and CTA, or — with a `part`
+// scratch of wgrad_thin_part_floats() floats (deterministic mode) — private CTA slots summed in CTA order
 int launch_wgrad_thin_multi(cudaStream_t st, int steps, int B, int Y, int X, int Cin, int Cout, const float* in, size_t in_step_stride,
-                            const float* g, size_t g_step_stride, float* dW, float* db, int max_ctas) {
+                            const float* g, size_t g_step_stride, float* dW, float* db, int max_ctas, float* part) {
+    if (part && (max_ctas <= 0 || max_ctas > 2 * 148)) max_ctas = 2 * 148;
     if (((uintptr_t)in & 15) && Cin == 32) return fail(SOL_ERR_INVALID, "wgrad: 32-channel input must be 16-byte aligned");
     if (((uintptr_t)g & 15) && Cout == 32) return fail(SOL_ERR_INVALID, "wgrad: 32-channel gradient must be 16-byte aligned");
-    if (Cout == 32 && Cin == 2) return launch_wgrad_expand<2>(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db, max_ctas);
-    if (Cout == 32 && Cin == 3) return launch_wgrad_expand<3>(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db, max_ctas);
-    if (Cout == 32 && Cin == 4) return launch_wgrad_expand<4>(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db, max_ctas);
-    if (Cin == 32 && Cout == 2) return launch_wgrad_reduce2(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db, max_ctas);
+    if (Cout == 32 && Cin == 2) return launch_wgrad_expand<2>(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db, max_ctas, part);
+    if (Cout == 32 && Cin == 3) return launch_wgrad_expand<3>(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db, max_ctas, part);
+    if (Cout == 32 && Cin == 4) return launch_wgrad_expand<4>(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db, max_ctas, part);
+    if (Cin == 32 && Cout == 2) return launch_wgrad_reduce2(st, steps, B, Y, X, in, in_step_stride, g, g_step_stride, dW, db, max_ctas, part);
     return fail(SOL_ERR_UNSUPPORTED, "wgrad: unsupported (Cin, Cout) pair");
 }
 

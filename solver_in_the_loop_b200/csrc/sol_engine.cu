@@ -322,6 +322,10 @@ extern "C" int sol_set_option(const char* name, int value) {
         sol::g_pdl = value ? 1 : 0;
         return SOL_OK;
     }
+    if (strcmp(name, "deterministic") == 0) {
+        sol::g_deterministic = value ? 1 : 0;
+        return SOL_OK;
+    }
     if (strcmp(name, "fuse_stencil") == 0) {
         sol::g_fuse_stencil = value ? 1 : 0;
         return SOL_OK;
@@ -555,6 +559,9 @@ struct sol_unroll {
     float* gst;        // deferred weight gradient: [10 layers][msteps][B,Y,X,32] output-gradient stash
     float* g0_st;      // [msteps][B,Y,X,32] output gradient of layer 0
     bool deferred_wgrad = false;   // decided per backward sweep: option wgrad_path >= 2 and the grid tiles evenly (Y%16, X%8)
+    float* thin_part = nullptr;    // deterministic mode: private CTA slots of the thin-layer weight gradients
+    float* loss_part = nullptr;    // deterministic mode: [msteps][loss_part_stride] per-CTA loss partials
+    int loss_part_stride = 0;
     unsigned int* amax = nullptr;  // [24] running max|x| (bit patterns): [l] input activations of layer l, [12 + l] its output gradients (l = 1..10)
     bool track_amax = false;       // the 3xFP16 conv kernels of this sweep keep them up to date (else the weight-gradient launches measure them)
     float* gcorr_st;   // [msteps][B,Y,X,2]  output gradient of layer 11
@@ -644,6 +651,9 @@ int carve(sol_unroll* u, void* ws, size_t* total) {
         u->partials = cv.take<float>(u->partial_stride * 10);
     }
     u->amax = cv.take<unsigned int>(24);
+    u->thin_part = cv.take<float>(wgrad_thin_part_floats());
+    u->loss_part_stride = p->sm_count;
+    u->loss_part = cv.take<float>((size_t)c.msteps * u->loss_part_stride);
     u->iters = cv.take<int>((size_t)2 * c.msteps * c.B);
     u->re_buf = cv.take<float>(c.B);
     *total = align_up(cv.off, 256);
@@ -778,6 +788,8 @@ int do_forward(sol_unroll* u, cudaStream_t st, const float* weights, const float
         re = u->re_buf;
     }
     if (gt_vy) SOL_CUDA(cudaMemsetAsync(loss_steps, 0, sizeof(float) * m, st));
+    const bool det = sol::g_deterministic != 0 && !ring;
+    if (det && gt_vy) SOL_CUDA(cudaMemsetAsync(u->loss_part, 0, sizeof(float) * (size_t)m * u->loss_part_stride, st));
     const bool mars = c.model == SOL_MODEL_MARS_MOON;
     if (conv_path_is_tc() && mars) {
         SOL_TRY(launch_split_weights_multi(st, weights + u->L[1].w_off, u->L[2].w_off - u->L[1].w_off, u->wprep_fwd, 10));
@@ -806,7 +818,7 @@ int do_forward(sol_unroll* u, cudaStream_t st, const float* weights, const float
             SOL_TRY(cnn_forward(u, st, weights, s, u->corr));
             SOL_TRY(launch_correct_loss(p, st, B, u->vy3, u->vx3, u->corr, c.sig_vy, c.sig_vx, gt_vy ? gt_vy + (size_t)i * NY : nullptr,
                                         gt_vx ? gt_vx + (size_t)i * NX : nullptr, 1.0f / (float)m, nvy, nvx, s.gl_vy, s.gl_vx,
-                                        gt_vy ? loss_steps + i : nullptr));
+                                        gt_vy ? loss_steps + i : nullptr, (det && gt_vy) ? u->loss_part + (size_t)i * u->loss_part_stride : nullptr));
             cvy = nvy; cvx = nvx;
             continue;
         }
@@ -836,8 +848,11 @@ int do_forward(sol_unroll* u, cudaStream_t st, const float* weights, const float
         NvtxRange r_loss("correct + loss");
         SOL_TRY(launch_correct_loss(p, st, B, u->vy3, u->vx3, u->corr, c.sig_vy, c.sig_vx, gt_vy ? gt_vy + (size_t)i * NY : nullptr,
                                     gt_vx ? gt_vx + (size_t)i * NX : nullptr, 1.0f / (float)m, nvy, nvx, s.gl_vy, s.gl_vx,
-                                    gt_vy ? loss_steps + i : nullptr));
+                                    gt_vy ? loss_steps + i : nullptr, (det && gt_vy) ? u->loss_part + (size_t)i * u->loss_part_stride : nullptr));
         cvy = nvy; cvx = nvx; crho = nrho;
+    }
+    if (det && gt_vy) {      // ordered sum of the per-CTA loss partials of every step (unused slots are zero)
+        SOL_TRY(launch_loss_finalize(st, m, u->loss_part, u->loss_part_stride, loss_steps));
     }
     u->forward_done = !ring;
     u->last_re = u->re_buf;
@@ -868,10 +883,11 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
     // (a) iterative solvers: the adjoint solve of a step keeps only B SMs busy for ~100 us: weight-gradient items fill that window.
     // (b) direct projection (no window worth filling): the adjoint conv chain needs at most 2 CTAs on tiles/2 SMs, so a persistent
     //     background launch on the SMs beyond that runs beside it without lengthening its critical path.
-    const bool overlap = u->deferred_wgrad && sol::g_wgrad_overlap && B + 17 <= p->sm_count && !burgers && !direct_for_batch(p, B);
+    const bool det = sol::g_deterministic != 0;       // one stream, private CTA slots for the thin layers
+    const bool overlap = u->deferred_wgrad && sol::g_wgrad_overlap && !det && B + 17 <= p->sm_count && !burgers && !direct_for_batch(p, B);
     const int bg_free = p->sm_count - (tiles_step + 1) / 2;      // SMs the two-per-SM conv tiles leave alone
     const int bg_ctas = std::min(sol::g_wgrad_bg_ctas, bg_free);
-    const bool background = u->deferred_wgrad && sol::g_wgrad_overlap && !overlap && !burgers && bg_ctas >= 16 && m >= 2 * sol::g_wgrad_bg_chunk;
+    const bool background = u->deferred_wgrad && sol::g_wgrad_overlap && !det && !overlap && !burgers && bg_ctas >= 16 && m >= 2 * sol::g_wgrad_bg_chunk;
     const int sm_budget = overlap ? p->sm_count - B - 1 : p->sm_count;        // SMs left beside the solve's B CTAs
     const int nct32 = tiles_step < sm_budget ? tiles_step : sm_budget;
     if ((overlap || background) && !u->sstream) {
@@ -884,10 +900,11 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
         if (l == 11)
             return launch_wgrad_thin_multi(s, it.nsteps, B, p->Y, p->X, 32, 2, u->stash[it.step0].acts[10], in_stride,
                                            u->gcorr_st + (size_t)it.step0 * p->NC() * B * 2, (size_t)p->NC() * B * 2, gw + u->L[11].w_off,
-                                           gw + u->L[11].b_off, 2 * ctas);
+                                           gw + u->L[11].b_off, 2 * ctas, det ? u->thin_part : nullptr);
         if (l == 0)
             return launch_wgrad_thin_multi(s, it.nsteps, B, p->Y, p->X, u->L[0].cin, 32, u->stash[it.step0].feat, in_stride,
-                                           u->g0_st + (size_t)it.step0 * u->nA, u->nA, gw + u->L[0].w_off, gw + u->L[0].b_off, 2 * ctas);
+                                           u->g0_st + (size_t)it.step0 * u->nA, u->nA, gw + u->L[0].w_off, gw + u->L[0].b_off, 2 * ctas,
+                                           det ? u->thin_part : nullptr);
         int nctas = 0;
         const float* act_in = u->stash[it.step0].acts[l - 1];
         const float* g_out = u->gst + ((size_t)(l - 1) * m + it.step0) * u->nA;

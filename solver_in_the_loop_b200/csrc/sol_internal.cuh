@@ -163,7 +163,10 @@ int launch_add_faces(const sol_plan* p, cudaStream_t st, int B, const float* gy,
 // v_out = v + sigma*corr (zero on the far row/col); optional loss + loss gradient
 int launch_correct_loss(const sol_plan* p, cudaStream_t st, int B, const float* vy, const float* vx, const float* corr,
                         float sy, float sx, const float* gt_vy, const float* gt_vx, float inv_m,
-                        float* vy_out, float* vx_out, float* gl_vy, float* gl_vx, float* loss);
+                        float* vy_out, float* vx_out, float* gl_vy, float* gl_vx, float* loss, float* loss_part = nullptr);
+// deterministic loss: loss[i] = sum of the per-CTA partials loss_part[i * stride + 0 .. nparts) in CTA order, for i < msteps
+int launch_loss_finalize(cudaStream_t st, int msteps, const float* loss_part, int stride, float* loss);
+int correct_loss_grid(const sol_plan* p, int B);
 // g_corr[B,Y,X,2] = sigma * G[:Y,:X]
 int launch_corr_bwd(const sol_plan* p, cudaStream_t st, int B, const float* Gy, const float* Gx, float sy, float sx, float* g_corr);
 // G3 = G + g_feat[...,0:2]/sigma (padded)
@@ -214,7 +217,9 @@ int launch_wgrad(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const 
                  int accumulate, float* partials, bool finalize);
 
 int launch_wgrad_thin_multi(cudaStream_t st, int steps, int B, int Y, int X, int Cin, int Cout, const float* in, size_t in_step_stride,
-                            const float* g, size_t g_step_stride, float* dW, float* db, int max_ctas = 0);
+                            const float* g, size_t g_step_stride, float* dW, float* db, int max_ctas = 0, float* part = nullptr);
+size_t wgrad_thin_part_floats();     // scratch of the deterministic mode (private CTA slots)
+extern int g_deterministic;          // option "deterministic": ordered reductions instead of floating-point atomics (thin wgrads, loss)
 int launch_wgrad_finalize_n(cudaStream_t st, int nctas, const float* partials, float* dW, float* db, int accumulate);
 
 // ---- deferred tensor-core weight gradient (sol_wgrad_tc.cu) ----

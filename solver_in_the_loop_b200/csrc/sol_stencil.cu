@@ -17,7 +17,8 @@ int g_pdl = 1;
 // Measured on B200 at the bench shape (SOL-32, 3 simulations, 30 iterations, two runs each): fuse_small/fuse_solver_io =
 // 1/0: 21.42 ms, 0/0: 20.9 ms, 1/1: 21.03 ms, 0/1: 20.39 ms per iteration.
 int g_fuse_small = 0;        // fold corr_bwd (correction-gradient scaling) into diffuse_bc_bwd: one launch fewer, but slower
-int g_fuse_solver_io = 1;    // fold to_feature / feat_bwd into the projection kernel (2 launches fewer per step)
+int g_fuse_solver_io = 1;
+int g_deterministic = 0;      // ordered reductions instead of floating-point atomics where the engine has the choice (see sol_b200.h)    // fold to_feature / feat_bwd into the projection kernel (2 launches fewer per step)
 
 static inline int grid_for(size_t n, int threads, int sm_count) {
     size_t blocks = (n + threads - 1) / threads;
@@ -323,7 +324,8 @@ __global__ void __launch_bounds__(256) k_correct_loss(int B, int Y, int X, const
                                                       const float* __restrict__ corr, float sy, float sx,
                                                       const float* __restrict__ gt_vy, const float* __restrict__ gt_vx, float inv_m,
                                                       float* __restrict__ vy_out, float* __restrict__ vx_out,
-                                                      float* __restrict__ gl_vy, float* __restrict__ gl_vx, float* loss) {
+                                                      float* __restrict__ gl_vy, float* __restrict__ gl_vx, float* loss,
+                                                      float* __restrict__ loss_part) {
     pdl_sync();
     const int NY = (Y + 1) * X, NX = Y * (X + 1), NF = NY + NX, NC = Y * X;
     const size_t total = (size_t)B * NF;
@@ -361,19 +363,39 @@ __global__ void __launch_bounds__(256) k_correct_loss(int B, int Y, int X, const
         if (threadIdx.x < 32) {
             float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0f;
             v = warp_sum(v);
-            if (threadIdx.x == 0) atomicAdd(loss, v);
+            // deterministic mode: one partial per CTA, summed in CTA order by k_loss_finalize
+            if (threadIdx.x == 0) { if (loss_part) loss_part[blockIdx.x] = v; else atomicAdd(loss, v); }
         }
     }
 }
 
 int launch_correct_loss(const sol_plan* p, cudaStream_t st, int B, const float* vy, const float* vx, const float* corr,
                         float sy, float sx, const float* gt_vy, const float* gt_vx, float inv_m,
-                        float* vy_out, float* vx_out, float* gl_vy, float* gl_vx, float* loss) {
+                        float* vy_out, float* vx_out, float* gl_vy, float* gl_vx, float* loss, float* loss_part) {
+    const int g = correct_loss_grid(p, B);
+    SOL_CUDA(launch_kernel(k_correct_loss, g, dim3(256), 0, st, B, p->Y, p->X, vy, vx, corr, sy, sx, gt_vy, gt_vx, inv_m, vy_out, vx_out, gl_vy, gl_vx,
+                                      gt_vy ? loss : nullptr, gt_vy ? loss_part : nullptr));
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
+int correct_loss_grid(const sol_plan* p, int B) {
     const size_t total = (size_t)B * (p->NY() + p->NX());
     int g = grid_for(total, 256, p->sm_count);
-    if (g > p->sm_count) g = p->sm_count;   // few atomics on the loss scalar
-    SOL_CUDA(launch_kernel(k_correct_loss, g, dim3(256), 0, st, B, p->Y, p->X, vy, vx, corr, sy, sx, gt_vy, gt_vx, inv_m, vy_out, vx_out, gl_vy, gl_vx,
-                                      gt_vy ? loss : nullptr));
+    if (g > p->sm_count) g = p->sm_count;   // few atomics on the loss scalar / few partials
+    return g;
+}
+
+__global__ void __launch_bounds__(32) k_loss_finalize(const float* __restrict__ part, int stride, int nparts, float* __restrict__ loss) {
+    pdl_sync();
+    if (threadIdx.x != 0) return;
+    float s = 0.0f;
+    for (int c = 0; c < nparts; ++c) s += part[(size_t)blockIdx.x * stride + c];      // fixed order
+    loss[blockIdx.x] = s;
+}
+
+int launch_loss_finalize(cudaStream_t st, int msteps, const float* loss_part, int stride, float* loss) {
+    SOL_CUDA(launch_kernel(k_loss_finalize, dim3(msteps), dim3(32), 0, st, loss_part, stride, stride, loss));
     SOL_LAUNCHED();
     return SOL_OK;
 }

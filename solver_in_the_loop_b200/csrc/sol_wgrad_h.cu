@@ -314,14 +314,17 @@ k_wgrad_c32_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant_
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(bar_drained);
         }
-        {   // bias slot: reduce the per-thread channel sums through shared memory (all stages are free now)
-            float* bsm = reinterpret_cast<float*>(gbase);
-            if (tt < 32) bsm[tt] = 0.0f;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+        {   // bias slot: the per-thread channel sums go through shared memory and are added in thread order (deterministic)
+            float* bsm = reinterpret_cast<float*>(gbase);         // [128 threads][8] (all stages are free now)
 #pragma unroll
-            for (int c = 0; c < 8; ++c) atomicAdd(bsm + oct * 8 + c, bsum[c]);
+            for (int c = 0; c < 8; ++c) bsm[tt * 8 + c] = bsum[c];
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (tt < 32) part[25 * 32 * 32 + tt] = ((int)blockIdx.x < a.accumulate) ? part[25 * 32 * 32 + tt] + bsm[tt] : bsm[tt];
+            if (tt < 32) {
+                float sb = 0.0f;
+                const int o8 = tt >> 3, c = tt & 7;              // channel tt = octet o8, lane c: threads with (t & 3) == o8 own it
+                for (int t = o8; t < 128; t += 4) sb += bsm[t * 8 + c];
+                part[25 * 32 * 32 + tt] = ((int)blockIdx.x < a.accumulate) ? part[25 * 32 * 32 + tt] + sb : sb;
+            }
         }
     }
 
@@ -353,7 +356,8 @@ __global__ void __launch_bounds__(256) k_amax(const float4* __restrict__ x, size
 // next layer find no free slot (no prologue overlap), and the side stream's tail delays the end of the sweep.  Default off.
 int g_wgrad_bg_ctas = 0;
 int g_wgrad_bg_chunk = 4;
-int g_wgrad_issuers = 2;     // MMA-issuing warps of k_wgrad_c32_h (tuning)
+int g_wgrad_issuers = 1;     // MMA-issuing warps of k_wgrad_c32_h: measured 12.37 (2) vs 12.39 ms (1) per iteration — the UMMAs of one CTA execute in
+                             // order whichever warp issues them (only co-resident CTAs overlap their per-instruction overhead), so one is the default
 
 int launch_amax(cudaStream_t st, const float* x, size_t n, uint32_t* slot) {
     if (n % 4 || ((uintptr_t)x & 15)) return fail(SOL_ERR_INVALID, "amax: needs a 16-byte aligned tensor of 4k floats");

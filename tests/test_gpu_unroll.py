@@ -190,3 +190,31 @@ def test_rollout_matches_unrolled_forward(cuda_device):
     assert rel(rv, pv) < 1e-6 and rel(rx, px) < 1e-6 and rel(rr, prho) < 1e-6
     with pytest.raises(engine.SolError):
         short.backward(w)          # a rollout keeps no adjoint stash
+
+
+def test_deterministic_option_is_bitwise_reproducible(cuda_device):
+    """Option "deterministic": ordered reductions for the per-step losses and the first / last layer's weight gradients.  With one
+    unrolled step the weight gradient does not pass through the advection adjoint (the only order-dependent scatter left), so two
+    runs must agree bit for bit — and with the default atomics path to round-off."""
+    Y, X, B, m = 64, 32, 3, 1
+    engine, geom, rho, vy, vx, re, gty, gtx, sig, params, plan, un, w = _setup(Y, X, B, m, cuda_device)
+    d = lambda t: dev(t, cuda_device)
+    args = (w, d(re), d(vy), d(vx), d(gty), d(gtx))
+    g_ref = torch.zeros(un.nparams, device=cuda_device)
+    l_ref = un.train_iter(*args, g_ref).clone()
+    torch.cuda.synchronize()
+    outs = []
+    try:
+        engine.set_option("deterministic", 1)
+        for use_graph in (False, True, True):
+            u2 = engine.Unroll(plan, m, B, sig, use_graph=use_graph)
+            g = torch.zeros(un.nparams, device=cuda_device)
+            for _ in range(3 if use_graph else 1):
+                l = u2.train_iter(*args, g).clone()
+            torch.cuda.synchronize()
+            outs.append((l, g.clone()))
+    finally:
+        engine.set_option("deterministic", 0)
+    for l, g in outs[1:]:
+        assert torch.equal(l, outs[0][0]) and torch.equal(g, outs[0][1])
+    assert rel(outs[0][0], l_ref) < 1e-6 and rel(outs[0][1], g_ref) < 1e-5
