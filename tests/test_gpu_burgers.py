@@ -91,11 +91,12 @@ def test_burgers_unrolled_training_parity(cuda_device, R, B, m, force):
     ls, pv, px, _ = un.forward(w, None, d(vy), d(vx), d(gty), d(gtx), return_pred=True)
     for i in range(m):
         print("step", i, "state rel", rel(pv[i], states[i][0]), rel(px[i], states[i][1]), "loss", float(ls[i]), float(losses[i]))
-        assert rel(pv[i], states[i][0]) < 2e-5 and rel(px[i], states[i][1]) < 2e-5
-        assert abs(float(ls[i]) - float(losses[i])) < 1e-4 * abs(float(losses[i]))
+        assert rel(pv[i], states[i][0]) < 1e-5 and rel(px[i], states[i][1]) < 1e-5
+        assert abs(float(ls[i]) - float(losses[i])) < 1e-5 * abs(float(losses[i]))
     gw, gy0, gx0 = un.backward(w, want_input_grad=True)
     print("grad rel", rel(gw, gref), "input grad rel", rel(gy0, vy0.grad), rel(gx0, vx0.grad))
-    assert rel(gw, gref) < 1e-4
+    assert rel(gw, gref) < 2e-5
+    # (input gradient: discontinuous coordinate derivative of the semi-Lagrangian sample, see test_gpu_quoted_configs.py)
     assert rel(gy0, vy0.grad) < 1e-3 and rel(gx0, vx0.grad) < 1e-3
 
 

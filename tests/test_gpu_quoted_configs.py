@@ -119,8 +119,9 @@ def test_sol32_full_iteration_parity(cuda_device):
         assert e["vy"] < FIELD_TOL and e["vx"] < FIELD_TOL and e["rho"] < FIELD_TOL, e
         assert e["loss"] < 1e-5, e
     # 32 steps of discontinuous back-trace derivatives between the loss and the first correction (see module docstring)
-    assert r["grad"] < 1e-4, r["grad"]
-    assert r["grad_graph"] < 1e-4 and r["losses_graph"] < 1e-5
+    # (measured 1.2e-6; the bound is the short-unroll bound)
+    assert r["grad"] < 2e-5, r["grad"]
+    assert r["grad_graph"] < 2e-5 and r["losses_graph"] < 1e-5
 
 
 def test_c2_parity(cuda_device):

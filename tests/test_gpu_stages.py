@@ -109,7 +109,8 @@ def test_pressure_solve_and_project(case, cuda_device, cluster, precond):
             assert int(it.max()) < (40 if precond else 4000) and int(it.min()) >= 5
         oy, ox, op, it2 = plan.project(dev(vy, cuda_device), dev(vx, cuda_device), return_pressure=True)
         print("project rel", rel(oy, ry), rel(ox, rx), rel(op, rp), it2.tolist())
-        assert rel(oy, ry) < 1e-5 and rel(ox, rx) < 1e-4 and rel(op, rp) < (5e-6 if direct else 2e-4)
+        # north_star: 1e-5 on the projected velocity; the iterative solvers stop at their fp32 residual floor (pressure 3e-5)
+        assert rel(oy, ry) < 1e-5 and rel(ox, rx) < (1e-5 if direct else 3e-5) and rel(op, rp) < (5e-6 if direct else 2e-4)
         # divergence-free on fluid cells, obstacle faces exactly zero, idempotent
         d2 = plan.divergence(oy, ox)
         act = torch.tensor(geom.active, device=cuda_device, dtype=torch.float32)
@@ -173,7 +174,7 @@ def test_step_forward_and_adjoint(case, cuda_device):
     rrho, ry, rx, aux = so.karman_step(c["rho"], vyt, vxt, c["re"], geom, return_aux=True)
     out = plan.step_fwd(dev(c["re"], cuda_device), dev(c["vy"], cuda_device), dev(c["vx"], cuda_device), rho=dev(c["rho"], cuda_device))
     print("step rel", rel(out["vy"], ry), rel(out["vx"], rx), rel(out["rho"], rrho), rel(out["p"], aux["p"]), out["iters"].tolist())
-    assert rel(out["vy"], ry) < 1e-5 and rel(out["vx"], rx) < 1e-4 and rel(out["rho"], rrho) < 1e-5
+    assert rel(out["vy"], ry) < 1e-5 and rel(out["vx"], rx) < 1e-5 and rel(out["rho"], rrho) < 1e-5
     assert rel(out["vy1"], aux["vy1"]) < 1e-6
     g = torch.Generator().manual_seed(5)
     gy = torch.randn(ry.shape, generator=g, dtype=torch.float64); gx = torch.randn(rx.shape, generator=g, dtype=torch.float64)
@@ -194,7 +195,7 @@ def test_step_256x128_cluster_cg(cuda_device, eng):
     rrho, ry, rx, aux = so.karman_step(rho, vyt, vxt, re, geom, return_aux=True)
     out = plan.step_fwd(dev(re, cuda_device), dev(vy, cuda_device), dev(vx, cuda_device), rho=dev(rho, cuda_device))
     print("256x128 step rel", rel(out["vy"], ry), rel(out["vx"], rx), rel(out["rho"], rrho), rel(out["p"], aux["p"]), out["iters"].tolist())
-    assert rel(out["vy"], ry) < 2e-5 and rel(out["vx"], rx) < 2e-4 and rel(out["rho"], rrho) < 1e-5
+    assert rel(out["vy"], ry) < 1e-5 and rel(out["vx"], rx) < 1e-5 and rel(out["rho"], rrho) < 1e-5
     g = torch.Generator().manual_seed(5)
     gy = torch.randn(ry.shape, generator=g, dtype=torch.float64); gx = torch.randn(rx.shape, generator=g, dtype=torch.float64)
     ((ry * gy).sum() + (rx * gx).sum()).backward()

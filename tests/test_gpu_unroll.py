@@ -18,12 +18,16 @@ def dev(t, device):
     return t.to(device=device, dtype=torch.float32).contiguous()
 
 
+FIELD_TOL = 1e-5        # north_star: forward + adjoint fields within 1e-5 relative L2 (measured: < 4e-6)
+GRAD_TOL = 2e-5         # weight gradient of a short unroll (measured: 1e-6 .. 7e-6)
+
+
 def _setup(Y, X, B, m, device, use_graph=False, spin=25, direct=1):
     from solver_in_the_loop_b200 import engine
-    geom, rho, vy, vx, re, gty, gtx, sig = so.make_case(Y=Y, X=X, B=B, msteps=m, spin=spin)
-    params = so.init_params(seed=0)
-    for k in range(1, len(params), 2):      # non-zero biases so that their gradients are exercised
-        params[k] = 0.01 * torch.randn(params[k].shape, generator=torch.Generator().manual_seed(k), dtype=torch.float64)
+    # inputs in general position (no back-trace exactly on a cell border), rounded to fp32, non-zero biases:
+    # see the module docstring of test_gpu_quoted_configs.py
+    from test_gpu_quoted_configs import general_position_case
+    geom, rho, vy, vx, re, gty, gtx, sig, params = general_position_case(Y, X, B, m, spin, wscale=1.0)
     plan = engine.Plan.karman(Y, X, B)
     plan.set_cg(tol_abs=1e-7, tol_rel=1e-6, max_it=4000, cluster=0)
     plan.set_option("direct_solve", direct)
@@ -80,8 +84,9 @@ def test_unrolled_forward_backward_parity(cuda_device, conv_path, Y, X, B, m, di
     for i in range(m):
         print("step", i, "state rel", rel(pv[i], states[i][1]), rel(px[i], states[i][2]), rel(prho[i], states[i][0]),
               "loss", float(ls[i]), float(losses[i]))
-        assert rel(pv[i], states[i][1]) < 2e-5 and rel(px[i], states[i][2]) < 2e-4 and rel(prho[i], states[i][0]) < 2e-5
-        assert abs(float(ls[i]) - float(losses[i])) < 1e-4 * abs(float(losses[i]))
+        # north_star: fields within 1e-5 relative L2
+        assert rel(pv[i], states[i][1]) < FIELD_TOL and rel(px[i], states[i][2]) < FIELD_TOL and rel(prho[i], states[i][0]) < FIELD_TOL
+        assert abs(float(ls[i]) - float(losses[i])) < 1e-5 * abs(float(losses[i]))
     gw, gy0, gx0 = un.backward(w, want_input_grad=True)
     print("grad rel", rel(gw, gref), "input grad rel", rel(gy0, vy0.grad), rel(gx0, vx0.grad), "cg iters", un.cg_iters().tolist())
     # per-layer report
@@ -90,7 +95,7 @@ def test_unrolled_forward_backward_parity(cuda_device, conv_path, Y, X, B, m, di
         n = 25 * ci * co
         print("  layer", li, "dW rel", rel(gw[o:o + n], gref[o:o + n]), "db rel", rel(gw[o + n:o + n + co], gref[o + n:o + n + co]))
         o += n + co
-    assert rel(gw, gref) < 1e-4
+    assert rel(gw, gref) < GRAD_TOL
     # the coordinate gradient of the semi-Lagrangian sample is discontinuous across cell borders:
     # fp32 vs fp64 back-traces that land on different sides give O(1) entry-wise differences
     assert rel(gy0, vy0.grad) < 1e-3 and rel(gx0, vx0.grad) < 1e-3
@@ -163,11 +168,11 @@ def test_model_mercury_unrolled_parity(cuda_device):
     assert un.nparams == so.param_count("mercury") == w.numel()
     ls, pv, px, _ = un.forward(w, d(re), d(vy), d(vx), d(gty), d(gtx), return_pred=True)
     for i in range(m):
-        assert rel(pv[i], states[i][1]) < 2e-5 and rel(px[i], states[i][2]) < 2e-4
-        assert abs(float(ls[i]) - float(losses[i])) < 1e-4 * abs(float(losses[i]))
+        assert rel(pv[i], states[i][1]) < FIELD_TOL and rel(px[i], states[i][2]) < FIELD_TOL
+        assert abs(float(ls[i]) - float(losses[i])) < 1e-5 * abs(float(losses[i]))
     gw = un.backward(w)
     print("mercury grad rel", rel(gw, gref))
-    assert rel(gw, gref) < 1e-4
+    assert rel(gw, gref) < GRAD_TOL
     un_g = engine.Unroll(plan, m, B, sig, model=_lib.SOL_MODEL_MERCURY, use_graph=True)
     g1 = torch.zeros_like(gw)
     for _ in range(4):
