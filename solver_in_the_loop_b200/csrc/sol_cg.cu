@@ -23,6 +23,8 @@
 #include "sol_cells.cuh"
 #include "sol_internal.cuh"
 
+SOL_TRACE_TU()
+
 namespace cg = cooperative_groups;
 
 namespace sol {
@@ -298,6 +300,7 @@ static int launch_cg_t(const CgArgs& a, cudaStream_t st, int TY) {
         cfg.attrs = attr;
         cfg.numAttrs = 1;
     }
+    if (g_trace_names) trace_record_launch((const void*)kern);
     SOL_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     SOL_LAUNCHED();
     return SOL_OK;

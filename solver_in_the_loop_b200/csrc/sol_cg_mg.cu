@@ -22,6 +22,8 @@
 #include "sol_cells.cuh"
 #include "sol_internal.cuh"
 
+SOL_TRACE_TU()
+
 namespace sol {
 
 struct MgArgs {

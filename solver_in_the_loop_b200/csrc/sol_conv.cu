@@ -15,6 +15,8 @@
 //   k_wgrad_expand / k_wgrad_reduce   weight gradients of the thin layers (register-tiled, persistent)
 #include "sol_internal.cuh"
 
+SOL_TRACE_TU()
+
 namespace sol {
 
 constexpr int THIN_SLOT = 25 * 4 * 32 + 32;      // floats of one CTA's partial slot in the deterministic thin weight-gradient mode

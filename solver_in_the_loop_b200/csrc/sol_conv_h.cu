@@ -29,6 +29,8 @@
 #include "sol_internal.cuh"
 #include "sol_tc_common.cuh"
 
+SOL_TRACE_TU()
+
 namespace sol {
 
 namespace {

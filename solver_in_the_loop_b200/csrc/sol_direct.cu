@@ -20,6 +20,8 @@
 #include "sol_direct_host.h"
 #include "sol_internal.cuh"
 
+SOL_TRACE_TU()
+
 namespace sol {
 
 namespace {
@@ -605,6 +607,7 @@ static int launch_direct_t(const DirectArgs& a, cudaStream_t st, int mode) {
             ++na;
         }
         cfg.attrs = attr; cfg.numAttrs = na;
+        if (g_trace_names) trace_record_launch(mode == 0 ? (const void*)k0 : (const void*)k1);
         if (mode == 0) SOL_CUDA(cudaLaunchKernelEx(&cfg, k0, a));
         else SOL_CUDA(cudaLaunchKernelEx(&cfg, k1, a));
         SOL_LAUNCHED();
@@ -640,6 +643,7 @@ static int launch_direct_big_t(const DirectArgs& a, cudaStream_t st, int mode) {
             ++na;
         }
         cfg.attrs = attr; cfg.numAttrs = na;
+        if (g_trace_names) trace_record_launch(mode == 0 ? (const void*)k0 : (const void*)k1);
         if (mode == 0) SOL_CUDA(cudaLaunchKernelEx(&cfg, k0, a));
         else SOL_CUDA(cudaLaunchKernelEx(&cfg, k1, a));
         SOL_LAUNCHED();

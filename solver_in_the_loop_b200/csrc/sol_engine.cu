@@ -13,6 +13,8 @@
 
 #include "sol_internal.cuh"
 
+SOL_TRACE_TU()
+
 using namespace sol;
 
 namespace sol {
@@ -159,6 +161,45 @@ extern "C" int sol_abi_version(void) { return SOL_ABI_VERSION; }
 extern "C" const char* sol_last_error_string(void) { return sol::g_err; }
 extern "C" unsigned long long sol_launch_count(void) { return sol::g_launches.load(); }
 
+// ---- chain trace (diagnostics, see sol_internal.cuh) ----
+namespace sol {
+bool g_trace_names = false;
+static std::vector<void (*)(const TraceCtl&)>& trace_setters() { static std::vector<void (*)(const TraceCtl&)> v; return v; }
+static std::vector<const void*>& trace_launches() { static std::vector<const void*> v; return v; }
+void trace_register(void (*setter)(const TraceCtl&)) { trace_setters().push_back(setter); }
+void trace_record_launch(const void* kern) { trace_launches().push_back(kern); }
+}  // namespace sol
+
+// buf: device array of `cap` uint64 time stamps, count: device counter (zeroed by the caller); null buf switches tracing off.
+extern "C" void sol_debug_chain_trace(unsigned long long* buf, unsigned int* count, unsigned int cap) {
+    sol::TraceCtl c{buf, count, cap};
+    for (auto f : sol::trace_setters()) f(c);
+    cudaDeviceSynchronize();
+}
+// record_names = 1: remember the kernel of every launch from now on (clears the list); the list is read back as
+// newline-separated names in launch order (returns the number of launches recorded).
+extern "C" int sol_debug_chain_names(int record_names, char* out, int cap) {
+    if (record_names >= 0) { sol::g_trace_names = record_names != 0; if (record_names) sol::trace_launches().clear(); }
+    int pos = 0;
+    if (out && cap > 0) {
+        for (const void* k : sol::trace_launches()) {
+            const char* name = nullptr;
+            if (cudaFuncGetName(&name, k) != cudaSuccess || !name) name = "?";
+            const int n = (int)strlen(name);
+            if (pos + n + 2 > cap) break;
+            memcpy(out + pos, name, n); pos += n; out[pos++] = '\n';
+        }
+        out[pos] = 0;
+    }
+    return (int)sol::trace_launches().size();
+}
+
+// Every setter that shapes the launch sequence of an unrolled iteration (process-wide options, per-plan solver settings, the
+// Burgers scalars) bumps this counter; a captured graph is replayed only while the counter still has the value it was
+// captured at, otherwise the iteration is run eagerly and captured again.
+static std::atomic<unsigned long long> g_cfg_epoch{1};
+static inline void cfg_changed() { g_cfg_epoch.fetch_add(1, std::memory_order_relaxed); }
+
 extern "C" size_t sol_model_param_count(int model, int cin0) {
     std::vector<LayerDesc> L;
     if (build_layers(model, cin0, L) != SOL_OK) return 0;
@@ -231,12 +272,14 @@ extern "C" int sol_plan_set_cg(sol_plan* p, float tol_abs, float tol_rel, int ma
     SOL_CHECK(p != nullptr, "sol_plan_set_cg: plan is NULL");
     SOL_CHECK(tol_abs >= 0.f && tol_rel >= 0.f && max_it >= 0, "sol_plan_set_cg: negative tolerance / iteration cap");
     SOL_CHECK(cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8, "sol_plan_set_cg: cluster must be 0,1,2,4,8");
+    cfg_changed();
     p->tol_abs = tol_abs; p->tol_rel = tol_rel; p->max_it = max_it; p->cluster = cluster;
     return SOL_OK;
 }
 
 extern "C" int sol_plan_set_option(sol_plan* p, const char* name, int value) {
     SOL_CHECK(p != nullptr && name != nullptr, "sol_plan_set_option: NULL pointer");
+    cfg_changed();
     if (strcmp(name, "cg_rows") == 0) {
         SOL_CHECK(value == 0 || value == 2 || value == 4 || value == 8 || value == 16, "cg_rows must be 0,2,4,8,16");
         p->cg_rows = value;
@@ -271,6 +314,7 @@ extern "C" int sol_plan_query(sol_plan* p, const char* name, int* value) {
 
 extern "C" int sol_set_option(const char* name, int value) {
     SOL_CHECK(name != nullptr, "sol_set_option: NULL name");
+    cfg_changed();
     if (strcmp(name, "conv_path") == 0) {
         SOL_CHECK(value >= 0 && value <= 3, "conv_path must be 0,1,2,3");
         sol::g_conv_path = value == 0 ? 2 : value;
@@ -580,6 +624,7 @@ struct sol_unroll {
     // CUDA graph cache
     cudaGraphExec_t gexec = nullptr;
     const void* gkey[13] = {nullptr};
+    unsigned long long gepoch = 0;      // g_cfg_epoch the graph was captured at
     int warm = 0;
     // graph work runs on a private non-blocking stream (the caller's may be the legacy default
     // stream, which cannot be captured); fork/join with events keeps the caller's stream ordering
@@ -1157,7 +1202,8 @@ extern "C" int sol_unroll_train_iter(sol_unroll* u, void* stream, const float* w
     };
     SOL_CUDA(cudaEventRecord(u->ev_fork, caller));
     SOL_CUDA(cudaStreamWaitEvent(st, u->ev_fork, 0));
-    const bool same = memcmp(key, u->gkey, sizeof(key)) == 0;
+    const unsigned long long epoch = g_cfg_epoch.load(std::memory_order_relaxed);
+    const bool same = memcmp(key, u->gkey, sizeof(key)) == 0 && epoch == u->gepoch;
     if (same && u->gexec) {
         SOL_CUDA(cudaGraphLaunch(u->gexec, st));
         sol::g_launches.fetch_add(u->graph_kernels, std::memory_order_relaxed);
@@ -1167,6 +1213,7 @@ extern "C" int sol_unroll_train_iter(sol_unroll* u, void* stream, const float* w
         // first call with these buffers: run eagerly (also sets every kernel attribute outside capture)
         if (u->gexec) { cudaGraphExecDestroy(u->gexec); u->gexec = nullptr; }
         memcpy(u->gkey, key, sizeof(key));
+        u->gepoch = epoch;
         u->warm = 1;
         SOL_TRY(run());
         return join();
@@ -1200,6 +1247,7 @@ extern "C" int sol_unroll_set_burgers(sol_unroll* u, float viscosity, const floa
     u->visc = viscosity; u->bk_y = diff_kernel_y; u->bk_x = diff_kernel_x; u->bf_vy = f_vy; u->bf_vx = f_vx;
     u->sig_fy = sig_fy; u->sig_fx = sig_fx;
     u->burgers_set = true;
+    cfg_changed();
     return SOL_OK;
 }
 

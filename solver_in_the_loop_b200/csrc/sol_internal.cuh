@@ -58,8 +58,20 @@ inline int fail(int code, const char* fmt, const char* a = "", const char* b = "
 // prologue work), and triggers its own dependents only after that wait, which makes completion
 // transitive along the stream.  With the attribute off (option "pdl" = 0) both are no-ops.
 extern int g_pdl;
+
+// Diagnostics (sol_debug_chain_trace, scripts/chain_trace.py): with a trace buffer installed, thread 0 of CTA 0 of EVERY kernel
+// stamps %globaltimer right after its griddepcontrol.wait, i.e. at the moment its predecessor in the stream has completed.
+// Kernels of one stream form a serial chain, so the difference of consecutive stamps is the cost of a kernel inside the
+// replayed graph (programmatic overlap included) — what a serialising profiler cannot show.  The control block lives in
+// __constant__ memory, one copy per translation unit (no relocatable device code): SOL_TRACE_TU() registers the copy's setter.
+struct TraceCtl { unsigned long long* buf; unsigned int* count; unsigned int cap; };
+void trace_register(void (*setter)(const TraceCtl&));
+extern bool g_trace_names;                       // host side: record the kernel of every launch (same order as the stamps)
+void trace_record_launch(const void* kern);
+
 template <typename... P, typename... A>
 inline cudaError_t launch_kernel(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+    if (g_trace_names) trace_record_launch((const void*)kern);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -69,7 +81,24 @@ inline cudaError_t launch_kernel(void (*kern)(P...), dim3 grid, dim3 block, size
     return cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);
 }
 #ifdef __CUDACC__
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+static __constant__ TraceCtl c_trace;
+#define SOL_TRACE_TU()                                                                                                        \
+    namespace {                                                                                                               \
+    struct TraceTu {                                                                                                          \
+        TraceTu() { sol::trace_register([](const sol::TraceCtl& c) { cudaMemcpyToSymbol(sol::c_trace, &c, sizeof(c)); }); }  \
+    } trace_tu__;                                                                                                             \
+    }
+__device__ __forceinline__ void trace_stamp() {
+    if (c_trace.buf && (threadIdx.x | threadIdx.y | threadIdx.z | blockIdx.x | blockIdx.y | blockIdx.z) == 0) {
+        const unsigned int s = atomicAdd(c_trace.count, 1u);
+        if (s < c_trace.cap) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            c_trace.buf[s] = t;
+        }
+    }
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); trace_stamp(); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
 #endif

@@ -9,6 +9,8 @@
 #include "sol_cells.cuh"
 #include "sol_internal.cuh"
 
+SOL_TRACE_TU()
+
 namespace sol {
 
 thread_local char g_err[512] = "";

@@ -12,6 +12,8 @@
 #include "sol_cells.cuh"
 #include "sol_internal.cuh"
 
+SOL_TRACE_TU()
+
 namespace sol {
 
 namespace {

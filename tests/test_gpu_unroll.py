@@ -116,6 +116,30 @@ def test_graph_replay_matches_eager(cuda_device):
     assert rel(g1, g0) < 1e-5    # thin-layer weight gradients use float atomics (order varies)
 
 
+def test_graph_is_recaptured_after_a_setter(cuda_device):
+    """A captured iteration must not outlive the configuration it was captured with: every setter bumps the
+    engine's configuration epoch and the next call runs eagerly and re-captures."""
+    Y, X, B, m = 64, 32, 2, 2
+    engine, geom, rho, vy, vx, re, gty, gtx, sig, params, plan, un, w = _setup(Y, X, B, m, cuda_device)
+    un_g = engine.Unroll(plan, m, B, sig, use_graph=True)
+    d = lambda t: dev(t, cuda_device)
+    args = (w, d(re), d(vy), d(vx), d(gty), d(gtx))
+    g = torch.zeros(un.nparams, device=cuda_device)
+    try:
+        for _ in range(3):      # eager, capture, replay
+            l_direct = un_g.train_iter(*args, g).clone()
+        torch.cuda.synchronize()
+        assert int(un_g.cg_iters().max()) == 0           # direct projection: no iterations
+        plan.set_option("direct_solve", 0)
+        for _ in range(3):
+            l_iter = un_g.train_iter(*args, g).clone()
+            torch.cuda.synchronize()
+            assert int(un_g.cg_iters().min()) >= 1       # the iterative solver really ran (no stale replay)
+        assert rel(l_iter, l_direct) < 1e-5
+    finally:
+        plan.set_option("direct_solve", 1)
+
+
 @pytest.mark.parametrize("direct", [1, 0], ids=["direct", "mgpcg"])
 def test_full_size_properties(cuda_device, direct):
     """BASELINE config sizes (128x64, B=3, msteps=32) through size-independent properties:
