@@ -104,6 +104,8 @@ int sol_plan_query(sol_plan* plan, const char* name, int* value);
  *         atomics (sol_advect_bwd) remain order-dependent at round-off level.  0 (default) = atomics
  *   "fuse_stencil" 1 (default) = viscosity + BC and the three advections of a step are ONE launch with the stencil halo staged in
  *         shared memory (OPEN plans), 0 = one kernel per stage (global gathers)
+ *   "thin_path" 0 (default) = first / last conv layers (Cin <= 4 -> 32, 32 -> Cout <= 4) on the row-pair kernels of
+ *         sol_conv_thin.cu, 1 = the first-generation one-pixel-per-thread kernels (validation)
  *   "nvtx" 1 = NVTX ranges around the stages of the unrolled sweeps (for nsys / ncu --nvtx; host-side, default 0)
  *   "tc_base_offset_mode" (debug) how the UMMA shared-memory descriptors encode unaligned starts */
 int sol_set_option(const char* name, int value);

@@ -89,7 +89,7 @@ for rep in range(a.reps):
     if rep == 0:
         continue                                    # first traced replay: cold constants
     for i in range(n - 1):
-        nm = names[i].split("(")[0].replace("void ", "").replace("sol::", "").replace("(anonymous namespace)::", "")
+        nm = names[i].replace("(anonymous namespace)::", "").split("(")[0].replace("void ", "").replace("sol::", "")
         agg.setdefault(nm, []).append(dt[i])
 print("one iteration %dx%d B=%d msteps=%d: %d launches; CUDA-event ms / first-to-last-stamp ms per traced replay: %s"
       % (Y, X, B, m, n_launch, " ".join("%.3f/%.3f" % (x, y / 1000.0) for x, y in tot)))

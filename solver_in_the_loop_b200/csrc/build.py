@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-SOURCES = ["sol_stencil.cu", "sol_stencil_fused.cu", "sol_cg.cu", "sol_cg_mg.cu", "sol_direct.cu", "sol_conv.cu", "sol_conv_tc.cu", "sol_conv_h.cu", "sol_wgrad_tc.cu", "sol_wgrad_h.cu", "sol_engine.cu"]
+SOURCES = ["sol_stencil.cu", "sol_stencil_fused.cu", "sol_cg.cu", "sol_cg_mg.cu", "sol_direct.cu", "sol_conv.cu", "sol_conv_thin.cu", "sol_conv_tc.cu", "sol_conv_h.cu", "sol_wgrad_tc.cu", "sol_wgrad_h.cu", "sol_engine.cu"]
 LIB = os.path.join(PKG, "libsol_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(256) k_wgrad_generic(const float* __restrict__
 }
 
 int launch_conv5x5(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const float* in, const float* w, const float* bias,
-                   const float* addend, const float* ref, int act, float slope, float* out, unsigned int* amax_out) {
+                   const float* addend, const float* ref, int act, float slope, float* out, unsigned int* amax_out, bool weights_ready) {
     ConvArgs a;
     a.in = in; a.w = w; a.bias = bias; a.addend = addend; a.ref = ref; a.out = out;
     a.B = B; a.Y = Y; a.X = X; a.act = act; a.slope = slope; a.amax_out = amax_out;
@@ -480,6 +480,11 @@ int launch_conv5x5(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, cons
     }
     if (((uintptr_t)in & 15) && Cin == 32) return fail(SOL_ERR_INVALID, "conv5x5: 32-channel input must be 16-byte aligned");
     if (((uintptr_t)w & 15) || ((uintptr_t)out & 15 && Cout == 32)) return fail(SOL_ERR_INVALID, "conv5x5: weights / 32-channel output must be 16-byte aligned");
+    if (g_thin_path == 0 && ((Cout == 32 && Cin >= 2 && Cin <= 4) || (Cin == 32 && Cout >= 2 && Cout <= 4))) {
+        if (((uintptr_t)in & 15) && Cin == 32) return fail(SOL_ERR_INVALID, "conv5x5: 32-channel input must be 16-byte aligned");
+        if (Cout == 32 && ((addend && ((uintptr_t)addend & 15)) || (ref && ((uintptr_t)ref & 15)))) return fail(SOL_ERR_INVALID, "conv5x5: addend / ref must be 16-byte aligned");
+        return launch_conv5x5_thin(st, B, Y, X, Cin, Cout, in, w, bias, addend, ref, act, slope, out, amax_out, weights_ready);
+    }
     if (Cout == 32 && Cin == 2) return launch_expand<2>(a, st);
     if (Cout == 32 && Cin == 3) return launch_expand<3>(a, st);
     if (Cout == 32 && Cin == 4) return launch_expand<4>(a, st);
@@ -611,6 +616,26 @@ __global__ void __launch_bounds__(256) k_wgrad_finalize(int nctas, const float* 
     for (int c = 0; c < nctas; ++c) s += part[(size_t)c * WG_E + e];
     float* dst = (e < 25 * 32 * 32) ? (dW + e) : (db + (e - 25 * 32 * 32));
     *dst = accumulate ? (*dst + s) : s;
+}
+
+// All ten 32 -> 32 layers in ONE launch (blockIdx.y = layer): the layers' [weights | bias] blocks are WG_E floats each and
+// adjacent in the Keras-ordered gradient buffer, so layer l writes out + l * WG_E.  Same fixed summation order per entry
+// as k_wgrad_finalize: CTA slots in four interleaved chains (c = 0, 4, 8, ..; 1, 5, ..; ...) combined at the end.
+struct FinalizeMulti { int nctas[10]; };
+__global__ void __launch_bounds__(256) k_wgrad_finalize_multi(const FinalizeMulti f, const float* __restrict__ part, size_t part_stride,
+                                                              float* __restrict__ out) {
+    pdl_sync();
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= WG_E) return;
+    const int l = blockIdx.y, n = f.nctas[l];
+    const float* p = part + (size_t)l * part_stride + e;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    int c = 0;
+    for (; c + 3 < n; c += 4) {
+        s0 += p[(size_t)c * WG_E]; s1 += p[(size_t)(c + 1) * WG_E]; s2 += p[(size_t)(c + 2) * WG_E]; s3 += p[(size_t)(c + 3) * WG_E];
+    }
+    for (; c < n; ++c) s0 += p[(size_t)c * WG_E];
+    out[(size_t)l * WG_E + e] = (s0 + s1) + (s2 + s3);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -961,6 +986,14 @@ size_t wgrad_workspace_floats(int Cin, int Cout) {
 
 int launch_wgrad_finalize_n(cudaStream_t st, int nctas, const float* partials, float* dW, float* db, int accumulate) {
     SOL_CUDA(launch_kernel(k_wgrad_finalize, dim3(cdiv(WG_E, 256)), dim3(256), 0, st, nctas, partials, dW, db, accumulate));
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
+int launch_wgrad_finalize_multi(cudaStream_t st, const int* nctas10, const float* partials, size_t part_stride, float* out) {
+    FinalizeMulti f;
+    for (int l = 0; l < 10; ++l) f.nctas[l] = nctas10[l];
+    SOL_CUDA(launch_kernel(k_wgrad_finalize_multi, dim3(cdiv(WG_E, 256), 10), dim3(256), 0, st, f, partials, part_stride, out));
     SOL_LAUNCHED();
     return SOL_OK;
 }

@@ -1,0 +1,278 @@
+// First / last layers of the correction CNN and their data gradients: 5x5 'same' convolutions Cin <= 4 -> 32 and
+// 32 -> Cout <= 4 (reference: karman-2d/karman_train.py:103 and :135, burgers/burgers_train.py:115-150), exact fp32.
+//
+// At the bench shape (3 x 128 x 64 = 24,576 pixels on 148 SMs) these layers are pure latency: 59 / 39 MFMA per launch
+// are 1.6 / 1.1 us of FP32 issue for the whole GPU, but the first-generation kernels (sol_conv.cu: one pixel x 32 couts
+// per thread, 5 warps per SM, 9 shared loads per 32 FMAs) measured 12 - 30 us inside the replayed iteration
+// (profiles/r02/r02_n_chain_trace_sol32.txt).  These kernels trade registers for parallelism instead:
+//   * a CTA is ONE pair of image rows x 32 columns; its four warps split the 32 output channels (expand) or the 32 input
+//     channels (reduce), so an SM holds 10 - 12 warps of independent work instead of 5;
+//   * lane = x (conflict-free shared reads, coalesced global traffic), a thread owns the two vertically adjacent pixels:
+//     one 6-row column of inputs and one set of warp-uniform 128-bit weight loads feed 5 taps x 2 pixels;
+//   * all global loads of a thread are issued before the first shared store; one barrier; the reduce kernel sums its four
+//     channel groups through shared memory in a fixed order (deterministic).
+#include "sol_internal.cuh"
+
+SOL_TRACE_TU()
+
+namespace sol {
+
+namespace {
+
+struct ThinArgs {
+    const float* in;
+    const float* w;
+    const float* bias;
+    const float* addend;
+    const float* ref;
+    float* out;
+    int B, Y, X;
+    int act;
+    float slope;
+    unsigned int* amax_out;
+    int weights_ready;          // 1: the weights were complete before the previous kernel of the stream started (fetch them before the wait)
+};
+
+__device__ __forceinline__ float thin_act(float v, int act, float slope, float ref) {
+    if (act == SOL_ACT_LRELU) return v > 0.0f ? v : slope * v;
+    if (act == SOL_ACT_DLRELU) return ref > 0.0f ? v : slope * v;
+    return v;
+}
+
+constexpr int TW = 32, TROWS = 2, PW = TW + 4, PH = TROWS + 4;
+
+// Asynchronous global -> shared copies (LDGSTS): no staging registers, every copy of a thread is in flight at once (ptxas
+// interleaves register-staged loads and stores in groups of four, which serialises the L2 latency); `ok` = false zero-fills.
+__device__ __forceinline__ uint32_t thin_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async_4(void* dst, const float* src, bool ok) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(thin_smem_u32(dst)), "l"(src), "r"(ok ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src, bool ok) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(thin_smem_u32(dst)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+
+// ---- Cin <= 4 -> 32.  warp = 8 output channels, lane = x, thread = pixels (y0, x) and (y0 + 1, x) ----
+template <int CIN>
+__global__ void __launch_bounds__(128) k_conv5x5_expand2(const ThinArgs a) {
+    __shared__ float4 ws4[25 * CIN * 8];            // [tap][ci][32 couts]
+    __shared__ float tin[CIN * PH * PW];            // planar [ci][row][px]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TROWS, b = blockIdx.z;
+    constexpr int TOTALW = 25 * CIN * 8, ITERW = (TOTALW + 127) / 128;
+    constexpr int TOTAL = PH * PW * CIN, ITER = (TOTAL + 127) / 128;
+    const float4* wg = reinterpret_cast<const float4*>(a.w);
+    auto fetch_weights = [&]() {
+#pragma unroll
+        for (int it = 0; it < ITERW; ++it) { const int idx = tid + it * 128; if (idx < TOTALW) cp_async_16(ws4 + idx, wg + idx, true); }
+    };
+    if (a.weights_ready) fetch_weights();      // settled weights do not depend on the predecessor kernel: fetch them before waiting for it
+    pdl_sync();      // (triggering the dependent kernel only after the FMA loops measured slower: 11.75 vs 11.44 ms per iteration)
+    if (!a.weights_ready) fetch_weights();
+    {
+        const float* inb = a.in + (size_t)b * a.Y * a.X * CIN;
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int idx = tid + it * 128;
+            const int row = idx / (PW * CIN), rem = idx - row * (PW * CIN);     // [row][px][ci] order = global order
+            const int px = rem / CIN, ci = rem - px * CIN;
+            const int gy = y0 + row - 2, gx = x0 + px - 2;
+            const bool ok = gy >= 0 && gy < a.Y && gx >= 0 && gx < a.X;
+            if (idx < TOTAL) cp_async_4(tin + (ci * PH + row) * PW + px, ok ? inb + ((size_t)gy * a.X + gx) * CIN + ci : inb, ok);
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    float acc[2][8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { acc[0][c] = 0.0f; acc[1][c] = 0.0f; }
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) {
+            float v[PH];
+#pragma unroll
+            for (int r = 0; r < PH; ++r) v[r] = tin[(ci * PH + r) * PW + lane + dx];
+#pragma unroll
+            for (int dy = 0; dy < 5; ++dy) {
+                const float4* wq = ws4 + ((dy * 5 + dx) * CIN + ci) * 8 + warp * 2;
+                const float4 w0 = wq[0], w1 = wq[1];
+#pragma unroll
+                for (int pz = 0; pz < 2; ++pz) {
+                    const float u = v[dy + pz];
+                    acc[pz][0] = fmaf(u, w0.x, acc[pz][0]); acc[pz][1] = fmaf(u, w0.y, acc[pz][1]);
+                    acc[pz][2] = fmaf(u, w0.z, acc[pz][2]); acc[pz][3] = fmaf(u, w0.w, acc[pz][3]);
+                    acc[pz][4] = fmaf(u, w1.x, acc[pz][4]); acc[pz][5] = fmaf(u, w1.y, acc[pz][5]);
+                    acc[pz][6] = fmaf(u, w1.z, acc[pz][6]); acc[pz][7] = fmaf(u, w1.w, acc[pz][7]);
+                }
+            }
+        }
+    }
+    const int gx = x0 + lane;
+    unsigned int amax = 0u;
+    float4 bv0 = make_float4(0.f, 0.f, 0.f, 0.f), bv1 = bv0;
+    if (a.bias) { bv0 = __ldg(reinterpret_cast<const float4*>(a.bias) + warp * 2); bv1 = __ldg(reinterpret_cast<const float4*>(a.bias) + warp * 2 + 1); }
+#pragma unroll
+    for (int pz = 0; pz < 2; ++pz) {
+        const int gy = y0 + pz;
+        if (gy < a.Y && gx < a.X) {
+            const size_t o4 = (((size_t)b * a.Y + gy) * a.X + gx) * 8 + warp * 2;
+            float4 f0 = make_float4(acc[pz][0] + bv0.x, acc[pz][1] + bv0.y, acc[pz][2] + bv0.z, acc[pz][3] + bv0.w);
+            float4 f1 = make_float4(acc[pz][4] + bv1.x, acc[pz][5] + bv1.y, acc[pz][6] + bv1.z, acc[pz][7] + bv1.w);
+            if (a.addend) {
+                const float4 d0 = __ldg(reinterpret_cast<const float4*>(a.addend) + o4), d1 = __ldg(reinterpret_cast<const float4*>(a.addend) + o4 + 1);
+                f0.x += d0.x; f0.y += d0.y; f0.z += d0.z; f0.w += d0.w; f1.x += d1.x; f1.y += d1.y; f1.z += d1.z; f1.w += d1.w;
+            }
+            float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+            if (a.act == SOL_ACT_DLRELU) { r0 = __ldg(reinterpret_cast<const float4*>(a.ref) + o4); r1 = __ldg(reinterpret_cast<const float4*>(a.ref) + o4 + 1); }
+            f0.x = thin_act(f0.x, a.act, a.slope, r0.x); f0.y = thin_act(f0.y, a.act, a.slope, r0.y);
+            f0.z = thin_act(f0.z, a.act, a.slope, r0.z); f0.w = thin_act(f0.w, a.act, a.slope, r0.w);
+            f1.x = thin_act(f1.x, a.act, a.slope, r1.x); f1.y = thin_act(f1.y, a.act, a.slope, r1.y);
+            f1.z = thin_act(f1.z, a.act, a.slope, r1.z); f1.w = thin_act(f1.w, a.act, a.slope, r1.w);
+            float4* out4 = reinterpret_cast<float4*>(a.out) + o4;
+            out4[0] = f0; out4[1] = f1;
+            amax = max(amax, max(max(__float_as_uint(f0.x) & 0x7fffffffu, __float_as_uint(f0.y) & 0x7fffffffu),
+                                 max(__float_as_uint(f0.z) & 0x7fffffffu, __float_as_uint(f0.w) & 0x7fffffffu)));
+            amax = max(amax, max(max(__float_as_uint(f1.x) & 0x7fffffffu, __float_as_uint(f1.y) & 0x7fffffffu),
+                                 max(__float_as_uint(f1.z) & 0x7fffffffu, __float_as_uint(f1.w) & 0x7fffffffu)));
+        }
+    }
+    if (a.amax_out) {       // one atomic per warp (warp-uniform branch: every lane reaches the reduction)
+        amax = __reduce_max_sync(0xffffffffu, amax);
+        if (lane == 0 && amax) atomicMax(a.amax_out, amax);
+    }
+}
+
+// ---- 32 -> Cout <= 4.  warp = 8 input channels, lane = x, thread = pixels (y0, x) and (y0 + 1, x); the four channel
+//      groups are summed through shared memory by warp 0 in group order ----
+constexpr int PS = 36;                              // padded pixel stride (floats): 128-bit reads of consecutive pixels are conflict-free
+template <int COUT>
+constexpr int reduce2_smem_floats() { return 25 * 32 * COUT + PH * PW * PS; }
+
+template <int COUT>
+__global__ void __launch_bounds__(128) k_conv5x5_reduce2(const ThinArgs a) {
+    extern __shared__ float4 thin_smem4[];
+    float* ws = reinterpret_cast<float*>(thin_smem4);           // [25][32][COUT] (the Keras order)
+    float* tin = ws + 25 * 32 * COUT;                           // [PH * PW][PS]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TROWS, b = blockIdx.z;
+    constexpr int TOTALW = 25 * 32 * COUT / 4, ITERW = (TOTALW + 127) / 128;
+    constexpr int TOTAL = PH * PW * 8, ITER = (TOTAL + 127) / 128;      // 1728 float4: 13.5 per thread
+    const float4* wg = reinterpret_cast<const float4*>(a.w);
+    auto fetch_weights = [&]() {
+#pragma unroll
+        for (int it = 0; it < ITERW; ++it) { const int idx = tid + it * 128; if (idx < TOTALW) cp_async_16(thin_smem4 + idx, wg + idx, true); }
+    };
+    if (a.weights_ready) fetch_weights();
+    pdl_sync();      // (triggering the dependent kernel only after the FMA loops measured slower: 11.75 vs 11.44 ms per iteration)
+    if (!a.weights_ready) fetch_weights();
+    {
+        const float* inb = a.in + (size_t)b * a.Y * a.X * 32;
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int idx = tid + it * 128;
+            const int c4 = idx & 7, pix = idx >> 3;
+            const int row = pix / PW, px = pix - row * PW;
+            const int gy = y0 + row - 2, gx = x0 + px - 2;
+            const bool ok = gy >= 0 && gy < a.Y && gx >= 0 && gx < a.X;
+            if (idx < TOTAL) cp_async_16(tin + pix * PS + c4 * 4, ok ? inb + ((size_t)gy * a.X + gx) * 32 + c4 * 4 : inb, ok);
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    float acc[2][COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) { acc[0][c] = 0.0f; acc[1][c] = 0.0f; }
+#pragma unroll
+    for (int cq = 0; cq < 2; ++cq) {
+        const int c4 = warp * 2 + cq;                           // float4 chunk of input channels
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) {
+            float4 iv[PH];
+#pragma unroll
+            for (int r = 0; r < PH; ++r) iv[r] = *reinterpret_cast<const float4*>(tin + (r * PW + lane + dx) * PS + c4 * 4);
+#pragma unroll
+            for (int dy = 0; dy < 5; ++dy) {
+                float wq[4 * COUT];                             // [ci 0..3][co]: 4*COUT consecutive floats, warp-uniform
+                const float4* wp = reinterpret_cast<const float4*>(ws + ((dy * 5 + dx) * 32 + c4 * 4) * COUT);
+#pragma unroll
+                for (int q = 0; q < COUT; ++q) {
+                    const float4 w = wp[q];
+                    wq[4 * q] = w.x; wq[4 * q + 1] = w.y; wq[4 * q + 2] = w.z; wq[4 * q + 3] = w.w;
+                }
+#pragma unroll
+                for (int pz = 0; pz < 2; ++pz) {
+                    const float4 u = iv[dy + pz];
+#pragma unroll
+                    for (int co = 0; co < COUT; ++co)
+                        acc[pz][co] = fmaf(u.x, wq[co], fmaf(u.y, wq[COUT + co], fmaf(u.z, wq[2 * COUT + co], fmaf(u.w, wq[3 * COUT + co], acc[pz][co]))));
+                }
+            }
+        }
+    }
+    __syncthreads();                        // everyone is done with the input tile: reuse it for the group sums
+    float* red = tin;                       // [3 groups][2 * COUT][32 lanes]
+    if (warp > 0) {
+#pragma unroll
+        for (int pz = 0; pz < 2; ++pz)
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) red[((warp - 1) * 2 * COUT + pz * COUT + co) * 32 + lane] = acc[pz][co];
+    }
+    __syncthreads();
+    if (warp > 0) return;
+    const int gx = x0 + lane;
+#pragma unroll
+    for (int pz = 0; pz < 2; ++pz) {
+        const int gy = y0 + pz;
+        if (gy >= a.Y || gx >= a.X) continue;
+        const size_t o = (((size_t)b * a.Y + gy) * a.X + gx) * COUT;
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+            float v = acc[pz][co];
+#pragma unroll
+            for (int g = 0; g < 3; ++g) v += red[(g * 2 * COUT + pz * COUT + co) * 32 + lane];
+            if (a.bias) v += __ldg(a.bias + co);
+            if (a.addend) v += __ldg(a.addend + o + co);
+            const float rf = (a.act == SOL_ACT_DLRELU) ? __ldg(a.ref + o + co) : 0.0f;
+            a.out[o + co] = thin_act(v, a.act, a.slope, rf);
+        }
+    }
+}
+
+template <int CIN>
+int launch_expand2(const ThinArgs& a, cudaStream_t st) {
+    SOL_CUDA(launch_kernel(k_conv5x5_expand2<CIN>, dim3(cdiv(a.X, TW), cdiv(a.Y, TROWS), a.B), dim3(128), 0, st, a));
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
+template <int COUT>
+int launch_reduce2(const ThinArgs& a, cudaStream_t st) {
+    constexpr size_t smem = (size_t)reduce2_smem_floats<COUT>() * sizeof(float);
+    static_assert(smem <= 48 * 1024, "static shared-memory limit");
+    SOL_CUDA(launch_kernel(k_conv5x5_reduce2<COUT>, dim3(cdiv(a.X, TW), cdiv(a.Y, TROWS), a.B), dim3(128), smem, st, a));
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
+}  // namespace
+
+int g_thin_path = 0;        // option "thin_path": 0 = the row-pair kernels of this file, 1 = the first-generation kernels of sol_conv.cu
+
+// Returns SOL_ERR_UNSUPPORTED for channel counts this file does not cover (the caller falls back to the generic kernel).
+int launch_conv5x5_thin(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const float* in, const float* w, const float* bias,
+                        const float* addend, const float* ref, int act, float slope, float* out, unsigned int* amax_out, bool weights_ready) {
+    ThinArgs a;
+    a.weights_ready = weights_ready ? 1 : 0;
+    a.in = in; a.w = w; a.bias = bias; a.addend = addend; a.ref = ref; a.out = out;
+    a.B = B; a.Y = Y; a.X = X; a.act = act; a.slope = slope; a.amax_out = amax_out;
+    if (Cout == 32 && Cin == 2) return launch_expand2<2>(a, st);
+    if (Cout == 32 && Cin == 3) return launch_expand2<3>(a, st);
+    if (Cout == 32 && Cin == 4) return launch_expand2<4>(a, st);
+    if (Cin == 32 && Cout == 2) return launch_reduce2<2>(a, st);
+    if (Cin == 32 && Cout == 3) return launch_reduce2<3>(a, st);
+    if (Cin == 32 && Cout == 4) return launch_reduce2<4>(a, st);
+    return SOL_ERR_UNSUPPORTED;
+}
+
+}  // namespace sol

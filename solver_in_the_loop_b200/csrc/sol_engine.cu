@@ -370,6 +370,11 @@ extern "C" int sol_set_option(const char* name, int value) {
         sol::g_deterministic = value ? 1 : 0;
         return SOL_OK;
     }
+    if (strcmp(name, "thin_path") == 0) {
+        SOL_CHECK(value == 0 || value == 1, "thin_path must be 0 (row-pair kernels) or 1 (first-generation kernels)");
+        sol::g_thin_path = value;
+        return SOL_OK;
+    }
     if (strcmp(name, "fuse_stencil") == 0) {
         sol::g_fuse_stencil = value ? 1 : 0;
         return SOL_OK;
@@ -737,8 +742,9 @@ int cnn_forward(sol_unroll* u, cudaStream_t st, const float* w, const StepStash&
     }
     const bool tc = conv_path_is_tc();
     unsigned int* am = u->track_amax ? u->amax : nullptr;       // am[l]: max|input of layer l| over the sweep
+    // (thin layers: the weights were settled before the sweep started, hence before the preceding kernel)
     SOL_TRY(launch_conv5x5(st, B, Y, X, L[0].cin, 32, s.feat, w + L[0].w_off, w + L[0].b_off, nullptr, nullptr, SOL_ACT_LRELU, a, s.acts[0],
-                           am ? am + 1 : nullptr));
+                           am ? am + 1 : nullptr, true));
     for (int k = 1; k <= 5; ++k) {
         const LayerDesc& l1 = L[2 * k - 1];
         const LayerDesc& l2 = L[2 * k];
@@ -751,7 +757,7 @@ int cnn_forward(sol_unroll* u, cudaStream_t st, const float* w, const StepStash&
         SOL_TRY(layer_conv(u, st, t_k, w + l2.w_off, p2, w + l2.b_off, a_prev, nullptr, SOL_ACT_LRELU, a, a_k,
                            (am && k < 5) ? am + 2 * k + 1 : nullptr));
     }
-    return launch_conv5x5(st, B, Y, X, 32, 2, s.acts[10], w + L[11].w_off, w + L[11].b_off, nullptr, nullptr, SOL_ACT_NONE, a, corr);
+    return launch_conv5x5(st, B, Y, X, 32, 2, s.acts[10], w + L[11].w_off, w + L[11].b_off, nullptr, nullptr, SOL_ACT_NONE, a, corr, nullptr, true);
 }
 
 int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, const StepStash& s, const float* g_corr, float* g_feat,
@@ -783,7 +789,7 @@ int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, cons
     if (!deferred)
         SOL_TRY(launch_wgrad(st, B, Y, X, 32, 2, s.acts[10], g_corr, gw + L[11].w_off, gw + L[11].b_off, 1, nullptr, false));
     unsigned int* gm = (u->track_amax && deferred) ? u->amax + 12 : nullptr;       // gm[l]: max|output gradient of layer l| over the sweep
-    SOL_TRY(launch_conv5x5(st, B, Y, X, 2, 32, g_corr, wT + L[11].w_off, nullptr, nullptr, s.acts[10], SOL_ACT_DLRELU, a, gS, gm ? gm + 10 : nullptr));
+    SOL_TRY(launch_conv5x5(st, B, Y, X, 2, 32, g_corr, wT + L[11].w_off, nullptr, nullptr, s.acts[10], SOL_ACT_DLRELU, a, gS, gm ? gm + 10 : nullptr, true));
     for (int k = 5; k >= 1; --k) {
         const LayerDesc& l1 = L[2 * k - 1];
         const LayerDesc& l2 = L[2 * k];
@@ -810,7 +816,7 @@ int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, cons
     // input layer (cin0 -> 32): gS is the gradient w.r.t. its pre-activation
     if (!deferred)
         SOL_TRY(launch_wgrad(st, B, Y, X, L[0].cin, 32, s.feat, gS, gw + L[0].w_off, gw + L[0].b_off, 1, nullptr, false));
-    return launch_conv5x5(st, B, Y, X, 32, L[0].cin, gS, wT + L[0].w_off, nullptr, nullptr, nullptr, SOL_ACT_NONE, a, g_feat);
+    return launch_conv5x5(st, B, Y, X, 32, L[0].cin, gS, wT + L[0].w_off, nullptr, nullptr, nullptr, SOL_ACT_NONE, a, g_feat, nullptr, true);
 }
 
 // nsteps_override > 0: forward-only rollout of that many frames which recycles the stash of step 0 (no adjoint afterwards)
@@ -1098,8 +1104,16 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
         }
         for (int l = 0; l <= 11; ++l)
             if (done[l] > 0) { SOL_TRY(launch_item(st, WgItem{l, 0, done[l]}, nct32)); done[l] = 0; }
+        // the ten hidden layers' [weights | bias] blocks are adjacent in the Keras-ordered buffer: one reduction launch
+        bool adjacent = true;
         for (int l = 1; l <= 10; ++l)
-            SOL_TRY(launch_wgrad_finalize_n(st, slots[l], u->partials + u->partial_stride * (l - 1), gw + u->L[l].w_off, gw + u->L[l].b_off, 0));
+            adjacent &= u->L[l].b_off == u->L[l].w_off + 25 * 32 * 32 && (l == 10 || u->L[l + 1].w_off == u->L[l].b_off + 32);
+        if (adjacent) {
+            SOL_TRY(launch_wgrad_finalize_multi(st, slots + 1, u->partials, u->partial_stride, gw + u->L[1].w_off));
+        } else {
+            for (int l = 1; l <= 10; ++l)
+                SOL_TRY(launch_wgrad_finalize_n(st, slots[l], u->partials + u->partial_stride * (l - 1), gw + u->L[l].w_off, gw + u->L[l].b_off, 0));
+        }
         return SOL_OK;
     }
     if (!mars) return SOL_OK;      // model_mercury accumulated into gw step by step

@@ -239,9 +239,17 @@ bool mg3_selected(const sol_plan* p);
 
 // ---- convolutions (sol_conv.cu) ----
 int launch_conv5x5(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const float* in, const float* w, const float* bias,
-                   const float* addend, const float* ref, int act, float slope, float* out, unsigned int* amax_out = nullptr);
+                   const float* addend, const float* ref, int act, float slope, float* out, unsigned int* amax_out = nullptr,
+                   bool weights_ready = false);
+// first / last layers (sol_conv_thin.cu): SOL_ERR_UNSUPPORTED for channel counts it does not cover.  weights_ready: the weights
+// were complete before the PREVIOUS kernel of the stream started, so they may be fetched before the programmatic wait.
+int launch_conv5x5_thin(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const float* in, const float* w, const float* bias,
+                        const float* addend, const float* ref, int act, float slope, float* out, unsigned int* amax_out, bool weights_ready);
+extern int g_thin_path;
 int launch_flip_weights(cudaStream_t st, int Cin, int Cout, const float* w, float* wT);
 size_t wgrad_workspace_floats(int Cin, int Cout);
+// the ten 32 -> 32 layers at once: layer l sums nctas10[l] slots of partials + l * part_stride into out + l * (25*32*32 + 32)
+int launch_wgrad_finalize_multi(cudaStream_t st, const int* nctas10, const float* partials, size_t part_stride, float* out);
 int launch_wgrad(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const float* in, const float* g_out, float* dW, float* db,
                  int accumulate, float* partials, bool finalize);
 

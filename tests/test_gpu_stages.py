@@ -209,7 +209,7 @@ def test_step_256x128_cluster_cg(cuda_device, eng):
 # convolutions
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("cin,cout", [(3, 32), (32, 32), (32, 2), (2, 32), (32, 3), (4, 32), (32, 4), (32, 64), (64, 2), (2, 64), (64, 32)])
-@pytest.mark.parametrize("shape", [(2, 24, 32), (1, 20, 40)], ids=["2x24x32", "1x20x40"])
+@pytest.mark.parametrize("shape", [(2, 24, 32), (1, 20, 40), (1, 21, 37)], ids=["2x24x32", "1x20x40", "1x21x37"])
 def test_conv5x5(eng, cuda_device, cin, cout, shape):
     B, Y, X = shape
     g = torch.Generator().manual_seed(cin * 100 + cout)
@@ -226,6 +226,33 @@ def test_conv5x5(eng, cuda_device, cin, cout, shape):
     o = eng.conv5x5(dev(x, cuda_device), dev(w, cuda_device), None, addend=dev(add, cuda_device), ref=dev(ref_t, cuda_device), act=2)
     expect = (so._conv(x, w, None) + add) * torch.where(ref_t > 0, 1.0, 0.3)
     assert rel(o, expect) < 2e-6
+
+
+@pytest.mark.parametrize("cin,cout", [(3, 32), (2, 32), (4, 32), (32, 2), (32, 3), (32, 4)])
+def test_conv5x5_thin_paths_agree(eng, cuda_device, cin, cout):
+    """First / last layers: the row-pair kernels (sol_conv_thin.cu, default) against the first-generation kernels
+    (option thin_path = 1) and the fp64 oracle, bench shape and a ragged one, all epilogues."""
+    for B, Y, X in ((3, 128, 64), (1, 19, 45)):
+        g = torch.Generator().manual_seed(cin * 10 + cout)
+        x = torch.randn(B, Y, X, cin, generator=g, dtype=torch.float64)
+        w = torch.randn(5, 5, cin, cout, generator=g, dtype=torch.float64) * 0.1
+        b = torch.randn(cout, generator=g, dtype=torch.float64)
+        add = torch.randn(B, Y, X, cout, generator=g, dtype=torch.float64)
+        ref_t = torch.randn(B, Y, X, cout, generator=g, dtype=torch.float64)
+        outs = {}
+        try:
+            for path in (0, 1):
+                eng.set_option("thin_path", path)
+                outs[path] = (eng.conv5x5(dev(x, cuda_device), dev(w, cuda_device), dev(b, cuda_device)),
+                              eng.conv5x5(dev(x, cuda_device), dev(w, cuda_device), dev(b, cuda_device), addend=dev(add, cuda_device), act=1),
+                              eng.conv5x5(dev(x, cuda_device), dev(w, cuda_device), None, addend=dev(add, cuda_device), ref=dev(ref_t, cuda_device), act=2))
+        finally:
+            eng.set_option("thin_path", 0)
+        base = so._conv(x, w, b)
+        expect = (base, torch.nn.functional.leaky_relu(base + add, 0.3), (so._conv(x, w, None) + add) * torch.where(ref_t > 0, 1.0, 0.3))
+        for k in range(3):
+            assert rel(outs[0][k], expect[k]) < 2e-6 and rel(outs[1][k], expect[k]) < 2e-6
+            assert rel(outs[0][k], outs[1][k]) < 1e-6
 
 
 _TC_KERNELS = {"fp16x3": (2, 0), "fp16x3-two-sets": (2, 1), "fp16x3-one-set": (2, 2), "tf32x3": (3, 0)}

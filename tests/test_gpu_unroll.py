@@ -24,10 +24,13 @@ GRAD_TOL = 2e-5         # weight gradient of a short unroll (measured: 1e-6 .. 7
 
 def _setup(Y, X, B, m, device, use_graph=False, spin=25, direct=1):
     from solver_in_the_loop_b200 import engine
-    # inputs in general position (no back-trace exactly on a cell border), rounded to fp32, non-zero biases:
-    # see the module docstring of test_gpu_quoted_configs.py
+    # inputs in general position (no back-trace exactly on a cell border), rounded to fp32, non-zero biases, weights scaled
+    # like a trained correction: see the module docstring of test_gpu_quoted_configs.py.  (With unscaled Glorot weights the
+    # corrected states are rough, and a single fp32-vs-fp64 back-trace that lands on the other side of a cell border moves
+    # the weight gradient by up to 4e-5 at 64x32 - measured with the SIMT conv + multigrid variant - which says nothing
+    # about the kernels.)
     from test_gpu_quoted_configs import general_position_case
-    geom, rho, vy, vx, re, gty, gtx, sig, params = general_position_case(Y, X, B, m, spin, wscale=1.0)
+    geom, rho, vy, vx, re, gty, gtx, sig, params = general_position_case(Y, X, B, m, spin, wscale=0.1)
     plan = engine.Plan.karman(Y, X, B)
     plan.set_cg(tol_abs=1e-7, tol_rel=1e-6, max_it=4000, cluster=0)
     plan.set_option("direct_solve", direct)
