@@ -5,8 +5,14 @@
 // are 1.6 / 1.1 us of FP32 issue for the whole GPU, but the first-generation kernels (sol_conv.cu: one pixel x 32 couts
 // per thread, 5 warps per SM, 9 shared loads per 32 FMAs) measured 12 - 30 us inside the replayed iteration
 // (profiles/r02/r02_n_chain_trace_sol32.txt).  These kernels trade registers for parallelism instead:
-//   * a CTA is ONE pair of image rows x 32 columns; its four warps split the 32 output channels (expand) or the 32 input
-//     channels (reduce), so an SM holds 10 - 12 warps of independent work instead of 5;
+//   * a CTA is P pairs of image rows x 32 columns; the four warps of a row pair split the 32 output channels (expand) or the
+//     32 input channels (reduce), so an SM holds 10 - 12 warps of independent work instead of 5;
+//   * P is chosen so that the grid fits ONE wave with ONE CTA per SM (132 CTAs of 12 warps at the bench shape), and that is
+//     enforced by a shared-memory request of more than half an SM: with programmatic dependent launch the CTAs become
+//     resident while the PREVIOUS kernel is still running, wherever there is room at that moment - behind k_direct_apply
+//     (129 CTAs x 1024 threads) the 19 idle SMs absorbed most of the 384 small CTAs of the first version and the layer took
+//     15 us instead of 7 (scripts/chain_trace.py with fuse_solver_io = 0 / 1).  The other half of the SM stays free for the
+//     early CTAs of the next kernel;
 //   * lane = x (conflict-free shared reads, coalesced global traffic), a thread owns the two vertically adjacent pixels:
 //     one 6-row column of inputs and one set of warp-uniform 128-bit weight loads feed 5 taps x 2 pixels;
 //   * all global loads of a thread are issued before the first shared store; one barrier; the reduce kernel sums its four
@@ -39,7 +45,7 @@ __device__ __forceinline__ float thin_act(float v, int act, float slope, float r
     return v;
 }
 
-constexpr int TW = 32, TROWS = 2, PW = TW + 4, PH = TROWS + 4;
+constexpr int TW = 32, PW = TW + 4;
 
 // Asynchronous global -> shared copies (LDGSTS): no staging registers, every copy of a thread is in flight at once (ptxas
 // interleaves register-staged loads and stores in groups of four, which serialises the L2 latency); `ok` = false zero-fills.
@@ -52,19 +58,21 @@ __device__ __forceinline__ void cp_async_16(void* dst, const void* src, bool ok)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 
-// ---- Cin <= 4 -> 32.  warp = 8 output channels, lane = x, thread = pixels (y0, x) and (y0 + 1, x) ----
-template <int CIN>
-__global__ void __launch_bounds__(128) k_conv5x5_expand2(const ThinArgs a) {
+// ---- Cin <= 4 -> 32.  warp = (row pair, 8 output channels), lane = x, thread = pixels (y, x) and (y + 1, x) ----
+template <int CIN, int P>
+__global__ void __launch_bounds__(128 * P) k_conv5x5_expand2(const ThinArgs a) {
+    constexpr int NT = 128 * P, TR = 2 * P, PH = TR + 4;
     __shared__ float4 ws4[25 * CIN * 8];            // [tap][ci][32 couts]
     __shared__ float tin[CIN * PH * PW];            // planar [ci][row][px]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TROWS, b = blockIdx.z;
-    constexpr int TOTALW = 25 * CIN * 8, ITERW = (TOTALW + 127) / 128;
-    constexpr int TOTAL = PH * PW * CIN, ITER = (TOTAL + 127) / 128;
+    const int cg = warp & 3, rp = warp >> 2;        // channel group, row pair
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TR, b = blockIdx.z;
+    constexpr int TOTALW = 25 * CIN * 8, ITERW = (TOTALW + NT - 1) / NT;
+    constexpr int TOTAL = PH * PW * CIN, ITER = (TOTAL + NT - 1) / NT;
     const float4* wg = reinterpret_cast<const float4*>(a.w);
     auto fetch_weights = [&]() {
 #pragma unroll
-        for (int it = 0; it < ITERW; ++it) { const int idx = tid + it * 128; if (idx < TOTALW) cp_async_16(ws4 + idx, wg + idx, true); }
+        for (int it = 0; it < ITERW; ++it) { const int idx = tid + it * NT; if (idx < TOTALW) cp_async_16(ws4 + idx, wg + idx, true); }
     };
     if (a.weights_ready) fetch_weights();      // settled weights do not depend on the predecessor kernel: fetch them before waiting for it
     pdl_sync();      // (triggering the dependent kernel only after the FMA loops measured slower: 11.75 vs 11.44 ms per iteration)
@@ -73,7 +81,7 @@ __global__ void __launch_bounds__(128) k_conv5x5_expand2(const ThinArgs a) {
         const float* inb = a.in + (size_t)b * a.Y * a.X * CIN;
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
-            const int idx = tid + it * 128;
+            const int idx = tid + it * NT;
             const int row = idx / (PW * CIN), rem = idx - row * (PW * CIN);     // [row][px][ci] order = global order
             const int px = rem / CIN, ci = rem - px * CIN;
             const int gy = y0 + row - 2, gx = x0 + px - 2;
@@ -90,12 +98,12 @@ __global__ void __launch_bounds__(128) k_conv5x5_expand2(const ThinArgs a) {
     for (int ci = 0; ci < CIN; ++ci) {
 #pragma unroll
         for (int dx = 0; dx < 5; ++dx) {
-            float v[PH];
+            float v[6];
 #pragma unroll
-            for (int r = 0; r < PH; ++r) v[r] = tin[(ci * PH + r) * PW + lane + dx];
+            for (int r = 0; r < 6; ++r) v[r] = tin[(ci * PH + 2 * rp + r) * PW + lane + dx];
 #pragma unroll
             for (int dy = 0; dy < 5; ++dy) {
-                const float4* wq = ws4 + ((dy * 5 + dx) * CIN + ci) * 8 + warp * 2;
+                const float4* wq = ws4 + ((dy * 5 + dx) * CIN + ci) * 8 + cg * 2;
                 const float4 w0 = wq[0], w1 = wq[1];
 #pragma unroll
                 for (int pz = 0; pz < 2; ++pz) {
@@ -111,12 +119,12 @@ __global__ void __launch_bounds__(128) k_conv5x5_expand2(const ThinArgs a) {
     const int gx = x0 + lane;
     unsigned int amax = 0u;
     float4 bv0 = make_float4(0.f, 0.f, 0.f, 0.f), bv1 = bv0;
-    if (a.bias) { bv0 = __ldg(reinterpret_cast<const float4*>(a.bias) + warp * 2); bv1 = __ldg(reinterpret_cast<const float4*>(a.bias) + warp * 2 + 1); }
+    if (a.bias) { bv0 = __ldg(reinterpret_cast<const float4*>(a.bias) + cg * 2); bv1 = __ldg(reinterpret_cast<const float4*>(a.bias) + cg * 2 + 1); }
 #pragma unroll
     for (int pz = 0; pz < 2; ++pz) {
-        const int gy = y0 + pz;
+        const int gy = y0 + 2 * rp + pz;
         if (gy < a.Y && gx < a.X) {
-            const size_t o4 = (((size_t)b * a.Y + gy) * a.X + gx) * 8 + warp * 2;
+            const size_t o4 = (((size_t)b * a.Y + gy) * a.X + gx) * 8 + cg * 2;
             float4 f0 = make_float4(acc[pz][0] + bv0.x, acc[pz][1] + bv0.y, acc[pz][2] + bv0.z, acc[pz][3] + bv0.w);
             float4 f1 = make_float4(acc[pz][4] + bv1.x, acc[pz][5] + bv1.y, acc[pz][6] + bv1.z, acc[pz][7] + bv1.w);
             if (a.addend) {
@@ -143,34 +151,36 @@ __global__ void __launch_bounds__(128) k_conv5x5_expand2(const ThinArgs a) {
     }
 }
 
-// ---- 32 -> Cout <= 4.  warp = 8 input channels, lane = x, thread = pixels (y0, x) and (y0 + 1, x); the four channel
-//      groups are summed through shared memory by warp 0 in group order ----
+// ---- 32 -> Cout <= 4.  warp = (row pair, 8 input channels), lane = x, thread = pixels (y, x) and (y + 1, x); the four channel
+//      groups of a row pair are summed through shared memory by its first warp in group order ----
 constexpr int PS = 36;                              // padded pixel stride (floats): 128-bit reads of consecutive pixels are conflict-free
-template <int COUT>
-constexpr int reduce2_smem_floats() { return 25 * 32 * COUT + PH * PW * PS; }
+template <int COUT, int P>
+constexpr int reduce2_smem_floats() { return 25 * 32 * COUT + (2 * P + 4) * PW * PS; }
 
-template <int COUT>
-__global__ void __launch_bounds__(128) k_conv5x5_reduce2(const ThinArgs a) {
+template <int COUT, int P>
+__global__ void __launch_bounds__(128 * P) k_conv5x5_reduce2(const ThinArgs a) {
+    constexpr int NT = 128 * P, TR = 2 * P, PH = TR + 4;
     extern __shared__ float4 thin_smem4[];
     float* ws = reinterpret_cast<float*>(thin_smem4);           // [25][32][COUT] (the Keras order)
     float* tin = ws + 25 * 32 * COUT;                           // [PH * PW][PS]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TROWS, b = blockIdx.z;
-    constexpr int TOTALW = 25 * 32 * COUT / 4, ITERW = (TOTALW + 127) / 128;
-    constexpr int TOTAL = PH * PW * 8, ITER = (TOTAL + 127) / 128;      // 1728 float4: 13.5 per thread
+    const int cg = warp & 3, rp = warp >> 2;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TR, b = blockIdx.z;
+    constexpr int TOTALW = 25 * 32 * COUT / 4, ITERW = (TOTALW + NT - 1) / NT;
+    constexpr int TOTAL = PH * PW * 8, ITER = (TOTAL + NT - 1) / NT;
     const float4* wg = reinterpret_cast<const float4*>(a.w);
     auto fetch_weights = [&]() {
 #pragma unroll
-        for (int it = 0; it < ITERW; ++it) { const int idx = tid + it * 128; if (idx < TOTALW) cp_async_16(thin_smem4 + idx, wg + idx, true); }
+        for (int it = 0; it < ITERW; ++it) { const int idx = tid + it * NT; if (idx < TOTALW) cp_async_16(thin_smem4 + idx, wg + idx, true); }
     };
     if (a.weights_ready) fetch_weights();
-    pdl_sync();      // (triggering the dependent kernel only after the FMA loops measured slower: 11.75 vs 11.44 ms per iteration)
+    pdl_sync();
     if (!a.weights_ready) fetch_weights();
     {
         const float* inb = a.in + (size_t)b * a.Y * a.X * 32;
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
-            const int idx = tid + it * 128;
+            const int idx = tid + it * NT;
             const int c4 = idx & 7, pix = idx >> 3;
             const int row = pix / PW, px = pix - row * PW;
             const int gy = y0 + row - 2, gx = x0 + px - 2;
@@ -185,12 +195,12 @@ __global__ void __launch_bounds__(128) k_conv5x5_reduce2(const ThinArgs a) {
     for (int c = 0; c < COUT; ++c) { acc[0][c] = 0.0f; acc[1][c] = 0.0f; }
 #pragma unroll
     for (int cq = 0; cq < 2; ++cq) {
-        const int c4 = warp * 2 + cq;                           // float4 chunk of input channels
+        const int c4 = cg * 2 + cq;                             // float4 chunk of input channels
 #pragma unroll
         for (int dx = 0; dx < 5; ++dx) {
-            float4 iv[PH];
+            float4 iv[6];
 #pragma unroll
-            for (int r = 0; r < PH; ++r) iv[r] = *reinterpret_cast<const float4*>(tin + (r * PW + lane + dx) * PS + c4 * 4);
+            for (int r = 0; r < 6; ++r) iv[r] = *reinterpret_cast<const float4*>(tin + ((2 * rp + r) * PW + lane + dx) * PS + c4 * 4);
 #pragma unroll
             for (int dy = 0; dy < 5; ++dy) {
                 float wq[4 * COUT];                             // [ci 0..3][co]: 4*COUT consecutive floats, warp-uniform
@@ -211,19 +221,19 @@ __global__ void __launch_bounds__(128) k_conv5x5_reduce2(const ThinArgs a) {
         }
     }
     __syncthreads();                        // everyone is done with the input tile: reuse it for the group sums
-    float* red = tin;                       // [3 groups][2 * COUT][32 lanes]
-    if (warp > 0) {
+    float* red = tin + rp * (3 * 2 * COUT * 32);      // [3 groups][2 * COUT][32 lanes] per row pair
+    if (cg > 0) {
 #pragma unroll
         for (int pz = 0; pz < 2; ++pz)
 #pragma unroll
-            for (int co = 0; co < COUT; ++co) red[((warp - 1) * 2 * COUT + pz * COUT + co) * 32 + lane] = acc[pz][co];
+            for (int co = 0; co < COUT; ++co) red[((cg - 1) * 2 * COUT + pz * COUT + co) * 32 + lane] = acc[pz][co];
     }
     __syncthreads();
-    if (warp > 0) return;
+    if (cg > 0) return;
     const int gx = x0 + lane;
 #pragma unroll
     for (int pz = 0; pz < 2; ++pz) {
-        const int gy = y0 + pz;
+        const int gy = y0 + 2 * rp + pz;
         if (gy >= a.Y || gx >= a.X) continue;
         const size_t o = (((size_t)b * a.Y + gy) * a.X + gx) * COUT;
 #pragma unroll
@@ -239,24 +249,76 @@ __global__ void __launch_bounds__(128) k_conv5x5_reduce2(const ThinArgs a) {
     }
 }
 
+// P = row pairs per CTA: the smallest that lets the grid fit one wave (one CTA per SM); then the shared-memory request is raised
+// above half an SM so that the early (programmatic) placement cannot put two CTAs on one SM.  Larger grids: P = 4, no padding.
+struct ThinGeom { int P; bool one_wave; };
+int g_thin_cap_mask = 7;        // tuning: bit 0 expand layers, bit 1 reduce layers with Cout = 2 (forward), bit 2 other reduce layers
+ThinGeom thin_geom(int B, int Y, int X) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    for (int P = 1; P <= 4; ++P)
+        if ((long)cdiv(X, TW) * cdiv(Y, 2 * P) * B <= sms) return ThinGeom{P, true};
+    return ThinGeom{4, false};
+}
+constexpr size_t HALF_SM_PLUS = 114 * 1024;      // static + dynamic request that allows one CTA per SM only (2 x (114 + 1) KB > 228 KB per SM) and
+                                                 // still leaves room for one 112 KB CTA of the direct solver (the adjoint sweep runs it next)
+
+template <int CIN, int P>
+int launch_expand2_p(const ThinArgs& a, cudaStream_t st, bool one_wave) {
+    constexpr size_t kStatic = (size_t)25 * CIN * 8 * sizeof(float4) + (size_t)CIN * (2 * P + 4) * PW * sizeof(float);
+    const size_t smem = one_wave ? HALF_SM_PLUS - kStatic : 0;
+    static size_t attr_bytes = 0;      // one process per GPU; raised by the first (eager, never captured) call of a shape
+    if (smem > attr_bytes) {
+        SOL_CUDA(cudaFuncSetAttribute(k_conv5x5_expand2<CIN, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_bytes = smem;
+    }
+    SOL_CUDA(launch_kernel(k_conv5x5_expand2<CIN, P>, dim3(cdiv(a.X, TW), cdiv(a.Y, 2 * P), a.B), dim3(128 * P), smem, st, a));
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
 template <int CIN>
 int launch_expand2(const ThinArgs& a, cudaStream_t st) {
-    SOL_CUDA(launch_kernel(k_conv5x5_expand2<CIN>, dim3(cdiv(a.X, TW), cdiv(a.Y, TROWS), a.B), dim3(128), 0, st, a));
+    ThinGeom g = thin_geom(a.B, a.Y, a.X);
+    g.one_wave = g.one_wave && (g_thin_cap_mask & 1);
+    switch (g.P) {
+        case 1: return launch_expand2_p<CIN, 1>(a, st, g.one_wave);
+        case 2: return launch_expand2_p<CIN, 2>(a, st, g.one_wave);
+        case 3: return launch_expand2_p<CIN, 3>(a, st, g.one_wave);
+        default: return launch_expand2_p<CIN, 4>(a, st, g.one_wave);
+    }
+}
+
+template <int COUT, int P>
+int launch_reduce2_p(const ThinArgs& a, cudaStream_t st, bool one_wave) {
+    constexpr size_t need = (size_t)reduce2_smem_floats<COUT, P>() * sizeof(float);
+    static_assert(need <= HALF_SM_PLUS, "shared-memory budget");
+    const size_t smem = one_wave ? HALF_SM_PLUS : need;
+    static size_t attr_bytes = 0;
+    if (smem > attr_bytes) {
+        SOL_CUDA(cudaFuncSetAttribute(k_conv5x5_reduce2<COUT, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_bytes = smem;
+    }
+    SOL_CUDA(launch_kernel(k_conv5x5_reduce2<COUT, P>, dim3(cdiv(a.X, TW), cdiv(a.Y, 2 * P), a.B), dim3(128 * P), smem, st, a));
     SOL_LAUNCHED();
     return SOL_OK;
 }
 
 template <int COUT>
 int launch_reduce2(const ThinArgs& a, cudaStream_t st) {
-    constexpr size_t smem = (size_t)reduce2_smem_floats<COUT>() * sizeof(float);
-    static_assert(smem <= 48 * 1024, "static shared-memory limit");
-    SOL_CUDA(launch_kernel(k_conv5x5_reduce2<COUT>, dim3(cdiv(a.X, TW), cdiv(a.Y, TROWS), a.B), dim3(128), smem, st, a));
-    SOL_LAUNCHED();
-    return SOL_OK;
+    ThinGeom g = thin_geom(a.B, a.Y, a.X);
+    g.one_wave = g.one_wave && (g_thin_cap_mask & (COUT == 2 ? 2 : 4));
+    switch (g.P) {
+        case 1: return launch_reduce2_p<COUT, 1>(a, st, g.one_wave);
+        case 2: return launch_reduce2_p<COUT, 2>(a, st, g.one_wave);
+        case 3: return launch_reduce2_p<COUT, 3>(a, st, g.one_wave);
+        default: return launch_reduce2_p<COUT, 4>(a, st, g.one_wave);
+    }
 }
 
 }  // namespace
 
+void set_thin_cap_mask(int m) { g_thin_cap_mask = m; }
 int g_thin_path = 0;        // option "thin_path": 0 = the row-pair kernels of this file, 1 = the first-generation kernels of sol_conv.cu
 
 // Returns SOL_ERR_UNSUPPORTED for channel counts this file does not cover (the caller falls back to the generic kernel).

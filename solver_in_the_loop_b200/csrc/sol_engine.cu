@@ -375,6 +375,11 @@ extern "C" int sol_set_option(const char* name, int value) {
         sol::g_thin_path = value;
         return SOL_OK;
     }
+    if (strcmp(name, "thin_cap") == 0) {
+        SOL_CHECK(value >= 0 && value <= 7, "thin_cap is a 3-bit mask");
+        sol::set_thin_cap_mask(value);
+        return SOL_OK;
+    }
     if (strcmp(name, "fuse_stencil") == 0) {
         sol::g_fuse_stencil = value ? 1 : 0;
         return SOL_OK;

@@ -246,6 +246,7 @@ int launch_conv5x5(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, cons
 int launch_conv5x5_thin(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const float* in, const float* w, const float* bias,
                         const float* addend, const float* ref, int act, float slope, float* out, unsigned int* amax_out, bool weights_ready);
 extern int g_thin_path;
+void set_thin_cap_mask(int m);
 int launch_flip_weights(cudaStream_t st, int Cin, int Cout, const float* w, float* wT);
 size_t wgrad_workspace_floats(int Cin, int Cout);
 // the ten 32 -> 32 layers at once: layer l sums nctas10[l] slots of partials + l * part_stride into out + l * (25*32*32 + 32)
