@@ -260,6 +260,9 @@ ThinGeom thin_geom(int B, int Y, int X) {
         if ((long)cdiv(X, TW) * cdiv(Y, 2 * P) * B <= sms) return ThinGeom{P, true};
     return ThinGeom{4, false};
 }
+// (Measured, not adopted: cudaFuncAttributePreferredSharedMemoryCarveout = max on these kernels lets the direct solver of the adjoint
+// sweep become resident beside them — an SM keeps the L1 / shared-memory split of the kernel that arrived first — and takes it
+// from 15.1 to 13.6 us, but the hidden conv layers that inherit the split lose more: 9.9 -> 10.3 us, 10.95 -> 11.10 ms per iteration.)
 constexpr size_t HALF_SM_PLUS = 114 * 1024;      // static + dynamic request that allows one CTA per SM only (2 x (114 + 1) KB > 228 KB per SM) and
                                                  // still leaves room for one 112 KB CTA of the direct solver (the adjoint sweep runs it next)
 
