@@ -306,6 +306,114 @@ static int launch_cg_t(const CgArgs& a, cudaStream_t st, int TY) {
     return SOL_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// ANY grid size (fallback for X not in {32, 64, 128} or Y not tiling the register kernels): the same recurrences and stop rule, one
+// CTA of 1024 threads per simulation, x / r / p / q in a global scratch (L2-resident), cells strided over the threads.  Not a fast
+// path: it exists so that every resolution the reference's scripts accept (karman.py -r, burgers -l) runs through the same ABI.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_sum_max(float& s, float& m, float* red, int tid) {
+    s = wsum(s); m = wmax_nonneg(m);
+    __syncthreads();                                  // previous use of `red` is over
+    if ((tid & 31) == 0) { red[tid >> 5] = s; red[32 + (tid >> 5)] = m; }
+    __syncthreads();
+    s = red[tid & 31]; m = red[32 + (tid & 31)];      // 32 warps
+    s = wsum(s); m = wmax_nonneg(m);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(1024, 1) k_cg_any(const CgArgs a, float* __restrict__ scratch) {
+    pdl_sync();
+    __shared__ float red[64];
+    const int Y = a.Y, X = a.X, N = Y * X, tid = threadIdx.x, b = blockIdx.x;
+    const size_t NY = (size_t)(Y + 1) * X, NX = (size_t)Y * (X + 1);
+    float* x = scratch + (size_t)b * 4 * N;
+    float* r = x + N; float* p = r + N; float* q = p + N;
+    const float* vy = MODE == 1 ? a.vy_in + (size_t)b * NY : nullptr;
+    const float* vx = MODE == 1 ? a.vx_in + (size_t)b * NX : nullptr;
+    const float* rhs = MODE == 0 ? a.rhs + (size_t)b * N : nullptr;
+    float rr = 0.0f, rmax = 0.0f;
+    for (int c = tid; c < N; c += 1024) {
+        const int j = c / X, i = c - j * X;
+        float d;
+        if (MODE == 1) {
+            d = (a.my[(j + 1) * X + i] * vy[(j + 1) * X + i] - a.my[j * X + i] * vy[j * X + i]) +
+                (a.mx[j * (X + 1) + i + 1] * vx[j * (X + 1) + i + 1] - a.mx[j * (X + 1) + i] * vx[j * (X + 1) + i]);
+        } else {
+            d = a.active[c] ? rhs[c] : 0.0f;
+        }
+        x[c] = 0.0f; r[c] = d; p[c] = d;
+        rr = fmaf(d, d, rr); rmax = fmaxf(rmax, fabsf(d));
+    }
+    block_sum_max(rr, rmax, red, tid);
+    const float tol = fmaxf(a.tol_abs, a.tol_rel * rmax);
+    int it = 0;
+    while (it < a.max_it && rmax > 0.0f && rmax >= tol) {
+        __syncthreads();                              // p of every thread is in place
+        float pq = 0.0f, dummy = 0.0f;
+        for (int c = tid; c < N; c += 1024) {
+            const int j = c / X, i = c - j * X;
+            const float nb = ((j > 0 ? p[c - X] : 0.0f) + (j + 1 < Y ? p[c + X] : 0.0f)) + ((i > 0 ? p[c - 1] : 0.0f) + (i + 1 < X ? p[c + 1] : 0.0f));
+            const float pc = p[c];
+            const float qc = a.active[c] ? fmaf(-a.diag[c], pc, nb) : 0.0f;
+            q[c] = qc;
+            pq = fmaf(pc, qc, pq);
+        }
+        block_sum_max(pq, dummy, red, tid);
+        const float alpha = (pq != 0.0f) ? __fdividef(rr, pq) : 0.0f;
+        float rr_new = 0.0f;
+        rmax = 0.0f;
+        for (int c = tid; c < N; c += 1024) {
+            x[c] = fmaf(alpha, p[c], x[c]);
+            const float rc = fmaf(-alpha, q[c], r[c]);
+            r[c] = rc;
+            rr_new = fmaf(rc, rc, rr_new); rmax = fmaxf(rmax, fabsf(rc));
+        }
+        block_sum_max(rr_new, rmax, red, tid);        // (its barriers also order the stencil reads above against the p update below)
+        const float beta = (rr != 0.0f) ? __fdividef(rr_new, rr) : 0.0f;
+        rr = rr_new;
+        for (int c = tid; c < N; c += 1024) p[c] = fmaf(beta, p[c], r[c]);
+        ++it;
+    }
+    if (a.iters && tid == 0) a.iters[b] = it;
+    __syncthreads();
+    if (MODE == 0) {
+        float* po = a.p_out + (size_t)b * N;
+        for (int c = tid; c < N; c += 1024) po[c] = a.active[c] ? x[c] : -rhs[c] / a.diag[c];
+        return;
+    }
+    float* vyo = a.vy_out + (size_t)b * NY;
+    float* vxo = a.vx_out + (size_t)b * NX;
+    for (int f = tid; f < (Y + 1) * X; f += 1024) {   // y faces: p = 0 outside the domain
+        const int j = f / X, i = f - j * X;
+        const float hi = j < Y ? x[j * X + i] : 0.0f, lo = j > 0 ? x[(j - 1) * X + i] : 0.0f;
+        vyo[f] = a.my[f] * (vy[f] - (hi - lo));
+    }
+    for (int f = tid; f < Y * (X + 1); f += 1024) {   // x faces
+        const int j = f / (X + 1), i = f - j * (X + 1);
+        const float hi = i < X ? x[j * X + i] : 0.0f, lo = i > 0 ? x[j * X + i - 1] : 0.0f;
+        vxo[f] = a.mx[f] * (vx[f] - (hi - lo));
+    }
+    if (a.p_out) {
+        float* po = a.p_out + (size_t)b * N;
+        for (int c = tid; c < N; c += 1024) po[c] = x[c];
+    }
+}
+
+static int launch_cg_any(const sol_plan* p, const CgArgs& a, cudaStream_t st, int mode) {
+    sol_plan* mp = const_cast<sol_plan*>(p);
+    if (!mp->cg_any_scratch) {          // first use (never inside a stream capture: the first call with a set of buffers is eager)
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)
+            return fail(SOL_ERR_UNSUPPORTED, "cg (generic grid): the scratch buffer must be allocated by an eager call first");
+        SOL_CUDA(cudaMalloc((void**)&mp->cg_any_scratch, (size_t)p->B_max * 4 * p->Y * p->X * sizeof(float)));
+    }
+    if (mode == 0) SOL_CUDA(launch_kernel(k_cg_any<0>, dim3(a.B), dim3(1024), 0, st, a, mp->cg_any_scratch));
+    else SOL_CUDA(launch_kernel(k_cg_any<1>, dim3(a.B), dim3(1024), 0, st, a, mp->cg_any_scratch));
+    SOL_LAUNCHED();
+    return SOL_OK;
+}
+
 template <int X, int MODE>
 static int dispatch_cg(const CgArgs& a, cudaStream_t st, int CL, int R, int TY) {
     // R <= 8: up to 1024 threads (64 registers each); R == 16: up to 512 threads (128 registers)
@@ -382,8 +490,11 @@ int launch_cg(const sol_plan* p, cudaStream_t st, int B, int mode, const float* 
     a.rhs = rhs; a.p_out = p_out; a.vy_in = vy; a.vx_in = vx; a.vy_out = vy_out; a.vx_out = vx_out;
     a.tol_abs = p->tol_abs; a.tol_rel = p->tol_rel; a.max_it = p->max_it; a.iters = iters;
     int CL, R, TY;
-    if (!cg_geometry(p->Y, p->X, p->cluster, p->cg_rows, CL, R, TY))
-        return fail(SOL_ERR_UNSUPPORTED, "cg: needs X in {32,64,128} and Y = cluster*TY*R with R in {2,4,8,16} and X*TY <= 1024");
+    if (!cg_geometry(p->Y, p->X, p->cluster, p->cg_rows, CL, R, TY)) {
+        if (p->cluster > 1 || p->cg_rows > 0)
+            return fail(SOL_ERR_UNSUPPORTED, "cg: an explicit cluster / rows-per-thread setting needs X in {32,64,128} and Y = cluster*TY*R with R in {2,4,8,16}, X*TY <= 1024");
+        return launch_cg_any(p, a, st, mode);          // any other grid: the generic one-CTA-per-simulation kernel
+    }
 #define SOL_CG_X(XX)                                          \
     if (p->X == XX) {                                         \
         if (mode == 0) return dispatch_cg<XX, 0>(a, st, CL, R, TY); \

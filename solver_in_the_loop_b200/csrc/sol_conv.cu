@@ -1005,9 +1005,9 @@ static int wgrad_ctas(int B, int Y) {
 
 int launch_wgrad(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const float* in, const float* g_out, float* dW, float* db,
                  int accumulate, float* partials, bool finalize) {
-    if (Cin == 32 && Cout == 32) {
+    // (rows that are not a multiple of 4 pixels: the generic kernel below, accumulating straight into dW / db)
+    if (Cin == 32 && Cout == 32 && X % 4 == 0) {
         if (!partials) return fail(SOL_ERR_WORKSPACE, "wgrad 32->32 needs the partials workspace");
-        if (X % 4) return fail(SOL_ERR_UNSUPPORTED, "wgrad 32->32 needs X % 4 == 0");
         const int nctas = wgrad_ctas(B, Y);
         if (in) {
             WgradArgs a;
@@ -1030,7 +1030,8 @@ int launch_wgrad(cudaStream_t st, int B, int Y, int X, int Cin, int Cout, const 
         }
         return SOL_OK;
     }
-    if (!in) return SOL_OK;   // finalize-only call on a thin layer: nothing to do
+    if (!in) return SOL_OK;   // finalize-only call on a layer without partial sums: nothing to do
+    if (!dW || !db) return fail(SOL_ERR_INVALID, "wgrad: dW / db required");
     const bool thin = (Cout == 32 && Cin >= 2 && Cin <= 4) || (Cin == 32 && Cout == 2);
     if (!thin) {
         int CP = 32;

@@ -263,6 +263,7 @@ extern "C" int sol_plan_destroy(sol_plan* p) {
     cudaFree(p->active); cudaFree(p->diag); cudaFree(p->face_my); cudaFree(p->face_mx);
     cudaFree(p->inflow); cudaFree(p->bc_mask_y); cudaFree(p->bc_val_y);
     cudaFree(p->mg.dinv); cudaFree(p->mg.diag); cudaFree(p->mg.cinv);
+    cudaFree(p->cg_any_scratch);
     direct_free(p);
     delete p;
     return SOL_OK;
@@ -807,13 +808,16 @@ int cnn_backward(sol_unroll* u, cudaStream_t st, const float* w, float* gw, cons
         float* gN = (k >= 2) ? gout(2 * k - 2, fN) : (deferred ? u->g0_st + (size_t)step * u->nA : fN);
         // gS = d/d(a_{k-1} + conv_{2k}(t_k) + b)
         if (!deferred) {
-            SOL_TRY(launch_wgrad(st, B, Y, X, 32, 32, t_k, gS, nullptr, nullptr, !first, u->partials + u->partial_stride * (2 * k - 1), false));
+            // (X % 4 != 0: no partial-sum kernel for such rows, the generic kernel accumulates into gw directly — zeroed at the start of the sweep)
+            if (X % 4 == 0) SOL_TRY(launch_wgrad(st, B, Y, X, 32, 32, t_k, gS, nullptr, nullptr, !first, u->partials + u->partial_stride * (2 * k - 1), false));
+            else SOL_TRY(launch_wgrad(st, B, Y, X, 32, 32, t_k, gS, gw + l2.w_off, gw + l2.b_off, 1, nullptr, false));
                 }
         const float* p2 = tc ? u->wprep_bwd + tc_weights_floats() * (2 * k - 1) : nullptr;
         const float* p1 = tc ? u->wprep_bwd + tc_weights_floats() * (2 * k - 2) : nullptr;
         SOL_TRY(layer_conv(u, st, gS, wT + l2.w_off, p2, nullptr, nullptr, t_k, SOL_ACT_DLRELU, a, gT, gm ? gm + 2 * k - 1 : nullptr));
         if (!deferred) {
-            SOL_TRY(launch_wgrad(st, B, Y, X, 32, 32, a_prev, gT, nullptr, nullptr, !first, u->partials + u->partial_stride * (2 * k - 2), false));
+            if (X % 4 == 0) SOL_TRY(launch_wgrad(st, B, Y, X, 32, 32, a_prev, gT, nullptr, nullptr, !first, u->partials + u->partial_stride * (2 * k - 2), false));
+            else SOL_TRY(launch_wgrad(st, B, Y, X, 32, 32, a_prev, gT, gw + l1.w_off, gw + l1.b_off, 1, nullptr, false));
                 }
         SOL_TRY(layer_conv(u, st, gT, wT + l1.w_off, p1, nullptr, gS, a_prev, SOL_ACT_DLRELU, a, gN, (gm && k >= 2) ? gm + 2 * k - 2 : nullptr));
         gS = gN;
@@ -1121,7 +1125,7 @@ int do_backward(sol_unroll* u, cudaStream_t st, const float* weights, const floa
         }
         return SOL_OK;
     }
-    if (!mars) return SOL_OK;      // model_mercury accumulated into gw step by step
+    if (!mars || p->X % 4 != 0) return SOL_OK;      // accumulated into gw step by step
     for (int l = 1; l <= 10; ++l)
         SOL_TRY(launch_wgrad(st, B, p->Y, p->X, 32, 32, nullptr, nullptr, gw + u->L[l].w_off, gw + u->L[l].b_off, 0,
                              u->partials + u->partial_stride * (l - 1), true));

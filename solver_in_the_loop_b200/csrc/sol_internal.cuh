@@ -134,6 +134,7 @@ struct sol_direct {
 };
 
 struct sol_plan {
+    float* cg_any_scratch = nullptr;   // generic-grid CG fallback (sol_cg.cu): [B_max][4][Y*X], allocated on first use
     int Y = 0, X = 0, B_max = 0;
     float dx = 1.f;
     int boundary = SOL_BOUNDARY_OPEN;

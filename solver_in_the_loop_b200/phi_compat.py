@@ -199,16 +199,50 @@ class Fluid:
         return StaggeredGrid([torch.full_like(v._vy, float(value)), torch.full_like(v._vx, float(value))], v.box)
 
 
-# ---- simulator -------------------------------------------------------------------------------------
+# ---- pressure-solver plug-in slot (karman_train.py:51,167-168: pressure_solver=None | SparseCG(...) | CUDASolver()) ---------------
+class SparseCG:
+    """PhiFlow's ``SparseCG(accuracy=1e-5, max_iterations=2000)``: selects the on-chip CG kernels with the reference's recurrences and
+    stop rule (max|r| < accuracy) instead of the default direct projection."""
+
+    def __init__(self, accuracy=1e-5, gradient_accuracy="same", max_iterations=2000, max_gradient_iterations="same", autodiff=False):
+        self.accuracy = float(accuracy)
+        self.max_iterations = int(max_iterations)
+        self.preconditioned = False
+
+
+class CUDASolver(SparseCG):
+    """``phi.tf.tf_cuda_pressuresolver.CUDASolver`` (the reference's --cuda flag): same stop rule; here the multigrid-preconditioned
+    CG kernel."""
+
+    def __init__(self, accuracy=1e-5, max_iterations=2000):
+        SparseCG.__init__(self, accuracy=accuracy, max_iterations=max_iterations)
+        self.preconditioned = True
+
+
+class DirectProjection:
+    """The engine's default: precomputed fast Poisson solve + capacitance correction (exact, no stop rule)."""
+
+
 class IncompressibleFlow:
     def __init__(self, pressure_solver=None, make_input_divfree=False, make_output_divfree=True):
-        if pressure_solver is not None:
-            raise SolError("pressure_solver plug-ins are replaced by the built-in sm_100a CG kernel")
         if make_input_divfree or not make_output_divfree:
             raise SolError("only make_input_divfree=False, make_output_divfree=True (the reference's setting) is implemented")
         self._plans = {}
         self.cg = dict(tol_abs=1e-5, tol_rel=0.0, max_it=2000, cluster=0)     # SparseCG defaults
+        self.direct_solve, self.cg_precond = 1, 1
+        if isinstance(pressure_solver, SparseCG):
+            self.cg = dict(tol_abs=pressure_solver.accuracy, tol_rel=0.0, max_it=pressure_solver.max_iterations, cluster=0)
+            self.direct_solve, self.cg_precond = 0, int(pressure_solver.preconditioned)
+        elif pressure_solver is not None and not isinstance(pressure_solver, DirectProjection):
+            raise SolError("pressure_solver must be None, DirectProjection(), SparseCG(...) or CUDASolver(...) from phi_compat "
+                           "(PhiFlow solver objects cannot run inside the sm_100a engine)")
         self.last_iterations = None
+
+    def _configure(self, plan: Plan) -> Plan:
+        plan.set_cg(**self.cg)
+        plan.set_option("direct_solve", self.direct_solve)
+        plan.set_option("cg_precond", self.cg_precond)
+        return plan
 
 
 class KarmanFlow(IncompressibleFlow):
@@ -247,8 +281,7 @@ class KarmanFlow(IncompressibleFlow):
             a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
             return np.ascontiguousarray(a.reshape(-1, Y + 1, X)[0], dtype=np.float32)
 
-        plan = Plan(Y, X, B, dx, _lib.SOL_BOUNDARY_OPEN, solid, inflow, bc(velBCyMask), bc(velBCy), device=dev)
-        plan.set_cg(**self.cg)
+        plan = self._configure(Plan(Y, X, B, dx, _lib.SOL_BOUNDARY_OPEN, solid, inflow, bc(velBCyMask), bc(velBCy), device=dev))
         self._plans[key] = plan
         return plan
 

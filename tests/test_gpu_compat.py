@@ -57,6 +57,39 @@ def test_reference_apply_loop(cuda_device):
     assert st.velocity.staggered_tensor().shape == (1, 2 * res + 1, res + 1, 2)
 
 
+def test_pressure_solver_plugin_slot(cuda_device):
+    """karman_train.py:51,167-168: `KarmanFlow(pressure_solver=...)`.  None / DirectProjection() = the exact direct projection (no
+    iterations), SparseCG(accuracy) = the CG kernels with the reference's stop rule, CUDASolver() (--cuda) = the preconditioned CG;
+    anything else is refused.  All three give the same step within their stop rule."""
+    from solver_in_the_loop_b200.engine import SolError
+    from solver_in_the_loop_b200.phi_compat import (OPEN, CUDASolver, DirectProjection, Domain, Fluid, KarmanFlow, SparseCG, StaggeredGrid, box,
+                                                    unstack_staggered_tensor)
+    res, L, Re = 32, 100, 3.2e5
+    st0 = Fluid(Domain(resolution=[res * 2, res], box=box[0:L * 2, 0:L], boundaries=OPEN), buoyancy_factor=0)
+    vn = st0.velocity.staggered_tensor()
+    vn[..., 0] = 1.0
+    vn[..., vn.shape[1] // 2 + 10:vn.shape[1] // 2 + 20, vn.shape[2] // 2 - 2:vn.shape[2] // 2 + 2, 1] = 1.0
+    st0 = st0.copied_with(velocity=StaggeredGrid(unstack_staggered_tensor(vn), st0.velocity.box))
+    vnp = np.zeros(tuple(st0.velocity.data[0].data.shape))
+    vnp[..., 0:2, 0:vnp.shape[2] - 1, 0] = 1.0
+    vnp[..., 0:vnp.shape[1], 0:1, 0] = 1.0
+    vnp[..., 0:vnp.shape[1], -1:, 0] = 1.0
+    outs = {}
+    for name, solver in (("default", None), ("direct", DirectProjection()), ("cg", SparseCG(accuracy=1e-5)), ("cuda", CUDASolver())):
+        sim = KarmanFlow(pressure_solver=solver)
+        st = st0
+        for _ in range(3):
+            st = sim.step(st, re=Re, res=res, velBCy=vnp, velBCyMask=np.copy(vnp))
+        outs[name] = (st.velocity.data[0].data.clone(), st.velocity.data[1].data.clone(), int(sim.last_iterations.max()))
+    assert outs["default"][2] == 0 and outs["direct"][2] == 0
+    assert outs["cg"][2] > outs["cuda"][2] > 0                  # plain CG needs more iterations than the preconditioned one
+    for name in ("direct", "cg", "cuda"):
+        tol = 0.0 if name == "direct" else 5e-3                 # the reference's stop rule truncates the pressure at ~7e-3
+        assert rel(outs[name][0], outs["default"][0]) <= tol and rel(outs[name][1], outs["default"][1]) <= tol
+    with pytest.raises(SolError):
+        KarmanFlow(pressure_solver=object())
+
+
 def test_phi2_flavoured_surface(cuda_device):
     """karman-2d-phi2/karman_train.py:149-196 signature: step(density_in, velocity_in, re, res, ...) -> [density, velocity];
     physical-units viscosity and inflow-before-advection, checked against the oracle with the matching switches."""

@@ -36,6 +36,35 @@ def test_karman_generate_train_apply(cuda_device, tmp_path):
         assert float((v2 - v).norm() / v.norm()) < 1e-5
 
 
+def test_karman_generated_trajectory_matches_oracle(cuda_device, tmp_path):
+    """karman.py (data generation, karman-2d/Makefile:20-23): every written frame of the rollout against the oracle's trajectory from
+    the same warm start (karman.py:107-110) and Reynolds number — not just shapes."""
+    from oracle import sol_oracle as so
+    from solver_in_the_loop_b200 import formats
+    from solver_in_the_loop_b200.scripts import karman
+    data = str(tmp_path / "traj")
+    res, L, Re, T = 32, 100, 3.2e5, 13
+    st = karman.main(["-o", data, "-r", str(res), "-l", str(L), "--re", str(Re), "-t", str(T), "--skipsteps", "0", "--sim-index", "0"])
+    geom = so.KarmanGeom(2 * res, res, L)
+    rho, vy, vx = so.warm_start(geom, 1)
+    re_t = torch.tensor([Re], dtype=torch.float64)
+    rel = lambda a, b: float((torch.as_tensor(a).double().cpu() - b).norm() / (b.norm() + 1e-30))
+    Y, X = 2 * res, res
+    worst = 0.0
+    for i in range(T):
+        if i > 0:
+            rho, vy, vx = so.karman_step(rho, vy, vx, re_t, geom)
+        v = formats.read_zipped_array(data + "/sim_000000/velo_%06d.npz" % i)
+        d = formats.read_zipped_array(data + "/sim_000000/dens_%06d.npz" % i)
+        assert v.shape == (1, Y + 1, X + 1, 2) and d.shape == (1, Y, X, 1)
+        e = (rel(v[0, :, :X, 0], vy[0]), rel(v[0, :Y, :, 1], vx[0]), rel(d[0, ..., 0], rho[0]))
+        worst = max(worst, *e)
+        assert max(e) < 1e-5, (i, e)
+    print("generated trajectory vs oracle, worst relative L2 over %d frames: %.2e" % (T, worst))
+    vfin = st.velocity.staggered_tensor()
+    assert rel(vfin[0, :, :X, 0], vy[0]) < 1e-5 and rel(vfin[0, :Y, :, 1], vx[0]) < 1e-5
+
+
 def test_burgers_generate_train_apply(cuda_device, tmp_path):
     """burgers/Makefile:20-23, 75-77: burgers.py (20 travelling sine forces, random smooth initial state) -> burgers_train.py -> burgers_apply.py."""
     from solver_in_the_loop_b200 import formats
