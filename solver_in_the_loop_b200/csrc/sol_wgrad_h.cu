@@ -358,6 +358,10 @@ __global__ void __launch_bounds__(256) k_amax(const float4* __restrict__ x, size
 // next layer find no free slot (no prologue overlap), and the side stream's tail delays the end of the sweep.  Default off.
 int g_wgrad_bg_ctas = 0;
 int g_wgrad_bg_chunk = 4;
+// Also measured and rejected (scripts/probes/wgrad_paired_ctas_experiment.diff, profiles/r02/r02_z_*): TWO co-resident CTAs per SM that
+// split the tap groups 4 + 3 (256 TMEM columns and one 95 KB stage each).  Parity-green, but 187 us per layer against 166: unlike the
+// K-major conv operands, the MN-major SWIZZLE_64B operand fetch of this kernel is already at its shared-memory rate with one CTA, so
+// interleaving two instruction streams gains nothing and the duplicated tile split costs.
 int g_wgrad_issuers = 1;     // MMA-issuing warps of k_wgrad_c32_h: measured 12.37 (2) vs 12.39 ms (1) per iteration — the UMMAs of one CTA execute in
                              // order whichever warp issues them (only co-resident CTAs overlap their per-instruction overhead), so one is the default
 
