@@ -42,6 +42,7 @@ OPS = ("UTCHMMA", "UTCQMMA", "UTCBAR", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "
 
 
 def base_name(full):
+    full = full.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
     n = full.split("(")[0].replace("void ", "").strip()
     n = n.split("<")[0]
     return n.split("::")[-1]

@@ -260,9 +260,11 @@ ThinGeom thin_geom(int B, int Y, int X) {
         if ((long)cdiv(X, TW) * cdiv(Y, 2 * P) * B <= sms) return ThinGeom{P, true};
     return ThinGeom{4, false};
 }
-// (Measured, not adopted: cudaFuncAttributePreferredSharedMemoryCarveout = max on these kernels lets the direct solver of the adjoint
-// sweep become resident beside them — an SM keeps the L1 / shared-memory split of the kernel that arrived first — and takes it
-// from 15.1 to 13.6 us, but the hidden conv layers that inherit the split lose more: 9.9 -> 10.3 us, 10.95 -> 11.10 ms per iteration.)
+// Shared-memory split.  An SM keeps the L1 / shared-memory carve-out of the kernel whose CTAs arrived first, and the early CTAs of the
+// NEXT kernel can only join if their shared memory still fits that split.  The reduce kernels are followed (adjoint sweep: directly)
+// by the cluster kernel of the direct solver, 112 KB per CTA: they ask for the maximum carve-out so that it becomes resident beside
+// them (15.1 -> 12.9 us).  The expand kernels must NOT: the hidden conv layers behind them would inherit the split for the whole
+// chain and lose more (9.9 -> 10.3 us per layer; profiles/r02/r02_v_*, r02_w_*).
 constexpr size_t HALF_SM_PLUS = 114 * 1024;      // static + dynamic request that allows one CTA per SM only (2 x (114 + 1) KB > 228 KB per SM) and
                                                  // still leaves room for one 112 KB CTA of the direct solver (the adjoint sweep runs it next)
 
@@ -301,6 +303,11 @@ int launch_reduce2_p(const ThinArgs& a, cudaStream_t st, bool one_wave) {
     if (smem > attr_bytes) {
         SOL_CUDA(cudaFuncSetAttribute(k_conv5x5_reduce2<COUT, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_bytes = smem;
+    }
+    static bool carve_done = false;
+    if (!carve_done) {
+        SOL_CUDA(cudaFuncSetAttribute(k_conv5x5_reduce2<COUT, P>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        carve_done = true;
     }
     SOL_CUDA(launch_kernel(k_conv5x5_reduce2<COUT, P>, dim3(cdiv(a.X, TW), cdiv(a.Y, 2 * P), a.B), dim3(128 * P), smem, st, a));
     SOL_LAUNCHED();

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_diffuse_advect(const FusedArgs a
             float out = cc + alpha * ((R(ju, i) + R(jdn, i) + R(j, ir) + R(j, il)) - 4.0f * cc);      // = c + alpha*lap5 (sol_cells.cuh)
             if (a.bcm) out = out * (1.0f - __ldg(a.bcm + j * X + i)) + __ldg(a.bcv + j * X + i);
             d_vy[k] = out;
-            if (j >= y0 && (j < y0 + FT_TY || (j == Y && y0 + FT_TY == Y)) && i >= x0 && i < x0 + FT_TX) a.vy1[(size_t)b * NY + j * X + i] = out;
+            if (j >= y0 && (j < y0 + FT_TY || (j == Y && y0 + FT_TY >= Y)) && i >= x0 && i < x0 + FT_TX) a.vy1[(size_t)b * NY + j * X + i] = out;
         }
         // x component, face (j, i) of the [Y, X+1] grid
         if (j >= 0 && j < Y && i >= 0 && i <= X) {
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_diffuse_advect(const FusedArgs a
     DY.win.p = d_vy + (DY.win.j0 - jd0) * FT_DW + (DY.win.i0 - id0);
     DX.win.p = d_vx + (DX.win.j0 - jd0) * FT_DW + (DX.win.i0 - id0);
     const float s = a.s;
-    const int ty_rows = (y0 + FT_TY == Y) ? FT_TY + 1 : FT_TY;            // the last tile row owns the far y-face row
+    const int ty_rows = (y0 + FT_TY >= Y) ? (Y - y0) + 1 : FT_TY;         // the last tile row owns the far y-face row (Y need not be a multiple of the tile)
     const int tx_cols = (x0 + FT_TX >= X) ? min(FT_TX, X - x0) + 1 : FT_TX;   // the last tile column owns the far x-face column
     const int tw = min(FT_TX, X - x0);
     for (int k = tid; k < ty_rows * tw; k += FT_THREADS) {                // y-faces

@@ -55,10 +55,12 @@ def test_unroll_misuse_is_reported(cuda_device):
         engine.set_option("no_such_option", 1)
 
 
-def test_unsupported_grid_is_reported_not_emulated(cuda_device):
+def test_unsupported_settings_are_reported_not_emulated(cuda_device):
     from solver_in_the_loop_b200 import engine
-    plan = engine.Plan.karman(96, 48, 1)                    # X = 48: no pressure-solve kernel for this width
+    plan = engine.Plan.karman(96, 48, 1)                    # X = 48: only the generic CG kernel covers this width ...
     vy, vx = plan.faces(1)
+    plan.project(vy, vx)
+    plan.set_cg(tol_abs=1e-5, tol_rel=0.0, max_it=2000, cluster=2)      # ... and it has no cluster variant: refused, not emulated
     with pytest.raises(engine.SolError) as e:
         plan.project(vy, vx)
     assert "error 3" in str(e.value) or "X in" in str(e.value)
