@@ -268,6 +268,11 @@ def main():
     from solver_in_the_loop_b200.trainer import SolTrainer
 
     apply_config(args)
+    # stdout carries ONE JSON line and nothing else: libraries (NCCL prints its version banner straight to file descriptor 1) are sent
+    # to stderr for the whole run, the line goes to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -275,7 +280,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("SOL_NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        if os.environ.get("SOL_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = os.environ["SOL_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert world == args.gpus or world == 1, "launch with torch.distributed.run --nproc-per-node N for --gpus N"
     dev = torch.device("cuda", local)
@@ -505,7 +511,8 @@ def main():
                 line["roofline_conv"] = roof_conv
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
