@@ -57,3 +57,20 @@ def test_trainer_step_matches_oracle_adam(cuda_device, clip):
     assert abs(float(l) - float(loss)) < 1e-5 * float(loss)
     assert rel(tr.grad, g) < 2e-5
     assert float((upd - upd_ref).norm() / upd_ref.norm()) < 1e-3
+
+
+def test_pressure_solver_plugin_classes_cpu():
+    """karman_train.py:51,167-168: the pressure_solver slot of IncompressibleFlow / KarmanFlow (host logic only; the GPU behaviour is
+    covered by tests/test_gpu_compat.py)."""
+    import pytest
+    from solver_in_the_loop_b200._lib import SolError
+    from solver_in_the_loop_b200.phi_compat import CUDASolver, DirectProjection, KarmanFlow, SparseCG
+    assert KarmanFlow().direct_solve == 1 and KarmanFlow(DirectProjection()).direct_solve == 1
+    cg = KarmanFlow(pressure_solver=SparseCG(accuracy=3e-6, max_iterations=777))
+    assert cg.direct_solve == 0 and cg.cg_precond == 0 and cg.cg == dict(tol_abs=3e-6, tol_rel=0.0, max_it=777, cluster=0)
+    cu = KarmanFlow(pressure_solver=CUDASolver())
+    assert cu.direct_solve == 0 and cu.cg_precond == 1 and cu.cg["tol_abs"] == 1e-5 and cu.cg["max_it"] == 2000
+    with pytest.raises(SolError):
+        KarmanFlow(pressure_solver="SparseCG")
+    with pytest.raises(SolError):
+        KarmanFlow(make_input_divfree=True)
